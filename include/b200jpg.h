@@ -1,0 +1,242 @@
+/*
+ * b200jpg.h -- C ABI of the B200-native JPEG block pipeline.
+ *
+ * This is the drop-in boundary for the per-MCU worker path of image-rs/jpeg-decoder v0.3.2
+ * (reference at /root/reference): everything after Huffman decoding -- dequantise + IDCT,
+ * plane assembly, chroma upsampling, colour conversion -- runs as hand-written sm_100a CUDA
+ * kernels.  Plain pointers and sizes only; no C++ or torch types.  Each entry point cites the
+ * reference interface it replaces.  INTEGRATION.md shows the Rust `extern "C"` block a
+ * maintainer of the reference would add to bind these.
+ *
+ * There is no CPU fallback: every function that needs the device returns
+ * B200JPG_ERR_INTERNAL when CUDA is unavailable.
+ */
+#ifndef B200JPG_H
+#define B200JPG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define B200JPG_API
+#else
+#define B200JPG_API __attribute__((visibility("default")))
+#endif
+
+/* ---- status codes: src/error.rs:37-48 (Error::{Format, Unsupported, Io, Internal}) ------------ */
+enum {
+    B200JPG_OK = 0,
+    B200JPG_ERR_FORMAT = -1,      /* Error::Format(String)                       */
+    B200JPG_ERR_UNSUPPORTED = -2, /* Error::Unsupported(UnsupportedFeature)      */
+    B200JPG_ERR_IO = -3,          /* Error::Io (truncated input)                 */
+    B200JPG_ERR_INTERNAL = -4     /* Error::Internal: CUDA failure, contract violations the
+                                     reference turns into assert!/panic (src/worker/rayon.rs:85,
+                                     src/worker/immediate.rs:31,47)               */
+};
+
+/* ---- ColorTransform: src/decoder.rs:79-98, same order ---------------------------------------- */
+enum {
+    B200JPG_CT_NONE = 0,
+    B200JPG_CT_UNKNOWN = 1,
+    B200JPG_CT_GRAYSCALE = 2,
+    B200JPG_CT_RGB = 3,
+    B200JPG_CT_YCBCR = 4,
+    B200JPG_CT_CMYK = 5,
+    B200JPG_CT_YCCK = 6,
+    B200JPG_CT_JCS_BG_YCC = 7,
+    B200JPG_CT_JCS_BG_RGB = 8
+};
+
+/* ---- PixelFormat: src/decoder.rs:40-49 ; CodingProcess: src/parser.rs:26-33 ------------------- */
+enum { B200JPG_PF_L8 = 0, B200JPG_PF_L16 = 1, B200JPG_PF_RGB24 = 2, B200JPG_PF_CMYK32 = 3 };
+enum { B200JPG_CP_DCT_SEQUENTIAL = 0, B200JPG_CP_DCT_PROGRESSIVE = 1, B200JPG_CP_LOSSLESS = 2 };
+
+/* ---- arithmetic variant of the block kernels (the reference ships two) --------- */
+enum {
+    B200JPG_ARITH_SCALAR = 0, /* src/idct.rs:260-370 + src/decoder.rs:1486-1508: the
+                                 `platform_independent` i32 fixed-point path (canonical, default) */
+    B200JPG_ARITH_SSSE3 = 1   /* src/arch/ssse3.rs: the 16-bit saturating path an x86-64 build of
+                                 the reference runs by default, emulated bit-exactly            */
+};
+
+/* kernel selection, for tests and profiling (0 = pick the fastest applicable kernel) */
+enum { B200JPG_KERNEL_AUTO = 0, B200JPG_KERNEL_GENERIC = 1, B200JPG_KERNEL_FAST = 2 };
+
+/* ---- parser::Component: src/parser.rs:77-89 (geometry from update_component_sizes, 292-310) --- */
+typedef struct {
+    uint8_t identifier;
+    uint8_t h;  /* horizontal_sampling_factor 1..4 */
+    uint8_t v;  /* vertical_sampling_factor 1..4   */
+    uint8_t tq; /* quantization_table_index 0..3   */
+    uint16_t dct_scale; /* 1, 2, 4 or 8 */
+    uint16_t size_w, size_h;   /* component.size (samples)          */
+    uint16_t block_w, block_h; /* component.block_size (8x8 blocks) */
+} b200jpg_component;
+
+typedef struct {
+    int device;       /* CUDA device ordinal                                              */
+    int arith;        /* B200JPG_ARITH_*                                                  */
+    int k1_kernel;    /* B200JPG_KERNEL_* for dequant+IDCT                                 */
+    int k2_kernel;    /* B200JPG_KERNEL_* for upsample+colour                              */
+    void *stream;     /* cudaStream_t to enqueue on; NULL = the context creates its own    */
+    int reserved[4];
+} b200jpg_options;
+
+typedef struct b200jpg_ctx b200jpg_ctx;
+
+B200JPG_API void b200jpg_default_options(b200jpg_options *opt);
+/* One context per device (and per host thread that wants its own stream). */
+B200JPG_API int b200jpg_create(const b200jpg_options *opt, b200jpg_ctx **ctx);
+B200JPG_API void b200jpg_destroy(b200jpg_ctx *ctx);
+B200JPG_API const char *b200jpg_last_error(const b200jpg_ctx *ctx);
+B200JPG_API const char *b200jpg_version(void);
+/* number of kernels this context has launched since creation (bench.py's gpu_launches) */
+B200JPG_API uint64_t b200jpg_launch_count(const b200jpg_ctx *ctx);
+B200JPG_API int b200jpg_synchronize(b200jpg_ctx *ctx);
+
+/* parser::update_component_sizes, src/parser.rs:292-310: fills size_* / block_* of comps[] from the
+ * sampling factors and dct_scale already set in them. */
+B200JPG_API int b200jpg_update_component_sizes(uint16_t width, uint16_t height, b200jpg_component *comps,
+                                               int ncomp, uint16_t *mcu_w, uint16_t *mcu_h);
+/* idct::choose_idct_size, src/idct.rs:14-28 */
+B200JPG_API int b200jpg_choose_idct_size(uint16_t full_w, uint16_t full_h, uint16_t req_w, uint16_t req_h);
+
+/* ============================================================================================
+ * Worker-shaped API: trait Worker, src/worker/mod.rs:24-35 (impls src/worker/immediate.rs,
+ * src/worker/rayon.rs, src/worker/multithreaded.rs), obtained per decode like WorkerScope
+ * (src/worker/mod.rs:44-95).  Single-threaded use per worker, like the RefCell'd scope.
+ * ========================================================================================== */
+typedef struct b200jpg_worker b200jpg_worker;
+B200JPG_API int b200jpg_worker_new(b200jpg_ctx *ctx, b200jpg_worker **w);
+B200JPG_API void b200jpg_worker_free(b200jpg_worker *w);
+/* Worker::start(RowData{index, component, quantization_table}), src/worker/mod.rs:18-25: allocates
+ * the zeroed plane block_w*block_h*dct_scale^2 on the device and resets the row offset.
+ * qt_natural: 64 entries in natural (de-zigzagged) order, src/decoder.rs:490-496. */
+B200JPG_API int b200jpg_worker_start(b200jpg_worker *w, int index, const b200jpg_component *c,
+                                     const uint16_t qt_natural[64]);
+/* Worker::append_row((index, Vec<i16>)), src/worker/mod.rs:26: one MCU row of one component,
+ * n_i16 must be block_w * v * 64 (assert at src/worker/immediate.rs:47).  The coefficients are
+ * copied before returning; the IDCT itself is deferred to get_result (one launch per component). */
+B200JPG_API int b200jpg_worker_append_row(b200jpg_worker *w, int index, const int16_t *coefs, size_t n_i16);
+/* Worker::append_rows, src/worker/mod.rs:29-34: `nrows` consecutive MCU rows, contiguous. */
+B200JPG_API int b200jpg_worker_append_rows(b200jpg_worker *w, int index, const int16_t *coefs, size_t n_i16,
+                                           size_t nrows);
+/* Worker::get_result(index) -> Vec<u8>, src/worker/mod.rs:27: runs the IDCT kernel over everything
+ * appended and copies the plane to the host (plane_out may be NULL to leave it on the device
+ * only; *plane_len receives the plane size either way).  The device plane stays alive for
+ * b200jpg_worker_compute_image. */
+B200JPG_API int b200jpg_worker_get_result(b200jpg_worker *w, int index, uint8_t *plane_out, size_t cap,
+                                          size_t *plane_len);
+/* decoder::compute_image over the planes still resident in the worker (indices 0..ncomp-1):
+ * src/decoder.rs:1300-1336 without the host round trip of the planes. */
+B200JPG_API int b200jpg_worker_compute_image(b200jpg_worker *w, int ncomp, uint16_t out_w, uint16_t out_h,
+                                             int color_transform, uint8_t *out, size_t cap, size_t *out_len);
+
+/* decoder::compute_image(components, data: Vec<Vec<u8>>, output_size, color_transform),
+ * src/decoder.rs:1300-1336 -> worker::compute_image_parallel, src/worker/mod.rs:97-128 /
+ * src/worker/rayon.rs:193-219: host planes in, interleaved pixels out. */
+B200JPG_API int b200jpg_compute_image(b200jpg_ctx *ctx, const b200jpg_component *comps, int ncomp,
+                                      const uint8_t *const *planes, const size_t *plane_len, uint16_t out_w,
+                                      uint16_t out_h, int color_transform, uint8_t *out, size_t cap,
+                                      size_t *out_len);
+
+/* ============================================================================================
+ * Batched hot path: n independent images, dense coefficients -> pixels.  New surface (the
+ * reference has no batching); per image it is exactly start + append_rows +
+ * get_result per component followed by compute_image.
+ * ========================================================================================== */
+typedef struct {
+    uint16_t width, height; /* output size (frame.output_size, src/parser.rs:50-61) */
+    uint8_t ncomp;          /* 1, 3 or 4 */
+    uint8_t color_transform;
+    uint16_t reserved;
+    b200jpg_component comps[4];
+    const uint16_t *qt[4];   /* natural order, 64 entries each */
+    const int16_t *coefs[4]; /* host: block_w*block_h*64 i16 per component, blocks in raster order,
+                                coefficients in natural order (src/decoder.rs:962-967).  May be NULL
+                                when the plan is only used with device-resident coefficients. */
+} b200jpg_image_desc;
+
+typedef struct b200jpg_batch b200jpg_batch;
+typedef struct {
+    size_t coef_bytes;  /* size of the coefficient slab (device) */
+    size_t plane_bytes; /* size of the plane slab (device)       */
+    size_t out_bytes;   /* size of the pixel slab (device)       */
+    size_t n_blocks;    /* 8x8 blocks over all components        */
+    size_t n_pixels;    /* sum of width*height                   */
+    size_t k1_algorithmic_bytes; /* 128 B read + dct_scale^2 B written per block */
+    size_t k2_algorithmic_bytes; /* plane bytes read once + pixel bytes written  */
+} b200jpg_batch_info;
+
+/* Validates every image (same errors as the reference: NonIntegerSubsamplingRatio
+ * src/upsampler.rs:93-98, invalid (ncomp, transform) src/decoder.rs:1344-1386), lays out the slabs
+ * and uploads the per-component tables.  statuses[i] (optional) receives the per-image code; a bad
+ * image does not poison the batch, it is skipped. */
+B200JPG_API int b200jpg_batch_create(b200jpg_ctx *ctx, const b200jpg_image_desc *imgs, size_t n, int *statuses,
+                                     b200jpg_batch **batch);
+B200JPG_API void b200jpg_batch_free(b200jpg_batch *b);
+B200JPG_API int b200jpg_batch_get_info(const b200jpg_batch *b, b200jpg_batch_info *info);
+/* byte offsets of image i inside the slabs */
+B200JPG_API int b200jpg_batch_image_layout(const b200jpg_batch *b, size_t i, size_t coef_off[4], size_t plane_off[4],
+                                           size_t *out_off, size_t *out_len);
+/* Device-resident run: K1 over d_coefs -> d_planes, then K2 over d_planes -> d_out, enqueued on the
+ * context's stream (no synchronisation).  stages: bit0 = K1, bit1 = K2. */
+B200JPG_API int b200jpg_batch_run_device(b200jpg_batch *b, const void *d_coefs, void *d_planes, void *d_out,
+                                         int stages);
+/* Host-to-host run through internal device slabs: H2D of the coefficients named in the descs,
+ * K1, K2, D2H of the pixels into outs[i] (out_caps[i] bytes), chunked and double-buffered over
+ * two streams.  pinned: non-zero if the caller's buffers are page-locked (then copies are truly
+ * asynchronous). */
+B200JPG_API int b200jpg_batch_run_host(b200jpg_batch *b, const b200jpg_image_desc *imgs, uint8_t *const *outs,
+                                       const size_t *out_caps, int *statuses);
+/* convenience: create + run_host + free */
+B200JPG_API int b200jpg_decode_batch(b200jpg_ctx *ctx, const b200jpg_image_desc *imgs, size_t n,
+                                     uint8_t *const *outs, const size_t *out_caps, int *statuses);
+
+/* page-locked host memory helpers (cudaHostAlloc / cudaFreeHost) */
+B200JPG_API void *b200jpg_host_alloc(size_t bytes);
+B200JPG_API void b200jpg_host_free(void *p);
+
+/* ============================================================================================
+ * Whole-file decoder: Decoder<R>, src/decoder.rs:101-295.  Marker parsing and Huffman decoding
+ * (src/parser.rs, src/huffman.rs, src/decoder.rs:297-1298) run on the host in C++; the worker
+ * path runs on the GPU through the API above.
+ * ========================================================================================== */
+typedef struct b200jpg_decoder b200jpg_decoder;
+typedef struct {
+    uint16_t width, height;
+    int pixel_format;   /* B200JPG_PF_* */
+    int coding_process; /* B200JPG_CP_* */
+} b200jpg_image_info; /* ImageInfo, src/decoder.rs:64-74 */
+
+/* Decoder::new(reader), src/decoder.rs:134: `data` must stay valid for the decoder's lifetime. */
+B200JPG_API int b200jpg_decoder_new(b200jpg_ctx *ctx, const uint8_t *data, size_t len, b200jpg_decoder **d);
+B200JPG_API void b200jpg_decoder_free(b200jpg_decoder *d);
+B200JPG_API void b200jpg_decoder_set_color_transform(b200jpg_decoder *d, int color_transform); /* :158 */
+B200JPG_API void b200jpg_decoder_set_max_decoding_buffer_size(b200jpg_decoder *d, size_t max); /* :163 */
+B200JPG_API int b200jpg_decoder_read_info(b200jpg_decoder *d);                                  /* :265 */
+/* Decoder::info(), :171 -- returns 1 and fills *info once read_info/decode succeeded, else 0 */
+B200JPG_API int b200jpg_decoder_info(const b200jpg_decoder *d, b200jpg_image_info *info);
+B200JPG_API int b200jpg_decoder_scale(b200jpg_decoder *d, uint16_t req_w, uint16_t req_h, uint16_t *w,
+                                      uint16_t *h); /* :278 */
+/* Decoder::decode(), :293 -- pixels are owned by the decoder until free / next decode */
+B200JPG_API int b200jpg_decoder_decode(b200jpg_decoder *d, const uint8_t **pixels, size_t *len);
+B200JPG_API const char *b200jpg_decoder_error(const b200jpg_decoder *d);
+/* icc_profile :211, exif_data :199, xmp_data :206 -- return 1 if present */
+B200JPG_API int b200jpg_decoder_icc_profile(b200jpg_decoder *d, const uint8_t **data, size_t *len);
+B200JPG_API int b200jpg_decoder_exif_data(const b200jpg_decoder *d, const uint8_t **data, size_t *len);
+B200JPG_API int b200jpg_decoder_xmp_data(const b200jpg_decoder *d, const uint8_t **data, size_t *len);
+/* Host half only (no GPU needed): marker parsing + entropy decoding into dense coefficient
+ * buffers, i.e. everything decode() does before the worker boundary.  Fills *desc with pointers
+ * owned by the decoder (valid until free / next call); desc->color_transform is
+ * determine_color_transform() (src/decoder.rs:698-764). */
+B200JPG_API int b200jpg_decoder_entropy_decode(b200jpg_decoder *d, b200jpg_image_desc *desc);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,132 @@
+// decoder_api.cpp -- C ABI of the whole-file decoder (include/b200jpg.h, "Whole-file decoder"):
+// Decoder::{new, read_info, info, scale, decode, icc_profile, exif_data, xmp_data,
+// set_color_transform, set_max_decoding_buffer_size}, reference src/decoder.rs:132-295.
+// Host half: HostDecoder (host_decoder.cpp).  Worker half: the GPU batch path (pipeline.cu).
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/b200jpg.h"
+#include "host_decoder.h"
+
+using b200jpg::HostDecoder;
+
+struct b200jpg_decoder {
+    b200jpg_ctx* ctx;
+    HostDecoder host;
+    std::vector<uint8_t> pixels;
+    std::vector<uint8_t> icc;
+    std::string err;
+    b200jpg_decoder(b200jpg_ctx* c, const uint8_t* data, size_t len) : ctx(c), host(data, len) {}
+};
+
+// Fills `desc` with what decode_planes hands to compute_image (src/decoder.rs:617-696).
+static int fill_desc(b200jpg_decoder* d, b200jpg_image_desc* desc) {
+    const auto& f = d->host.frame();
+    memset(desc, 0, sizeof *desc);
+    desc->width = f.output_w;
+    desc->height = f.output_h;
+    desc->ncomp = (uint8_t)f.comps.size();
+    desc->color_transform = (uint8_t)d->host.determine_color_transform();
+    for (size_t i = 0; i < f.comps.size() && i < 4; i++) {
+        // "not all components have data", src/decoder.rs:1306-1308
+        if (!d->host.component_has_data((int)i)) {
+            d->err = "invalid JPEG format: not all components have data";
+            return B200JPG_ERR_FORMAT;
+        }
+        desc->comps[i] = f.comps[i];
+        desc->qt[i] = d->host.component_qtable((int)i);
+        desc->coefs[i] = d->host.coefficients((int)i);
+    }
+    return B200JPG_OK;
+}
+
+extern "C" {
+
+int b200jpg_decoder_new(b200jpg_ctx* ctx, const uint8_t* data, size_t len, b200jpg_decoder** d) {
+    if (!d || (!data && len)) return B200JPG_ERR_INTERNAL;
+    *d = new b200jpg_decoder(ctx, data, len);
+    return B200JPG_OK;
+}
+void b200jpg_decoder_free(b200jpg_decoder* d) { delete d; }
+void b200jpg_decoder_set_color_transform(b200jpg_decoder* d, int ct) {
+    if (d) d->host.set_color_transform(ct);
+}
+void b200jpg_decoder_set_max_decoding_buffer_size(b200jpg_decoder* d, size_t max) {
+    if (d) d->host.set_max_decoding_buffer_size(max);
+}
+int b200jpg_decoder_read_info(b200jpg_decoder* d) {
+    if (!d) return B200JPG_ERR_INTERNAL;
+    int rc = d->host.read_info();
+    if (rc) d->err = d->host.error();
+    return rc;
+}
+int b200jpg_decoder_info(const b200jpg_decoder* d, b200jpg_image_info* info) {
+    if (!d || !info || !d->host.has_frame()) return 0;
+    const auto& f = d->host.frame();
+    info->width = f.output_w;
+    info->height = f.output_h;
+    info->pixel_format = d->host.pixel_format();
+    info->coding_process = f.coding_process;
+    return 1;
+}
+int b200jpg_decoder_scale(b200jpg_decoder* d, uint16_t req_w, uint16_t req_h, uint16_t* w, uint16_t* h) {
+    if (!d || !w || !h) return B200JPG_ERR_INTERNAL;
+    int rc = d->host.scale(req_w, req_h, w, h);
+    if (rc) d->err = d->host.error();
+    return rc;
+}
+int b200jpg_decoder_entropy_decode(b200jpg_decoder* d, b200jpg_image_desc* desc) {
+    if (!d || !desc) return B200JPG_ERR_INTERNAL;
+    int rc = d->host.entropy_decode();
+    if (rc) {
+        d->err = d->host.error();
+        return rc;
+    }
+    return fill_desc(d, desc);
+}
+int b200jpg_decoder_decode(b200jpg_decoder* d, const uint8_t** pixels, size_t* len) {
+    if (!d || !pixels || !len) return B200JPG_ERR_INTERNAL;
+    b200jpg_image_desc desc;
+    int rc = b200jpg_decoder_entropy_decode(d, &desc);
+    if (rc) return rc;
+    if (!d->ctx) {  // no CPU fallback for the worker path
+        d->err = "internal: decoder was created without a device context; the worker path only exists on the GPU";
+        return B200JPG_ERR_INTERNAL;
+    }
+    d->pixels.assign((size_t)desc.width * desc.height * desc.ncomp, 0);
+    uint8_t* out = d->pixels.data();
+    size_t cap = d->pixels.size();
+    int status = B200JPG_OK;
+    rc = b200jpg_decode_batch(d->ctx, &desc, 1, &out, &cap, &status);
+    if (rc == B200JPG_OK) rc = status;
+    if (rc) {
+        d->err = b200jpg_last_error(d->ctx);
+        return rc;
+    }
+    *pixels = d->pixels.data();
+    *len = d->pixels.size();
+    return B200JPG_OK;
+}
+const char* b200jpg_decoder_error(const b200jpg_decoder* d) { return d ? d->err.c_str() : "no decoder"; }
+int b200jpg_decoder_icc_profile(b200jpg_decoder* d, const uint8_t** data, size_t* len) {
+    if (!d || !data || !len || !d->host.icc_profile(&d->icc)) return 0;
+    *data = d->icc.data();
+    *len = d->icc.size();
+    return 1;
+}
+int b200jpg_decoder_exif_data(const b200jpg_decoder* d, const uint8_t** data, size_t* len) {
+    if (!d || !data || !len || !d->host.exif()) return 0;
+    *data = d->host.exif()->data();
+    *len = d->host.exif()->size();
+    return 1;
+}
+int b200jpg_decoder_xmp_data(const b200jpg_decoder* d, const uint8_t** data, size_t* len) {
+    if (!d || !data || !len || !d->host.xmp()) return 0;
+    *data = d->host.xmp()->data();
+    *len = d->host.xmp()->size();
+    return 1;
+}
+
+}  // extern "C"

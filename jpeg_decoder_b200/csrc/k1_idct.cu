@@ -1,0 +1,481 @@
+// k1_idct.cu -- K1: dequantise + inverse DCT, coefficient slab -> plane slab (sm_100a).
+//
+// Replaces dequantize_and_idct_block (reference src/idct.rs:205-239) as driven by
+// ImmediateWorker::append_row_immediate (src/worker/immediate.rs:39-60) /
+// append_row_locked (src/worker/rayon.rs:71-112), and the SSSE3 variant
+// src/arch/ssse3.rs:124-192.  Arithmetic specification: SURVEY.md Appendix A.1/A.2.
+//
+// Two kernels:
+//   k1_idct8_tma      the hot one: scalar arithmetic, 8x8.  Persistent CTAs, one producer warp
+//                     streaming 128-block tiles (16 KB) into a 4-stage shared-memory ring with 2-D
+//                     TMA (128B swizzle, so that "one thread = one block" reads are bank-conflict
+//                     free), four consumer warps each doing a whole block per thread in registers
+//                     (no transposes, no shared-memory temporaries), coalesced 8-byte row stores
+//                     (32 lanes x 8 B = 256 contiguous bytes per plane row).
+//   k1_idct_generic   every other case (scaled IDCT 4x4/2x2/1x1, SSSE3 arithmetic), plain loads.
+//
+// Roofline: HBM.  Algorithmic bytes per block = 128 read + dct_scale^2 written (192 at scale 8).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "device_types.h"
+#include "kernels.h"
+
+namespace b200jpg {
+
+// ---------------------------------------------------------------------------------------------
+// Scalar arithmetic, src/idct.rs.  Everything is Wrapping<i32>: unsigned ops wrap, `>>` on int is
+// an arithmetic shift.
+// ---------------------------------------------------------------------------------------------
+// stbi_f2f(x) = (x * 4096 + 0.5) as i32 in f32, src/idct.rs:572-574; values checked in
+// tests/test_oracle_kat.py against the oracle, which evaluates the f32 expression.
+#define F2F_0_5411961 2217u
+#define F2F_N1_847759065 ((unsigned)-7567)
+#define F2F_0_765366865 3135u
+#define F2F_1_175875602 4816u
+#define F2F_0_298631336 1223u
+#define F2F_2_053119869 8410u
+#define F2F_3_072711026 12586u
+#define F2F_1_501321110 6149u
+#define F2F_N0_899976223 ((unsigned)-3685)
+#define F2F_N2_562915447 ((unsigned)-10497)
+#define F2F_N1_961570560 ((unsigned)-8034)
+#define F2F_N0_390180644 ((unsigned)-1597)
+
+__device__ __forceinline__ int sar(unsigned x, int n) { return (int)x >> n; }
+
+// d = { sat_u8(a) << 8 | sat_u8(b) } | (c << 16)   (one I2IP instruction)
+__device__ __forceinline__ unsigned pack_sat_u8(int a, int b, unsigned c) {
+    unsigned d;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+// bytes (b0,b1,b2,b3) = clamp(v0..v3)
+__device__ __forceinline__ unsigned pack4_sat_u8(int v0, int v1, int v2, int v3) {
+    return pack_sat_u8(v1, v0, pack_sat_u8(v3, v2, 0u));
+}
+
+// One 1-D pass of the stb_image butterfly, src/idct.rs:378-447.  `s0` already carries any bias the
+// caller folded in; xs is added to the even part (x_scale).
+#define IDCT_1D(s0, s1, s2, s3, s4, s5, s6, s7, xs, x0, x1, x2, x3, t0, t1, t2, t3) \
+    {                                                                                \
+        unsigned p1_ = ((s2) + (s6)) * F2F_0_5411961;                                \
+        unsigned e2_ = p1_ + (s6) * F2F_N1_847759065;                                \
+        unsigned e3_ = p1_ + (s2) * F2F_0_765366865;                                 \
+        unsigned e0_ = (((s0) + (s4)) << 12) + (xs);                                 \
+        unsigned e1_ = (((s0) - (s4)) << 12) + (xs);                                 \
+        x0 = e0_ + e3_;                                                              \
+        x3 = e0_ - e3_;                                                              \
+        x1 = e1_ + e2_;                                                              \
+        x2 = e1_ - e2_;                                                              \
+        unsigned q3_ = (s7) + (s3), q4_ = (s5) + (s1), q1_ = (s7) + (s1), q2_ = (s5) + (s3); \
+        unsigned p5_ = (q3_ + q4_) * F2F_1_175875602;                                \
+        q1_ = p5_ + q1_ * F2F_N0_899976223;                                          \
+        q2_ = p5_ + q2_ * F2F_N2_562915447;                                          \
+        q3_ = q3_ * F2F_N1_961570560;                                                \
+        q4_ = q4_ * F2F_N0_390180644;                                                \
+        t3 = (s1) * F2F_1_501321110 + (q1_ + q4_);                                   \
+        t2 = (s3) * F2F_3_072711026 + (q2_ + q3_);                                   \
+        t1 = (s5) * F2F_2_053119869 + (q2_ + q4_);                                   \
+        t0 = (s7) * F2F_0_298631336 + (q1_ + q3_);                                   \
+    }
+
+__device__ __forceinline__ unsigned sext_lo(unsigned w) { return (unsigned)(int)(short)(w & 0xffffu); }
+__device__ __forceinline__ unsigned sext_hi(unsigned w) { return (unsigned)((int)w >> 16); }
+
+// Full-precision reference form of one 8x8 block (zero-AC shortcuts included, src/idct.rs:279-295,
+// 344-353).  Used by the generic kernel and as the exact slow path of the fast kernel.
+__device__ void idct8x8_scalar_exact(const short* __restrict__ c, const unsigned* __restrict__ q, uint8_t* dst,
+                                     unsigned stride) {
+    unsigned temp[64];
+#pragma unroll 1
+    for (int i = 0; i < 8; i++) {
+        bool acz = (c[i + 8] | c[i + 16] | c[i + 24] | c[i + 32] | c[i + 40] | c[i + 48] | c[i + 56]) == 0;
+        if (acz) {
+            unsigned dc = ((unsigned)(int)c[i] * q[i]) << 2;
+#pragma unroll
+            for (int k = 0; k < 8; k++) temp[i + 8 * k] = dc;
+        } else {
+            unsigned s[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) s[k] = (unsigned)(int)c[i + 8 * k] * q[i + 8 * k];
+            unsigned x0, x1, x2, x3, t0, t1, t2, t3;
+            IDCT_1D(s[0], s[1], s[2], s[3], s[4], s[5], s[6], s[7], 512u, x0, x1, x2, x3, t0, t1, t2, t3);
+            temp[i] = (unsigned)sar(x0 + t3, 10);
+            temp[i + 56] = (unsigned)sar(x0 - t3, 10);
+            temp[i + 8] = (unsigned)sar(x1 + t2, 10);
+            temp[i + 48] = (unsigned)sar(x1 - t2, 10);
+            temp[i + 16] = (unsigned)sar(x2 + t1, 10);
+            temp[i + 40] = (unsigned)sar(x2 - t1, 10);
+            temp[i + 24] = (unsigned)sar(x3 + t0, 10);
+            temp[i + 32] = (unsigned)sar(x3 - t0, 10);
+        }
+    }
+    const unsigned XS = 65536u + (128u << 17);
+#pragma unroll 1
+    for (int r = 0; r < 8; r++) {
+        const unsigned* s = temp + 8 * r;
+        // the row shortcut (src/idct.rs:344-353) is algebraically identical to the general form
+        unsigned x0, x1, x2, x3, t0, t1, t2, t3;
+        IDCT_1D(s[0], s[1], s[2], s[3], s[4], s[5], s[6], s[7], XS, x0, x1, x2, x3, t0, t1, t2, t3);
+        uint2 o;
+        o.x = pack4_sat_u8(sar(x0 + t3, 17), sar(x1 + t2, 17), sar(x2 + t1, 17), sar(x3 + t0, 17));
+        o.y = pack4_sat_u8(sar(x3 - t0, 17), sar(x2 - t1, 17), sar(x1 - t2, 17), sar(x0 - t3, 17));
+        *reinterpret_cast<uint2*>(dst + (size_t)r * stride) = o;
+    }
+}
+
+// src/idct.rs:456-517
+__device__ void idct4x4_scalar(const short* __restrict__ c, const unsigned* __restrict__ q, uint8_t* dst, unsigned stride) {
+    unsigned temp[16];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        unsigned s0 = (unsigned)(int)c[i] * q[i], s1 = (unsigned)(int)c[i + 8] * q[i + 8];
+        unsigned s2 = (unsigned)(int)c[i + 16] * q[i + 16], s3 = (unsigned)(int)c[i + 24] * q[i + 24];
+        unsigned x0 = (s0 + s2) << 2, x2 = (s0 - s2) << 2;
+        unsigned p1 = (s1 + s3) * F2F_0_5411961;
+        unsigned t0 = (unsigned)sar(p1 + s3 * F2F_N1_847759065 + 512u, 10);
+        unsigned t2 = (unsigned)sar(p1 + s1 * F2F_0_765366865 + 512u, 10);
+        temp[i] = x0 + t2;
+        temp[i + 12] = x0 - t2;
+        temp[i + 4] = x2 + t0;
+        temp[i + 8] = x2 - t0;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        unsigned s0 = temp[i * 4], s1 = temp[i * 4 + 1], s2 = temp[i * 4 + 2], s3 = temp[i * 4 + 3];
+        unsigned x0 = ((s0 + s2) << 12) + (1u << 16) + (128u << 17);
+        unsigned x2 = ((s0 - s2) << 12) + (1u << 16) + (128u << 17);
+        unsigned p1 = (s1 + s3) * F2F_0_5411961;
+        unsigned t0 = p1 + s3 * F2F_N1_847759065;
+        unsigned t2 = p1 + s1 * F2F_0_765366865;
+        *reinterpret_cast<unsigned*>(dst + (size_t)i * stride) =
+            pack4_sat_u8(sar(x0 + t2, 17), sar(x2 + t0, 17), sar(x2 - t0, 17), sar(x0 - t2, 17));
+    }
+}
+
+// src/idct.rs:519-553
+__device__ void idct2x2_scalar(const short* __restrict__ c, const unsigned* __restrict__ q, uint8_t* dst, unsigned stride) {
+    unsigned s00 = (unsigned)(int)c[0] * q[0], s10 = (unsigned)(int)c[8] * q[8];
+    unsigned s01 = (unsigned)(int)c[1] * q[1], s11 = (unsigned)(int)c[9] * q[9];
+    unsigned x0 = s00 + s10 + 4u + (128u << 3), x2 = s00 - s10 + 4u + (128u << 3);
+    unsigned x1 = s01 + s11, x3 = s01 - s11;
+    unsigned r0 = pack4_sat_u8(sar(x0 + x1, 3), sar(x0 - x1, 3), 0, 0);
+    unsigned r1 = pack4_sat_u8(sar(x2 + x3, 3), sar(x2 - x3, 3), 0, 0);
+    *reinterpret_cast<unsigned short*>(dst) = (unsigned short)r0;
+    *reinterpret_cast<unsigned short*>(dst + stride) = (unsigned short)r1;
+}
+
+// src/idct.rs:555-565 (Wrapping<i32> division truncates toward zero)
+__device__ void idct1x1_scalar(const short* __restrict__ c, const unsigned* __restrict__ q, uint8_t* dst) {
+    int s0 = (int)((unsigned)(int)c[0] * q[0] + 1024u) / 8;
+    dst[0] = (uint8_t)min(max(s0, 0), 255);
+}
+
+// ---------------------------------------------------------------------------------------------
+// SSSE3 arithmetic, src/arch/ssse3.rs:8-84, 124-192: int16 lanes, saturating add/sub, mulhrs.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int sat16(int v) { return min(max(v, -32768), 32767); }
+__device__ __forceinline__ int adds16(int a, int b) { return sat16(a + b); }
+__device__ __forceinline__ int subs16(int a, int b) { return sat16(a - b); }
+__device__ __forceinline__ int mulhrs16(int a, int b) { return (int)(short)((((a * b) >> 14) + 1) >> 1); }
+
+__device__ void idct8_ssse3_lane(int* d, int st) {
+    int p2 = d[2 * st], p3 = d[6 * st];
+    int p1 = mulhrs16(adds16(p2, p3), 17734);
+    int t2 = subs16(subs16(p1, p3), mulhrs16(p3, 27779));
+    int t3 = adds16(p1, mulhrs16(p2, 25079));
+    p2 = d[0];
+    p3 = d[4 * st];
+    int t0 = adds16(p2, p3), t1 = subs16(p2, p3);
+    int x0 = adds16(t0, t3), x3 = subs16(t0, t3), x1 = adds16(t1, t2), x2 = subs16(t1, t2);
+    t0 = d[7 * st];
+    t1 = d[5 * st];
+    t2 = d[3 * st];
+    t3 = d[1 * st];
+    p3 = adds16(t0, t2);
+    int p4 = adds16(t1, t3);
+    p1 = adds16(t0, t3);
+    p2 = adds16(t1, t2);
+    int p5 = adds16(p3, p4);
+    p5 = adds16(p5, mulhrs16(p5, 5763));
+    t0 = mulhrs16(t0, 9786);
+    t1 = adds16(adds16(t1, t1), mulhrs16(t1, 1741));
+    t2 = adds16(adds16(t2, adds16(t2, t2)), mulhrs16(t2, 2383));
+    t3 = adds16(t3, mulhrs16(t3, 16427));
+    p1 = subs16(p5, mulhrs16(p1, 29490));
+    p2 = subs16(subs16(subs16(p5, p2), p2), mulhrs16(p2, 18446));
+    p3 = subs16(mulhrs16(p3, -31509), p3);
+    p4 = mulhrs16(p4, -12785);
+    t3 = adds16(adds16(p1, p4), t3);
+    t2 = adds16(adds16(p2, p3), t2);
+    t1 = adds16(adds16(p2, p4), t1);
+    t0 = adds16(adds16(p1, p3), t0);
+    d[0] = adds16(x0, t3);
+    d[7 * st] = subs16(x0, t3);
+    d[1 * st] = adds16(x1, t2);
+    d[6 * st] = subs16(x1, t2);
+    d[2 * st] = adds16(x2, t1);
+    d[5 * st] = subs16(x2, t1);
+    d[3 * st] = adds16(x3, t0);
+    d[4 * st] = subs16(x3, t0);
+}
+
+__device__ void idct8x8_ssse3(const short* __restrict__ c, const unsigned* __restrict__ q, uint8_t* dst, unsigned stride) {
+    int data[64];
+#pragma unroll 1
+    for (int i = 0; i < 64; i++) {
+        // _mm_mullo_epi16 then _mm_slli_epi16(.., 3): both wrap at 16 bits (ssse3.rs:151-158)
+        unsigned prod = ((unsigned)(unsigned short)c[i] * (q[i] & 0xffffu)) & 0xffffu;
+        data[i] = (int)(short)((prod << 3) & 0xffffu);
+    }
+#pragma unroll 1
+    for (int k = 0; k < 8; k++) idct8_ssse3_lane(data + k, 8);  // down the columns (ssse3.rs:162)
+#pragma unroll 1
+    for (int r = 0; r < 8; r++) idct8_ssse3_lane(data + 8 * r, 1);  // transpose-idct8-transpose = along rows
+#pragma unroll 1
+    for (int r = 0; r < 8; r++) {
+        const int* d = data + 8 * r;
+        uint2 o;  // adds(.., 8224) >> 6, packus (ssse3.rs:173-185)
+        o.x = pack4_sat_u8(adds16(d[0], 8224) >> 6, adds16(d[1], 8224) >> 6, adds16(d[2], 8224) >> 6, adds16(d[3], 8224) >> 6);
+        o.y = pack4_sat_u8(adds16(d[4], 8224) >> 6, adds16(d[5], 8224) >> 6, adds16(d[6], 8224) >> 6, adds16(d[7], 8224) >> 6);
+        *reinterpret_cast<uint2*>(dst + (size_t)r * stride) = o;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Generic kernel: one CTA per tile, one thread per block, coefficients read straight from HBM.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(K1_TILE) k1_idct_generic(K1Params p, int arith) {
+    const DevTile tile = p.tiles[blockIdx.x];
+    const unsigned t = threadIdx.x;
+    if (t >= tile.nvalid) return;
+    const DevComp comp = p.comps[tile.comp];
+    unsigned bx = (tile.bxy & 0xffffu) + t, by = tile.bxy >> 16;
+    by += bx / comp.block_w;
+    bx %= comp.block_w;
+    const unsigned* q = p.qtabs + (size_t)comp.qt_index * 64;
+    // stage the block into local memory with 16-byte loads
+    __align__(16) short c[64];
+    const uint4* src = reinterpret_cast<const uint4*>(p.coefs + ((size_t)tile.slab_row + t) * 64);
+#pragma unroll
+    for (int k = 0; k < 8; k++) reinterpret_cast<uint4*>(c)[k] = __ldg(src + k);
+    const unsigned sc = comp.dct_scale;
+    uint8_t* dst = p.planes + comp.plane_off + (size_t)by * sc * comp.stride + (size_t)bx * sc;
+    // dispatch: src/idct.rs:212-238 ; the SSSE3 variant only replaces the 8x8 kernel (src/idct.rs:247-253)
+    if (sc == 8) {
+        if (arith == 1) idct8x8_ssse3(c, q, dst, comp.stride);
+        else idct8x8_scalar_exact(c, q, dst, comp.stride);
+    } else if (sc == 4) {
+        idct4x4_scalar(c, q, dst, comp.stride);
+    } else if (sc == 2) {
+        idct2x2_scalar(c, q, dst, comp.stride);
+    } else {
+        idct1x1_scalar(c, q, dst);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// mbarrier / TMA helpers (PTX; SASS: SYNCS.*, UTMALDG)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+__device__ __forceinline__ uint4 lds128(unsigned addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* map, int x, int y, unsigned bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(bar)
+        : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// The hot kernel.
+// ---------------------------------------------------------------------------------------------
+constexpr int K1_STAGES = 4;
+constexpr int K1_CONSUMER_WARPS = K1_TILE / 32;
+constexpr int K1_THREADS = K1_TILE + 32;
+constexpr int K1_STAGE_BYTES = K1_TILE * 128;
+
+__global__ void __launch_bounds__(K1_THREADS, 3)
+k1_idct8_tma(const __grid_constant__ CUtensorMap tmap, K1Params p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // 1024-byte alignment is what the 128B swizzle pattern is defined against
+    const unsigned smem = (smem_u32(smem_raw) + 1023u) & ~1023u;  // shared-window address
+    __shared__ __align__(8) unsigned long long full_bar[K1_STAGES];
+    __shared__ __align__(8) unsigned long long empty_bar[K1_STAGES];
+
+    const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // contiguous tile range per CTA: consecutive tiles mostly share component and table
+    const unsigned t_begin = (unsigned)(((unsigned long long)blockIdx.x * p.ntiles) / gridDim.x);
+    const unsigned t_end = (unsigned)(((unsigned long long)(blockIdx.x + 1) * p.ntiles) / gridDim.x);
+
+    if (tid == 0) {
+        for (int s = 0; s < K1_STAGES; s++) {
+            mbar_init(smem_u32(&full_bar[s]), 1);
+            mbar_init(smem_u32(&empty_bar[s]), K1_CONSUMER_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == K1_CONSUMER_WARPS) {
+        // ---------------- producer warp: one elected lane issues the TMA loads ----------------
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+            for (unsigned t = t_begin; t < t_end; t++) {
+                const unsigned it = t - t_begin, stage = it % K1_STAGES, round = it / K1_STAGES;
+                if (round > 0) mbar_wait(smem_u32(&empty_bar[stage]), (round - 1) & 1);
+                const unsigned row = __ldg(&p.tiles[t].slab_row);
+                const unsigned bar = smem_u32(&full_bar[stage]);
+                mbar_expect_tx(bar, K1_STAGE_BYTES);
+                tma_load_2d(smem + stage * K1_STAGE_BYTES, &tmap, 0, (int)row, bar);
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumer warps: thread = one 8x8 block ---------------------------------
+    // swizzled address of 16-byte chunk j of row `tid`: (tid*128 + (j*16)) ^ ((tid & 7) << 4)
+    const unsigned row_off = tid * 128u, swz = (tid & 7u) << 4;
+    unsigned cur_comp = 0xffffffffu;
+    DevComp comp;
+    comp.plane_off = 0; comp.stride = 0; comp.block_w = 1; comp.qt_index = 0; comp.dct_scale = 8; comp.nblocks = 0; comp.pad = 0;
+    const uint4* q4 = nullptr;
+
+    for (unsigned t = t_begin; t < t_end; t++) {
+        const unsigned it = t - t_begin, stage = it % K1_STAGES, round = it / K1_STAGES;
+        const DevTile tile = p.tiles[t];
+        if (tile.comp != cur_comp) {  // warp-uniform
+            cur_comp = tile.comp;
+            comp = p.comps[cur_comp];
+            q4 = reinterpret_cast<const uint4*>(p.qtabs + (size_t)comp.qt_index * 64);
+        }
+        mbar_wait(smem_u32(&full_bar[stage]), round & 1);
+        const unsigned sbase = smem + stage * K1_STAGE_BYTES + row_off;
+        uint4 raw[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) raw[k] = lds128(sbase + ((k * 16u) ^ swz));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&empty_bar[stage]));  // slot can be refilled
+
+        if (tid >= tile.nvalid) continue;
+        unsigned bx = (tile.bxy & 0xffffu) + tid, by = tile.bxy >> 16;
+        if (comp.block_w >= (unsigned)K1_TILE) {
+            if (bx >= comp.block_w) { bx -= comp.block_w; by += 1; }
+        } else {
+            by += bx / comp.block_w;
+            bx %= comp.block_w;
+        }
+        uint8_t* dst = p.planes + comp.plane_off + (size_t)by * 8u * comp.stride + (size_t)bx * 8u;
+
+        // ---- dequantise: s[k][i] = c * q.  Column 0 values of row 0 carry a +2^19 bias so that one
+        // OR-reduction detects |s0| >= 2^19 (the only case where the reference's zero-AC column
+        // shortcut, src/idct.rs:279-295, differs from the butterfly); the bias cancels in xs below.
+        unsigned s[8][8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const uint4 qa = __ldg(q4 + 2 * k), qb = __ldg(q4 + 2 * k + 1);
+            const unsigned bias = (k == 0) ? 0x80000u : 0u;
+            s[k][0] = sext_lo(raw[k].x) * qa.x + bias;
+            s[k][1] = sext_hi(raw[k].x) * qa.y + bias;
+            s[k][2] = sext_lo(raw[k].y) * qa.z + bias;
+            s[k][3] = sext_hi(raw[k].y) * qa.w + bias;
+            s[k][4] = sext_lo(raw[k].z) * qb.x + bias;
+            s[k][5] = sext_hi(raw[k].z) * qb.y + bias;
+            s[k][6] = sext_lo(raw[k].w) * qb.z + bias;
+            s[k][7] = sext_hi(raw[k].w) * qb.w + bias;
+        }
+        const unsigned oor = (s[0][0] | s[0][1] | s[0][2] | s[0][3] | s[0][4] | s[0][5] | s[0][6] | s[0][7]) >> 20;
+        if (oor != 0) {
+            // exact reference form, re-reading the block from HBM (rare: 16-bit tables / corrupt data)
+            idct8x8_scalar_exact(p.coefs + ((size_t)tile.slab_row + tid) * 64,
+                                 reinterpret_cast<const unsigned*>(q4), dst, comp.stride);
+            continue;
+        }
+        // ---- column pass: xs = 512, minus the 2^19 << 12 = 2^31 bias carried by s[0][*]
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            unsigned x0, x1, x2, x3, t0, t1, t2, t3;
+            IDCT_1D(s[0][i], s[1][i], s[2][i], s[3][i], s[4][i], s[5][i], s[6][i], s[7][i], (512u + 0x80000000u),
+                    x0, x1, x2, x3, t0, t1, t2, t3);
+            s[0][i] = (unsigned)sar(x0 + t3, 10);
+            s[7][i] = (unsigned)sar(x0 - t3, 10);
+            s[1][i] = (unsigned)sar(x1 + t2, 10);
+            s[6][i] = (unsigned)sar(x1 - t2, 10);
+            s[2][i] = (unsigned)sar(x2 + t1, 10);
+            s[5][i] = (unsigned)sar(x2 - t1, 10);
+            s[3][i] = (unsigned)sar(x3 + t0, 10);
+            s[4][i] = (unsigned)sar(x3 - t0, 10);
+        }
+        // ---- row pass + clamp + 8-byte coalesced row stores
+        const unsigned XS = 65536u + (128u << 17);
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            unsigned x0, x1, x2, x3, t0, t1, t2, t3;
+            IDCT_1D(s[r][0], s[r][1], s[r][2], s[r][3], s[r][4], s[r][5], s[r][6], s[r][7], XS, x0, x1, x2, x3, t0, t1,
+                    t2, t3);
+            uint2 o;
+            o.x = pack4_sat_u8(sar(x0 + t3, 17), sar(x1 + t2, 17), sar(x2 + t1, 17), sar(x3 + t0, 17));
+            o.y = pack4_sat_u8(sar(x3 - t0, 17), sar(x2 - t1, 17), sar(x1 - t2, 17), sar(x0 - t3, 17));
+            *reinterpret_cast<uint2*>(dst + (size_t)r * comp.stride) = o;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side launchers
+// ---------------------------------------------------------------------------------------------
+cudaError_t launch_k1_generic(const K1Params& p, int arith, cudaStream_t stream) {
+    if (p.ntiles == 0) return cudaSuccess;
+    k1_idct_generic<<<p.ntiles, K1_TILE, 0, stream>>>(p, arith);
+    return cudaGetLastError();
+}
+
+size_t k1_tma_smem_bytes() { return (size_t)K1_STAGES * K1_STAGE_BYTES + 1024; }
+
+cudaError_t launch_k1_tma(const CUtensorMap& tmap, const K1Params& p, int num_sms, cudaStream_t stream) {
+    if (p.ntiles == 0) return cudaSuccess;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k1_idct8_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_tma_smem_bytes());
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    unsigned grid = (unsigned)num_sms * 3u;
+    if (grid > p.ntiles) grid = p.ntiles;
+    k1_idct8_tma<<<grid, K1_THREADS, k1_tma_smem_bytes(), stream>>>(tmap, p);
+    return cudaGetLastError();
+}
+
+}  // namespace b200jpg

@@ -1,0 +1,309 @@
+// k2_color.cu -- K2: chroma upsampling + colour conversion + interleave, plane slab -> pixel slab.
+//
+// Replaces compute_image (reference src/decoder.rs:1300-1336) -> compute_image_parallel
+// (src/worker/mod.rs:97-128, src/worker/rayon.rs:193-219) -> Upsampler::upsample_and_interleave_row
+// (src/upsampler.rs:47-63) with the upsamplers of src/upsampler.rs:119-250 and the colour functions of
+// src/decoder.rs:1391-1508 / src/arch/ssse3.rs:196-288.  Arithmetic: SURVEY.md Appendix A.3/A.4.
+//
+// The reference's "fancy" upsamplers special-case the first/last sample; all of them are the
+// clamped-edge form of one triangle filter:
+//   H2V1: out[2i] = (3 in[i] + in[i-1] + 2) >> 2, out[2i+1] = (3 in[i] + in[i+1] + 2) >> 2 with in[-1] := in[0],
+//         in[w] := in[w-1]   ((4a + 2) >> 2 == a reproduces `out[0] = in[0]`, upsampler.rs:151,161)
+//   H2V2: t[i] = 3 near[i] + far[i]; out[2i] = (3 t[i] + t[i-1] + 8) >> 4, out[2i+1] = (3 t[i] + t[i+1] + 8) >> 4,
+//         clamped ((4t + 8) >> 4 == (t + 2) >> 2 reproduces upsampler.rs:216,226 and the in_w == 1 case 208-213)
+//   near/far rows (upsampler.rs:174-180): even row 2k -> near k, far max(k-1,0); odd row 2k+1 -> near k,
+//         far min(k+1, in_h-1)   (the f32 expression evaluated exactly; tested against the oracle's f32 form)
+//
+// Kernels: k2_generic (every upsampler / transform / arithmetic variant, one thread per pixel),
+//          k2_ycbcr420 (H2V2 chroma + YCbCr, 16 px x 2 rows per thread, DP4A filter, 128-bit I/O),
+//          k2_ycbcr444 (H1V1 + YCbCr, 16 px per thread, 128-bit stores).
+// Roofline: HBM.  Algorithmic bytes per image = plane bytes read once + width*height*ncomp written.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "device_types.h"
+#include "kernels.h"
+
+namespace b200jpg {
+
+__device__ __forceinline__ unsigned pack_sat_u8(int a, int b, unsigned c) {
+    unsigned d;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// src/decoder.rs:1486-1508.  stbi_f2f(x) = (x * 2^20 + 0.5) as i32 evaluated in f32:
+// 1.40200 -> 1470104, 0.34414 -> 360857, 0.71414 -> 748830, 1.77200 -> 1858077
+// (checked against the oracle's f32 evaluation in tests/test_oracle_kat.py).
+#define C_R_CR 1470104
+#define C_G_CB 360857
+#define C_G_CR 748830
+#define C_B_CB 1858077
+#define YCC_HALF (1 << 19)
+
+// (r, g, b) before clamping, already shifted down: no intermediate can overflow i32.
+__device__ __forceinline__ void ycbcr_scalar(int y, int cb, int cr, int& r, int& g, int& b) {
+    // fold the -128 of cb/cr into the constant term: one IMAD chain per channel
+    const int yr = y * (1 << 20) + (YCC_HALF - 128 * C_R_CR);
+    const int yg = y * (1 << 20) + (YCC_HALF + 128 * C_G_CB + 128 * C_G_CR);
+    const int yb = y * (1 << 20) + (YCC_HALF - 128 * C_B_CB);
+    r = (yr + C_R_CR * cr) >> 20;
+    g = (yg - C_G_CB * cb - C_G_CR * cr) >> 20;
+    b = (yb + C_B_CB * cb) >> 20;
+}
+
+__device__ __forceinline__ int sat16(int v) { return min(max(v, -32768), 32767); }
+__device__ __forceinline__ int mulhrs16(int a, int b) { return (int)(short)((((a * b) >> 14) + 1) >> 1); }
+// src/arch/ssse3.rs:208-244
+__device__ __forceinline__ void ycbcr_ssse3(int y, int cb, int cr, int& r, int& g, int& b) {
+    const int y6 = sat16((y << 6) + 32);
+    const int cb6 = sat16((cb << 6) - 8192), cr6 = sat16((cr << 6) - 8192);
+    const int cr_140200 = sat16(mulhrs16(cr6, 13173) + cr6);
+    const int cb_034414 = mulhrs16(cb6, 11276);
+    const int cr_071414 = mulhrs16(cr6, 23401);
+    const int cb_177200 = sat16(mulhrs16(cb6, 25297) + cb6);
+    r = sat16(y6 + cr_140200) >> 6;
+    g = sat16(y6 - sat16(cb_034414 + cr_071414)) >> 6;
+    b = sat16(y6 + cb_177200) >> 6;
+}
+
+__device__ __forceinline__ uint8_t clamp_u8(int v) { return (uint8_t)min(max(v, 0), 255); }
+
+// One upsampled sample of one component at output position (x, y): src/upsampler.rs:119-250
+__device__ __forceinline__ int upsample_at(const uint8_t* __restrict__ plane, const DevUpComp& c, unsigned x, unsigned y) {
+    switch (c.kind) {
+    case UP_H1V1: return plane[(size_t)y * c.stride + x];
+    case UP_H2V1: {
+        const uint8_t* in = plane + (size_t)y * c.stride;
+        const int i = (int)(x >> 1);
+        const int j = (x & 1) ? min(i + 1, (int)c.in_w - 1) : max(i - 1, 0);
+        return (3 * in[i] + in[j] + 2) >> 2;
+    }
+    case UP_H1V2: {
+        const int k = (int)(y >> 1);
+        const int f = (y & 1) ? min(k + 1, (int)c.in_h - 1) : max(k - 1, 0);
+        return (3 * plane[(size_t)k * c.stride + x] + plane[(size_t)f * c.stride + x] + 2) >> 2;
+    }
+    case UP_H2V2: {
+        const int k = (int)(y >> 1);
+        const int f = (y & 1) ? min(k + 1, (int)c.in_h - 1) : max(k - 1, 0);
+        const uint8_t* n = plane + (size_t)k * c.stride;
+        const uint8_t* fr = plane + (size_t)f * c.stride;
+        const int i = (int)(x >> 1);
+        const int j = (x & 1) ? min(i + 1, (int)c.in_w - 1) : max(i - 1, 0);
+        const int ti = 3 * n[i] + fr[i], tj = 3 * n[j] + fr[j];
+        return (3 * ti + tj + 8) >> 4;
+    }
+    default: return plane[(size_t)(y / c.vs) * c.stride + x / c.hs];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Generic kernel: one thread per output pixel.
+// grid.x = ceil(max_w/256) * max_h, grid.y = image
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k2_generic(K2Params p, unsigned first, unsigned xchunks) {
+    const DevImage& img = p.images[first + blockIdx.y];
+    if (img.path != K2_PATH_GENERIC) return;
+    const unsigned y = blockIdx.x / xchunks;
+    const unsigned x = (blockIdx.x % xchunks) * 256u + threadIdx.x;
+    if (y >= img.height || x >= img.width) return;
+    const unsigned W = img.width, n = img.ncomp;
+    uint8_t* out = p.out + img.out_off;
+    if (img.cc == CC_GRAY) {  // src/decoder.rs:1310-1332: compact stride -> width
+        out[(size_t)y * W + x] = p.planes[img.c[0].plane_off + (size_t)y * img.c[0].stride + x];
+        return;
+    }
+    int v[4] = {0, 0, 0, 0};
+    for (unsigned k = 0; k < n; k++) v[k] = upsample_at(p.planes + img.c[k].plane_off, img.c[k], x, y);
+    uint8_t* o = out + ((size_t)y * W + x) * n;
+    switch (img.cc) {
+    case CC_RGB:  // src/decoder.rs:1391-1404
+        o[0] = (uint8_t)v[0]; o[1] = (uint8_t)v[1]; o[2] = (uint8_t)v[2];
+        break;
+    case CC_YCBCR: {  // src/decoder.rs:1406-1437
+        int r, g, b;
+        if (x < img.ssse3_pixels) ycbcr_ssse3(v[0], v[1], v[2], r, g, b);
+        else ycbcr_scalar(v[0], v[1], v[2], r, g, b);
+        o[0] = clamp_u8(r); o[1] = clamp_u8(g); o[2] = clamp_u8(b);
+        break;
+    }
+    case CC_YCCK: {  // src/decoder.rs:1439-1456 (always the scalar formula)
+        int r, g, b;
+        ycbcr_scalar(v[0], v[1], v[2], r, g, b);
+        o[0] = clamp_u8(r); o[1] = clamp_u8(g); o[2] = clamp_u8(b); o[3] = (uint8_t)(255 - v[3]);
+        break;
+    }
+    case CC_CMYK:  // src/decoder.rs:1458-1474
+        o[0] = (uint8_t)(255 - v[0]); o[1] = (uint8_t)(255 - v[1]); o[2] = (uint8_t)(255 - v[2]); o[3] = (uint8_t)(255 - v[3]);
+        break;
+    default:  // color_no_convert, src/decoder.rs:1476-1484: components planar inside each row
+        for (unsigned k = 0; k < n; k++) out[(size_t)y * W * n + (size_t)k * W + x] = (uint8_t)v[k];
+        break;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 4:2:0 YCbCr fast path.  Thread = 16 output pixels x the output row pair (2p-1, 2p): both rows
+// blend the same two chroma rows (p-1, p) with swapped weights, so every chroma byte is read once.
+// Preconditions (checked by the planner): ncomp 3, comp0 H1V1, comps 1,2 H2V2, scalar arithmetic,
+// width % 16 == 0, strides and offsets 16-byte (luma) / 8-byte (chroma) aligned.
+// grid.x = ceil(G/128) * P, G = width/16, P = height/2 + 1; grid.y = image
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned prmt(unsigned a, unsigned b, unsigned sel) {
+    unsigned d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
+struct Chroma16 {  // upsampled chroma for 16 pixels of the two rows of the pair
+    int odd[16];   // output row 2p-1 (near = chroma row p-1)
+    int even[16];  // output row 2p   (near = chroma row p)
+};
+
+// a*: chroma row A = max(p-1,0); b*: chroma row B = min(p, in_h-1).  lo/hi = samples i0..i0+3 / i0+4..i0+7,
+// L / R = clamped halo samples i0-1 / i0+8.
+__device__ __forceinline__ void h2v2_16(unsigned a_lo, unsigned a_hi, unsigned aL, unsigned aR, unsigned b_lo,
+                                        unsigned b_hi, unsigned bL, unsigned bR, Chroma16& o) {
+    // shifted words: s0 = (L, 0, 1, 2), s1 = (3, 4, 5, 6), s2 = (7, R, -, -)
+    const unsigned as0 = prmt(aL, a_lo, 0x6540), as1 = prmt(a_lo, a_hi, 0x6543), as2 = prmt(a_hi, aR, 0x0043);
+    const unsigned bs0 = prmt(bL, b_lo, 0x6540), bs1 = prmt(b_lo, b_hi, 0x6543), bs2 = prmt(b_hi, bR, 0x0043);
+    // P[j] = (a[i-1], a[i], b[i-1], b[i]) for i = i0 + j
+    unsigned P[9];
+    P[0] = prmt(as0, bs0, 0x5410);
+    P[1] = prmt(a_lo, b_lo, 0x5410);
+    P[2] = prmt(as0, bs0, 0x7632);
+    P[3] = prmt(a_lo, b_lo, 0x7632);
+    P[4] = prmt(as1, bs1, 0x5410);
+    P[5] = prmt(a_hi, b_hi, 0x5410);
+    P[6] = prmt(as1, bs1, 0x7632);
+    P[7] = prmt(a_hi, b_hi, 0x7632);
+    P[8] = prmt(as2, bs2, 0x5410);
+    // weights on (a[i-1], a[i], b[i-1], b[i]); t = 3 near + far
+    const unsigned W_A_EVEN = 0x03010903u;  // near = A: out[2i]   = 3 t[i] + t[i-1]
+    const unsigned W_A_ODD = 0x01030309u;   // near = A: out[2i-1] = 3 t[i-1] + t[i]
+    const unsigned W_B_EVEN = 0x09030301u;  // near = B: out[2i]
+    const unsigned W_B_ODD = 0x03090103u;   // near = B: out[2i-1]
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        o.odd[2 * j] = (int)(__dp4a(P[j], W_A_EVEN, 8u) >> 4);
+        o.odd[2 * j + 1] = (int)(__dp4a(P[j + 1], W_A_ODD, 8u) >> 4);
+        o.even[2 * j] = (int)(__dp4a(P[j], W_B_EVEN, 8u) >> 4);
+        o.even[2 * j + 1] = (int)(__dp4a(P[j + 1], W_B_ODD, 8u) >> 4);
+    }
+}
+
+// 16 pixels: y bytes in yv (4 words), chroma ints -> 48 output bytes at `dst` (16-byte aligned)
+__device__ __forceinline__ void ycbcr_store16(const uint4 yv, const int* cb, const int* cr, uint8_t* dst) {
+    const unsigned yw[4] = {yv.x, yv.y, yv.z, yv.w};
+    unsigned ow[12];
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        int r[4], g[4], b[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int y = (int)((yw[w] >> (8 * k)) & 0xffu);
+            ycbcr_scalar(y, cb[4 * w + k], cr[4 * w + k], r[k], g[k], b[k]);
+        }
+        // bytes: R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3
+        ow[3 * w + 0] = pack_sat_u8(g[0], r[0], pack_sat_u8(r[1], b[0], 0u));
+        ow[3 * w + 1] = pack_sat_u8(b[1], g[1], pack_sat_u8(g[2], r[2], 0u));
+        ow[3 * w + 2] = pack_sat_u8(r[3], b[2], pack_sat_u8(b[3], g[3], 0u));
+    }
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    d4[0] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    d4[1] = make_uint4(ow[4], ow[5], ow[6], ow[7]);
+    d4[2] = make_uint4(ow[8], ow[9], ow[10], ow[11]);
+}
+
+__global__ void __launch_bounds__(128) k2_ycbcr420(K2Params p, unsigned first, unsigned gchunks) {
+    const DevImage& img = p.images[first + blockIdx.y];
+    if (img.path != K2_PATH_420) return;
+    const unsigned pr = blockIdx.x / gchunks;  // row pair
+    const unsigned g = (blockIdx.x % gchunks) * 128u + threadIdx.x;
+    const unsigned W = img.width, H = img.height;
+    if (pr > H / 2 || g * 16u >= W) return;
+    const DevUpComp cy = img.c[0], ccb = img.c[1], ccr = img.c[2];
+    const unsigned in_w = ccb.in_w, in_h = ccb.in_h;
+    const unsigned rA = pr > 0 ? pr - 1 : 0, rB = min(pr, in_h - 1);
+    const unsigned i0 = g * 8u;
+    const unsigned iL = i0 > 0 ? i0 - 1 : 0, iR = min(i0 + 8u, in_w - 1);
+
+    Chroma16 cb, cr;
+    {
+        const uint8_t* a = p.planes + ccb.plane_off + (size_t)rA * ccb.stride;
+        const uint8_t* b = p.planes + ccb.plane_off + (size_t)rB * ccb.stride;
+        const uint2 av = __ldg(reinterpret_cast<const uint2*>(a + i0)), bv = __ldg(reinterpret_cast<const uint2*>(b + i0));
+        h2v2_16(av.x, av.y, __ldg(a + iL), __ldg(a + iR), bv.x, bv.y, __ldg(b + iL), __ldg(b + iR), cb);
+    }
+    {
+        const uint8_t* a = p.planes + ccr.plane_off + (size_t)rA * ccr.stride;
+        const uint8_t* b = p.planes + ccr.plane_off + (size_t)rB * ccr.stride;
+        const uint2 av = __ldg(reinterpret_cast<const uint2*>(a + i0)), bv = __ldg(reinterpret_cast<const uint2*>(b + i0));
+        h2v2_16(av.x, av.y, __ldg(a + iL), __ldg(a + iR), bv.x, bv.y, __ldg(b + iL), __ldg(b + iR), cr);
+    }
+    const uint8_t* yplane = p.planes + cy.plane_off;
+    uint8_t* out = p.out + img.out_off;
+    if (pr > 0) {  // output row 2p-1
+        const unsigned y = 2 * pr - 1;
+        const uint4 yv = __ldg(reinterpret_cast<const uint4*>(yplane + (size_t)y * cy.stride + g * 16u));
+        ycbcr_store16(yv, cb.odd, cr.odd, out + ((size_t)y * W + g * 16u) * 3u);
+    }
+    if (2 * pr < H) {  // output row 2p
+        const unsigned y = 2 * pr;
+        const uint4 yv = __ldg(reinterpret_cast<const uint4*>(yplane + (size_t)y * cy.stride + g * 16u));
+        ycbcr_store16(yv, cb.even, cr.even, out + ((size_t)y * W + g * 16u) * 3u);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 4:4:4 YCbCr fast path: thread = 16 pixels of one row.
+// grid.x = ceil(G/128) * height, grid.y = image
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k2_ycbcr444(K2Params p, unsigned first, unsigned gchunks) {
+    const DevImage& img = p.images[first + blockIdx.y];
+    if (img.path != K2_PATH_444) return;
+    const unsigned y = blockIdx.x / gchunks;
+    const unsigned g = (blockIdx.x % gchunks) * 128u + threadIdx.x;
+    const unsigned W = img.width;
+    if (y >= img.height || g * 16u >= W) return;
+    const uint4 yv = __ldg(reinterpret_cast<const uint4*>(p.planes + img.c[0].plane_off + (size_t)y * img.c[0].stride + g * 16u));
+    const uint4 bv = __ldg(reinterpret_cast<const uint4*>(p.planes + img.c[1].plane_off + (size_t)y * img.c[1].stride + g * 16u));
+    const uint4 rv = __ldg(reinterpret_cast<const uint4*>(p.planes + img.c[2].plane_off + (size_t)y * img.c[2].stride + g * 16u));
+    const unsigned bw[4] = {bv.x, bv.y, bv.z, bv.w}, rw[4] = {rv.x, rv.y, rv.z, rv.w};
+    int cb[16], cr[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        cb[k] = (int)((bw[k >> 2] >> (8 * (k & 3))) & 0xffu);
+        cr[k] = (int)((rw[k >> 2] >> (8 * (k & 3))) & 0xffu);
+    }
+    ycbcr_store16(yv, cb, cr, p.out + img.out_off + ((size_t)y * W + g * 16u) * 3u);
+}
+
+// ---------------------------------------------------------------------------------------------
+cudaError_t launch_k2_generic(const K2Params& p, unsigned first, unsigned count, unsigned max_w, unsigned max_h,
+                              cudaStream_t stream) {
+    if (count == 0 || max_w == 0 || max_h == 0) return cudaSuccess;
+    const unsigned xchunks = (max_w + 255u) / 256u;
+    dim3 grid(xchunks * max_h, count);
+    k2_generic<<<grid, 256, 0, stream>>>(p, first, xchunks);
+    return cudaGetLastError();
+}
+cudaError_t launch_k2_420(const K2Params& p, unsigned first, unsigned count, unsigned max_w, unsigned max_h,
+                          cudaStream_t stream) {
+    if (count == 0 || max_w == 0 || max_h == 0) return cudaSuccess;
+    const unsigned gchunks = (max_w / 16u + 127u) / 128u;
+    dim3 grid(gchunks * (max_h / 2u + 1u), count);
+    k2_ycbcr420<<<grid, 128, 0, stream>>>(p, first, gchunks);
+    return cudaGetLastError();
+}
+cudaError_t launch_k2_444(const K2Params& p, unsigned first, unsigned count, unsigned max_w, unsigned max_h,
+                          cudaStream_t stream) {
+    if (count == 0 || max_w == 0 || max_h == 0) return cudaSuccess;
+    const unsigned gchunks = (max_w / 16u + 127u) / 128u;
+    dim3 grid(gchunks * max_h, count);
+    k2_ycbcr444<<<grid, 128, 0, stream>>>(p, first, gchunks);
+    return cudaGetLastError();
+}
+
+}  // namespace b200jpg

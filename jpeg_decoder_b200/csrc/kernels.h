@@ -1,0 +1,41 @@
+// kernels.h -- launch interface between the host planner (pipeline.cu) and the kernels.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "device_types.h"
+
+namespace b200jpg {
+
+struct K1Params {
+    const DevTile* tiles;
+    const DevComp* comps;
+    const unsigned* qtabs;  // u32[64] per table, natural order
+    const short* coefs;     // coefficient slab base
+    uint8_t* planes;        // plane slab base
+    unsigned ntiles;
+};
+
+struct K2Params {
+    const DevImage* images;
+    const uint8_t* planes;
+    uint8_t* out;
+    unsigned nimages;
+};
+
+cudaError_t launch_k1_generic(const K1Params& p, int arith, cudaStream_t stream);
+cudaError_t launch_k1_tma(const CUtensorMap& tmap, const K1Params& p, int num_sms, cudaStream_t stream);
+size_t k1_tma_smem_bytes();
+
+// K2: max_w/max_h = largest output size in [first, first+count); the grid covers that and images
+// smaller than it exit early.  `path` selects the kernel; images whose DevImage::path differs are
+// skipped by it, so a heterogeneous batch is covered by one launch per path in use.
+cudaError_t launch_k2_generic(const K2Params& p, unsigned first, unsigned count, unsigned max_w, unsigned max_h,
+                              cudaStream_t stream);
+cudaError_t launch_k2_420(const K2Params& p, unsigned first, unsigned count, unsigned max_w, unsigned max_h,
+                          cudaStream_t stream);
+cudaError_t launch_k2_444(const K2Params& p, unsigned first, unsigned count, unsigned max_w, unsigned max_h,
+                          cudaStream_t stream);
+
+}  // namespace b200jpg

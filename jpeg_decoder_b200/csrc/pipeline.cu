@@ -1,0 +1,924 @@
+// pipeline.cu -- host side of the C ABI (include/b200jpg.h): context, batch planner, worker-shaped
+// API and the host<->device pipelines around the kernels of k1_idct.cu / k2_color.cu.
+//
+// Reference interfaces mirrored here: trait Worker (src/worker/mod.rs:24-35) and its immediate
+// implementation (src/worker/immediate.rs), compute_image (src/decoder.rs:1300-1336),
+// choose_color_convert_func (src/decoder.rs:1339-1389), Upsampler::new / choose_upsampler
+// (src/upsampler.rs:20-45, 76-105), update_component_sizes (src/parser.rs:292-310).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/b200jpg.h"
+#include "device_types.h"
+#include "kernels.h"
+
+using namespace b200jpg;
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_tensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                             const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                             CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                             CUtensorMapFloatOOBfill);
+
+struct b200jpg_ctx {
+    int device = 0;
+    int arith = B200JPG_ARITH_SCALAR;
+    int k1_kernel = B200JPG_KERNEL_AUTO;
+    int k2_kernel = B200JPG_KERNEL_AUTO;
+    cudaStream_t stream = nullptr;   // main stream (caller's or ours)
+    cudaStream_t stream2 = nullptr;  // second stream of the host pipeline
+    bool own_stream = false;
+    int num_sms = 148;
+    uint64_t launches = 0;
+    PFN_tensorMapEncodeTiled encode = nullptr;
+    std::string err;
+};
+
+static int fail(b200jpg_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+static int cuda_fail(b200jpg_ctx* ctx, cudaError_t e, const char* what) {
+    return fail(ctx, B200JPG_ERR_INTERNAL, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU_TRY(ctx, call)                                            \
+    do {                                                             \
+        cudaError_t e_ = (call);                                     \
+        if (e_ != cudaSuccess) return cuda_fail((ctx), e_, #call);   \
+    } while (0)
+
+extern "C" {
+
+void b200jpg_default_options(b200jpg_options* opt) {
+    memset(opt, 0, sizeof *opt);
+    opt->device = 0;
+    opt->arith = B200JPG_ARITH_SCALAR;
+}
+
+const char* b200jpg_version(void) { return "b200jpg 0.1 (sm_100a)"; }
+
+int b200jpg_create(const b200jpg_options* opt, b200jpg_ctx** out) {
+    if (!out) return B200JPG_ERR_INTERNAL;
+    *out = nullptr;
+    b200jpg_options o;
+    if (opt) o = *opt; else b200jpg_default_options(&o);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0 || o.device < 0 || o.device >= ndev) return B200JPG_ERR_INTERNAL;  // no CPU fallback
+    b200jpg_ctx* ctx = new b200jpg_ctx();
+    ctx->device = o.device;
+    ctx->arith = o.arith;
+    ctx->k1_kernel = o.k1_kernel;
+    ctx->k2_kernel = o.k2_kernel;
+    if (cudaSetDevice(o.device) != cudaSuccess) { delete ctx; return B200JPG_ERR_INTERNAL; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, o.device) != cudaSuccess) { delete ctx; return B200JPG_ERR_INTERNAL; }
+    ctx->num_sms = prop.multiProcessorCount;
+    if (prop.major < 10) {  // kernels are built for sm_100a only
+        delete ctx;
+        return B200JPG_ERR_INTERNAL;
+    }
+    if (o.stream) {
+        ctx->stream = (cudaStream_t)o.stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return B200JPG_ERR_INTERNAL; }
+        ctx->own_stream = true;
+    }
+    if (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return B200JPG_ERR_INTERNAL; }
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+        ctx->encode = (PFN_tensorMapEncodeTiled)fn;
+    *out = ctx;
+    return B200JPG_OK;
+}
+
+void b200jpg_destroy(b200jpg_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    delete ctx;
+}
+const char* b200jpg_last_error(const b200jpg_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+uint64_t b200jpg_launch_count(const b200jpg_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int b200jpg_synchronize(b200jpg_ctx* ctx) {
+    if (!ctx) return B200JPG_ERR_INTERNAL;
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream2));
+    return B200JPG_OK;
+}
+
+void* b200jpg_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void b200jpg_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+// src/parser.rs:283-310
+static int ceil_div_u16(uint32_t x, uint32_t y, uint16_t* r) {
+    if (x == 0 || y == 0) return B200JPG_ERR_FORMAT;
+    *r = (uint16_t)(1 + ((x - 1) / y));
+    return B200JPG_OK;
+}
+int b200jpg_update_component_sizes(uint16_t width, uint16_t height, b200jpg_component* comps, int ncomp,
+                                   uint16_t* mcu_w, uint16_t* mcu_h) {
+    if (!comps || ncomp <= 0) return B200JPG_ERR_FORMAT;
+    uint32_t h_max = 0, v_max = 0;
+    for (int i = 0; i < ncomp; i++) {
+        h_max = std::max<uint32_t>(h_max, comps[i].h);
+        v_max = std::max<uint32_t>(v_max, comps[i].v);
+    }
+    uint16_t mw, mh;
+    if (ceil_div_u16(width, h_max * 8, &mw) || ceil_div_u16(height, v_max * 8, &mh)) return B200JPG_ERR_FORMAT;
+    for (int i = 0; i < ncomp; i++) {
+        b200jpg_component* c = &comps[i];
+        if (ceil_div_u16((uint32_t)width * c->h * c->dct_scale, h_max * 8, &c->size_w)) return B200JPG_ERR_FORMAT;
+        if (ceil_div_u16((uint32_t)height * c->v * c->dct_scale, v_max * 8, &c->size_h)) return B200JPG_ERR_FORMAT;
+        c->block_w = (uint16_t)(mw * c->h);
+        c->block_h = (uint16_t)(mh * c->v);
+    }
+    if (mcu_w) *mcu_w = mw;
+    if (mcu_h) *mcu_h = mh;
+    return B200JPG_OK;
+}
+// src/idct.rs:14-28
+int b200jpg_choose_idct_size(uint16_t full_w, uint16_t full_h, uint16_t req_w, uint16_t req_h) {
+    static const uint32_t scales[3] = {1, 2, 4};
+    for (int k = 0; k < 3; k++) {
+        uint16_t sw = (uint16_t)(((uint32_t)full_w * scales[k] - 1) / 8 + 1);
+        uint16_t sh = (uint16_t)(((uint32_t)full_h * scales[k] - 1) / 8 + 1);
+        if (sw >= req_w || sh >= req_h) return (int)scales[k];
+    }
+    return 8;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// batch plan
+// ---------------------------------------------------------------------------------------------
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct ImageLayout {
+    size_t coef_off[4] = {0, 0, 0, 0};
+    size_t plane_off[4] = {0, 0, 0, 0};
+    size_t coef_bytes[4] = {0, 0, 0, 0};
+    size_t out_off = 0, out_len = 0;
+    unsigned tile_first = 0, tile_count = 0;
+    int status = B200JPG_OK;
+};
+
+struct b200jpg_batch {
+    b200jpg_ctx* ctx = nullptr;
+    size_t n = 0;
+    std::vector<ImageLayout> layout;
+    std::vector<DevComp> comps;
+    std::vector<DevTile> tiles;
+    std::vector<DevImage> images;
+    std::vector<unsigned> qtabs;  // 64 per table
+    b200jpg_batch_info info{};
+    bool all_scale8 = true;
+    bool k1_tma_aligned = true;
+    unsigned path_max_w[3] = {0, 0, 0}, path_max_h[3] = {0, 0, 0};
+    bool path_used[3] = {false, false, false};
+    // device copies of the tables
+    DevComp* d_comps = nullptr;
+    DevTile* d_tiles = nullptr;
+    DevImage* d_images = nullptr;
+    unsigned* d_qtabs = nullptr;
+    // tensor map cache (one slab pointer at a time)
+    const void* tmap_base = nullptr;
+    CUtensorMap tmap;
+    // internal slabs for the host pipeline
+    void* d_coefs = nullptr;
+    void* d_planes = nullptr;
+    void* d_out = nullptr;
+    bool planes_absolute = false;  // plane_off holds absolute device addresses (worker path)
+};
+
+struct PlanOverrides {
+    const unsigned long long (*plane_addr)[4] = nullptr;  // per image absolute device addresses of the planes
+};
+
+// choose_upsampler, src/upsampler.rs:76-105
+static int choose_upsampler(uint8_t h, uint8_t v, uint8_t hmax, uint8_t vmax, uint16_t out_w, uint16_t out_h,
+                            DevUpComp* u, std::string* err) {
+    bool h1 = h == hmax || out_w == 1, v1 = v == vmax || out_h == 1;
+    bool h2 = h * 2 == hmax, v2 = v * 2 == vmax;
+    u->hs = u->vs = 1;
+    if (h1 && v1) u->kind = UP_H1V1;
+    else if (h2 && v1) u->kind = UP_H2V1;
+    else if (h1 && v2) u->kind = UP_H1V2;
+    else if (h2 && v2) u->kind = UP_H2V2;
+    else if (h == 0 || v == 0 || hmax % h != 0 || vmax % v != 0) {
+        *err = "unsupported JPEG feature: NonIntegerSubsamplingRatio";
+        return B200JPG_ERR_UNSUPPORTED;
+    } else {
+        u->kind = UP_GENERIC;
+        u->hs = hmax / h;
+        u->vs = vmax / v;
+    }
+    return B200JPG_OK;
+}
+
+// choose_color_convert_func, src/decoder.rs:1339-1389
+static int choose_color_convert(int ncomp, int ct, unsigned* cc, std::string* err) {
+    auto bad = [&](const char* what) {
+        *err = std::string("invalid JPEG format: Invalid number of channels (") + (ncomp == 3 ? "3" : "4") + ") for " + what + " data";
+        return B200JPG_ERR_FORMAT;
+    };
+    if (ncomp != 3 && ncomp != 4) {
+        *err = "internal: component count must be 1, 3 or 4 (the reference panics)";
+        return B200JPG_ERR_INTERNAL;
+    }
+    switch (ct) {
+    case B200JPG_CT_NONE: *cc = CC_NOCONVERT; return B200JPG_OK;
+    case B200JPG_CT_GRAYSCALE: return bad("Grayscale");
+    case B200JPG_CT_RGB: if (ncomp == 3) { *cc = CC_RGB; return B200JPG_OK; } return bad("RGB");
+    case B200JPG_CT_YCBCR: if (ncomp == 3) { *cc = CC_YCBCR; return B200JPG_OK; } return bad("YCbCr");
+    case B200JPG_CT_CMYK: if (ncomp == 4) { *cc = CC_CMYK; return B200JPG_OK; } return bad("CMYK");
+    case B200JPG_CT_YCCK: if (ncomp == 4) { *cc = CC_YCCK; return B200JPG_OK; } return bad("YCCK");
+    case B200JPG_CT_JCS_BG_YCC: *err = "unsupported JPEG feature: ColorTransform(JcsBgYcc)"; return B200JPG_ERR_UNSUPPORTED;
+    case B200JPG_CT_JCS_BG_RGB: *err = "unsupported JPEG feature: ColorTransform(JcsBgRgb)"; return B200JPG_ERR_UNSUPPORTED;
+    default: *err = "invalid JPEG format: Unknown colour transform"; return B200JPG_ERR_FORMAT;
+    }
+}
+
+// Validates one image and fills its DevImage (without offsets).
+static int plan_image(const b200jpg_ctx* ctx, const b200jpg_image_desc& d, DevImage* img, std::string* err) {
+    memset(img, 0, sizeof *img);
+    const int n = d.ncomp;
+    if (n != 1 && n != 3 && n != 4) {
+        *err = "internal: component count must be 1, 3 or 4";
+        return B200JPG_ERR_INTERNAL;
+    }
+    if (d.width == 0 || d.height == 0) {
+        *err = "invalid JPEG format: invalid dimensions";
+        return B200JPG_ERR_FORMAT;
+    }
+    for (int i = 0; i < n; i++) {
+        const b200jpg_component& c = d.comps[i];
+        if (!(c.dct_scale == 1 || c.dct_scale == 2 || c.dct_scale == 4 || c.dct_scale == 8)) {
+            *err = "internal: Unsupported IDCT scale";  // src/idct.rs:237
+            return B200JPG_ERR_INTERNAL;
+        }
+        if (c.block_w == 0 || c.block_h == 0 || c.h == 0 || c.v == 0 || c.h > 4 || c.v > 4 || c.size_w == 0 || c.size_h == 0) {
+            *err = "internal: component geometry not initialised";
+            return B200JPG_ERR_INTERNAL;
+        }
+        if ((size_t)c.size_w > (size_t)c.block_w * c.dct_scale || (size_t)c.size_h > (size_t)c.block_h * c.dct_scale) {
+            *err = "internal: component size exceeds its block grid";
+            return B200JPG_ERR_INTERNAL;
+        }
+    }
+    img->width = d.width;
+    img->height = d.height;
+    img->ncomp = (unsigned)n;
+    uint8_t hmax = 0, vmax = 0;
+    size_t wmax = 0;
+    for (int i = 0; i < n; i++) {
+        hmax = std::max(hmax, d.comps[i].h);
+        vmax = std::max(vmax, d.comps[i].v);
+        wmax = std::max<size_t>(wmax, d.comps[i].size_w);
+    }
+    if (n == 1) {
+        // src/decoder.rs:1310-1332: crop only, the colour transform is not consulted
+        img->cc = CC_GRAY;
+        img->c[0].kind = UP_H1V1;
+        img->c[0].hs = img->c[0].vs = 1;
+        // output is component.size, which must agree with the requested output size
+        if (d.comps[0].size_w != d.width || d.comps[0].size_h != d.height) {
+            *err = "internal: single-component output size differs from component.size";
+            return B200JPG_ERR_INTERNAL;
+        }
+    } else {
+        int rc = choose_color_convert(n, d.color_transform, &img->cc, err);
+        if (rc) return rc;
+        for (int i = 0; i < n; i++) {
+            rc = choose_upsampler(d.comps[i].h, d.comps[i].v, hmax, vmax, d.width, d.height, &img->c[i], err);
+            if (rc) return rc;
+        }
+        if (img->cc == CC_NOCONVERT && wmax * hmax != d.width) {
+            // color_no_convert unwrap()s past the end of the row when the line buffers are longer
+            // than the row (src/decoder.rs:1476-1484)
+            *err = "internal: ColorTransform::None needs line buffers of exactly the row width (the reference panics)";
+            return B200JPG_ERR_INTERNAL;
+        }
+    }
+    for (int i = 0; i < n; i++) {
+        const b200jpg_component& c = d.comps[i];
+        DevUpComp& u = img->c[i];
+        u.stride = (unsigned)c.block_w * c.dct_scale;
+        u.in_w = c.size_w;
+        u.in_h = c.size_h;
+        const size_t rows = (size_t)c.block_h * c.dct_scale;
+        // every sample the upsampler can touch must exist (the reference would panic on the slice)
+        bool ok = true;
+        switch (u.kind) {
+        case UP_H1V1: ok = d.width <= u.stride && d.height <= rows; break;
+        case UP_H2V1: ok = (size_t)u.in_w * 2 >= d.width && d.height <= rows; break;
+        case UP_H1V2: ok = d.width <= u.stride && (size_t)u.in_h * 2 >= d.height; break;
+        case UP_H2V2: ok = (size_t)u.in_w * 2 >= d.width && (size_t)u.in_h * 2 >= d.height; break;
+        default: ok = (size_t)u.in_w * u.hs >= d.width && ((size_t)d.height + u.vs - 1) / u.vs <= rows; break;
+        }
+        if (!ok) {
+            *err = "internal: output size is not covered by the component planes";
+            return B200JPG_ERR_INTERNAL;
+        }
+    }
+    // SSSE3 colour path: first (W/8 - 1) * 8 pixels of each row, src/arch/ssse3.rs:206, only for YCbCr
+    img->ssse3_pixels = 0;
+    if (ctx->arith == B200JPG_ARITH_SSSE3 && img->cc == CC_YCBCR) {
+        unsigned nv = d.width / 8;
+        img->ssse3_pixels = nv ? (nv - 1) * 8 : 0;
+    }
+    // kernel choice
+    img->path = K2_PATH_GENERIC;
+    if (ctx->k2_kernel != B200JPG_KERNEL_GENERIC && img->cc == CC_YCBCR && img->ssse3_pixels == 0 && d.width % 16 == 0) {
+        const DevUpComp* u = img->c;
+        if (u[0].kind == UP_H1V1 && u[1].kind == UP_H2V2 && u[2].kind == UP_H2V2 && u[0].stride % 16 == 0 &&
+            u[1].stride % 8 == 0 && u[2].stride % 8 == 0 && u[1].in_w == u[2].in_w && u[1].in_h == u[2].in_h &&
+            u[1].in_w * 2 == d.width)
+            img->path = K2_PATH_420;
+        else if (u[0].kind == UP_H1V1 && u[1].kind == UP_H1V1 && u[2].kind == UP_H1V1 && u[0].stride % 16 == 0 &&
+                 u[1].stride % 16 == 0 && u[2].stride % 16 == 0)
+            img->path = K2_PATH_444;
+    }
+    return B200JPG_OK;
+}
+
+static void batch_release_device(b200jpg_batch* b) {
+    if (!b) return;
+    cudaFree(b->d_comps);
+    cudaFree(b->d_tiles);
+    cudaFree(b->d_images);
+    cudaFree(b->d_qtabs);
+    cudaFree(b->d_coefs);
+    cudaFree(b->d_planes);
+    cudaFree(b->d_out);
+    b->d_comps = nullptr; b->d_tiles = nullptr; b->d_images = nullptr; b->d_qtabs = nullptr;
+    b->d_coefs = nullptr; b->d_planes = nullptr; b->d_out = nullptr;
+}
+
+static int batch_create_impl(b200jpg_ctx* ctx, const b200jpg_image_desc* imgs, size_t n, int* statuses,
+                             const PlanOverrides& ov, b200jpg_batch** out) {
+    if (!ctx || !out || (!imgs && n)) return B200JPG_ERR_INTERNAL;
+    *out = nullptr;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    b200jpg_batch* b = new b200jpg_batch();
+    b->ctx = ctx;
+    b->n = n;
+    b->layout.resize(n);
+    b->images.resize(n);
+    b->planes_absolute = ov.plane_addr != nullptr;
+    std::map<std::string, unsigned> qt_index;
+    size_t coef_off = 0, plane_off = 0, out_off = 0;
+    int first_error = B200JPG_OK;
+    std::string first_msg;
+    for (size_t i = 0; i < n; i++) {
+        const b200jpg_image_desc& d = imgs[i];
+        ImageLayout& L = b->layout[i];
+        std::string err;
+        int rc = plan_image(ctx, d, &b->images[i], &err);
+        for (int k = 0; rc == B200JPG_OK && k < d.ncomp; k++)
+            if (!d.qt[k]) {
+                rc = B200JPG_ERR_FORMAT;
+                err = "invalid JPEG format: use of unset quantization table";  // src/decoder.rs:810-815
+            }
+        L.status = rc;
+        if (statuses) statuses[i] = rc;
+        if (rc) {
+            if (!first_error) { first_error = rc; first_msg = err; }
+            b->images[i].ncomp = 0;  // skipped by every kernel
+            b->images[i].width = b->images[i].height = 0;
+            b->images[i].path = 0xffffffffu;
+            continue;
+        }
+        DevImage& img = b->images[i];
+        L.tile_first = (unsigned)b->tiles.size();
+        for (int k = 0; k < d.ncomp; k++) {
+            const b200jpg_component& c = d.comps[k];
+            const size_t nblocks = (size_t)c.block_w * c.block_h;
+            const size_t plane_bytes = nblocks * c.dct_scale * c.dct_scale;
+            // quantisation table, expanded to u32 and de-duplicated by content
+            std::string key((const char*)d.qt[k], 128);
+            auto it = qt_index.find(key);
+            unsigned qi;
+            if (it == qt_index.end()) {
+                qi = (unsigned)(b->qtabs.size() / 64);
+                for (int j = 0; j < 64; j++) b->qtabs.push_back(d.qt[k][j]);
+                qt_index.emplace(key, qi);
+            } else {
+                qi = it->second;
+            }
+            coef_off = align_up(coef_off, 1024);
+            plane_off = align_up(plane_off, 256);
+            L.coef_off[k] = coef_off;
+            L.coef_bytes[k] = nblocks * 128;
+            L.plane_off[k] = ov.plane_addr ? (size_t)ov.plane_addr[i][k] : plane_off;
+            DevComp dc;
+            dc.plane_off = L.plane_off[k];
+            dc.stride = (unsigned)c.block_w * c.dct_scale;
+            dc.block_w = c.block_w;
+            dc.qt_index = qi;
+            dc.dct_scale = c.dct_scale;
+            dc.nblocks = (unsigned)nblocks;
+            dc.pad = 0;
+            const unsigned comp_index = (unsigned)b->comps.size();
+            b->comps.push_back(dc);
+            if (c.dct_scale != 8) b->all_scale8 = false;
+            if (dc.plane_off % 8 != 0) b->k1_tma_aligned = false;
+            for (size_t first = 0; first < nblocks; first += K1_TILE) {
+                DevTile t;
+                t.comp = comp_index;
+                t.slab_row = (unsigned)(coef_off / 128 + first);
+                t.bxy = (unsigned)(first % c.block_w) | ((unsigned)(first / c.block_w) << 16);
+                t.nvalid = (unsigned)std::min<size_t>(K1_TILE, nblocks - first);
+                b->tiles.push_back(t);
+            }
+            img.c[k].plane_off = L.plane_off[k];
+            b->info.n_blocks += nblocks;
+            b->info.k1_algorithmic_bytes += nblocks * (128 + (size_t)c.dct_scale * c.dct_scale);
+            b->info.k2_algorithmic_bytes += plane_bytes;
+            coef_off += nblocks * 128;
+            plane_off += plane_bytes;
+        }
+        L.tile_count = (unsigned)b->tiles.size() - L.tile_first;
+        out_off = align_up(out_off, 256);
+        L.out_off = out_off;
+        L.out_len = (size_t)d.width * d.height * d.ncomp;
+        img.out_off = out_off;
+        out_off += L.out_len;
+        b->info.n_pixels += (size_t)d.width * d.height;
+        b->info.k2_algorithmic_bytes += L.out_len;
+        if (img.path < 3) {
+            b->path_used[img.path] = true;
+            b->path_max_w[img.path] = std::max(b->path_max_w[img.path], img.width);
+            b->path_max_h[img.path] = std::max(b->path_max_h[img.path], img.height);
+        }
+    }
+    if (coef_off / 128 + K1_TILE >= 0xffffffffull) {
+        delete b;
+        return fail(ctx, B200JPG_ERR_INTERNAL, "batch too large: more than 2^32 blocks");
+    }
+    b->info.coef_bytes = align_up(coef_off, 1024);
+    b->info.plane_bytes = ov.plane_addr ? 0 : align_up(plane_off, 256);
+    b->info.out_bytes = align_up(out_off, 256);
+    if (first_error) ctx->err = first_msg;
+
+    auto upload = [&](void** dptr, const void* src, size_t bytes) -> cudaError_t {
+        *dptr = nullptr;
+        if (bytes == 0) return cudaSuccess;
+        cudaError_t e = cudaMalloc(dptr, bytes);
+        if (e != cudaSuccess) return e;
+        // pageable source: the copy is staged before the call returns, so the vectors may be reused
+        return cudaMemcpyAsync(*dptr, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    };
+    cudaError_t e = upload((void**)&b->d_comps, b->comps.data(), b->comps.size() * sizeof(DevComp));
+    if (e == cudaSuccess) e = upload((void**)&b->d_tiles, b->tiles.data(), b->tiles.size() * sizeof(DevTile));
+    if (e == cudaSuccess) e = upload((void**)&b->d_images, b->images.data(), b->images.size() * sizeof(DevImage));
+    if (e == cudaSuccess) e = upload((void**)&b->d_qtabs, b->qtabs.data(), b->qtabs.size() * sizeof(unsigned));
+    if (e != cudaSuccess) {
+        batch_release_device(b);
+        delete b;
+        return cuda_fail(ctx, e, "batch table upload");
+    }
+    *out = b;
+    return B200JPG_OK;
+}
+
+static int ensure_tensor_map(b200jpg_batch* b, const void* d_coefs) {
+    b200jpg_ctx* ctx = b->ctx;
+    if (b->tmap_base == d_coefs) return B200JPG_OK;
+    if (!ctx->encode) return fail(ctx, B200JPG_ERR_INTERNAL, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t rows = b->info.coef_bytes / 128;
+    cuuint64_t gdim[2] = {64, rows};
+    cuuint64_t gstride[1] = {128};
+    cuuint32_t box[2] = {64, (cuuint32_t)K1_TILE};
+    cuuint32_t estride[2] = {1, 1};
+    CUresult r = ctx->encode(&b->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(d_coefs), gdim, gstride, box,
+                             estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char buf[96];
+        snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+        return fail(ctx, B200JPG_ERR_INTERNAL, buf);
+    }
+    b->tmap_base = d_coefs;
+    return B200JPG_OK;
+}
+
+// K1 over tiles [tile_first, tile_first+tile_count), K2 over images [img_first, img_first+img_count)
+static int batch_launch(b200jpg_batch* b, const void* d_coefs, void* d_planes, void* d_out, int stages, unsigned tile_first,
+                        unsigned tile_count, unsigned img_first, unsigned img_count, cudaStream_t stream) {
+    b200jpg_ctx* ctx = b->ctx;
+    if ((stages & 1) && tile_count) {
+        K1Params p;
+        p.tiles = b->d_tiles + tile_first;
+        p.comps = b->d_comps;
+        p.qtabs = b->d_qtabs;
+        p.coefs = (const short*)d_coefs;
+        p.planes = (uint8_t*)d_planes;
+        p.ntiles = tile_count;
+        const bool tma_ok = ctx->arith == B200JPG_ARITH_SCALAR && b->all_scale8 && b->k1_tma_aligned &&
+                            ((uintptr_t)d_coefs % 16 == 0) && ((uintptr_t)d_planes % 8 == 0);
+        if (ctx->k1_kernel == B200JPG_KERNEL_FAST && !tma_ok)
+            return fail(ctx, B200JPG_ERR_INTERNAL, "k1_kernel=FAST requested but the batch is not eligible (needs scalar arithmetic, dct_scale 8)");
+        if (tma_ok && ctx->k1_kernel != B200JPG_KERNEL_GENERIC) {
+            int rc = ensure_tensor_map(b, d_coefs);
+            if (rc) return rc;
+            CU_TRY(ctx, launch_k1_tma(b->tmap, p, ctx->num_sms, stream));
+        } else {
+            CU_TRY(ctx, launch_k1_generic(p, ctx->arith, stream));
+        }
+        ctx->launches++;
+    }
+    if ((stages & 2) && img_count) {
+        K2Params p;
+        p.images = b->d_images;
+        p.planes = (const uint8_t*)d_planes;
+        p.out = (uint8_t*)d_out;
+        p.nimages = (unsigned)b->n;
+        if (ctx->k2_kernel == B200JPG_KERNEL_FAST && b->path_used[K2_PATH_GENERIC])
+            return fail(ctx, B200JPG_ERR_INTERNAL, "k2_kernel=FAST requested but some image needs the generic kernel");
+        for (unsigned first = img_first; first < img_first + img_count; first += 65535u) {
+            const unsigned count = std::min(65535u, img_first + img_count - first);
+            for (int path = 0; path < 3; path++) {
+                if (!b->path_used[path]) continue;
+                cudaError_t e = cudaSuccess;
+                if (path == K2_PATH_GENERIC) e = launch_k2_generic(p, first, count, b->path_max_w[path], b->path_max_h[path], stream);
+                else if (path == K2_PATH_420) e = launch_k2_420(p, first, count, b->path_max_w[path], b->path_max_h[path], stream);
+                else e = launch_k2_444(p, first, count, b->path_max_w[path], b->path_max_h[path], stream);
+                if (e != cudaSuccess) return cuda_fail(ctx, e, "K2 launch");
+                ctx->launches++;
+            }
+        }
+    }
+    return B200JPG_OK;
+}
+
+extern "C" {
+
+int b200jpg_batch_create(b200jpg_ctx* ctx, const b200jpg_image_desc* imgs, size_t n, int* statuses, b200jpg_batch** batch) {
+    PlanOverrides ov;
+    return batch_create_impl(ctx, imgs, n, statuses, ov, batch);
+}
+
+void b200jpg_batch_free(b200jpg_batch* b) {
+    if (!b) return;
+    cudaSetDevice(b->ctx->device);
+    cudaStreamSynchronize(b->ctx->stream);
+    cudaStreamSynchronize(b->ctx->stream2);
+    batch_release_device(b);
+    delete b;
+}
+
+int b200jpg_batch_get_info(const b200jpg_batch* b, b200jpg_batch_info* info) {
+    if (!b || !info) return B200JPG_ERR_INTERNAL;
+    *info = b->info;
+    return B200JPG_OK;
+}
+
+int b200jpg_batch_image_layout(const b200jpg_batch* b, size_t i, size_t coef_off[4], size_t plane_off[4], size_t* out_off,
+                               size_t* out_len) {
+    if (!b || i >= b->n) return B200JPG_ERR_INTERNAL;
+    const ImageLayout& L = b->layout[i];
+    for (int k = 0; k < 4; k++) {
+        if (coef_off) coef_off[k] = L.coef_off[k];
+        if (plane_off) plane_off[k] = L.plane_off[k];
+    }
+    if (out_off) *out_off = L.out_off;
+    if (out_len) *out_len = L.out_len;
+    return L.status;
+}
+
+int b200jpg_batch_run_device(b200jpg_batch* b, const void* d_coefs, void* d_planes, void* d_out, int stages) {
+    if (!b) return B200JPG_ERR_INTERNAL;
+    b200jpg_ctx* ctx = b->ctx;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    return batch_launch(b, d_coefs, d_planes, d_out, stages, 0, (unsigned)b->tiles.size(), 0, (unsigned)b->n, ctx->stream);
+}
+
+// Host -> host: chunked, double-buffered over two streams (H2D | K1 | K2 | D2H overlap across chunks).
+int b200jpg_batch_run_host(b200jpg_batch* b, const b200jpg_image_desc* imgs, uint8_t* const* outs, const size_t* out_caps,
+                           int* statuses) {
+    if (!b || !imgs || !outs) return B200JPG_ERR_INTERNAL;
+    b200jpg_ctx* ctx = b->ctx;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    if (!b->d_coefs && b->info.coef_bytes) CU_TRY(ctx, cudaMalloc(&b->d_coefs, b->info.coef_bytes));
+    if (!b->d_planes && b->info.plane_bytes) CU_TRY(ctx, cudaMalloc(&b->d_planes, b->info.plane_bytes));
+    if (!b->d_out && b->info.out_bytes) CU_TRY(ctx, cudaMalloc(&b->d_out, b->info.out_bytes));
+    // the table uploads were enqueued on ctx->stream; make the second stream wait for them
+    cudaEvent_t ready;
+    CU_TRY(ctx, cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    CU_TRY(ctx, cudaEventRecord(ready, ctx->stream));
+    CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream2, ready, 0));
+    cudaEventDestroy(ready);
+
+    const size_t chunk_target = (size_t)192 << 20;  // bytes of coefficients per chunk
+    int result = B200JPG_OK;
+    size_t i = 0;
+    int which = 0;
+    while (i < b->n) {
+        size_t j = i, bytes = 0;
+        while (j < b->n && (j == i || bytes < chunk_target)) {
+            for (int k = 0; k < 4; k++) bytes += b->layout[j].coef_bytes[k];
+            j++;
+        }
+        cudaStream_t s = which ? ctx->stream2 : ctx->stream;
+        which ^= 1;
+        unsigned tile_first = 0, tile_count = 0;
+        bool have_tiles = false;
+        for (size_t m = i; m < j; m++) {
+            const ImageLayout& L = b->layout[m];
+            if (statuses) statuses[m] = L.status;
+            if (L.status) continue;
+            if (out_caps && out_caps[m] < L.out_len) {
+                if (statuses) statuses[m] = B200JPG_ERR_INTERNAL;
+                result = fail(ctx, B200JPG_ERR_INTERNAL, "output buffer too small");
+                continue;
+            }
+            for (int k = 0; k < imgs[m].ncomp; k++) {
+                if (!imgs[m].coefs[k]) {
+                    if (statuses) statuses[m] = B200JPG_ERR_FORMAT;
+                    result = fail(ctx, B200JPG_ERR_FORMAT, "invalid JPEG format: not all components have data");
+                    continue;
+                }
+                CU_TRY(ctx, cudaMemcpyAsync((char*)b->d_coefs + L.coef_off[k], imgs[m].coefs[k], L.coef_bytes[k],
+                                            cudaMemcpyHostToDevice, s));
+            }
+            if (!have_tiles) { tile_first = L.tile_first; have_tiles = true; }
+            tile_count = L.tile_first + L.tile_count - tile_first;
+        }
+        int rc = batch_launch(b, b->d_coefs, b->d_planes, b->d_out, 3, tile_first, tile_count, (unsigned)i, (unsigned)(j - i), s);
+        if (rc) return rc;
+        for (size_t m = i; m < j; m++) {
+            const ImageLayout& L = b->layout[m];
+            if (L.status || (statuses && statuses[m])) continue;
+            CU_TRY(ctx, cudaMemcpyAsync(outs[m], (char*)b->d_out + L.out_off, L.out_len, cudaMemcpyDeviceToHost, s));
+        }
+        i = j;
+    }
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream2));
+    return result;
+}
+
+int b200jpg_decode_batch(b200jpg_ctx* ctx, const b200jpg_image_desc* imgs, size_t n, uint8_t* const* outs,
+                         const size_t* out_caps, int* statuses) {
+    b200jpg_batch* b = nullptr;
+    int rc = b200jpg_batch_create(ctx, imgs, n, statuses, &b);
+    if (rc) return rc;
+    rc = b200jpg_batch_run_host(b, imgs, outs, out_caps, statuses);
+    b200jpg_batch_free(b);
+    return rc;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// worker-shaped API (trait Worker, src/worker/mod.rs:24-35; ImmediateWorker, src/worker/immediate.rs)
+// ---------------------------------------------------------------------------------------------
+struct WorkerSlot {
+    bool started = false;
+    bool have_result = false;
+    b200jpg_component comp{};
+    uint16_t qt[64];
+    size_t offset_i16 = 0;      // coefficients appended so far
+    size_t rows = 0;            // MCU rows appended so far
+    int16_t* h_coefs = nullptr; // pinned staging, block_w*block_h*64
+    void* d_coefs = nullptr;
+    void* d_plane = nullptr;
+    size_t plane_len = 0;
+};
+
+struct b200jpg_worker {
+    b200jpg_ctx* ctx = nullptr;
+    WorkerSlot slot[4];
+};
+
+static void slot_release(WorkerSlot& s) {
+    if (s.h_coefs) cudaFreeHost(s.h_coefs);
+    cudaFree(s.d_coefs);
+    cudaFree(s.d_plane);
+    s = WorkerSlot();
+}
+
+extern "C" {
+
+int b200jpg_worker_new(b200jpg_ctx* ctx, b200jpg_worker** w) {
+    if (!ctx || !w) return B200JPG_ERR_INTERNAL;
+    *w = new b200jpg_worker();
+    (*w)->ctx = ctx;
+    return B200JPG_OK;
+}
+
+void b200jpg_worker_free(b200jpg_worker* w) {
+    if (!w) return;
+    cudaSetDevice(w->ctx->device);
+    cudaStreamSynchronize(w->ctx->stream);
+    for (auto& s : w->slot) slot_release(s);
+    delete w;
+}
+
+int b200jpg_worker_start(b200jpg_worker* w, int index, const b200jpg_component* c, const uint16_t qt_natural[64]) {
+    if (!w || !c || !qt_natural) return B200JPG_ERR_INTERNAL;
+    b200jpg_ctx* ctx = w->ctx;
+    if (index < 0 || index >= 4) return fail(ctx, B200JPG_ERR_INTERNAL, "worker index out of range");
+    WorkerSlot& s = w->slot[index];
+    // assert!(self.results[data.index].is_empty()), src/worker/immediate.rs:31
+    if (s.started && !s.have_result) return fail(ctx, B200JPG_ERR_INTERNAL, "Worker::start on a component whose result was not collected");
+    if (!(c->dct_scale == 1 || c->dct_scale == 2 || c->dct_scale == 4 || c->dct_scale == 8))
+        return fail(ctx, B200JPG_ERR_INTERNAL, "Unsupported IDCT scale");
+    if (c->block_w == 0 || c->block_h == 0 || c->v == 0 || c->block_h % c->v != 0)
+        return fail(ctx, B200JPG_ERR_INTERNAL, "component geometry not initialised");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    slot_release(s);
+    s.comp = *c;
+    memcpy(s.qt, qt_natural, 128);
+    const size_t nblocks = (size_t)c->block_w * c->block_h;
+    s.plane_len = nblocks * c->dct_scale * c->dct_scale;
+    CU_TRY(ctx, cudaHostAlloc((void**)&s.h_coefs, nblocks * 128, cudaHostAllocDefault));
+    CU_TRY(ctx, cudaMalloc(&s.d_coefs, nblocks * 128));
+    CU_TRY(ctx, cudaMalloc(&s.d_plane, s.plane_len));
+    // the plane starts zeroed; MCU rows never appended stay 0 (src/worker/rayon.rs:46)
+    CU_TRY(ctx, cudaMemsetAsync(s.d_plane, 0, s.plane_len, ctx->stream));
+    s.started = true;
+    return B200JPG_OK;
+}
+
+int b200jpg_worker_append_rows(b200jpg_worker* w, int index, const int16_t* coefs, size_t n_i16, size_t nrows) {
+    if (!w || !coefs) return B200JPG_ERR_INTERNAL;
+    b200jpg_ctx* ctx = w->ctx;
+    if (index < 0 || index >= 4 || !w->slot[index].started || w->slot[index].have_result)
+        return fail(ctx, B200JPG_ERR_INTERNAL, "Worker::append_row on a component that was not started");
+    WorkerSlot& s = w->slot[index];
+    const size_t per_row = (size_t)s.comp.block_w * s.comp.v * 64;
+    // assert_eq!(data.len(), block_count * 64), src/worker/immediate.rs:47
+    if (n_i16 != per_row * nrows) return fail(ctx, B200JPG_ERR_INTERNAL, "Worker::append_row: data.len() != block_count * 64");
+    if (s.offset_i16 + n_i16 > (size_t)s.comp.block_w * s.comp.block_h * 64)
+        return fail(ctx, B200JPG_ERR_INTERNAL, "Worker::append_row: more rows than the plane holds");
+    memcpy(s.h_coefs + s.offset_i16, coefs, n_i16 * sizeof(int16_t));
+    s.offset_i16 += n_i16;
+    s.rows += nrows;
+    return B200JPG_OK;
+}
+
+int b200jpg_worker_append_row(b200jpg_worker* w, int index, const int16_t* coefs, size_t n_i16) {
+    return b200jpg_worker_append_rows(w, index, coefs, n_i16, 1);
+}
+
+int b200jpg_worker_get_result(b200jpg_worker* w, int index, uint8_t* plane_out, size_t cap, size_t* plane_len) {
+    if (!w) return B200JPG_ERR_INTERNAL;
+    b200jpg_ctx* ctx = w->ctx;
+    if (index < 0 || index >= 4) return fail(ctx, B200JPG_ERR_INTERNAL, "worker index out of range");
+    WorkerSlot& s = w->slot[index];
+    if (!s.started) {  // mem::take of an empty Vec
+        if (plane_len) *plane_len = 0;
+        return B200JPG_OK;
+    }
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    if (!s.have_result && s.rows > 0) {
+        // one-component pseudo image covering exactly the appended MCU rows
+        b200jpg_image_desc d;
+        memset(&d, 0, sizeof d);
+        d.ncomp = 1;
+        d.comps[0] = s.comp;
+        d.comps[0].block_h = (uint16_t)(s.rows * s.comp.v);
+        d.comps[0].size_w = (uint16_t)std::min<size_t>(s.comp.size_w ? s.comp.size_w : 1, (size_t)s.comp.block_w * s.comp.dct_scale);
+        d.comps[0].size_h = (uint16_t)std::max<size_t>(1, std::min<size_t>(s.comp.size_h, (size_t)d.comps[0].block_h * s.comp.dct_scale));
+        d.width = d.comps[0].size_w;
+        d.height = d.comps[0].size_h;
+        d.color_transform = B200JPG_CT_GRAYSCALE;
+        d.qt[0] = s.qt;
+        b200jpg_batch* b = nullptr;
+        PlanOverrides ov;
+        int rc = batch_create_impl(ctx, &d, 1, nullptr, ov, &b);
+        if (rc) return rc;
+        if (b->layout[0].status) {
+            rc = b->layout[0].status;
+            b200jpg_batch_free(b);
+            return rc;
+        }
+        cudaError_t e = cudaMemcpyAsync(s.d_coefs, s.h_coefs, s.offset_i16 * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess)
+            rc = batch_launch(b, s.d_coefs, s.d_plane, nullptr, 1, 0, (unsigned)b->tiles.size(), 0, 1, ctx->stream);
+        if (e == cudaSuccess && rc == B200JPG_OK) e = cudaStreamSynchronize(ctx->stream);
+        b200jpg_batch_free(b);
+        if (e != cudaSuccess) return cuda_fail(ctx, e, "worker get_result");
+        if (rc) return rc;
+    }
+    s.have_result = true;
+    if (plane_len) *plane_len = s.plane_len;
+    if (plane_out) {
+        if (cap < s.plane_len) return fail(ctx, B200JPG_ERR_INTERNAL, "plane buffer too small");
+        CU_TRY(ctx, cudaMemcpyAsync(plane_out, s.d_plane, s.plane_len, cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return B200JPG_OK;
+}
+
+static int compute_image_device(b200jpg_ctx* ctx, const b200jpg_component* comps, int ncomp, const void* const* d_planes,
+                                uint16_t out_w, uint16_t out_h, int color_transform, uint8_t* out, size_t cap, size_t* out_len) {
+    b200jpg_image_desc d;
+    memset(&d, 0, sizeof d);
+    if (ncomp < 1 || ncomp > 4) return fail(ctx, B200JPG_ERR_FORMAT, "invalid JPEG format: not all components have data");
+    d.ncomp = (uint8_t)ncomp;
+    d.width = out_w;
+    d.height = out_h;
+    d.color_transform = (uint8_t)color_transform;
+    static const uint16_t dummy_qt[64] = {1};
+    unsigned long long addr[1][4] = {{0, 0, 0, 0}};
+    for (int i = 0; i < ncomp; i++) {
+        d.comps[i] = comps[i];
+        d.qt[i] = dummy_qt;
+        addr[0][i] = (unsigned long long)(uintptr_t)d_planes[i];
+    }
+    if (ncomp == 1) {  // src/decoder.rs:1314-1316: the output is component.size
+        d.width = comps[0].size_w;
+        d.height = comps[0].size_h;
+    }
+    b200jpg_batch* b = nullptr;
+    PlanOverrides ov;
+    ov.plane_addr = addr;
+    int rc = batch_create_impl(ctx, &d, 1, nullptr, ov, &b);
+    if (rc) return rc;
+    rc = b->layout[0].status;
+    const size_t len = b->layout[0].out_len;
+    void* d_out = nullptr;
+    if (rc == B200JPG_OK && cap < len) rc = fail(ctx, B200JPG_ERR_INTERNAL, "output buffer too small");
+    cudaError_t e = cudaSuccess;
+    if (rc == B200JPG_OK) e = cudaMalloc(&d_out, len ? len : 1);
+    if (rc == B200JPG_OK && e == cudaSuccess) rc = batch_launch(b, nullptr, nullptr, d_out, 2, 0, 0, 0, 1, ctx->stream);
+    if (rc == B200JPG_OK && e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, len, cudaMemcpyDeviceToHost, ctx->stream);
+    if (rc == B200JPG_OK && e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_out);
+    b200jpg_batch_free(b);
+    if (rc) return rc;
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "compute_image");
+    if (out_len) *out_len = len;
+    return B200JPG_OK;
+}
+
+int b200jpg_worker_compute_image(b200jpg_worker* w, int ncomp, uint16_t out_w, uint16_t out_h, int color_transform,
+                                 uint8_t* out, size_t cap, size_t* out_len) {
+    if (!w || !out) return B200JPG_ERR_INTERNAL;
+    b200jpg_ctx* ctx = w->ctx;
+    if (ncomp < 1 || ncomp > 4) return fail(ctx, B200JPG_ERR_FORMAT, "invalid JPEG format: not all components have data");
+    b200jpg_component comps[4];
+    const void* planes[4];
+    for (int i = 0; i < ncomp; i++) {
+        // "not all components have data", src/decoder.rs:1306-1308
+        if (!w->slot[i].started || !w->slot[i].have_result) return fail(ctx, B200JPG_ERR_FORMAT, "invalid JPEG format: not all components have data");
+        comps[i] = w->slot[i].comp;
+        planes[i] = w->slot[i].d_plane;
+    }
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    return compute_image_device(ctx, comps, ncomp, planes, out_w, out_h, color_transform, out, cap, out_len);
+}
+
+int b200jpg_compute_image(b200jpg_ctx* ctx, const b200jpg_component* comps, int ncomp, const uint8_t* const* planes,
+                          const size_t* plane_len, uint16_t out_w, uint16_t out_h, int color_transform, uint8_t* out, size_t cap,
+                          size_t* out_len) {
+    if (!ctx || !comps || !planes || !plane_len || !out) return B200JPG_ERR_INTERNAL;
+    // data.is_empty() || data.iter().any(Vec::is_empty), src/decoder.rs:1306-1308
+    if (ncomp < 1 || ncomp > 4) return fail(ctx, B200JPG_ERR_FORMAT, "invalid JPEG format: not all components have data");
+    for (int i = 0; i < ncomp; i++)
+        if (!planes[i] || plane_len[i] == 0) return fail(ctx, B200JPG_ERR_FORMAT, "invalid JPEG format: not all components have data");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    void* d[4] = {nullptr, nullptr, nullptr, nullptr};
+    int rc = B200JPG_OK;
+    for (int i = 0; i < ncomp && rc == B200JPG_OK; i++) {
+        const size_t need = (size_t)comps[i].block_w * comps[i].block_h * comps[i].dct_scale * comps[i].dct_scale;
+        if (plane_len[i] < need) {
+            rc = fail(ctx, B200JPG_ERR_INTERNAL, "plane shorter than block_w*block_h*dct_scale^2 (the reference would panic on the slice)");
+            break;
+        }
+        cudaError_t e = cudaMalloc(&d[i], need ? need : 1);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d[i], planes[i], need, cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) rc = cuda_fail(ctx, e, "compute_image upload");
+    }
+    if (rc == B200JPG_OK) rc = compute_image_device(ctx, comps, ncomp, d, out_w, out_h, color_transform, out, cap, out_len);
+    cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < 4; i++) cudaFree(d[i]);
+    return rc;
+}
+
+}  // extern "C"
