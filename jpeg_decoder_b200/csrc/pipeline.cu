@@ -653,15 +653,16 @@ int b200jpg_batch_run_host(b200jpg_batch* b, const b200jpg_image_desc* imgs, uin
                 result = fail(ctx, B200JPG_ERR_INTERNAL, "output buffer too small");
                 continue;
             }
-            for (int k = 0; k < imgs[m].ncomp; k++) {
-                if (!imgs[m].coefs[k]) {
-                    if (statuses) statuses[m] = B200JPG_ERR_FORMAT;
-                    result = fail(ctx, B200JPG_ERR_FORMAT, "invalid JPEG format: not all components have data");
-                    continue;
-                }
+            bool have_all = true;
+            for (int k = 0; k < imgs[m].ncomp; k++) have_all = have_all && imgs[m].coefs[k] != nullptr;
+            if (!have_all) {  // "not all components have data", src/decoder.rs:1306-1308
+                if (statuses) statuses[m] = B200JPG_ERR_FORMAT;
+                result = fail(ctx, B200JPG_ERR_FORMAT, "invalid JPEG format: not all components have data");
+                continue;
+            }
+            for (int k = 0; k < imgs[m].ncomp; k++)
                 CU_TRY(ctx, cudaMemcpyAsync((char*)b->d_coefs + L.coef_off[k], imgs[m].coefs[k], L.coef_bytes[k],
                                             cudaMemcpyHostToDevice, s));
-            }
             if (!have_tiles) { tile_first = L.tile_first; have_tiles = true; }
             tile_count = L.tile_first + L.tile_count - tile_first;
         }
@@ -755,7 +756,7 @@ int b200jpg_worker_start(b200jpg_worker* w, int index, const b200jpg_component* 
     const size_t nblocks = (size_t)c->block_w * c->block_h;
     s.plane_len = nblocks * c->dct_scale * c->dct_scale;
     CU_TRY(ctx, cudaHostAlloc((void**)&s.h_coefs, nblocks * 128, cudaHostAllocDefault));
-    CU_TRY(ctx, cudaMalloc(&s.d_coefs, nblocks * 128));
+    CU_TRY(ctx, cudaMalloc(&s.d_coefs, align_up(nblocks * 128, 1024)));  // the TMA tensor map spans whole KiB
     CU_TRY(ctx, cudaMalloc(&s.d_plane, s.plane_len));
     // the plane starts zeroed; MCU rows never appended stay 0 (src/worker/rayon.rs:46)
     CU_TRY(ctx, cudaMemsetAsync(s.d_plane, 0, s.plane_len, ctx->stream));
