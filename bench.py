@@ -38,6 +38,9 @@ def parse_args():
     ap.add_argument("--unique", type=int, default=8, help="distinct synthetic images (replicated to the batch)")
     ap.add_argument("--e2e-batch", type=int, default=256, help="images per end-to-end (host->host) step")
     ap.add_argument("--arith", default="scalar", choices=["scalar", "ssse3"])
+    ap.add_argument("--k1", default="auto", choices=["auto", "generic", "v1"], help="K1 kernel variant (profiling)")
+    ap.add_argument("--k2", default="auto", choices=["auto", "generic", "v1"], help="K2 kernel variant (profiling)")
+    ap.add_argument("--no-numa-bind", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the CPU baseline sample")
     return ap.parse_args()
@@ -104,6 +107,52 @@ class ClockSampler(threading.Thread):
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def bind_to_gpu_numa_node(torch, index):
+    """Pins this process to the CPUs of the GPU's NUMA node so that pinned buffers are allocated next to the
+    GPU's PCIe root (host<->device copies then do not cross the socket interconnect)."""
+    try:
+        pr = torch.cuda.get_device_properties(index)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return {"node": node, "cpus": len(cpus)}
+    except Exception:
+        pass
+    return None
+
+
+def pcie_probe(torch, dev, nbytes=1 << 30):
+    """Measured pinned-memory copy bandwidth (GB/s): the roofline of the end-to-end (host->host) number."""
+    h_a = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    h_b = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    d_a = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    d_b = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    def run(h2d, d2h):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            if h2d:
+                with torch.cuda.stream(s1):
+                    d_a.copy_(h_a, non_blocking=True)
+            if d2h:
+                with torch.cuda.stream(s2):
+                    h_b.copy_(d_b, non_blocking=True)
+        torch.cuda.synchronize()
+        return 3 * nbytes / (time.perf_counter() - t0) / 1e9
+    run(True, True)
+    return {"h2d": run(True, False), "d2h": run(False, True), "bidir_each": run(True, True)}
 
 
 def cpu_port_throughput(unique, nthreads, target_seconds, arith):
@@ -186,6 +235,8 @@ def main():
     cfg = workload.CONFIGS[args.config]
     B = args.batch or cfg["batch"]
     W, H = cfg["width"], cfg["height"]
+    all_cpus = os.sched_getaffinity(0)
+    numa = None if args.no_numa_bind else bind_to_gpu_numa_node(torch, local_rank)
     # control plane: rank 0 broadcasts the image -> GPU assignment (contiguous index ranges)
     table = workload.broadcast_assignment(B * world, world, dist if world > 1 else None, device=dev)
     lo, hi = int(table[rank, 0]), int(table[rank, 1])
@@ -193,9 +244,13 @@ def main():
     unique = workload.build_unique(args.config, args.unique)
     U = len(unique)
 
-    stream = torch.cuda.current_stream()
+    # an explicit (non-default) torch stream: the library enqueues on it and torch.cuda.Event times it
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     arith = J.ARITH_SSSE3 if args.arith == "ssse3" else J.ARITH_SCALAR
-    ctx = J.Context(device=local_rank, arith=arith, stream=stream.cuda_stream)
+    kmap = {"auto": J.KERNEL_AUTO, "generic": J.KERNEL_GENERIC, "v1": J.KERNEL_FAST_V1}
+    assert stream.cuda_stream != 0
+    ctx = J.Context(device=local_rank, arith=arith, k1_kernel=kmap[args.k1], k2_kernel=kmap[args.k2], stream=stream.cuda_stream)
     keep = []
     descs = []
     for i in range(lo, hi):
@@ -308,6 +363,8 @@ def main():
     ref0 = d_out[batch.layout(0)["out_off"]:batch.layout(0)["out_off"] + out_per_img].cpu().numpy()
     same = bool(np.array_equal(ref0, h_out.numpy()[:out_per_img]))
 
+    pcie = pcie_probe(torch, dev) if rank == 0 else None
+    os.sched_setaffinity(0, all_cpus)   # the CPU baseline uses every core
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
@@ -321,13 +378,15 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "i32", "data": "synthetic",
             "config": {"workload": cfg["desc"], "batch_per_gpu": B, "global_batch": B * world, "width": W, "height": H,
-                       "unique_images": U, "arith": args.arith, "parallelism": "images sharded by index, %d rank(s)" % world,
+                       "unique_images": U, "arith": args.arith, "k1": args.k1, "k2": args.k2, "parallelism": "images sharded by index, %d rank(s)" % world,
                        "l2": "inputs (%.1f GB/GPU) far exceed the 126 MB L2; no flush needed" % (info.coef_bytes / 1e9)},
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": Be * coef_per_img, "d2h_bytes_per_step": Be * out_per_img,
                     "images_per_step": Be, "steps": e_steps, "host_result_equals_device_result": same,
-                    "api": "b200jpg_batch_run_host (pinned host coefficient buffers -> pinned host pixels)"},
+                    "api": "b200jpg_batch_run_host (pinned host coefficient buffers -> pinned host pixels)",
+                    "pcie_gbs_measured": pcie, "numa_bind": numa,
+                    "gbs_each_direction": Be * coef_per_img * e_steps / e_dt / 1e9},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }

@@ -64,7 +64,7 @@ enum {
 };
 
 /* kernel selection, for tests and profiling (0 = pick the fastest applicable kernel) */
-enum { B200JPG_KERNEL_AUTO = 0, B200JPG_KERNEL_GENERIC = 1, B200JPG_KERNEL_FAST = 2 };
+enum { B200JPG_KERNEL_AUTO = 0, B200JPG_KERNEL_GENERIC = 1, B200JPG_KERNEL_FAST = 2, B200JPG_KERNEL_FAST_V1 = 3 /* K1 only: first-generation TMA kernel */ };
 
 /* ---- parser::Component: src/parser.rs:77-89 (geometry from update_component_sizes, 292-310) --- */
 typedef struct {

@@ -24,7 +24,7 @@ struct __align__(16) DevComp {
     unsigned qt_index;             // index into the u32[64] quantisation tables
     unsigned dct_scale;            // 1, 2, 4, 8
     unsigned nblocks;              // block_w * block_h
-    unsigned pad;
+    unsigned qflags;               // bit0: all 64 entries <= 255 (IDP.2A path); bits 8..15: constant-bank slot, 0xff = none
 };
 
 // One per K1 tile: up to K1_TILE consecutive blocks (raster order) of one component.  16 B.

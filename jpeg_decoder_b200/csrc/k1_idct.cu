@@ -370,7 +370,7 @@ k1_idct8_tma(const __grid_constant__ CUtensorMap tmap, K1Params p) {
     const unsigned row_off = tid * 128u, swz = (tid & 7u) << 4;
     unsigned cur_comp = 0xffffffffu;
     DevComp comp;
-    comp.plane_off = 0; comp.stride = 0; comp.block_w = 1; comp.qt_index = 0; comp.dct_scale = 8; comp.nblocks = 0; comp.pad = 0;
+    comp.plane_off = 0; comp.stride = 0; comp.block_w = 1; comp.qt_index = 0; comp.dct_scale = 8; comp.nblocks = 0; comp.qflags = 0;
     const uint4* q4 = nullptr;
 
     for (unsigned t = t_begin; t < t_end; t++) {
@@ -454,6 +454,183 @@ k1_idct8_tma(const __grid_constant__ CUtensorMap tmap, K1Params p) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// The hot kernel, second generation.  Differences from k1_idct8_tma:
+//  * no producer warp: thread 0 refills the ring at the top of each iteration (the slot it refills was
+//    drained one whole tile ago), so a CTA is 4 warps and 4 CTAs (16 warps) fit per SM instead of 12 warps;
+//  * 8-bit quantisation tables (every baseline JPEG) are dequantised with IDP.2A straight from the packed
+//    int16 pairs: s = dp2a(w, {q_even, 0, 0, q_odd}) -- no sign-extension instructions, and the packed
+//    table words of the first four tables of a batch live in the kernel-parameter constant bank, so they
+//    are instruction operands rather than loads.
+// ---------------------------------------------------------------------------------------------
+constexpr int K1V2_STAGES = 3;
+
+__device__ __forceinline__ unsigned dp2a_lo_su(unsigned a, unsigned b, unsigned c) {
+    unsigned d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ unsigned dp2a_hi_su(unsigned a, unsigned b, unsigned c) {
+    unsigned d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+#define K1_DEQ8_ROW(k, B0, B1, B2, B3)                          \
+    {                                                           \
+        const unsigned bias_ = (k == 0) ? 0x80000u : 0u;        \
+        s[k][0] = dp2a_lo_su(raw[k].x, (B0), bias_);            \
+        s[k][1] = dp2a_hi_su(raw[k].x, (B0), bias_);            \
+        s[k][2] = dp2a_lo_su(raw[k].y, (B1), bias_);            \
+        s[k][3] = dp2a_hi_su(raw[k].y, (B1), bias_);            \
+        s[k][4] = dp2a_lo_su(raw[k].z, (B2), bias_);            \
+        s[k][5] = dp2a_hi_su(raw[k].z, (B2), bias_);            \
+        s[k][6] = dp2a_lo_su(raw[k].w, (B3), bias_);            \
+        s[k][7] = dp2a_hi_su(raw[k].w, (B3), bias_);            \
+    }
+
+template <int SLOT>
+__device__ __forceinline__ void dequant_q8_const(const uint4 (&raw)[8], unsigned (&s)[8][8], const K1QCache& qc) {
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+        K1_DEQ8_ROW(k, qc.b[SLOT][4 * k + 0], qc.b[SLOT][4 * k + 1], qc.b[SLOT][4 * k + 2], qc.b[SLOT][4 * k + 3]);
+}
+
+__global__ void __launch_bounds__(K1_TILE, 4)
+k1_idct8_tma2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ K1QCache qc, K1Params p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const unsigned smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    __shared__ __align__(8) unsigned long long full_bar[K1V2_STAGES];
+    __shared__ __align__(8) unsigned long long empty_bar[K1V2_STAGES];
+
+    const unsigned tid = threadIdx.x, lane = tid & 31;
+    const unsigned t_begin = (unsigned)(((unsigned long long)blockIdx.x * p.ntiles) / gridDim.x);
+    const unsigned t_end = (unsigned)(((unsigned long long)(blockIdx.x + 1) * p.ntiles) / gridDim.x);
+    const unsigned n = t_end - t_begin;
+
+    unsigned row_ahead = 0;  // thread 0: slab row of the tile the next refill will fetch
+    if (tid == 0) {
+        for (int st = 0; st < K1V2_STAGES; st++) {
+            mbar_init(smem_u32(&full_bar[st]), 1);
+            mbar_init(smem_u32(&empty_bar[st]), K1_TILE / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+        for (unsigned it = 0; it < (unsigned)K1V2_STAGES && it < n; it++) {
+            const unsigned bar = smem_u32(&full_bar[it]);
+            mbar_expect_tx(bar, K1_STAGE_BYTES);
+            tma_load_2d(smem + it * K1_STAGE_BYTES, &tmap, 0, (int)__ldg(&p.tiles[t_begin + it].slab_row), bar);
+        }
+        if (n > (unsigned)K1V2_STAGES) row_ahead = __ldg(&p.tiles[t_begin + K1V2_STAGES].slab_row);
+    }
+    __syncthreads();
+
+    const unsigned row_off = tid * 128u, swz = (tid & 7u) << 4;
+    unsigned cur_comp = 0xffffffffu;
+    DevComp comp;
+    comp.plane_off = 0; comp.stride = 0; comp.block_w = 1; comp.qt_index = 0; comp.dct_scale = 8; comp.nblocks = 0; comp.qflags = 0;
+    const uint4* q4 = nullptr;
+    const uint4* qp4 = nullptr;
+
+    for (unsigned it = 0; it < n; it++) {
+        const unsigned stage = it % K1V2_STAGES, round = it / K1V2_STAGES;
+        // ---- refill: the slot drained during the previous iteration receives tile it-1+STAGES ----
+        if (tid == 0 && it > 0 && it - 1 + K1V2_STAGES < n) {
+            const unsigned ps = (it - 1) % K1V2_STAGES, pr = (it - 1) / K1V2_STAGES;
+            mbar_wait(smem_u32(&empty_bar[ps]), pr & 1);
+            const unsigned bar = smem_u32(&full_bar[ps]);
+            mbar_expect_tx(bar, K1_STAGE_BYTES);
+            tma_load_2d(smem + ps * K1_STAGE_BYTES, &tmap, 0, (int)row_ahead, bar);
+            if (it + K1V2_STAGES < n) row_ahead = __ldg(&p.tiles[t_begin + it + K1V2_STAGES].slab_row);
+        }
+        const DevTile tile = p.tiles[t_begin + it];
+        if (tile.comp != cur_comp) {  // warp-uniform
+            cur_comp = tile.comp;
+            comp = p.comps[cur_comp];
+            q4 = reinterpret_cast<const uint4*>(p.qtabs + (size_t)comp.qt_index * 64);
+            qp4 = reinterpret_cast<const uint4*>(p.qpack + (size_t)comp.qt_index * 32);
+        }
+        mbar_wait(smem_u32(&full_bar[stage]), round & 1);
+        const unsigned sbase = smem + stage * K1_STAGE_BYTES + row_off;
+        uint4 raw[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) raw[k] = lds128(sbase + ((k * 16u) ^ swz));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&empty_bar[stage]));
+
+        if (tid >= tile.nvalid) continue;
+        unsigned bx = (tile.bxy & 0xffffu) + tid, by = tile.bxy >> 16;
+        if (comp.block_w >= (unsigned)K1_TILE) {
+            if (bx >= comp.block_w) { bx -= comp.block_w; by += 1; }
+        } else {
+            by += bx / comp.block_w;
+            bx %= comp.block_w;
+        }
+        uint8_t* dst = p.planes + comp.plane_off + (size_t)by * 8u * comp.stride + (size_t)bx * 8u;
+
+        unsigned s[8][8];
+        const unsigned qslot = comp.qflags >> 8;
+        if (comp.qflags & 1u) {  // 8-bit table: IDP.2A dequantisation
+            if (qslot == 0) dequant_q8_const<0>(raw, s, qc);
+            else if (qslot == 1) dequant_q8_const<1>(raw, s, qc);
+            else if (qslot == 2) dequant_q8_const<2>(raw, s, qc);
+            else if (qslot == 3) dequant_q8_const<3>(raw, s, qc);
+            else {
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const uint4 b = __ldg(qp4 + k);
+                    K1_DEQ8_ROW(k, b.x, b.y, b.z, b.w);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const uint4 qa = __ldg(q4 + 2 * k), qb = __ldg(q4 + 2 * k + 1);
+                const unsigned bias = (k == 0) ? 0x80000u : 0u;
+                s[k][0] = sext_lo(raw[k].x) * qa.x + bias;
+                s[k][1] = sext_hi(raw[k].x) * qa.y + bias;
+                s[k][2] = sext_lo(raw[k].y) * qa.z + bias;
+                s[k][3] = sext_hi(raw[k].y) * qa.w + bias;
+                s[k][4] = sext_lo(raw[k].z) * qb.x + bias;
+                s[k][5] = sext_hi(raw[k].z) * qb.y + bias;
+                s[k][6] = sext_lo(raw[k].w) * qb.z + bias;
+                s[k][7] = sext_hi(raw[k].w) * qb.w + bias;
+            }
+        }
+        const unsigned oor = (s[0][0] | s[0][1] | s[0][2] | s[0][3] | s[0][4] | s[0][5] | s[0][6] | s[0][7]) >> 20;
+        if (oor != 0) {
+            idct8x8_scalar_exact(p.coefs + ((size_t)tile.slab_row + tid) * 64, reinterpret_cast<const unsigned*>(q4), dst, comp.stride);
+            continue;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            unsigned x0, x1, x2, x3, t0, t1, t2, t3;
+            IDCT_1D(s[0][i], s[1][i], s[2][i], s[3][i], s[4][i], s[5][i], s[6][i], s[7][i], (512u + 0x80000000u),
+                    x0, x1, x2, x3, t0, t1, t2, t3);
+            s[0][i] = (unsigned)sar(x0 + t3, 10);
+            s[7][i] = (unsigned)sar(x0 - t3, 10);
+            s[1][i] = (unsigned)sar(x1 + t2, 10);
+            s[6][i] = (unsigned)sar(x1 - t2, 10);
+            s[2][i] = (unsigned)sar(x2 + t1, 10);
+            s[5][i] = (unsigned)sar(x2 - t1, 10);
+            s[3][i] = (unsigned)sar(x3 + t0, 10);
+            s[4][i] = (unsigned)sar(x3 - t0, 10);
+        }
+        const unsigned XS = 65536u + (128u << 17);
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            unsigned x0, x1, x2, x3, t0, t1, t2, t3;
+            IDCT_1D(s[r][0], s[r][1], s[r][2], s[r][3], s[r][4], s[r][5], s[r][6], s[r][7], XS, x0, x1, x2, x3, t0, t1,
+                    t2, t3);
+            uint2 o;
+            o.x = pack4_sat_u8(sar(x0 + t3, 17), sar(x1 + t2, 17), sar(x2 + t1, 17), sar(x3 + t0, 17));
+            o.y = pack4_sat_u8(sar(x3 - t0, 17), sar(x2 - t1, 17), sar(x1 - t2, 17), sar(x0 - t3, 17));
+            *reinterpret_cast<uint2*>(dst + (size_t)r * comp.stride) = o;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host-side launchers
 // ---------------------------------------------------------------------------------------------
 cudaError_t launch_k1_generic(const K1Params& p, int arith, cudaStream_t stream) {
@@ -475,6 +652,22 @@ cudaError_t launch_k1_tma(const CUtensorMap& tmap, const K1Params& p, int num_sm
     unsigned grid = (unsigned)num_sms * 3u;
     if (grid > p.ntiles) grid = p.ntiles;
     k1_idct8_tma<<<grid, K1_THREADS, k1_tma_smem_bytes(), stream>>>(tmap, p);
+    return cudaGetLastError();
+}
+
+size_t k1_tma2_smem_bytes() { return (size_t)K1V2_STAGES * K1_STAGE_BYTES + 1024; }
+
+cudaError_t launch_k1_tma2(const CUtensorMap& tmap, const K1QCache& qc, const K1Params& p, int num_sms, cudaStream_t stream) {
+    if (p.ntiles == 0) return cudaSuccess;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k1_idct8_tma2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_tma2_smem_bytes());
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    unsigned grid = (unsigned)num_sms * 4u;
+    if (grid > p.ntiles) grid = p.ntiles;
+    k1_idct8_tma2<<<grid, K1_TILE, k1_tma2_smem_bytes(), stream>>>(tmap, qc, p);
     return cudaGetLastError();
 }
 

@@ -52,6 +52,16 @@ __device__ __forceinline__ void ycbcr_scalar(int y, int cb, int cr, int& r, int&
     b = (yb + C_B_CB * cb) >> 20;
 }
 
+// same value with y supplied as y << 16
+__device__ __forceinline__ void ycbcr_scalar_y16(int y16, int cb, int cr, int& r, int& g, int& b) {
+    const int yr = y16 * 16 + (YCC_HALF - 128 * C_R_CR);
+    const int yg = y16 * 16 + (YCC_HALF + 128 * C_G_CB + 128 * C_G_CR);
+    const int yb = y16 * 16 + (YCC_HALF - 128 * C_B_CB);
+    r = (yr + C_R_CR * cr) >> 20;
+    g = (yg - C_G_CB * cb - C_G_CR * cr) >> 20;
+    b = (yb + C_B_CB * cb) >> 20;
+}
+
 __device__ __forceinline__ int sat16(int v) { return min(max(v, -32768), 32767); }
 __device__ __forceinline__ int mulhrs16(int a, int b) { return (int)(short)((((a * b) >> 14) + 1) >> 1); }
 // src/arch/ssse3.rs:208-244
@@ -202,8 +212,9 @@ __device__ __forceinline__ void ycbcr_store16(const uint4 yv, const int* cb, con
         int r[4], g[4], b[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const int y = (int)((yw[w] >> (8 * k)) & 0xffu);
-            ycbcr_scalar(y, cb[4 * w + k], cr[4 * w + k], r[k], g[k], b[k]);
+            // one PRMT puts luma byte k at bits 16..23 (y << 16); the << 4 folds into the IMADs below
+            const int y16 = (int)prmt(yw[w], 0u, 0x4044u | ((unsigned)k << 8));
+            ycbcr_scalar_y16(y16, cb[4 * w + k], cr[4 * w + k], r[k], g[k], b[k]);
         }
         // bytes: R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3
         ow[3 * w + 0] = pack_sat_u8(g[0], r[0], pack_sat_u8(r[1], b[0], 0u));
@@ -257,6 +268,69 @@ __global__ void __launch_bounds__(128) k2_ycbcr420(K2Params p, unsigned first, u
 }
 
 // ---------------------------------------------------------------------------------------------
+// 4:2:0 YCbCr fast path, second generation: a thread walks K2_RP consecutive row pairs of its
+// 16-pixel column group.  Chroma row p of pair p is chroma row p-1 of pair p+1, so it stays in
+// registers (each chroma byte is loaded exactly once per thread column), and the image descriptor
+// loads, index arithmetic and pointer set-up are paid once per 2*K2_RP output rows.
+// grid = (ceil(G/128), ceil(P/K2_RP), images)
+// ---------------------------------------------------------------------------------------------
+constexpr unsigned K2_RP = 4;
+
+struct ChromaRow {  // one chroma row segment: samples i0..i0+7 plus the clamped halo samples
+    unsigned lo, hi, L, R;
+};
+
+__device__ __forceinline__ ChromaRow load_chroma_row(const uint8_t* row, unsigned i0, unsigned iL, unsigned iR) {
+    ChromaRow c;
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(row + i0));
+    c.lo = v.x;
+    c.hi = v.y;
+    c.L = __ldg(row + iL);
+    c.R = __ldg(row + iR);
+    return c;
+}
+
+__global__ void __launch_bounds__(128, 5) k2_ycbcr420_v2(K2Params p, unsigned first) {
+    const DevImage& img = p.images[first + blockIdx.z];
+    if (img.path != K2_PATH_420) return;
+    const unsigned g = blockIdx.x * 128u + threadIdx.x;
+    const unsigned W = img.width, H = img.height;
+    const unsigned npairs = H / 2 + 1;
+    const unsigned p0 = blockIdx.y * K2_RP;
+    if (p0 >= npairs || g * 16u >= W) return;
+    const unsigned p1 = min(p0 + K2_RP, npairs);
+    const unsigned in_w = img.c[1].in_w, in_h = img.c[1].in_h;
+    const unsigned sy = img.c[0].stride, sb = img.c[1].stride, sr = img.c[2].stride;
+    const uint8_t* yplane = p.planes + img.c[0].plane_off + g * 16u;
+    const uint8_t* bplane = p.planes + img.c[1].plane_off;
+    const uint8_t* rplane = p.planes + img.c[2].plane_off;
+    uint8_t* out = p.out + img.out_off + (size_t)g * 48u;
+    const unsigned i0 = g * 8u;
+    const unsigned iL = i0 > 0 ? i0 - 1 : 0, iR = min(i0 + 8u, in_w - 1);
+
+    // chroma row A of the first pair
+    const unsigned rA0 = p0 > 0 ? p0 - 1 : 0;
+    ChromaRow ba = load_chroma_row(bplane + (size_t)rA0 * sb, i0, iL, iR);
+    ChromaRow ra = load_chroma_row(rplane + (size_t)rA0 * sr, i0, iL, iR);
+    for (unsigned pr = p0; pr < p1; pr++) {
+        const unsigned rB = min(pr, in_h - 1);
+        // all loads of the iteration up front (independent, clamped rows) so their latencies overlap
+        const unsigned y_odd = pr > 0 ? 2 * pr - 1 : 0, y_even = min(2 * pr, H - 1);
+        const ChromaRow bb = load_chroma_row(bplane + (size_t)rB * sb, i0, iL, iR);
+        const ChromaRow rb = load_chroma_row(rplane + (size_t)rB * sr, i0, iL, iR);
+        const uint4 yv_odd = __ldg(reinterpret_cast<const uint4*>(yplane + (size_t)y_odd * sy));
+        const uint4 yv_even = __ldg(reinterpret_cast<const uint4*>(yplane + (size_t)y_even * sy));
+        Chroma16 cb, cr;
+        h2v2_16(ba.lo, ba.hi, ba.L, ba.R, bb.lo, bb.hi, bb.L, bb.R, cb);
+        h2v2_16(ra.lo, ra.hi, ra.L, ra.R, rb.lo, rb.hi, rb.L, rb.R, cr);
+        if (pr > 0) ycbcr_store16(yv_odd, cb.odd, cr.odd, out + (size_t)y_odd * W * 3u);      // output row 2p-1
+        if (2 * pr < H) ycbcr_store16(yv_even, cb.even, cr.even, out + (size_t)y_even * W * 3u);  // output row 2p
+        ba = bb;
+        ra = rb;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // 4:4:4 YCbCr fast path: thread = 16 pixels of one row.
 // grid.x = ceil(G/128) * height, grid.y = image
 // ---------------------------------------------------------------------------------------------
@@ -274,8 +348,8 @@ __global__ void __launch_bounds__(128) k2_ycbcr444(K2Params p, unsigned first, u
     int cb[16], cr[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-        cb[k] = (int)((bw[k >> 2] >> (8 * (k & 3))) & 0xffu);
-        cr[k] = (int)((rw[k >> 2] >> (8 * (k & 3))) & 0xffu);
+        cb[k] = (int)prmt(bw[k >> 2], 0u, 0x4440u | (unsigned)(k & 3));
+        cr[k] = (int)prmt(rw[k >> 2], 0u, 0x4440u | (unsigned)(k & 3));
     }
     ycbcr_store16(yv, cb, cr, p.out + img.out_off + ((size_t)y * W + g * 16u) * 3u);
 }
@@ -287,6 +361,14 @@ cudaError_t launch_k2_generic(const K2Params& p, unsigned first, unsigned count,
     const unsigned xchunks = (max_w + 255u) / 256u;
     dim3 grid(xchunks * max_h, count);
     k2_generic<<<grid, 256, 0, stream>>>(p, first, xchunks);
+    return cudaGetLastError();
+}
+cudaError_t launch_k2_420_v2(const K2Params& p, unsigned first, unsigned count, unsigned max_w, unsigned max_h,
+                             cudaStream_t stream) {
+    if (count == 0 || max_w == 0 || max_h == 0) return cudaSuccess;
+    const unsigned npairs = max_h / 2u + 1u;
+    dim3 grid((max_w / 16u + 127u) / 128u, (npairs + K2_RP - 1u) / K2_RP, count);
+    k2_ycbcr420_v2<<<grid, 128, 0, stream>>>(p, first);
     return cudaGetLastError();
 }
 cudaError_t launch_k2_420(const K2Params& p, unsigned first, unsigned count, unsigned max_w, unsigned max_h,

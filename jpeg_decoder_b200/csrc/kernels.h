@@ -12,6 +12,7 @@ struct K1Params {
     const DevTile* tiles;
     const DevComp* comps;
     const unsigned* qtabs;  // u32[64] per table, natural order
+    const unsigned* qpack;  // u32[32] per table: {q[2j], 0, 0, q[2j+1]} bytes, valid for 8-bit tables
     const short* coefs;     // coefficient slab base
     uint8_t* planes;        // plane slab base
     unsigned ntiles;
@@ -24,9 +25,15 @@ struct K2Params {
     unsigned nimages;
 };
 
+// packed 8-bit tables of up to four components, passed by value = constant bank operands
+struct K1QCache {
+    unsigned b[4][32];
+};
+
 cudaError_t launch_k1_generic(const K1Params& p, int arith, cudaStream_t stream);
 cudaError_t launch_k1_tma(const CUtensorMap& tmap, const K1Params& p, int num_sms, cudaStream_t stream);
 size_t k1_tma_smem_bytes();
+cudaError_t launch_k1_tma2(const CUtensorMap& tmap, const K1QCache& qc, const K1Params& p, int num_sms, cudaStream_t stream);
 
 // K2: max_w/max_h = largest output size in [first, first+count); the grid covers that and images
 // smaller than it exit early.  `path` selects the kernel; images whose DevImage::path differs are
@@ -35,6 +42,8 @@ cudaError_t launch_k2_generic(const K2Params& p, unsigned first, unsigned count,
                               cudaStream_t stream);
 cudaError_t launch_k2_420(const K2Params& p, unsigned first, unsigned count, unsigned max_w, unsigned max_h,
                           cudaStream_t stream);
+cudaError_t launch_k2_420_v2(const K2Params& p, unsigned first, unsigned count, unsigned max_w, unsigned max_h,
+                             cudaStream_t stream);
 cudaError_t launch_k2_444(const K2Params& p, unsigned first, unsigned count, unsigned max_w, unsigned max_h,
                           cudaStream_t stream);
 

@@ -191,6 +191,9 @@ struct b200jpg_batch {
     std::vector<DevTile> tiles;
     std::vector<DevImage> images;
     std::vector<unsigned> qtabs;  // 64 per table
+    std::vector<unsigned> qpack;  // 32 per table (8-bit tables: {q[2j], 0, 0, q[2j+1]})
+    std::vector<unsigned char> qt_is8;
+    K1QCache qcache;
     b200jpg_batch_info info{};
     bool all_scale8 = true;
     bool k1_tma_aligned = true;
@@ -201,6 +204,7 @@ struct b200jpg_batch {
     DevTile* d_tiles = nullptr;
     DevImage* d_images = nullptr;
     unsigned* d_qtabs = nullptr;
+    unsigned* d_qpack = nullptr;
     // tensor map cache (one slab pointer at a time)
     const void* tmap_base = nullptr;
     CUtensorMap tmap;
@@ -368,10 +372,11 @@ static void batch_release_device(b200jpg_batch* b) {
     cudaFree(b->d_tiles);
     cudaFree(b->d_images);
     cudaFree(b->d_qtabs);
+    cudaFree(b->d_qpack);
     cudaFree(b->d_coefs);
     cudaFree(b->d_planes);
     cudaFree(b->d_out);
-    b->d_comps = nullptr; b->d_tiles = nullptr; b->d_images = nullptr; b->d_qtabs = nullptr;
+    b->d_comps = nullptr; b->d_tiles = nullptr; b->d_images = nullptr; b->d_qtabs = nullptr; b->d_qpack = nullptr;
     b->d_coefs = nullptr; b->d_planes = nullptr; b->d_out = nullptr;
 }
 
@@ -421,7 +426,14 @@ static int batch_create_impl(b200jpg_ctx* ctx, const b200jpg_image_desc* imgs, s
             unsigned qi;
             if (it == qt_index.end()) {
                 qi = (unsigned)(b->qtabs.size() / 64);
-                for (int j = 0; j < 64; j++) b->qtabs.push_back(d.qt[k][j]);
+                bool is8 = true;
+                for (int j = 0; j < 64; j++) {
+                    b->qtabs.push_back(d.qt[k][j]);
+                    is8 = is8 && d.qt[k][j] <= 255;
+                }
+                for (int j = 0; j < 32; j++)
+                    b->qpack.push_back(is8 ? ((unsigned)d.qt[k][2 * j] | ((unsigned)d.qt[k][2 * j + 1] << 24)) : 0u);
+                b->qt_is8.push_back(is8 ? 1 : 0);
                 qt_index.emplace(key, qi);
             } else {
                 qi = it->second;
@@ -438,7 +450,8 @@ static int batch_create_impl(b200jpg_ctx* ctx, const b200jpg_image_desc* imgs, s
             dc.qt_index = qi;
             dc.dct_scale = c.dct_scale;
             dc.nblocks = (unsigned)nblocks;
-            dc.pad = 0;
+            // 8-bit tables take the IDP.2A path; the first four tables of the batch sit in the constant bank
+            dc.qflags = (b->qt_is8[qi] ? 1u : 0u) | ((qi < 4 ? qi : 0xffu) << 8);
             const unsigned comp_index = (unsigned)b->comps.size();
             b->comps.push_back(dc);
             if (c.dct_scale != 8) b->all_scale8 = false;
@@ -493,6 +506,10 @@ static int batch_create_impl(b200jpg_ctx* ctx, const b200jpg_image_desc* imgs, s
     if (e == cudaSuccess) e = upload((void**)&b->d_tiles, b->tiles.data(), b->tiles.size() * sizeof(DevTile));
     if (e == cudaSuccess) e = upload((void**)&b->d_images, b->images.data(), b->images.size() * sizeof(DevImage));
     if (e == cudaSuccess) e = upload((void**)&b->d_qtabs, b->qtabs.data(), b->qtabs.size() * sizeof(unsigned));
+    if (e == cudaSuccess) e = upload((void**)&b->d_qpack, b->qpack.data(), b->qpack.size() * sizeof(unsigned));
+    memset(&b->qcache, 0, sizeof b->qcache);
+    for (size_t t = 0; t < 4 && t < b->qt_is8.size(); t++)
+        memcpy(b->qcache.b[t], b->qpack.data() + 32 * t, 32 * sizeof(unsigned));
     if (e != cudaSuccess) {
         batch_release_device(b);
         delete b;
@@ -532,17 +549,19 @@ static int batch_launch(b200jpg_batch* b, const void* d_coefs, void* d_planes, v
         p.tiles = b->d_tiles + tile_first;
         p.comps = b->d_comps;
         p.qtabs = b->d_qtabs;
+        p.qpack = b->d_qpack;
         p.coefs = (const short*)d_coefs;
         p.planes = (uint8_t*)d_planes;
         p.ntiles = tile_count;
         const bool tma_ok = ctx->arith == B200JPG_ARITH_SCALAR && b->all_scale8 && b->k1_tma_aligned &&
                             ((uintptr_t)d_coefs % 16 == 0) && ((uintptr_t)d_planes % 8 == 0);
-        if (ctx->k1_kernel == B200JPG_KERNEL_FAST && !tma_ok)
+        if ((ctx->k1_kernel == B200JPG_KERNEL_FAST || ctx->k1_kernel == B200JPG_KERNEL_FAST_V1) && !tma_ok)
             return fail(ctx, B200JPG_ERR_INTERNAL, "k1_kernel=FAST requested but the batch is not eligible (needs scalar arithmetic, dct_scale 8)");
         if (tma_ok && ctx->k1_kernel != B200JPG_KERNEL_GENERIC) {
             int rc = ensure_tensor_map(b, d_coefs);
             if (rc) return rc;
-            CU_TRY(ctx, launch_k1_tma(b->tmap, p, ctx->num_sms, stream));
+            if (ctx->k1_kernel == B200JPG_KERNEL_FAST_V1) CU_TRY(ctx, launch_k1_tma(b->tmap, p, ctx->num_sms, stream));
+            else CU_TRY(ctx, launch_k1_tma2(b->tmap, b->qcache, p, ctx->num_sms, stream));
         } else {
             CU_TRY(ctx, launch_k1_generic(p, ctx->arith, stream));
         }
@@ -562,7 +581,8 @@ static int batch_launch(b200jpg_batch* b, const void* d_coefs, void* d_planes, v
                 if (!b->path_used[path]) continue;
                 cudaError_t e = cudaSuccess;
                 if (path == K2_PATH_GENERIC) e = launch_k2_generic(p, first, count, b->path_max_w[path], b->path_max_h[path], stream);
-                else if (path == K2_PATH_420) e = launch_k2_420(p, first, count, b->path_max_w[path], b->path_max_h[path], stream);
+                else if (path == K2_PATH_420 && ctx->k2_kernel == B200JPG_KERNEL_FAST_V1) e = launch_k2_420(p, first, count, b->path_max_w[path], b->path_max_h[path], stream);
+                else if (path == K2_PATH_420) e = launch_k2_420_v2(p, first, count, b->path_max_w[path], b->path_max_h[path], stream);
                 else e = launch_k2_444(p, first, count, b->path_max_w[path], b->path_max_h[path], stream);
                 if (e != cudaSuccess) return cuda_fail(ctx, e, "K2 launch");
                 ctx->launches++;
@@ -630,7 +650,7 @@ int b200jpg_batch_run_host(b200jpg_batch* b, const b200jpg_image_desc* imgs, uin
     CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream2, ready, 0));
     cudaEventDestroy(ready);
 
-    const size_t chunk_target = (size_t)192 << 20;  // bytes of coefficients per chunk
+    const size_t chunk_target = (size_t)96 << 20;  // bytes of coefficients per chunk
     int result = B200JPG_OK;
     size_t i = 0;
     int which = 0;
@@ -644,6 +664,8 @@ int b200jpg_batch_run_host(b200jpg_batch* b, const b200jpg_image_desc* imgs, uin
         which ^= 1;
         unsigned tile_first = 0, tile_count = 0;
         bool have_tiles = false;
+        const char* run_src = nullptr;
+        size_t run_dst = 0, run_bytes = 0;
         for (size_t m = i; m < j; m++) {
             const ImageLayout& L = b->layout[m];
             if (statuses) statuses[m] = L.status;
@@ -660,19 +682,39 @@ int b200jpg_batch_run_host(b200jpg_batch* b, const b200jpg_image_desc* imgs, uin
                 result = fail(ctx, B200JPG_ERR_FORMAT, "invalid JPEG format: not all components have data");
                 continue;
             }
-            for (int k = 0; k < imgs[m].ncomp; k++)
-                CU_TRY(ctx, cudaMemcpyAsync((char*)b->d_coefs + L.coef_off[k], imgs[m].coefs[k], L.coef_bytes[k],
-                                            cudaMemcpyHostToDevice, s));
+            for (int k = 0; k < imgs[m].ncomp; k++) {
+                // merge copies that are contiguous on both sides (one arena per batch is the common case)
+                const char* src = (const char*)imgs[m].coefs[k];
+                if (run_bytes && run_src + run_bytes == src && run_dst + run_bytes == L.coef_off[k]) {
+                    run_bytes += L.coef_bytes[k];
+                } else {
+                    if (run_bytes) CU_TRY(ctx, cudaMemcpyAsync((char*)b->d_coefs + run_dst, run_src, run_bytes, cudaMemcpyHostToDevice, s));
+                    run_src = src;
+                    run_dst = L.coef_off[k];
+                    run_bytes = L.coef_bytes[k];
+                }
+            }
             if (!have_tiles) { tile_first = L.tile_first; have_tiles = true; }
             tile_count = L.tile_first + L.tile_count - tile_first;
         }
+        if (run_bytes) CU_TRY(ctx, cudaMemcpyAsync((char*)b->d_coefs + run_dst, run_src, run_bytes, cudaMemcpyHostToDevice, s));
         int rc = batch_launch(b, b->d_coefs, b->d_planes, b->d_out, 3, tile_first, tile_count, (unsigned)i, (unsigned)(j - i), s);
         if (rc) return rc;
+        char* out_dst = nullptr;
+        size_t out_src = 0, out_bytes = 0;
         for (size_t m = i; m < j; m++) {
             const ImageLayout& L = b->layout[m];
             if (L.status || (statuses && statuses[m])) continue;
-            CU_TRY(ctx, cudaMemcpyAsync(outs[m], (char*)b->d_out + L.out_off, L.out_len, cudaMemcpyDeviceToHost, s));
+            if (out_bytes && out_dst + out_bytes == (char*)outs[m] && out_src + out_bytes == L.out_off) {
+                out_bytes += L.out_len;
+            } else {
+                if (out_bytes) CU_TRY(ctx, cudaMemcpyAsync(out_dst, (char*)b->d_out + out_src, out_bytes, cudaMemcpyDeviceToHost, s));
+                out_dst = (char*)outs[m];
+                out_src = L.out_off;
+                out_bytes = L.out_len;
+            }
         }
+        if (out_bytes) CU_TRY(ctx, cudaMemcpyAsync(out_dst, (char*)b->d_out + out_src, out_bytes, cudaMemcpyDeviceToHost, s));
         i = j;
     }
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
