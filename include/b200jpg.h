@@ -197,6 +197,10 @@ B200JPG_API int b200jpg_batch_run_host(b200jpg_batch *b, const b200jpg_image_des
 B200JPG_API int b200jpg_decode_batch(b200jpg_ctx *ctx, const b200jpg_image_desc *imgs, size_t n,
                                      uint8_t *const *outs, const size_t *out_caps, int *statuses);
 
+/* Profiling knob, not part of the drop-in surface: selects bit-identical code-generation variants of
+ * the hot kernels (K1: pipe-balance mode 0..7, K2 4:2:0: row pairs per thread 1/2/4/8); -1 = default. */
+B200JPG_API void b200jpg_debug_set_kernel_modes(int k1_mode, int k2_mode);
+
 /* page-locked host memory helpers (cudaHostAlloc / cudaFreeHost) */
 B200JPG_API void *b200jpg_host_alloc(size_t bytes);
 B200JPG_API void b200jpg_host_free(void *p);

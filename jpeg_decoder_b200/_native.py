@@ -76,6 +76,7 @@ EXPORTS = {
                                          C.POINTER(C.c_int)]),
     "b200jpg_decode_batch": (C.c_int, [C.c_void_p, C.POINTER(ImageDesc), C.c_size_t, C.POINTER(C.c_void_p),
                                        C.POINTER(C.c_size_t), C.POINTER(C.c_int)]),
+    "b200jpg_debug_set_kernel_modes": (None, [C.c_int, C.c_int]),
     "b200jpg_host_alloc": (C.c_void_p, [C.c_size_t]),
     "b200jpg_host_free": (None, [C.c_void_p]),
     "b200jpg_decoder_new": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),

@@ -18,9 +18,12 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "device_types.h"
 #include "kernels.h"
+
+#define K1_DEFAULT_MODE 0
 
 namespace b200jpg {
 
@@ -80,6 +83,29 @@ __device__ __forceinline__ unsigned pack4_sat_u8(int v0, int v1, int v2, int v3)
         t1 = (s5) * F2F_2_053119869 + (q2_ + q4_);                                   \
         t0 = (s7) * F2F_0_298631336 + (q1_ + q3_);                                   \
     }
+
+// Same 1-D pass with the odd part written as the 4x4 integer matrix it is (all products mod 2^32, so
+// bit-identical): 16 IMAD and no adds -- moves work from the ALU pipe to the FMA pipe.
+#define IDCT_1D_MATODD(s0, s1, s2, s3, s4, s5, s6, s7, xs, x0, x1, x2, x3, t0, t1, t2, t3) \
+    {                                                                                       \
+        unsigned p1_ = ((s2) + (s6)) * F2F_0_5411961;                                       \
+        unsigned e2_ = p1_ + (s6) * F2F_N1_847759065;                                       \
+        unsigned e3_ = p1_ + (s2) * F2F_0_765366865;                                        \
+        unsigned e0_ = (((s0) + (s4)) << 12) + (xs);                                        \
+        unsigned e1_ = (((s0) - (s4)) << 12) + (xs);                                        \
+        x0 = e0_ + e3_;                                                                     \
+        x3 = e0_ - e3_;                                                                     \
+        x1 = e1_ + e2_;                                                                     \
+        x2 = e1_ - e2_;                                                                     \
+        t0 = (s7) * (unsigned)-5680 + (s1) * 1131u + (s3) * (unsigned)-3218 + (s5) * 4816u;  \
+        t1 = (s5) * 1132u + (s3) * (unsigned)-5681 + (s1) * 3219u + (s7) * 4816u;            \
+        t2 = (s3) * (unsigned)-1129 + (s5) * (unsigned)-5681 + (s7) * (unsigned)-3218 + (s1) * 4816u; \
+        t3 = (s1) * 5683u + (s7) * 1131u + (s5) * 3219u + (s3) * 4816u;                      \
+    }
+
+// arithmetic right shift on the FMA pipe: high word of x * 2^(32-n)
+template <int N>
+__device__ __forceinline__ int sar_mulhi(unsigned x) { return __mulhi((int)x, 1 << (32 - N)); }
 
 __device__ __forceinline__ unsigned sext_lo(unsigned w) { return (unsigned)(int)(short)(w & 0xffffu); }
 __device__ __forceinline__ unsigned sext_hi(unsigned w) { return (unsigned)((int)w >> 16); }
@@ -495,6 +521,10 @@ __device__ __forceinline__ void dequant_q8_const(const uint4 (&raw)[8], unsigned
         K1_DEQ8_ROW(k, qc.b[SLOT][4 * k + 0], qc.b[SLOT][4 * k + 1], qc.b[SLOT][4 * k + 2], qc.b[SLOT][4 * k + 3]);
 }
 
+// MODE bit0: column-pass >>10 on the FMA pipe (IMAD.HI); bit1: row-pass >>17 on the FMA pipe;
+// bit2: matrix-form odd part in the row pass.  All variants are bit-identical; they only move work
+// between the ALU and FMA pipes (the kernel is integer-issue bound, not HBM bound).
+template <int MODE>
 __global__ void __launch_bounds__(K1_TILE, 4)
 k1_idct8_tma2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ K1QCache qc, K1Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -607,24 +637,31 @@ k1_idct8_tma2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
             unsigned x0, x1, x2, x3, t0, t1, t2, t3;
             IDCT_1D(s[0][i], s[1][i], s[2][i], s[3][i], s[4][i], s[5][i], s[6][i], s[7][i], (512u + 0x80000000u),
                     x0, x1, x2, x3, t0, t1, t2, t3);
-            s[0][i] = (unsigned)sar(x0 + t3, 10);
-            s[7][i] = (unsigned)sar(x0 - t3, 10);
-            s[1][i] = (unsigned)sar(x1 + t2, 10);
-            s[6][i] = (unsigned)sar(x1 - t2, 10);
-            s[2][i] = (unsigned)sar(x2 + t1, 10);
-            s[5][i] = (unsigned)sar(x2 - t1, 10);
-            s[3][i] = (unsigned)sar(x3 + t0, 10);
-            s[4][i] = (unsigned)sar(x3 - t0, 10);
+#define K1_SHR10(v) ((MODE & 1) ? (unsigned)sar_mulhi<10>(v) : (unsigned)sar((v), 10))
+            s[0][i] = K1_SHR10(x0 + t3);
+            s[7][i] = K1_SHR10(x0 - t3);
+            s[1][i] = K1_SHR10(x1 + t2);
+            s[6][i] = K1_SHR10(x1 - t2);
+            s[2][i] = K1_SHR10(x2 + t1);
+            s[5][i] = K1_SHR10(x2 - t1);
+            s[3][i] = K1_SHR10(x3 + t0);
+            s[4][i] = K1_SHR10(x3 - t0);
         }
         const unsigned XS = 65536u + (128u << 17);
 #pragma unroll
         for (int r = 0; r < 8; r++) {
             unsigned x0, x1, x2, x3, t0, t1, t2, t3;
-            IDCT_1D(s[r][0], s[r][1], s[r][2], s[r][3], s[r][4], s[r][5], s[r][6], s[r][7], XS, x0, x1, x2, x3, t0, t1,
-                    t2, t3);
+            if (MODE & 4) {
+                IDCT_1D_MATODD(s[r][0], s[r][1], s[r][2], s[r][3], s[r][4], s[r][5], s[r][6], s[r][7], XS, x0, x1, x2, x3, t0,
+                               t1, t2, t3);
+            } else {
+                IDCT_1D(s[r][0], s[r][1], s[r][2], s[r][3], s[r][4], s[r][5], s[r][6], s[r][7], XS, x0, x1, x2, x3, t0, t1,
+                        t2, t3);
+            }
+#define K1_SHR17(v) ((MODE & 2) ? sar_mulhi<17>(v) : sar((v), 17))
             uint2 o;
-            o.x = pack4_sat_u8(sar(x0 + t3, 17), sar(x1 + t2, 17), sar(x2 + t1, 17), sar(x3 + t0, 17));
-            o.y = pack4_sat_u8(sar(x3 - t0, 17), sar(x2 - t1, 17), sar(x1 - t2, 17), sar(x0 - t3, 17));
+            o.x = pack4_sat_u8(K1_SHR17(x0 + t3), K1_SHR17(x1 + t2), K1_SHR17(x2 + t1), K1_SHR17(x3 + t0));
+            o.y = pack4_sat_u8(K1_SHR17(x3 - t0), K1_SHR17(x2 - t1), K1_SHR17(x1 - t2), K1_SHR17(x0 - t3));
             *reinterpret_cast<uint2*>(dst + (size_t)r * comp.stride) = o;
         }
     }
@@ -655,19 +692,38 @@ cudaError_t launch_k1_tma(const CUtensorMap& tmap, const K1Params& p, int num_sm
     return cudaGetLastError();
 }
 
+// experiment knob (profiling only): B200JPG_K1_MODE=0..7 selects the pipe-balance variant
+int g_k1_mode = -1;
+static int k1_mode() {
+    if (g_k1_mode < 0) {
+        const char* e = getenv("B200JPG_K1_MODE");
+        g_k1_mode = e ? atoi(e) & 7 : K1_DEFAULT_MODE;
+    }
+    return g_k1_mode;
+}
+
 size_t k1_tma2_smem_bytes() { return (size_t)K1V2_STAGES * K1_STAGE_BYTES + 1024; }
 
 cudaError_t launch_k1_tma2(const CUtensorMap& tmap, const K1QCache& qc, const K1Params& p, int num_sms, cudaStream_t stream) {
     if (p.ntiles == 0) return cudaSuccess;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k1_idct8_tma2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_tma2_smem_bytes());
-        if (e != cudaSuccess) return e;
+        const void* fns[8] = {(const void*)k1_idct8_tma2<0>, (const void*)k1_idct8_tma2<1>, (const void*)k1_idct8_tma2<2>,
+                              (const void*)k1_idct8_tma2<3>, (const void*)k1_idct8_tma2<4>, (const void*)k1_idct8_tma2<5>,
+                              (const void*)k1_idct8_tma2<6>, (const void*)k1_idct8_tma2<7>};
+        for (const void* f : fns) {
+            cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_tma2_smem_bytes());
+            if (e != cudaSuccess) return e;
+        }
         attr_set = true;
     }
     unsigned grid = (unsigned)num_sms * 4u;
     if (grid > p.ntiles) grid = p.ntiles;
-    k1_idct8_tma2<<<grid, K1_TILE, k1_tma2_smem_bytes(), stream>>>(tmap, qc, p);
+    switch (k1_mode()) {
+#define K1_CASE(M) case M: k1_idct8_tma2<M><<<grid, K1_TILE, k1_tma2_smem_bytes(), stream>>>(tmap, qc, p); break;
+        K1_CASE(1) K1_CASE(2) K1_CASE(3) K1_CASE(4) K1_CASE(5) K1_CASE(6) K1_CASE(7)
+        default: k1_idct8_tma2<0><<<grid, K1_TILE, k1_tma2_smem_bytes(), stream>>>(tmap, qc, p); break;
+    }
     return cudaGetLastError();
 }
 

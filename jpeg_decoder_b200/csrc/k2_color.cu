@@ -20,6 +20,7 @@
 // Roofline: HBM.  Algorithmic bytes per image = plane bytes read once + width*height*ncomp written.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "device_types.h"
 #include "kernels.h"
@@ -274,7 +275,8 @@ __global__ void __launch_bounds__(128) k2_ycbcr420(K2Params p, unsigned first, u
 // loads, index arithmetic and pointer set-up are paid once per 2*K2_RP output rows.
 // grid = (ceil(G/128), ceil(P/K2_RP), images)
 // ---------------------------------------------------------------------------------------------
-constexpr unsigned K2_RP = 4;
+constexpr unsigned K2_RP_DEFAULT = 4;
+int g_k2_mode = -1;
 
 struct ChromaRow {  // one chroma row segment: samples i0..i0+7 plus the clamped halo samples
     unsigned lo, hi, L, R;
@@ -290,7 +292,8 @@ __device__ __forceinline__ ChromaRow load_chroma_row(const uint8_t* row, unsigne
     return c;
 }
 
-__global__ void __launch_bounds__(128, 5) k2_ycbcr420_v2(K2Params p, unsigned first) {
+template <unsigned K2_RP, int MINB>
+__global__ void __launch_bounds__(128, MINB) k2_ycbcr420_v2(K2Params p, unsigned first) {
     const DevImage& img = p.images[first + blockIdx.z];
     if (img.path != K2_PATH_420) return;
     const unsigned g = blockIdx.x * 128u + threadIdx.x;
@@ -367,8 +370,17 @@ cudaError_t launch_k2_420_v2(const K2Params& p, unsigned first, unsigned count, 
                              cudaStream_t stream) {
     if (count == 0 || max_w == 0 || max_h == 0) return cudaSuccess;
     const unsigned npairs = max_h / 2u + 1u;
-    dim3 grid((max_w / 16u + 127u) / 128u, (npairs + K2_RP - 1u) / K2_RP, count);
-    k2_ycbcr420_v2<<<grid, 128, 0, stream>>>(p, first);
+    int mode = g_k2_mode;  // experiment knob (profiling only): row pairs per thread
+    if (mode < 0) {
+        const char* e = getenv("B200JPG_K2_MODE");
+        mode = g_k2_mode = e ? atoi(e) : (int)K2_RP_DEFAULT;
+    }
+    const unsigned rp = mode == 1 ? 1u : (mode == 2 ? 2u : (mode == 8 ? 8u : 4u));
+    dim3 grid((max_w / 16u + 127u) / 128u, (npairs + rp - 1u) / rp, count);
+    if (rp == 1) k2_ycbcr420_v2<1, 8><<<grid, 128, 0, stream>>>(p, first);
+    else if (rp == 2) k2_ycbcr420_v2<2, 6><<<grid, 128, 0, stream>>>(p, first);
+    else if (rp == 8) k2_ycbcr420_v2<8, 5><<<grid, 128, 0, stream>>>(p, first);
+    else k2_ycbcr420_v2<4, 5><<<grid, 128, 0, stream>>>(p, first);
     return cudaGetLastError();
 }
 cudaError_t launch_k2_420(const K2Params& p, unsigned first, unsigned count, unsigned max_w, unsigned max_h,

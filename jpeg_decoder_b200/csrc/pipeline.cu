@@ -120,6 +120,11 @@ int b200jpg_synchronize(b200jpg_ctx* ctx) {
     return B200JPG_OK;
 }
 
+void b200jpg_debug_set_kernel_modes(int k1_mode, int k2_mode) {
+    g_k1_mode = k1_mode;
+    g_k2_mode = k2_mode;
+}
+
 void* b200jpg_host_alloc(size_t bytes) {
     void* p = nullptr;
     if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
