@@ -38,8 +38,8 @@ def parse_args():
     ap.add_argument("--unique", type=int, default=8, help="distinct synthetic images (replicated to the batch)")
     ap.add_argument("--e2e-batch", type=int, default=256, help="images per end-to-end (host->host) step")
     ap.add_argument("--arith", default="scalar", choices=["scalar", "ssse3"])
-    ap.add_argument("--k1", default="auto", choices=["auto", "generic", "v1"], help="K1 kernel variant (profiling)")
-    ap.add_argument("--k2", default="auto", choices=["auto", "generic", "v1"], help="K2 kernel variant (profiling)")
+    ap.add_argument("--k1", default="auto", choices=["auto", "generic"], help="K1 kernel variant (profiling)")
+    ap.add_argument("--k2", default="auto", choices=["auto", "generic"], help="K2 kernel variant (profiling)")
     ap.add_argument("--no-numa-bind", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the CPU baseline sample")
@@ -248,7 +248,7 @@ def main():
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     arith = J.ARITH_SSSE3 if args.arith == "ssse3" else J.ARITH_SCALAR
-    kmap = {"auto": J.KERNEL_AUTO, "generic": J.KERNEL_GENERIC, "v1": J.KERNEL_FAST_V1}
+    kmap = {"auto": J.KERNEL_AUTO, "generic": J.KERNEL_GENERIC}
     assert stream.cuda_stream != 0
     ctx = J.Context(device=local_rank, arith=arith, k1_kernel=kmap[args.k1], k2_kernel=kmap[args.k2], stream=stream.cuda_stream)
     keep = []

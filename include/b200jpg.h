@@ -64,7 +64,7 @@ enum {
 };
 
 /* kernel selection, for tests and profiling (0 = pick the fastest applicable kernel) */
-enum { B200JPG_KERNEL_AUTO = 0, B200JPG_KERNEL_GENERIC = 1, B200JPG_KERNEL_FAST = 2, B200JPG_KERNEL_FAST_V1 = 3 /* K1 only: first-generation TMA kernel */ };
+enum { B200JPG_KERNEL_AUTO = 0, B200JPG_KERNEL_GENERIC = 1, B200JPG_KERNEL_FAST = 2 };
 
 /* ---- parser::Component: src/parser.rs:77-89 (geometry from update_component_sizes, 292-310) --- */
 typedef struct {
@@ -198,7 +198,8 @@ B200JPG_API int b200jpg_decode_batch(b200jpg_ctx *ctx, const b200jpg_image_desc 
                                      uint8_t *const *outs, const size_t *out_caps, int *statuses);
 
 /* Profiling knob, not part of the drop-in surface: selects bit-identical code-generation variants of
- * the hot kernels (K1: pipe-balance mode 0..7, K2 4:2:0: row pairs per thread 1/2/4/8); -1 = default. */
+ * the hot kernels (K1: output-butterfly style 0 = IADD3 / 5 = IMAD; K2 4:2:0: row pairs per thread 1 / 4);
+ * -1 = default.  Used by scripts/sweep_kernels.py to produce profiles/sweep_*.jsonl. */
 B200JPG_API void b200jpg_debug_set_kernel_modes(int k1_mode, int k2_mode);
 
 /* page-locked host memory helpers (cudaHostAlloc / cudaFreeHost) */

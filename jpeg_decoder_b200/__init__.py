@@ -18,7 +18,7 @@ import numpy as np
 
 from ._native import (ARITH_SCALAR, ARITH_SSSE3, CP_DCT_PROGRESSIVE, CP_DCT_SEQUENTIAL, CP_LOSSLESS, CT_CMYK,
                       CT_GRAYSCALE, CT_JCS_BG_RGB, CT_JCS_BG_YCC, CT_NONE, CT_RGB, CT_UNKNOWN, CT_YCBCR, CT_YCCK,
-                      ERR_FORMAT, ERR_INTERNAL, ERR_IO, ERR_UNSUPPORTED, KERNEL_AUTO, KERNEL_FAST, KERNEL_FAST_V1, KERNEL_GENERIC, OK,
+                      ERR_FORMAT, ERR_INTERNAL, ERR_IO, ERR_UNSUPPORTED, KERNEL_AUTO, KERNEL_FAST, KERNEL_GENERIC, OK,
                       PF_CMYK32, PF_L8, PF_L16, PF_RGB24, BatchInfo, Component, ImageDesc, ImageInfo, Options, lib)
 
 __all__ = ["Context", "Worker", "Batch", "Decoder", "B200JpgError", "make_components", "make_image_desc",

@@ -12,7 +12,7 @@ CT_NONE, CT_UNKNOWN, CT_GRAYSCALE, CT_RGB, CT_YCBCR, CT_CMYK, CT_YCCK, CT_JCS_BG
 PF_L8, PF_L16, PF_RGB24, PF_CMYK32 = range(4)
 CP_DCT_SEQUENTIAL, CP_DCT_PROGRESSIVE, CP_LOSSLESS = range(3)
 ARITH_SCALAR, ARITH_SSSE3 = 0, 1
-KERNEL_AUTO, KERNEL_GENERIC, KERNEL_FAST, KERNEL_FAST_V1 = 0, 1, 2, 3
+KERNEL_AUTO, KERNEL_GENERIC, KERNEL_FAST = 0, 1, 2
 
 
 class Component(C.Structure):

@@ -6,12 +6,10 @@
 // src/arch/ssse3.rs:124-192.  Arithmetic specification: SURVEY.md Appendix A.1/A.2.
 //
 // Two kernels:
-//   k1_idct8_tma      the hot one: scalar arithmetic, 8x8.  Persistent CTAs, one producer warp
-//                     streaming 128-block tiles (16 KB) into a 4-stage shared-memory ring with 2-D
-//                     TMA (128B swizzle, so that "one thread = one block" reads are bank-conflict
-//                     free), four consumer warps each doing a whole block per thread in registers
-//                     (no transposes, no shared-memory temporaries), coalesced 8-byte row stores
-//                     (32 lanes x 8 B = 256 contiguous bytes per plane row).
+//   k1_idct8_tma      the hot one: scalar arithmetic, 8x8.  Persistent 4-warp CTAs streaming 128-block
+//                     tiles (16 KB) through a 3-stage shared-memory ring with 2-D TMA (128B swizzle) +
+//                     mbarriers, one thread = one block in registers, IDP.2A dequantisation with the
+//                     tables in the constant bank, coalesced 8-byte row stores.
 //   k1_idct_generic   every other case (scaled IDCT 4x4/2x2/1x1, SSSE3 arithmetic), plain loads.
 //
 // Roofline: HBM.  Algorithmic bytes per block = 128 read + dct_scale^2 written (192 at scale 8).
@@ -23,7 +21,7 @@
 #include "device_types.h"
 #include "kernels.h"
 
-#define K1_DEFAULT_MODE 0
+#define K1_DEFAULT_MODE 5
 
 namespace b200jpg {
 
@@ -84,28 +82,14 @@ __device__ __forceinline__ unsigned pack4_sat_u8(int v0, int v1, int v2, int v3)
         t0 = (s7) * F2F_0_298631336 + (q1_ + q3_);                                   \
     }
 
-// Same 1-D pass with the odd part written as the 4x4 integer matrix it is (all products mod 2^32, so
-// bit-identical): 16 IMAD and no adds -- moves work from the ALU pipe to the FMA pipe.
-#define IDCT_1D_MATODD(s0, s1, s2, s3, s4, s5, s6, s7, xs, x0, x1, x2, x3, t0, t1, t2, t3) \
-    {                                                                                       \
-        unsigned p1_ = ((s2) + (s6)) * F2F_0_5411961;                                       \
-        unsigned e2_ = p1_ + (s6) * F2F_N1_847759065;                                       \
-        unsigned e3_ = p1_ + (s2) * F2F_0_765366865;                                        \
-        unsigned e0_ = (((s0) + (s4)) << 12) + (xs);                                        \
-        unsigned e1_ = (((s0) - (s4)) << 12) + (xs);                                        \
-        x0 = e0_ + e3_;                                                                     \
-        x3 = e0_ - e3_;                                                                     \
-        x1 = e1_ + e2_;                                                                     \
-        x2 = e1_ - e2_;                                                                     \
-        t0 = (s7) * (unsigned)-5680 + (s1) * 1131u + (s3) * (unsigned)-3218 + (s5) * 4816u;  \
-        t1 = (s5) * 1132u + (s3) * (unsigned)-5681 + (s1) * 3219u + (s7) * 4816u;            \
-        t2 = (s3) * (unsigned)-1129 + (s5) * (unsigned)-5681 + (s7) * (unsigned)-3218 + (s1) * 4816u; \
-        t3 = (s1) * 5683u + (s7) * 1131u + (s5) * 3219u + (s3) * 4816u;                      \
-    }
-
-// arithmetic right shift on the FMA pipe: high word of x * 2^(32-n)
-template <int N>
-__device__ __forceinline__ int sar_mulhi(unsigned x) { return __mulhi((int)x, 1 << (32 - N)); }
+// add / subtract issued on the FMA pipe: IMAD with a multiplier (+1 / -1) that only the host knows,
+// read from the kernel-parameter constant bank so ptxas cannot fold it back into an IADD3
+#define fma_add(a, b) ((a) * p.one + (b))
+#define fma_sub(a, b) ((b) * p.minus_one + (a))
+// output butterfly x +- t in one of two styles: 0 = plain add (ptxas picks IADD3, ALU pipe, half rate),
+// 1 = IMAD with the opaque +-1 multiplier (FMA pipe, full rate)
+#define K1_BFLY_ADD(STYLE, x, t) ((STYLE) == 1 ? fma_add((t), (x)) : ((x) + (t)))
+#define K1_BFLY_SUB(STYLE, x, t) ((STYLE) == 1 ? fma_sub((x), (t)) : ((x) - (t)))
 
 __device__ __forceinline__ unsigned sext_lo(unsigned w) { return (unsigned)(int)(short)(w & 0xffffu); }
 __device__ __forceinline__ unsigned sext_hi(unsigned w) { return (unsigned)((int)w >> 16); }
@@ -347,148 +331,20 @@ __device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* map
 // ---------------------------------------------------------------------------------------------
 // The hot kernel.
 // ---------------------------------------------------------------------------------------------
-constexpr int K1_STAGES = 4;
-constexpr int K1_CONSUMER_WARPS = K1_TILE / 32;
-constexpr int K1_THREADS = K1_TILE + 32;
 constexpr int K1_STAGE_BYTES = K1_TILE * 128;
 
-__global__ void __launch_bounds__(K1_THREADS, 3)
-k1_idct8_tma(const __grid_constant__ CUtensorMap tmap, K1Params p) {
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // 1024-byte alignment is what the 128B swizzle pattern is defined against
-    const unsigned smem = (smem_u32(smem_raw) + 1023u) & ~1023u;  // shared-window address
-    __shared__ __align__(8) unsigned long long full_bar[K1_STAGES];
-    __shared__ __align__(8) unsigned long long empty_bar[K1_STAGES];
-
-    const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // contiguous tile range per CTA: consecutive tiles mostly share component and table
-    const unsigned t_begin = (unsigned)(((unsigned long long)blockIdx.x * p.ntiles) / gridDim.x);
-    const unsigned t_end = (unsigned)(((unsigned long long)(blockIdx.x + 1) * p.ntiles) / gridDim.x);
-
-    if (tid == 0) {
-        for (int s = 0; s < K1_STAGES; s++) {
-            mbar_init(smem_u32(&full_bar[s]), 1);
-            mbar_init(smem_u32(&empty_bar[s]), K1_CONSUMER_WARPS);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    __syncthreads();
-
-    if (warp == K1_CONSUMER_WARPS) {
-        // ---------------- producer warp: one elected lane issues the TMA loads ----------------
-        if (lane == 0) {
-            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
-            for (unsigned t = t_begin; t < t_end; t++) {
-                const unsigned it = t - t_begin, stage = it % K1_STAGES, round = it / K1_STAGES;
-                if (round > 0) mbar_wait(smem_u32(&empty_bar[stage]), (round - 1) & 1);
-                const unsigned row = __ldg(&p.tiles[t].slab_row);
-                const unsigned bar = smem_u32(&full_bar[stage]);
-                mbar_expect_tx(bar, K1_STAGE_BYTES);
-                tma_load_2d(smem + stage * K1_STAGE_BYTES, &tmap, 0, (int)row, bar);
-            }
-        }
-        return;
-    }
-
-    // ---------------- consumer warps: thread = one 8x8 block ---------------------------------
-    // swizzled address of 16-byte chunk j of row `tid`: (tid*128 + (j*16)) ^ ((tid & 7) << 4)
-    const unsigned row_off = tid * 128u, swz = (tid & 7u) << 4;
-    unsigned cur_comp = 0xffffffffu;
-    DevComp comp;
-    comp.plane_off = 0; comp.stride = 0; comp.block_w = 1; comp.qt_index = 0; comp.dct_scale = 8; comp.nblocks = 0; comp.qflags = 0;
-    const uint4* q4 = nullptr;
-
-    for (unsigned t = t_begin; t < t_end; t++) {
-        const unsigned it = t - t_begin, stage = it % K1_STAGES, round = it / K1_STAGES;
-        const DevTile tile = p.tiles[t];
-        if (tile.comp != cur_comp) {  // warp-uniform
-            cur_comp = tile.comp;
-            comp = p.comps[cur_comp];
-            q4 = reinterpret_cast<const uint4*>(p.qtabs + (size_t)comp.qt_index * 64);
-        }
-        mbar_wait(smem_u32(&full_bar[stage]), round & 1);
-        const unsigned sbase = smem + stage * K1_STAGE_BYTES + row_off;
-        uint4 raw[8];
-#pragma unroll
-        for (int k = 0; k < 8; k++) raw[k] = lds128(sbase + ((k * 16u) ^ swz));
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&empty_bar[stage]));  // slot can be refilled
-
-        if (tid >= tile.nvalid) continue;
-        unsigned bx = (tile.bxy & 0xffffu) + tid, by = tile.bxy >> 16;
-        if (comp.block_w >= (unsigned)K1_TILE) {
-            if (bx >= comp.block_w) { bx -= comp.block_w; by += 1; }
-        } else {
-            by += bx / comp.block_w;
-            bx %= comp.block_w;
-        }
-        uint8_t* dst = p.planes + comp.plane_off + (size_t)by * 8u * comp.stride + (size_t)bx * 8u;
-
-        // ---- dequantise: s[k][i] = c * q.  Column 0 values of row 0 carry a +2^19 bias so that one
-        // OR-reduction detects |s0| >= 2^19 (the only case where the reference's zero-AC column
-        // shortcut, src/idct.rs:279-295, differs from the butterfly); the bias cancels in xs below.
-        unsigned s[8][8];
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const uint4 qa = __ldg(q4 + 2 * k), qb = __ldg(q4 + 2 * k + 1);
-            const unsigned bias = (k == 0) ? 0x80000u : 0u;
-            s[k][0] = sext_lo(raw[k].x) * qa.x + bias;
-            s[k][1] = sext_hi(raw[k].x) * qa.y + bias;
-            s[k][2] = sext_lo(raw[k].y) * qa.z + bias;
-            s[k][3] = sext_hi(raw[k].y) * qa.w + bias;
-            s[k][4] = sext_lo(raw[k].z) * qb.x + bias;
-            s[k][5] = sext_hi(raw[k].z) * qb.y + bias;
-            s[k][6] = sext_lo(raw[k].w) * qb.z + bias;
-            s[k][7] = sext_hi(raw[k].w) * qb.w + bias;
-        }
-        const unsigned oor = (s[0][0] | s[0][1] | s[0][2] | s[0][3] | s[0][4] | s[0][5] | s[0][6] | s[0][7]) >> 20;
-        if (oor != 0) {
-            // exact reference form, re-reading the block from HBM (rare: 16-bit tables / corrupt data)
-            idct8x8_scalar_exact(p.coefs + ((size_t)tile.slab_row + tid) * 64,
-                                 reinterpret_cast<const unsigned*>(q4), dst, comp.stride);
-            continue;
-        }
-        // ---- column pass: xs = 512, minus the 2^19 << 12 = 2^31 bias carried by s[0][*]
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            unsigned x0, x1, x2, x3, t0, t1, t2, t3;
-            IDCT_1D(s[0][i], s[1][i], s[2][i], s[3][i], s[4][i], s[5][i], s[6][i], s[7][i], (512u + 0x80000000u),
-                    x0, x1, x2, x3, t0, t1, t2, t3);
-            s[0][i] = (unsigned)sar(x0 + t3, 10);
-            s[7][i] = (unsigned)sar(x0 - t3, 10);
-            s[1][i] = (unsigned)sar(x1 + t2, 10);
-            s[6][i] = (unsigned)sar(x1 - t2, 10);
-            s[2][i] = (unsigned)sar(x2 + t1, 10);
-            s[5][i] = (unsigned)sar(x2 - t1, 10);
-            s[3][i] = (unsigned)sar(x3 + t0, 10);
-            s[4][i] = (unsigned)sar(x3 - t0, 10);
-        }
-        // ---- row pass + clamp + 8-byte coalesced row stores
-        const unsigned XS = 65536u + (128u << 17);
-#pragma unroll
-        for (int r = 0; r < 8; r++) {
-            unsigned x0, x1, x2, x3, t0, t1, t2, t3;
-            IDCT_1D(s[r][0], s[r][1], s[r][2], s[r][3], s[r][4], s[r][5], s[r][6], s[r][7], XS, x0, x1, x2, x3, t0, t1,
-                    t2, t3);
-            uint2 o;
-            o.x = pack4_sat_u8(sar(x0 + t3, 17), sar(x1 + t2, 17), sar(x2 + t1, 17), sar(x3 + t0, 17));
-            o.y = pack4_sat_u8(sar(x3 - t0, 17), sar(x2 - t1, 17), sar(x1 - t2, 17), sar(x0 - t3, 17));
-            *reinterpret_cast<uint2*>(dst + (size_t)r * comp.stride) = o;
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// The hot kernel, second generation.  Differences from k1_idct8_tma:
-//  * no producer warp: thread 0 refills the ring at the top of each iteration (the slot it refills was
-//    drained one whole tile ago), so a CTA is 4 warps and 4 CTAs (16 warps) fit per SM instead of 12 warps;
+// Persistent CTAs of 4 warps (4 CTAs = 16 warps per SM), each owning a contiguous range of 128-block
+// tiles.  Thread 0 keeps a 3-stage shared-memory ring full with 2-D TMA loads (128B swizzle, so that the
+// "thread t reads block t" pattern is bank-conflict free); the slot it refills at the top of an
+// iteration was drained one whole tile earlier.  Each thread then does a whole 8x8 block in registers:
 //  * 8-bit quantisation tables (every baseline JPEG) are dequantised with IDP.2A straight from the packed
-//    int16 pairs: s = dp2a(w, {q_even, 0, 0, q_odd}) -- no sign-extension instructions, and the packed
+//    int16 pairs: s = dp2a(w, {q_even, 0, 0, q_odd}) -- no sign-extension instructions -- and the packed
 //    table words of the first four tables of a batch live in the kernel-parameter constant bank, so they
-//    are instruction operands rather than loads.
+//    are instruction operands rather than loads; 16-bit tables take the load + IMAD path;
+//  * column pass, row pass, clamp and pack without transposes or shared-memory temporaries;
+//  * 8-byte row stores: 32 lanes x 8 B = 256 contiguous bytes per plane row.
 // ---------------------------------------------------------------------------------------------
-constexpr int K1V2_STAGES = 3;
+constexpr int K1_STAGES = 3;
 
 __device__ __forceinline__ unsigned dp2a_lo_su(unsigned a, unsigned b, unsigned c) {
     unsigned d;
@@ -521,16 +377,17 @@ __device__ __forceinline__ void dequant_q8_const(const uint4 (&raw)[8], unsigned
         K1_DEQ8_ROW(k, qc.b[SLOT][4 * k + 0], qc.b[SLOT][4 * k + 1], qc.b[SLOT][4 * k + 2], qc.b[SLOT][4 * k + 3]);
 }
 
-// MODE bit0: column-pass >>10 on the FMA pipe (IMAD.HI); bit1: row-pass >>17 on the FMA pipe;
-// bit2: matrix-form odd part in the row pass.  All variants are bit-identical; they only move work
+// MODE = column-pass style + 4 * row-pass style of the output butterflies (K1_BFLY_ADD): 0 plain, 1 IMAD.
+// Measured (sweep_r01*.jsonl): ALU-pipe instructions issue at half rate on sm_100, IMAD at full rate, and the
+// kernel is bound by the ALU pipe in style 0 and by issue slots in style 1; 5 (= both IMAD) is the fastest.  All variants are bit-identical; they only move work
 // between the ALU and FMA pipes (the kernel is integer-issue bound, not HBM bound).
 template <int MODE>
 __global__ void __launch_bounds__(K1_TILE, 4)
-k1_idct8_tma2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ K1QCache qc, K1Params p) {
+k1_idct8_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ K1QCache qc, K1Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const unsigned smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    __shared__ __align__(8) unsigned long long full_bar[K1V2_STAGES];
-    __shared__ __align__(8) unsigned long long empty_bar[K1V2_STAGES];
+    __shared__ __align__(8) unsigned long long full_bar[K1_STAGES];
+    __shared__ __align__(8) unsigned long long empty_bar[K1_STAGES];
 
     const unsigned tid = threadIdx.x, lane = tid & 31;
     const unsigned t_begin = (unsigned)(((unsigned long long)blockIdx.x * p.ntiles) / gridDim.x);
@@ -539,19 +396,19 @@ k1_idct8_tma2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
 
     unsigned row_ahead = 0;  // thread 0: slab row of the tile the next refill will fetch
     if (tid == 0) {
-        for (int st = 0; st < K1V2_STAGES; st++) {
+        for (int st = 0; st < K1_STAGES; st++) {
             mbar_init(smem_u32(&full_bar[st]), 1);
             mbar_init(smem_u32(&empty_bar[st]), K1_TILE / 32);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
-        for (unsigned it = 0; it < (unsigned)K1V2_STAGES && it < n; it++) {
+        for (unsigned it = 0; it < (unsigned)K1_STAGES && it < n; it++) {
             const unsigned bar = smem_u32(&full_bar[it]);
             mbar_expect_tx(bar, K1_STAGE_BYTES);
             tma_load_2d(smem + it * K1_STAGE_BYTES, &tmap, 0, (int)__ldg(&p.tiles[t_begin + it].slab_row), bar);
         }
-        if (n > (unsigned)K1V2_STAGES) row_ahead = __ldg(&p.tiles[t_begin + K1V2_STAGES].slab_row);
+        if (n > (unsigned)K1_STAGES) row_ahead = __ldg(&p.tiles[t_begin + K1_STAGES].slab_row);
     }
     __syncthreads();
 
@@ -563,15 +420,15 @@ k1_idct8_tma2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
     const uint4* qp4 = nullptr;
 
     for (unsigned it = 0; it < n; it++) {
-        const unsigned stage = it % K1V2_STAGES, round = it / K1V2_STAGES;
+        const unsigned stage = it % K1_STAGES, round = it / K1_STAGES;
         // ---- refill: the slot drained during the previous iteration receives tile it-1+STAGES ----
-        if (tid == 0 && it > 0 && it - 1 + K1V2_STAGES < n) {
-            const unsigned ps = (it - 1) % K1V2_STAGES, pr = (it - 1) / K1V2_STAGES;
+        if (tid == 0 && it > 0 && it - 1 + K1_STAGES < n) {
+            const unsigned ps = (it - 1) % K1_STAGES, pr = (it - 1) / K1_STAGES;
             mbar_wait(smem_u32(&empty_bar[ps]), pr & 1);
             const unsigned bar = smem_u32(&full_bar[ps]);
             mbar_expect_tx(bar, K1_STAGE_BYTES);
             tma_load_2d(smem + ps * K1_STAGE_BYTES, &tmap, 0, (int)row_ahead, bar);
-            if (it + K1V2_STAGES < n) row_ahead = __ldg(&p.tiles[t_begin + it + K1V2_STAGES].slab_row);
+            if (it + K1_STAGES < n) row_ahead = __ldg(&p.tiles[t_begin + it + K1_STAGES].slab_row);
         }
         const DevTile tile = p.tiles[t_begin + it];
         if (tile.comp != cur_comp) {  // warp-uniform
@@ -635,33 +492,30 @@ k1_idct8_tma2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             unsigned x0, x1, x2, x3, t0, t1, t2, t3;
+            constexpr int CS = MODE & 3;  // output butterfly style of the column pass
             IDCT_1D(s[0][i], s[1][i], s[2][i], s[3][i], s[4][i], s[5][i], s[6][i], s[7][i], (512u + 0x80000000u),
                     x0, x1, x2, x3, t0, t1, t2, t3);
-#define K1_SHR10(v) ((MODE & 1) ? (unsigned)sar_mulhi<10>(v) : (unsigned)sar((v), 10))
-            s[0][i] = K1_SHR10(x0 + t3);
-            s[7][i] = K1_SHR10(x0 - t3);
-            s[1][i] = K1_SHR10(x1 + t2);
-            s[6][i] = K1_SHR10(x1 - t2);
-            s[2][i] = K1_SHR10(x2 + t1);
-            s[5][i] = K1_SHR10(x2 - t1);
-            s[3][i] = K1_SHR10(x3 + t0);
-            s[4][i] = K1_SHR10(x3 - t0);
+            s[0][i] = (unsigned)sar(K1_BFLY_ADD(CS, x0, t3), 10);
+            s[7][i] = (unsigned)sar(K1_BFLY_SUB(CS, x0, t3), 10);
+            s[1][i] = (unsigned)sar(K1_BFLY_ADD(CS, x1, t2), 10);
+            s[6][i] = (unsigned)sar(K1_BFLY_SUB(CS, x1, t2), 10);
+            s[2][i] = (unsigned)sar(K1_BFLY_ADD(CS, x2, t1), 10);
+            s[5][i] = (unsigned)sar(K1_BFLY_SUB(CS, x2, t1), 10);
+            s[3][i] = (unsigned)sar(K1_BFLY_ADD(CS, x3, t0), 10);
+            s[4][i] = (unsigned)sar(K1_BFLY_SUB(CS, x3, t0), 10);
         }
         const unsigned XS = 65536u + (128u << 17);
 #pragma unroll
         for (int r = 0; r < 8; r++) {
             unsigned x0, x1, x2, x3, t0, t1, t2, t3;
-            if (MODE & 4) {
-                IDCT_1D_MATODD(s[r][0], s[r][1], s[r][2], s[r][3], s[r][4], s[r][5], s[r][6], s[r][7], XS, x0, x1, x2, x3, t0,
-                               t1, t2, t3);
-            } else {
-                IDCT_1D(s[r][0], s[r][1], s[r][2], s[r][3], s[r][4], s[r][5], s[r][6], s[r][7], XS, x0, x1, x2, x3, t0, t1,
-                        t2, t3);
-            }
-#define K1_SHR17(v) ((MODE & 2) ? sar_mulhi<17>(v) : sar((v), 17))
+            constexpr int RS = (MODE >> 2) & 3;  // output butterfly style of the row pass
             uint2 o;
-            o.x = pack4_sat_u8(K1_SHR17(x0 + t3), K1_SHR17(x1 + t2), K1_SHR17(x2 + t1), K1_SHR17(x3 + t0));
-            o.y = pack4_sat_u8(K1_SHR17(x3 - t0), K1_SHR17(x2 - t1), K1_SHR17(x1 - t2), K1_SHR17(x0 - t3));
+            IDCT_1D(s[r][0], s[r][1], s[r][2], s[r][3], s[r][4], s[r][5], s[r][6], s[r][7], XS, x0, x1, x2, x3, t0, t1,
+                    t2, t3);
+            o.x = pack4_sat_u8(sar(K1_BFLY_ADD(RS, x0, t3), 17), sar(K1_BFLY_ADD(RS, x1, t2), 17), sar(K1_BFLY_ADD(RS, x2, t1), 17),
+                               sar(K1_BFLY_ADD(RS, x3, t0), 17));
+            o.y = pack4_sat_u8(sar(K1_BFLY_SUB(RS, x3, t0), 17), sar(K1_BFLY_SUB(RS, x2, t1), 17), sar(K1_BFLY_SUB(RS, x1, t2), 17),
+                               sar(K1_BFLY_SUB(RS, x0, t3), 17));
             *reinterpret_cast<uint2*>(dst + (size_t)r * comp.stride) = o;
         }
     }
@@ -676,53 +530,35 @@ cudaError_t launch_k1_generic(const K1Params& p, int arith, cudaStream_t stream)
     return cudaGetLastError();
 }
 
-size_t k1_tma_smem_bytes() { return (size_t)K1_STAGES * K1_STAGE_BYTES + 1024; }
-
-cudaError_t launch_k1_tma(const CUtensorMap& tmap, const K1Params& p, int num_sms, cudaStream_t stream) {
-    if (p.ntiles == 0) return cudaSuccess;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k1_idct8_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_tma_smem_bytes());
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
-    unsigned grid = (unsigned)num_sms * 3u;
-    if (grid > p.ntiles) grid = p.ntiles;
-    k1_idct8_tma<<<grid, K1_THREADS, k1_tma_smem_bytes(), stream>>>(tmap, p);
-    return cudaGetLastError();
-}
-
 // experiment knob (profiling only): B200JPG_K1_MODE=0..7 selects the pipe-balance variant
 int g_k1_mode = -1;
 static int k1_mode() {
     if (g_k1_mode < 0) {
         const char* e = getenv("B200JPG_K1_MODE");
-        g_k1_mode = e ? atoi(e) & 7 : K1_DEFAULT_MODE;
+        g_k1_mode = e ? atoi(e) & 15 : K1_DEFAULT_MODE;
     }
     return g_k1_mode;
 }
 
-size_t k1_tma2_smem_bytes() { return (size_t)K1V2_STAGES * K1_STAGE_BYTES + 1024; }
+size_t k1_tma_smem_bytes() { return (size_t)K1_STAGES * K1_STAGE_BYTES + 1024; }
 
-cudaError_t launch_k1_tma2(const CUtensorMap& tmap, const K1QCache& qc, const K1Params& p, int num_sms, cudaStream_t stream) {
+cudaError_t launch_k1_tma(const CUtensorMap& tmap, const K1QCache& qc, const K1Params& p, int num_sms, cudaStream_t stream) {
     if (p.ntiles == 0) return cudaSuccess;
     static bool attr_set = false;
     if (!attr_set) {
-        const void* fns[8] = {(const void*)k1_idct8_tma2<0>, (const void*)k1_idct8_tma2<1>, (const void*)k1_idct8_tma2<2>,
-                              (const void*)k1_idct8_tma2<3>, (const void*)k1_idct8_tma2<4>, (const void*)k1_idct8_tma2<5>,
-                              (const void*)k1_idct8_tma2<6>, (const void*)k1_idct8_tma2<7>};
+        const void* fns[2] = {(const void*)k1_idct8_tma<0>, (const void*)k1_idct8_tma<5>};
         for (const void* f : fns) {
-            cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_tma2_smem_bytes());
+            cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_tma_smem_bytes());
             if (e != cudaSuccess) return e;
         }
         attr_set = true;
     }
     unsigned grid = (unsigned)num_sms * 4u;
     if (grid > p.ntiles) grid = p.ntiles;
-    switch (k1_mode()) {
-#define K1_CASE(M) case M: k1_idct8_tma2<M><<<grid, K1_TILE, k1_tma2_smem_bytes(), stream>>>(tmap, qc, p); break;
-        K1_CASE(1) K1_CASE(2) K1_CASE(3) K1_CASE(4) K1_CASE(5) K1_CASE(6) K1_CASE(7)
-        default: k1_idct8_tma2<0><<<grid, K1_TILE, k1_tma2_smem_bytes(), stream>>>(tmap, qc, p); break;
+    switch (k1_mode() & 15) {
+#define K1_CASE(M) case M: k1_idct8_tma<M><<<grid, K1_TILE, k1_tma_smem_bytes(), stream>>>(tmap, qc, p); break;
+        K1_CASE(0)
+        default: k1_idct8_tma<5><<<grid, K1_TILE, k1_tma_smem_bytes(), stream>>>(tmap, qc, p); break;
     }
     return cudaGetLastError();
 }

@@ -54,10 +54,15 @@ __device__ __forceinline__ void ycbcr_scalar(int y, int cb, int cr, int& r, int&
 }
 
 // same value with y supplied as y << 16
-__device__ __forceinline__ void ycbcr_scalar_y16(int y16, int cb, int cr, int& r, int& g, int& b) {
-    const int yr = y16 * 16 + (YCC_HALF - 128 * C_R_CR);
-    const int yg = y16 * 16 + (YCC_HALF + 128 * C_G_CB + 128 * C_G_CR);
-    const int yb = y16 * 16 + (YCC_HALF - 128 * C_B_CB);
+// `sixteen` is (16, 16, 16) -- three separate words so the products are not merged -- passed through the kernel parameters so that ptxas keeps y16 * 16 + K as one IMAD (FMA
+// pipe, full rate) instead of a shift and three adds on the half-rate ALU pipe (K2Params::sixteen)
+struct YccRegs {  // opaque register copies of (16, 16, 16) and of the three additive constants
+    int3 mul, add;
+};
+__device__ __forceinline__ void ycbcr_scalar_y16(int y16, int cb, int cr, int& r, int& g, int& b, const YccRegs& k) {
+    const int yr = y16 * k.mul.x + k.add.x;
+    const int yg = y16 * k.mul.y + k.add.y;
+    const int yb = y16 * k.mul.z + k.add.z;
     r = (yr + C_R_CR * cr) >> 20;
     g = (yg - C_G_CB * cb - C_G_CR * cr) >> 20;
     b = (yb + C_B_CB * cb) >> 20;
@@ -205,7 +210,27 @@ __device__ __forceinline__ void h2v2_16(unsigned a_lo, unsigned a_hi, unsigned a
 }
 
 // 16 pixels: y bytes in yv (4 words), chroma ints -> 48 output bytes at `dst` (16-byte aligned)
-__device__ __forceinline__ void ycbcr_store16(const uint4 yv, const int* cb, const int* cr, uint8_t* dst) {
+// the three multipliers as opaque register values (so the additive constants can be IMAD immediates)
+__device__ __forceinline__ int3 opaque_regs(int3 v) {
+    int3 r;
+    asm volatile("mov.u32 %0, %1;" : "=r"(r.x) : "r"(v.x));
+    asm volatile("mov.u32 %0, %1;" : "=r"(r.y) : "r"(v.y));
+    asm volatile("mov.u32 %0, %1;" : "=r"(r.z) : "r"(v.z));
+    return r;
+}
+
+__device__ __forceinline__ YccRegs make_ycc_regs(int3 sixteen, bool opaque) {
+    YccRegs k;
+    k.mul = sixteen;
+    k.add = make_int3(YCC_HALF - 128 * C_R_CR, YCC_HALF + 128 * C_G_CB + 128 * C_G_CR, YCC_HALF - 128 * C_B_CB);
+    if (opaque) {
+        k.mul = opaque_regs(k.mul);
+        k.add = opaque_regs(k.add);
+    }
+    return k;
+}
+
+__device__ __forceinline__ void ycbcr_store16(const uint4 yv, const int* cb, const int* cr, uint8_t* dst, const YccRegs& sixteen) {
     const unsigned yw[4] = {yv.x, yv.y, yv.z, yv.w};
     unsigned ow[12];
 #pragma unroll
@@ -215,7 +240,7 @@ __device__ __forceinline__ void ycbcr_store16(const uint4 yv, const int* cb, con
         for (int k = 0; k < 4; k++) {
             // one PRMT puts luma byte k at bits 16..23 (y << 16); the << 4 folds into the IMADs below
             const int y16 = (int)prmt(yw[w], 0u, 0x4044u | ((unsigned)k << 8));
-            ycbcr_scalar_y16(y16, cb[4 * w + k], cr[4 * w + k], r[k], g[k], b[k]);
+            ycbcr_scalar_y16(y16, cb[4 * w + k], cr[4 * w + k], r[k], g[k], b[k], sixteen);
         }
         // bytes: R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3
         ow[3 * w + 0] = pack_sat_u8(g[0], r[0], pack_sat_u8(r[1], b[0], 0u));
@@ -228,54 +253,13 @@ __device__ __forceinline__ void ycbcr_store16(const uint4 yv, const int* cb, con
     d4[2] = make_uint4(ow[8], ow[9], ow[10], ow[11]);
 }
 
-__global__ void __launch_bounds__(128) k2_ycbcr420(K2Params p, unsigned first, unsigned gchunks) {
-    const DevImage& img = p.images[first + blockIdx.y];
-    if (img.path != K2_PATH_420) return;
-    const unsigned pr = blockIdx.x / gchunks;  // row pair
-    const unsigned g = (blockIdx.x % gchunks) * 128u + threadIdx.x;
-    const unsigned W = img.width, H = img.height;
-    if (pr > H / 2 || g * 16u >= W) return;
-    const DevUpComp cy = img.c[0], ccb = img.c[1], ccr = img.c[2];
-    const unsigned in_w = ccb.in_w, in_h = ccb.in_h;
-    const unsigned rA = pr > 0 ? pr - 1 : 0, rB = min(pr, in_h - 1);
-    const unsigned i0 = g * 8u;
-    const unsigned iL = i0 > 0 ? i0 - 1 : 0, iR = min(i0 + 8u, in_w - 1);
-
-    Chroma16 cb, cr;
-    {
-        const uint8_t* a = p.planes + ccb.plane_off + (size_t)rA * ccb.stride;
-        const uint8_t* b = p.planes + ccb.plane_off + (size_t)rB * ccb.stride;
-        const uint2 av = __ldg(reinterpret_cast<const uint2*>(a + i0)), bv = __ldg(reinterpret_cast<const uint2*>(b + i0));
-        h2v2_16(av.x, av.y, __ldg(a + iL), __ldg(a + iR), bv.x, bv.y, __ldg(b + iL), __ldg(b + iR), cb);
-    }
-    {
-        const uint8_t* a = p.planes + ccr.plane_off + (size_t)rA * ccr.stride;
-        const uint8_t* b = p.planes + ccr.plane_off + (size_t)rB * ccr.stride;
-        const uint2 av = __ldg(reinterpret_cast<const uint2*>(a + i0)), bv = __ldg(reinterpret_cast<const uint2*>(b + i0));
-        h2v2_16(av.x, av.y, __ldg(a + iL), __ldg(a + iR), bv.x, bv.y, __ldg(b + iL), __ldg(b + iR), cr);
-    }
-    const uint8_t* yplane = p.planes + cy.plane_off;
-    uint8_t* out = p.out + img.out_off;
-    if (pr > 0) {  // output row 2p-1
-        const unsigned y = 2 * pr - 1;
-        const uint4 yv = __ldg(reinterpret_cast<const uint4*>(yplane + (size_t)y * cy.stride + g * 16u));
-        ycbcr_store16(yv, cb.odd, cr.odd, out + ((size_t)y * W + g * 16u) * 3u);
-    }
-    if (2 * pr < H) {  // output row 2p
-        const unsigned y = 2 * pr;
-        const uint4 yv = __ldg(reinterpret_cast<const uint4*>(yplane + (size_t)y * cy.stride + g * 16u));
-        ycbcr_store16(yv, cb.even, cr.even, out + ((size_t)y * W + g * 16u) * 3u);
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
-// 4:2:0 YCbCr fast path, second generation: a thread walks K2_RP consecutive row pairs of its
-// 16-pixel column group.  Chroma row p of pair p is chroma row p-1 of pair p+1, so it stays in
-// registers (each chroma byte is loaded exactly once per thread column), and the image descriptor
-// loads, index arithmetic and pointer set-up are paid once per 2*K2_RP output rows.
-// grid = (ceil(G/128), ceil(P/K2_RP), images)
+// The kernel: a thread walks K2_RP consecutive row pairs of its 16-pixel column group (K2_RP = 1 is the
+// default: measured fastest because it keeps 8 CTAs = 32 warps per SM; 4 reuses chroma rows in registers
+// but halves the occupancy -- profiles/sweep_*.jsonl).
+// grid = (ceil(G/128), ceil(P/K2_RP), images), G = width/16, P = height/2 + 1
 // ---------------------------------------------------------------------------------------------
-constexpr unsigned K2_RP_DEFAULT = 4;
+constexpr unsigned K2_RP_DEFAULT = 1;
 int g_k2_mode = -1;
 
 struct ChromaRow {  // one chroma row segment: samples i0..i0+7 plus the clamped halo samples
@@ -293,7 +277,7 @@ __device__ __forceinline__ ChromaRow load_chroma_row(const uint8_t* row, unsigne
 }
 
 template <unsigned K2_RP, int MINB>
-__global__ void __launch_bounds__(128, MINB) k2_ycbcr420_v2(K2Params p, unsigned first) {
+__global__ void __launch_bounds__(128, MINB) k2_ycbcr420(K2Params p, unsigned first) {
     const DevImage& img = p.images[first + blockIdx.z];
     if (img.path != K2_PATH_420) return;
     const unsigned g = blockIdx.x * 128u + threadIdx.x;
@@ -310,6 +294,7 @@ __global__ void __launch_bounds__(128, MINB) k2_ycbcr420_v2(K2Params p, unsigned
     uint8_t* out = p.out + img.out_off + (size_t)g * 48u;
     const unsigned i0 = g * 8u;
     const unsigned iL = i0 > 0 ? i0 - 1 : 0, iR = min(i0 + 8u, in_w - 1);
+    const YccRegs sixteen = make_ycc_regs(p.sixteen, true);
 
     // chroma row A of the first pair
     const unsigned rA0 = p0 > 0 ? p0 - 1 : 0;
@@ -326,8 +311,8 @@ __global__ void __launch_bounds__(128, MINB) k2_ycbcr420_v2(K2Params p, unsigned
         Chroma16 cb, cr;
         h2v2_16(ba.lo, ba.hi, ba.L, ba.R, bb.lo, bb.hi, bb.L, bb.R, cb);
         h2v2_16(ra.lo, ra.hi, ra.L, ra.R, rb.lo, rb.hi, rb.L, rb.R, cr);
-        if (pr > 0) ycbcr_store16(yv_odd, cb.odd, cr.odd, out + (size_t)y_odd * W * 3u);      // output row 2p-1
-        if (2 * pr < H) ycbcr_store16(yv_even, cb.even, cr.even, out + (size_t)y_even * W * 3u);  // output row 2p
+        if (pr > 0) ycbcr_store16(yv_odd, cb.odd, cr.odd, out + (size_t)y_odd * W * 3u, sixteen);      // output row 2p-1
+        if (2 * pr < H) ycbcr_store16(yv_even, cb.even, cr.even, out + (size_t)y_even * W * 3u, sixteen);  // output row 2p
         ba = bb;
         ra = rb;
     }
@@ -354,7 +339,7 @@ __global__ void __launch_bounds__(128) k2_ycbcr444(K2Params p, unsigned first, u
         cb[k] = (int)prmt(bw[k >> 2], 0u, 0x4440u | (unsigned)(k & 3));
         cr[k] = (int)prmt(rw[k >> 2], 0u, 0x4440u | (unsigned)(k & 3));
     }
-    ycbcr_store16(yv, cb, cr, p.out + img.out_off + ((size_t)y * W + g * 16u) * 3u);
+    ycbcr_store16(yv, cb, cr, p.out + img.out_off + ((size_t)y * W + g * 16u) * 3u, make_ycc_regs(p.sixteen, true));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -366,8 +351,8 @@ cudaError_t launch_k2_generic(const K2Params& p, unsigned first, unsigned count,
     k2_generic<<<grid, 256, 0, stream>>>(p, first, xchunks);
     return cudaGetLastError();
 }
-cudaError_t launch_k2_420_v2(const K2Params& p, unsigned first, unsigned count, unsigned max_w, unsigned max_h,
-                             cudaStream_t stream) {
+cudaError_t launch_k2_420(const K2Params& p, unsigned first, unsigned count, unsigned max_w, unsigned max_h,
+                          cudaStream_t stream) {
     if (count == 0 || max_w == 0 || max_h == 0) return cudaSuccess;
     const unsigned npairs = max_h / 2u + 1u;
     int mode = g_k2_mode;  // experiment knob (profiling only): row pairs per thread
@@ -375,20 +360,10 @@ cudaError_t launch_k2_420_v2(const K2Params& p, unsigned first, unsigned count, 
         const char* e = getenv("B200JPG_K2_MODE");
         mode = g_k2_mode = e ? atoi(e) : (int)K2_RP_DEFAULT;
     }
-    const unsigned rp = mode == 1 ? 1u : (mode == 2 ? 2u : (mode == 8 ? 8u : 4u));
+    const unsigned rp = mode == 4 ? 4u : 1u;
     dim3 grid((max_w / 16u + 127u) / 128u, (npairs + rp - 1u) / rp, count);
-    if (rp == 1) k2_ycbcr420_v2<1, 8><<<grid, 128, 0, stream>>>(p, first);
-    else if (rp == 2) k2_ycbcr420_v2<2, 6><<<grid, 128, 0, stream>>>(p, first);
-    else if (rp == 8) k2_ycbcr420_v2<8, 5><<<grid, 128, 0, stream>>>(p, first);
-    else k2_ycbcr420_v2<4, 5><<<grid, 128, 0, stream>>>(p, first);
-    return cudaGetLastError();
-}
-cudaError_t launch_k2_420(const K2Params& p, unsigned first, unsigned count, unsigned max_w, unsigned max_h,
-                          cudaStream_t stream) {
-    if (count == 0 || max_w == 0 || max_h == 0) return cudaSuccess;
-    const unsigned gchunks = (max_w / 16u + 127u) / 128u;
-    dim3 grid(gchunks * (max_h / 2u + 1u), count);
-    k2_ycbcr420<<<grid, 128, 0, stream>>>(p, first, gchunks);
+    if (rp == 4) k2_ycbcr420<4, 5><<<grid, 128, 0, stream>>>(p, first);
+    else k2_ycbcr420<1, 8><<<grid, 128, 0, stream>>>(p, first);
     return cudaGetLastError();
 }
 cudaError_t launch_k2_444(const K2Params& p, unsigned first, unsigned count, unsigned max_w, unsigned max_h,

@@ -16,6 +16,7 @@ struct K1Params {
     const short* coefs;     // coefficient slab base
     uint8_t* planes;        // plane slab base
     unsigned ntiles;
+    unsigned one, minus_one;  // 1 and 0xffffffff (see fma_add in k1_idct.cu)
 };
 
 struct K2Params {
@@ -23,6 +24,7 @@ struct K2Params {
     const uint8_t* planes;
     uint8_t* out;
     unsigned nimages;
+    int3 sixteen;  // (16, 16, 16), see ycbcr_scalar_y16 in k2_color.cu
 };
 
 // packed 8-bit tables of up to four components, passed by value = constant bank operands
@@ -31,9 +33,8 @@ struct K1QCache {
 };
 
 cudaError_t launch_k1_generic(const K1Params& p, int arith, cudaStream_t stream);
-cudaError_t launch_k1_tma(const CUtensorMap& tmap, const K1Params& p, int num_sms, cudaStream_t stream);
 size_t k1_tma_smem_bytes();
-cudaError_t launch_k1_tma2(const CUtensorMap& tmap, const K1QCache& qc, const K1Params& p, int num_sms, cudaStream_t stream);
+cudaError_t launch_k1_tma(const CUtensorMap& tmap, const K1QCache& qc, const K1Params& p, int num_sms, cudaStream_t stream);
 
 // K2: max_w/max_h = largest output size in [first, first+count); the grid covers that and images
 // smaller than it exit early.  `path` selects the kernel; images whose DevImage::path differs are
@@ -42,8 +43,6 @@ cudaError_t launch_k2_generic(const K2Params& p, unsigned first, unsigned count,
                               cudaStream_t stream);
 cudaError_t launch_k2_420(const K2Params& p, unsigned first, unsigned count, unsigned max_w, unsigned max_h,
                           cudaStream_t stream);
-cudaError_t launch_k2_420_v2(const K2Params& p, unsigned first, unsigned count, unsigned max_w, unsigned max_h,
-                             cudaStream_t stream);
 cudaError_t launch_k2_444(const K2Params& p, unsigned first, unsigned count, unsigned max_w, unsigned max_h,
                           cudaStream_t stream);
 

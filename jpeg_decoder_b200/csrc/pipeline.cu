@@ -558,15 +558,16 @@ static int batch_launch(b200jpg_batch* b, const void* d_coefs, void* d_planes, v
         p.coefs = (const short*)d_coefs;
         p.planes = (uint8_t*)d_planes;
         p.ntiles = tile_count;
+        p.one = 1u;
+        p.minus_one = 0xffffffffu;
         const bool tma_ok = ctx->arith == B200JPG_ARITH_SCALAR && b->all_scale8 && b->k1_tma_aligned &&
                             ((uintptr_t)d_coefs % 16 == 0) && ((uintptr_t)d_planes % 8 == 0);
-        if ((ctx->k1_kernel == B200JPG_KERNEL_FAST || ctx->k1_kernel == B200JPG_KERNEL_FAST_V1) && !tma_ok)
+        if (ctx->k1_kernel == B200JPG_KERNEL_FAST && !tma_ok)
             return fail(ctx, B200JPG_ERR_INTERNAL, "k1_kernel=FAST requested but the batch is not eligible (needs scalar arithmetic, dct_scale 8)");
         if (tma_ok && ctx->k1_kernel != B200JPG_KERNEL_GENERIC) {
             int rc = ensure_tensor_map(b, d_coefs);
             if (rc) return rc;
-            if (ctx->k1_kernel == B200JPG_KERNEL_FAST_V1) CU_TRY(ctx, launch_k1_tma(b->tmap, p, ctx->num_sms, stream));
-            else CU_TRY(ctx, launch_k1_tma2(b->tmap, b->qcache, p, ctx->num_sms, stream));
+            CU_TRY(ctx, launch_k1_tma(b->tmap, b->qcache, p, ctx->num_sms, stream));
         } else {
             CU_TRY(ctx, launch_k1_generic(p, ctx->arith, stream));
         }
@@ -578,6 +579,7 @@ static int batch_launch(b200jpg_batch* b, const void* d_coefs, void* d_planes, v
         p.planes = (const uint8_t*)d_planes;
         p.out = (uint8_t*)d_out;
         p.nimages = (unsigned)b->n;
+        p.sixteen = make_int3(16, 16, 16);
         if (ctx->k2_kernel == B200JPG_KERNEL_FAST && b->path_used[K2_PATH_GENERIC])
             return fail(ctx, B200JPG_ERR_INTERNAL, "k2_kernel=FAST requested but some image needs the generic kernel");
         for (unsigned first = img_first; first < img_first + img_count; first += 65535u) {
@@ -586,8 +588,7 @@ static int batch_launch(b200jpg_batch* b, const void* d_coefs, void* d_planes, v
                 if (!b->path_used[path]) continue;
                 cudaError_t e = cudaSuccess;
                 if (path == K2_PATH_GENERIC) e = launch_k2_generic(p, first, count, b->path_max_w[path], b->path_max_h[path], stream);
-                else if (path == K2_PATH_420 && ctx->k2_kernel == B200JPG_KERNEL_FAST_V1) e = launch_k2_420(p, first, count, b->path_max_w[path], b->path_max_h[path], stream);
-                else if (path == K2_PATH_420) e = launch_k2_420_v2(p, first, count, b->path_max_w[path], b->path_max_h[path], stream);
+                else if (path == K2_PATH_420) e = launch_k2_420(p, first, count, b->path_max_w[path], b->path_max_h[path], stream);
                 else e = launch_k2_444(p, first, count, b->path_max_w[path], b->path_max_h[path], stream);
                 if (e != cudaSuccess) return cuda_fail(ctx, e, "K2 launch");
                 ctx->launches++;

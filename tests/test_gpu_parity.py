@@ -13,19 +13,19 @@ from test_oracle_kat import COEFS, EXPECTED, QT, SATURATED
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = [("scalar", "auto"), ("scalar", "generic"), ("scalar", "fast"), ("scalar", "v1"), ("ssse3", "auto")]
+VARIANTS = [("scalar", "auto"), ("scalar", "generic"), ("scalar", "fast"), ("ssse3", "auto")]
 
 
 @pytest.fixture(scope="module")
 def ctxs(J):
     import torch
     assert torch.cuda.is_available(), "GPU tests need a CUDA device"
-    kern = {"auto": J.KERNEL_AUTO, "generic": J.KERNEL_GENERIC, "fast": J.KERNEL_FAST, "v1": J.KERNEL_FAST_V1}
+    kern = {"auto": J.KERNEL_AUTO, "generic": J.KERNEL_GENERIC, "fast": J.KERNEL_FAST}
     out = {}
     for arith, k in VARIANTS:
         a = J.ARITH_SSSE3 if arith == "ssse3" else J.ARITH_SCALAR
         # "fast" pins K1 only: the K2 fast paths cover two layouts, the tests below choose per case
-        k2 = {"generic": J.KERNEL_GENERIC, "v1": J.KERNEL_FAST_V1}.get(k, J.KERNEL_AUTO)
+        k2 = J.KERNEL_GENERIC if k == "generic" else J.KERNEL_AUTO
         out[(arith, k)] = J.Context(device=0, arith=a, k1_kernel=kern[k], k2_kernel=k2)
     yield out
     for c in out.values():
@@ -198,7 +198,7 @@ def random_planes(rng, comps):
     return [rng.integers(0, 256, c.block_w * c.block_h * c.dct_scale * c.dct_scale).astype(np.uint8) for c in comps]
 
 
-@pytest.mark.parametrize("variant", [("scalar", "auto"), ("scalar", "generic"), ("scalar", "v1"), ("ssse3", "auto")])
+@pytest.mark.parametrize("variant", [("scalar", "auto"), ("scalar", "generic"), ("ssse3", "auto")])
 @pytest.mark.parametrize("sname", sorted(SAMPLINGS))
 def test_k2_upsample_ycbcr_bit_exact(J, oracle_mod, ctxs, variant, sname):
     """compute_image with random planes: every upsampler (src/upsampler.rs:119-250), odd sizes, 1-pixel edges."""
@@ -264,7 +264,7 @@ def test_k2_error_mapping(J, oracle_mod, ctxs):
 @pytest.mark.parametrize("variant", VARIANTS)
 def test_whole_files_bit_exact_and_golden(J, oracle_mod, ctxs, variant):
     ctx = ctxs[variant]
-    if variant[1] in ("fast", "v1"):
+    if variant[1] == "fast":
         pytest.skip("K1 FAST is pinned per batch (scaled / odd files need the generic kernel); covered by the batch tests")
     oa = oarith(oracle_mod, variant[0])
     n = 0
@@ -349,7 +349,7 @@ def test_heterogeneous_batch_with_bad_image(J, oracle_mod, ctxs):
         assert np.array_equal(got[:want.size], want)
 
 
-@pytest.mark.parametrize("k1", ["generic", "fast", "v1"])
+@pytest.mark.parametrize("k1", ["generic", "fast"])
 def test_full_size_batch_properties(J, oracle_mod, ctxs, k1):
     """BASELINE cfg2 geometry (1920x1080 4:2:0) at a reduced batch, device-resident path as bench.py uses it:
     every image bit-exact vs the oracle, and a checksum-of-checksums over the replicated batch."""
