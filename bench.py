@@ -313,9 +313,17 @@ def main():
     k2_gbs = info.k2_algorithmic_bytes / (ms_k2 * 1e-3) / 1e9
     dominant = "k1_dequant_idct8x8" if ms_k1 >= ms_k2 else "k2_upsample_color"
     dom_gbs = k1_gbs if ms_k1 >= ms_k2 else k2_gbs
+    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this
+    # same command (profiles/traffic.json, written by scripts/ncu_traffic.py); null if never captured
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tr.get("%s:%d" % (args.config, B), {}).get(dominant)
+    except Exception:
+        pass
     roofline = {
         "bound": "hbm", "kernel": dominant, "achieved": dom_gbs, "peak": peak, "unit": "GB/s", "frac": dom_gbs / peak,
-        "traffic": None, "peak_source": peak_src,
+        "traffic": traffic, "peak_source": peak_src,
         "kernels": {
             "k1_dequant_idct8x8": {"ms": ms_k1, "algorithmic_bytes": info.k1_algorithmic_bytes, "achieved": k1_gbs, "frac": k1_gbs / peak},
             "k2_upsample_color": {"ms": ms_k2, "algorithmic_bytes": info.k2_algorithmic_bytes, "achieved": k2_gbs, "frac": k2_gbs / peak},
