@@ -371,6 +371,23 @@ def main():
     ref0 = d_out[batch.layout(0)["out_off"]:batch.layout(0)["out_off"] + out_per_img].cpu().numpy()
     same = bool(np.array_equal(ref0, h_out.numpy()[:out_per_img]))
 
+    # ---- whole files: JPEG bytes -> pixels (host Huffman on the NUMA-local cores + GPU worker path) ----
+    files_e2e = None
+    if rank == 0 and world == 1:
+        nthreads = len(os.sched_getaffinity(0))
+        Bf = min(512, max(64, 8 * nthreads))
+        jpegs = [workload.synth_jpeg(W, H, cfg["seed"] + k, cfg["subsampling"]) for k in range(min(U, 4))]
+        flist = [jpegs[j % len(jpegs)] for j in range(Bf)]
+        f_out = torch.empty(Bf * out_per_img, dtype=torch.uint8, pin_memory=True).numpy()
+        f_outs = [f_out[j * out_per_img:(j + 1) * out_per_img] for j in range(Bf)]
+        J.decode_files(ctx, flist[:2 * nthreads], nthreads=nthreads, outs=f_outs[:2 * nthreads])   # warm-up
+        t0 = time.perf_counter()
+        _, fst, _ = J.decode_files(ctx, flist, nthreads=nthreads, outs=f_outs)
+        f_dt = time.perf_counter() - t0
+        assert all(s == 0 for s in fst)
+        files_e2e = {"value": Bf * W * H / 1e6 / f_dt, "unit": "MP/s", "images": Bf, "host_threads": nthreads,
+                     "jpeg_bytes_per_image": int(np.mean([len(j) for j in jpegs])),
+                     "api": "b200jpg_decode_files (JPEG bytes -> pixels; Huffman on the host, worker path on the GPU)"}
     pcie = pcie_probe(torch, dev) if rank == 0 else None
     os.sched_setaffinity(0, all_cpus)   # the CPU baseline uses every core
     cpu_baseline = None
@@ -393,7 +410,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": Be * coef_per_img, "d2h_bytes_per_step": Be * out_per_img,
                     "images_per_step": Be, "steps": e_steps, "host_result_equals_device_result": same,
                     "api": "b200jpg_batch_run_host (pinned host coefficient buffers -> pinned host pixels)",
-                    "pcie_gbs_measured": pcie, "numa_bind": numa,
+                    "pcie_gbs_measured": pcie, "numa_bind": numa, "files": files_e2e,
                     "gbs_each_direction": Be * coef_per_img * e_steps / e_dt / 1e9},
             "gpu_launches": int(launches),
             "clocks": clocks,

@@ -241,6 +241,26 @@ B200JPG_API int b200jpg_decoder_xmp_data(const b200jpg_decoder *d, const uint8_t
  * determine_color_transform() (src/decoder.rs:698-764). */
 B200JPG_API int b200jpg_decoder_entropy_decode(b200jpg_decoder *d, b200jpg_image_desc *desc);
 
+/* ============================================================================================
+ * Whole-file batches: what an outer par_iter over Decoder::decode() gives a
+ * user of the reference, with the host threads doing only marker parsing + Huffman decoding
+ * (src/parser.rs, src/huffman.rs, src/decoder.rs:794-1298) and the worker path on the GPU.
+ * ========================================================================================== */
+typedef struct {
+    const uint8_t *data; /* in: the JPEG file                                   */
+    size_t len;
+    uint8_t *out;        /* in: pixel buffer (ideally page-locked); unused by read_info_files */
+    size_t out_cap;
+    b200jpg_image_info info; /* out */
+    size_t out_len;      /* out: width*height*ncomp                              */
+    int status;          /* out: B200JPG_OK or the image's error                 */
+} b200jpg_file_job;
+
+/* Headers only (Decoder::read_info + info for each file), nthreads host threads (0 = all). */
+B200JPG_API int b200jpg_read_info_files(b200jpg_file_job *jobs, size_t n, int nthreads);
+/* Full decode of n files; per-image errors are reported in jobs[i].status and do not stop the batch. */
+B200JPG_API int b200jpg_decode_files(b200jpg_ctx *ctx, b200jpg_file_job *jobs, size_t n, int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

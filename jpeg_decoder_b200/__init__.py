@@ -19,10 +19,10 @@ import numpy as np
 from ._native import (ARITH_SCALAR, ARITH_SSSE3, CP_DCT_PROGRESSIVE, CP_DCT_SEQUENTIAL, CP_LOSSLESS, CT_CMYK,
                       CT_GRAYSCALE, CT_JCS_BG_RGB, CT_JCS_BG_YCC, CT_NONE, CT_RGB, CT_UNKNOWN, CT_YCBCR, CT_YCCK,
                       ERR_FORMAT, ERR_INTERNAL, ERR_IO, ERR_UNSUPPORTED, KERNEL_AUTO, KERNEL_FAST, KERNEL_GENERIC, OK,
-                      PF_CMYK32, PF_L8, PF_L16, PF_RGB24, BatchInfo, Component, ImageDesc, ImageInfo, Options, lib)
+                      PF_CMYK32, PF_L8, PF_L16, PF_RGB24, BatchInfo, Component, FileJob, ImageDesc, ImageInfo, Options, lib)
 
 __all__ = ["Context", "Worker", "Batch", "Decoder", "B200JpgError", "make_components", "make_image_desc",
-           "compute_image", "decode_batch", "Component", "ImageDesc"]
+           "compute_image", "decode_batch", "decode_files", "read_info_files", "Component", "ImageDesc"]
 
 
 class B200JpgError(Exception):
@@ -220,6 +220,35 @@ def decode_batch(ctx, descs):
     if rc and all(s == 0 for s in st):
         ctx.check(rc)
     return outs, list(st)
+
+
+def read_info_files(files, nthreads=0):
+    """b200jpg_read_info_files: [(status, ImageInfo, out_len)] for a list of bytes objects."""
+    n = len(files)
+    bufs = [np.frombuffer(bytes(f), dtype=np.uint8) for f in files]
+    jobs = (FileJob * n)()
+    for j, b in zip(jobs, bufs):
+        j.data, j.len = b.ctypes.data, b.size
+    lib().b200jpg_read_info_files(jobs, n, nthreads)
+    return [(j.status, j.info, j.out_len) for j in jobs]
+
+
+def decode_files(ctx, files, nthreads=0, outs=None):
+    """b200jpg_decode_files: list of bytes -> (list of uint8 arrays or None, list of status codes, list of ImageInfo)."""
+    n = len(files)
+    bufs = [np.frombuffer(bytes(f), dtype=np.uint8) for f in files]
+    jobs = (FileJob * n)()
+    for j, b in zip(jobs, bufs):
+        j.data, j.len = b.ctypes.data, b.size
+    lib().b200jpg_read_info_files(jobs, n, nthreads)
+    if outs is None:
+        outs = [np.zeros(j.out_len, dtype=np.uint8) if j.status == 0 else np.zeros(1, dtype=np.uint8) for j in jobs]
+    for j, o in zip(jobs, outs):
+        j.out, j.out_cap = o.ctypes.data, o.size
+    rc = lib().b200jpg_decode_files(ctx._h, jobs, n, nthreads)
+    if rc and all(j.status == 0 for j in jobs):
+        ctx.check(rc)
+    return [o[:j.out_len] if j.status == 0 else None for j, o in zip(jobs, outs)], [j.status for j in jobs], [j.info for j in jobs]
 
 
 class Decoder:

@@ -43,6 +43,11 @@ class ImageInfo(C.Structure):
     _fields_ = [("width", C.c_uint16), ("height", C.c_uint16), ("pixel_format", C.c_int), ("coding_process", C.c_int)]
 
 
+class FileJob(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("len", C.c_size_t), ("out", C.c_void_p), ("out_cap", C.c_size_t),
+                ("info", ImageInfo), ("out_len", C.c_size_t), ("status", C.c_int)]
+
+
 # every symbol include/b200jpg.h declares (tests/test_abi.py checks the two lists agree)
 EXPORTS = {
     "b200jpg_default_options": (None, [C.POINTER(Options)]),
@@ -92,6 +97,8 @@ EXPORTS = {
     "b200jpg_decoder_exif_data": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "b200jpg_decoder_xmp_data": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "b200jpg_decoder_entropy_decode": (C.c_int, [C.c_void_p, C.POINTER(ImageDesc)]),
+    "b200jpg_read_info_files": (C.c_int, [C.POINTER(FileJob), C.c_size_t, C.c_int]),
+    "b200jpg_decode_files": (C.c_int, [C.c_void_p, C.POINTER(FileJob), C.c_size_t, C.c_int]),
 }
 
 _lib = None

@@ -160,10 +160,26 @@ bool HuffTable::build(const uint8_t bits[16], const uint8_t* vals, int nvals, bo
 
 // ---- bit reader, src/huffman.rs:20-161 --------------------------------------------------------
 int HostDecoder::read_bits() {
+    // Fast path (same result as the byte loop below): when the next 8 input bytes contain no 0xFF, as many
+    // whole bytes as fit are appended in one go.
+    if (!has_marker_ && num_bits_ <= 56 && pos_ + 8 <= len_) {
+        uint64_t v;
+        memcpy(&v, data_ + pos_, 8);
+        // a byte is 0xFF iff its high bit is set and adding 1 to its low 7 bits reaches the high bit
+        const uint64_t ff = v & 0x8080808080808080ull & ((v & 0x7f7f7f7f7f7f7f7full) + 0x0101010101010101ull);
+        if (!ff) {
+            const unsigned nbytes = (64u - num_bits_) >> 3;  // 1..8
+            const uint64_t be = __builtin_bswap64(v);
+            const uint64_t chunk = nbytes == 8 ? be : (be >> (64 - 8 * nbytes)) << (64 - 8 * nbytes);
+            bits_ |= chunk >> num_bits_;
+            num_bits_ = (uint8_t)(num_bits_ + 8 * nbytes);
+            pos_ += nbytes;
+            return 0;
+        }
+    }
     while (num_bits_ <= 56) {
         uint8_t byte = 0;
         if (!has_marker_) {
-            // fast path: plenty of input and no 0xFF in sight
             TRY(read_u8(&byte));
         }
         if (byte == 0xFF) {
@@ -608,6 +624,115 @@ int HostDecoder::decode_block(int16_t* c, const HuffTable& dc, const HuffTable& 
     return 0;
 }
 
+// decode_block for sequential scans (ss = 0..63, al = 0), the hot loop of every baseline JPEG: identical
+// decisions and refill thresholds (16 bits before a code, 8 before the fast-AC probe, `count` before
+// receive_extend -- src/huffman.rs:31-96), with the bit buffer kept in locals.
+int HostDecoder::decode_block_seq(int16_t* c, const HuffTable& dc, const HuffTable& ac, uint16_t* eob_run, int16_t* pred) {
+    uint64_t bits = bits_;
+    unsigned nb = num_bits_;
+#define SEQ_REFILL()                   \
+    do {                               \
+        bits_ = bits;                  \
+        num_bits_ = (uint8_t)nb;       \
+        TRY(read_bits());              \
+        bits = bits_;                  \
+        nb = num_bits_;                \
+    } while (0)
+#define SEQ_SLOW_CODE(table, out)      \
+    do {                               \
+        bits_ = bits;                  \
+        num_bits_ = (uint8_t)nb;       \
+        TRY(huff_decode((table), &(out))); \
+        bits = bits_;                  \
+        nb = num_bits_;                \
+    } while (0)
+    {
+        if (nb < 16) SEQ_REFILL();
+        const unsigned idx = (unsigned)(bits >> 56);
+        uint8_t value;
+        const unsigned size = dc.lut_size[idx];
+        if (size) {
+            value = dc.lut_value[idx];
+            bits <<= size;
+            nb -= size;
+        } else {
+            SEQ_SLOW_CODE(dc, value);
+        }
+        int16_t diff = 0;
+        if (value != 0) {
+            if (value > 11) return fail(B200JPG_ERR_FORMAT, "invalid DC difference magnitude category");
+            if (nb < value) SEQ_REFILL();
+            const uint16_t u = (uint16_t)(bits >> (64 - value));
+            bits <<= value;
+            nb -= value;
+            diff = extend(u, value);
+        }
+        *pred = (int16_t)((uint16_t)*pred + (uint16_t)diff);
+        c[0] = *pred;
+    }
+    if (*eob_run > 0) {
+        *eob_run -= 1;
+        bits_ = bits;
+        num_bits_ = (uint8_t)nb;
+        return 0;
+    }
+    unsigned index = 1;
+    while (index < 64) {
+        if (nb < 8) SEQ_REFILL();
+        const unsigned idx = (unsigned)(bits >> 56);
+        const unsigned rs = ac.ac_run_size[idx];
+        if (rs != 0) {  // decode_fast_ac hit: code and value bits in one probe
+            bits <<= (rs & 0x0f);
+            nb -= (rs & 0x0f);
+            index += rs >> 4;
+            if (index >= 64) break;
+            c[UNZIGZAG[index]] = ac.ac_value[idx];
+            index++;
+            continue;
+        }
+        if (nb < 16) SEQ_REFILL();
+        const unsigned idx2 = (unsigned)(bits >> 56);
+        uint8_t byte;
+        const unsigned size = ac.lut_size[idx2];
+        if (size) {
+            byte = ac.lut_value[idx2];
+            bits <<= size;
+            nb -= size;
+        } else {
+            SEQ_SLOW_CODE(ac, byte);
+        }
+        const unsigned r = byte >> 4, sz = byte & 0x0f;
+        if (sz == 0) {
+            if (r == 15) {
+                index += 16;
+            } else {
+                *eob_run = (uint16_t)((1u << r) - 1);
+                if (r > 0) {
+                    if (nb < r) SEQ_REFILL();
+                    *eob_run = (uint16_t)(*eob_run + (uint16_t)(bits >> (64 - r)));
+                    bits <<= r;
+                    nb -= r;
+                }
+                break;
+            }
+        } else {
+            index += r;
+            if (index >= 64) break;
+            if (nb < sz) SEQ_REFILL();
+            const uint16_t u = (uint16_t)(bits >> (64 - sz));
+            bits <<= sz;
+            nb -= sz;
+            c[UNZIGZAG[index]] = extend(u, (uint8_t)sz);
+            index++;
+        }
+    }
+    bits_ = bits;
+    num_bits_ = (uint8_t)nb;
+    return 0;
+#undef SEQ_REFILL
+#undef SEQ_SLOW_CODE
+}
+
 int HostDecoder::refine_non_zeroes(int16_t* c, uint8_t start, uint8_t end, uint8_t zrl, int16_t bit, uint8_t* ret) {
     const uint8_t last = (uint8_t)(end - 1);
     uint8_t zero_run_length = zrl;
@@ -695,6 +820,7 @@ int HostDecoder::decode_scan(const ScanInfo& scan, const bool finished[4], bool*
 
     const bool is_progressive = frame.coding_process == B200JPG_CP_DCT_PROGRESSIVE;
     const bool is_interleaved = nc > 1;
+    const bool sequential = scan.ss_start == 0 && scan.ss_end == 64 && scan.al == 0 && scan.ah == 0;
     // where each scan component's blocks go: the progressive store, the final buffer (worker::start
     // zero-fills, src/decoder.rs:848-861, 874-880), or a dummy block
     int16_t* target[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -706,9 +832,14 @@ int HostDecoder::decode_scan(const ScanInfo& scan, const bool finished[4], bool*
         if (is_progressive) {
             target[i] = work_[ci].data();
         } else if (finished[i]) {
-            final_[ci].assign(count, 0);
             have_final_[ci] = false;
-            target[i] = final_[ci].data();
+            if (ext_[ci]) {
+                memset(ext_[ci], 0, count * sizeof(int16_t));
+                target[i] = ext_[ci];
+            } else {
+                final_[ci].assign(count, 0);
+                target[i] = final_[ci].data();
+            }
         }
     }
     bits_ = 0;
@@ -769,7 +900,9 @@ int HostDecoder::decode_scan(const ScanInfo& scan, const bool finished[4], bool*
                             c = dummy;
                             if (scan.ah == 0) memset(dummy, 0, sizeof dummy);
                         }
-                        if (scan.ah == 0)
+                        if (sequential)
+                            TRY(decode_block_seq(c, dc_[scan.dc_table[i]], ac_[scan.ac_table[i]], &eob_run, &dc_predictors[i]));
+                        else if (scan.ah == 0)
                             TRY(decode_block(c, dc_[scan.dc_table[i]], ac_[scan.ac_table[i]], scan, &eob_run, &dc_predictors[i]));
                         else
                             TRY(decode_block_sa(c, ac_[scan.ac_table[i]], scan, &eob_run));
@@ -793,7 +926,10 @@ int HostDecoder::decode_scan(const ScanInfo& scan, const bool finished[4], bool*
     for (int i = 0; i < nc; i++)
         if (finished[i]) {
             const int ci = scan.comp_index[i];
-            if (is_progressive) final_[ci] = work_[ci];
+            if (is_progressive) {
+                if (ext_[ci]) memcpy(ext_[ci], work_[ci].data(), work_[ci].size() * sizeof(int16_t));
+                else final_[ci] = work_[ci];
+            }
             have_final_[ci] = true;
         }
     return 0;
@@ -896,7 +1032,8 @@ int HostDecoder::decode_internal(bool stop_after_metadata) {
             if (finished_mask_[i] == ~(uint64_t)0) continue;
             if (!has_qt_[frame_.comps[i].tq]) continue;
             memcpy(final_qt_[i], qt_[frame_.comps[i].tq], 128);
-            final_[i] = work_[i];
+            if (ext_[i]) memcpy(ext_[i], work_[i].data(), work_[i].size() * sizeof(int16_t));
+            else final_[i] = work_[i];
             have_final_[i] = true;
         }
     return 0;

@@ -69,8 +69,10 @@ public:
     int pixel_format() const;
     // component i was fed to the worker (finished, or rendered partially at EOI)
     bool component_has_data(int i) const { return i >= 0 && i < 4 && have_final_[i]; }
-    const int16_t* coefficients(int i) const { return final_[i].data(); }
-    size_t coefficient_count(int i) const { return final_[i].size(); }
+    const int16_t* coefficients(int i) const { return ext_[i] ? ext_[i] : final_[i].data(); }
+    // Optional: caller-owned destination (e.g. page-locked memory) for component i's final coefficients,
+    // block_w*block_h*64 int16; must be set after read_info() and before entropy_decode().
+    void set_external_buffer(int i, int16_t* p) { if (i >= 0 && i < 4) ext_[i] = p; }
     // quantisation table captured when the component was handed to the worker (RowData, src/decoder.rs:850-857)
     const uint16_t* component_qtable(int i) const { return final_qt_[i]; }
     bool buffer_limit_exceeded() const;
@@ -104,6 +106,7 @@ private:
     int huff_decode(const HuffTable& t, uint8_t* out);
     int take_marker(bool* has, uint8_t* m);
     int decode_block(int16_t* c, const HuffTable& dc, const HuffTable& ac, const ScanInfo& s, uint16_t* eob_run, int16_t* pred);
+    int decode_block_seq(int16_t* c, const HuffTable& dc, const HuffTable& ac, uint16_t* eob_run, int16_t* pred);
     int decode_block_sa(int16_t* c, const HuffTable& ac, const ScanInfo& s, uint16_t* eob_run);
     int refine_non_zeroes(int16_t* c, uint8_t start, uint8_t end, uint8_t zrl, int16_t bit, uint8_t* ret);
 
@@ -129,6 +132,7 @@ private:
     bool has_work_ = false;
     uint64_t finished_mask_[4] = {0, 0, 0, 0};
     std::vector<int16_t> final_[4];
+    int16_t* ext_[4] = {nullptr, nullptr, nullptr, nullptr};
     bool have_final_[4] = {false, false, false, false};
     uint16_t final_qt_[4][64];
     // bit reader (src/huffman.rs:14-18)

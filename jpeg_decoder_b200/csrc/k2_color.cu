@@ -162,8 +162,9 @@ __global__ void __launch_bounds__(256) k2_generic(K2Params p, unsigned first, un
 // ---------------------------------------------------------------------------------------------
 // 4:2:0 YCbCr fast path.  Thread = 16 output pixels x the output row pair (2p-1, 2p): both rows
 // blend the same two chroma rows (p-1, p) with swapped weights, so every chroma byte is read once.
-// Preconditions (checked by the planner): ncomp 3, comp0 H1V1, comps 1,2 H2V2, scalar arithmetic,
-// width % 16 == 0, strides and offsets 16-byte (luma) / 8-byte (chroma) aligned.
+// Preconditions (checked by the planner): ncomp 3, comp0 H1V1, comps 1,2 H2V2, scalar arithmetic, strides and
+// offsets 16-byte (luma) / 8-byte (chroma) aligned.  Any width: rows whose start is not 16-byte aligned
+// (width % 16 != 0) fall back to 32-bit or byte stores inside store_words, the last group of a row is ragged.
 // grid.x = ceil(G/128) * P, G = width/16, P = height/2 + 1; grid.y = image
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned prmt(unsigned a, unsigned b, unsigned sel) {
@@ -230,7 +231,28 @@ __device__ __forceinline__ YccRegs make_ycc_regs(int3 sixteen, bool opaque) {
     return k;
 }
 
-__device__ __forceinline__ void ycbcr_store16(const uint4 yv, const int* cb, const int* cr, uint8_t* dst, const YccRegs& sixteen) {
+// Stores the first `nbytes` (<= 4*NW) bytes of ow[] at dst: 128-bit stores when dst is 16-byte aligned (always
+// the case when width % 16 == 0), 32-bit stores when 4-byte aligned, byte stores otherwise / for a ragged tail.
+template <int NW>
+__device__ __forceinline__ void store_words(uint8_t* dst, const unsigned (&ow)[NW], unsigned nbytes) {
+    const unsigned a = (unsigned)(uintptr_t)dst;
+    if (nbytes == 4u * NW && (a & 15u) == 0) {
+#pragma unroll
+        for (int k = 0; k < NW / 4; k++)
+            reinterpret_cast<uint4*>(dst)[k] = make_uint4(ow[4 * k], ow[4 * k + 1], ow[4 * k + 2], ow[4 * k + 3]);
+    } else if (nbytes == 4u * NW && (a & 3u) == 0) {
+#pragma unroll
+        for (int k = 0; k < NW; k++) reinterpret_cast<unsigned*>(dst)[k] = ow[k];
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4 * NW; k++)
+            if ((unsigned)k < nbytes) dst[k] = (uint8_t)(ow[k >> 2] >> (8 * (k & 3)));
+    }
+}
+
+// npx = number of valid pixels of this 16-pixel group (16 except for the last group of a ragged row)
+__device__ __forceinline__ void ycbcr_store16(const uint4 yv, const int* cb, const int* cr, uint8_t* dst, const YccRegs& sixteen,
+                                              unsigned npx) {
     const unsigned yw[4] = {yv.x, yv.y, yv.z, yv.w};
     unsigned ow[12];
 #pragma unroll
@@ -247,10 +269,7 @@ __device__ __forceinline__ void ycbcr_store16(const uint4 yv, const int* cb, con
         ow[3 * w + 1] = pack_sat_u8(b[1], g[1], pack_sat_u8(g[2], r[2], 0u));
         ow[3 * w + 2] = pack_sat_u8(r[3], b[2], pack_sat_u8(b[3], g[3], 0u));
     }
-    uint4* d4 = reinterpret_cast<uint4*>(dst);
-    d4[0] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-    d4[1] = make_uint4(ow[4], ow[5], ow[6], ow[7]);
-    d4[2] = make_uint4(ow[8], ow[9], ow[10], ow[11]);
+    store_words<12>(dst, ow, 3u * npx);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -295,6 +314,7 @@ __global__ void __launch_bounds__(128, MINB) k2_ycbcr420(K2Params p, unsigned fi
     const unsigned i0 = g * 8u;
     const unsigned iL = i0 > 0 ? i0 - 1 : 0, iR = min(i0 + 8u, in_w - 1);
     const YccRegs sixteen = make_ycc_regs(p.sixteen, true);
+    const unsigned npx = min(16u, W - g * 16u);
 
     // chroma row A of the first pair
     const unsigned rA0 = p0 > 0 ? p0 - 1 : 0;
@@ -311,8 +331,8 @@ __global__ void __launch_bounds__(128, MINB) k2_ycbcr420(K2Params p, unsigned fi
         Chroma16 cb, cr;
         h2v2_16(ba.lo, ba.hi, ba.L, ba.R, bb.lo, bb.hi, bb.L, bb.R, cb);
         h2v2_16(ra.lo, ra.hi, ra.L, ra.R, rb.lo, rb.hi, rb.L, rb.R, cr);
-        if (pr > 0) ycbcr_store16(yv_odd, cb.odd, cr.odd, out + (size_t)y_odd * W * 3u, sixteen);      // output row 2p-1
-        if (2 * pr < H) ycbcr_store16(yv_even, cb.even, cr.even, out + (size_t)y_even * W * 3u, sixteen);  // output row 2p
+        if (pr > 0) ycbcr_store16(yv_odd, cb.odd, cr.odd, out + (size_t)y_odd * W * 3u, sixteen, npx);      // output row 2p-1
+        if (2 * pr < H) ycbcr_store16(yv_even, cb.even, cr.even, out + (size_t)y_even * W * 3u, sixteen, npx);  // output row 2p
         ba = bb;
         ra = rb;
     }
@@ -322,6 +342,16 @@ __global__ void __launch_bounds__(128, MINB) k2_ycbcr420(K2Params p, unsigned fi
 // 4:4:4 YCbCr fast path: thread = 16 pixels of one row.
 // grid.x = ceil(G/128) * height, grid.y = image
 // ---------------------------------------------------------------------------------------------
+// 16 bytes of a plane row whose stride is a multiple of 8 (not necessarily 16): two aligned 8-byte loads, the
+// second only when it still lies inside the row
+__device__ __forceinline__ uint4 load_row16(const uint8_t* row, unsigned g, unsigned stride) {
+    const uint2* src = reinterpret_cast<const uint2*>(row + g * 16u);
+    const uint2 lo = __ldg(src);
+    uint2 hi = make_uint2(0u, 0u);
+    if (g * 16u + 8u < stride) hi = __ldg(src + 1);
+    return make_uint4(lo.x, lo.y, hi.x, hi.y);
+}
+
 __global__ void __launch_bounds__(128) k2_ycbcr444(K2Params p, unsigned first, unsigned gchunks) {
     const DevImage& img = p.images[first + blockIdx.y];
     if (img.path != K2_PATH_444) return;
@@ -329,9 +359,9 @@ __global__ void __launch_bounds__(128) k2_ycbcr444(K2Params p, unsigned first, u
     const unsigned g = (blockIdx.x % gchunks) * 128u + threadIdx.x;
     const unsigned W = img.width;
     if (y >= img.height || g * 16u >= W) return;
-    const uint4 yv = __ldg(reinterpret_cast<const uint4*>(p.planes + img.c[0].plane_off + (size_t)y * img.c[0].stride + g * 16u));
-    const uint4 bv = __ldg(reinterpret_cast<const uint4*>(p.planes + img.c[1].plane_off + (size_t)y * img.c[1].stride + g * 16u));
-    const uint4 rv = __ldg(reinterpret_cast<const uint4*>(p.planes + img.c[2].plane_off + (size_t)y * img.c[2].stride + g * 16u));
+    const uint4 yv = load_row16(p.planes + img.c[0].plane_off + (size_t)y * img.c[0].stride, g, img.c[0].stride);
+    const uint4 bv = load_row16(p.planes + img.c[1].plane_off + (size_t)y * img.c[1].stride, g, img.c[1].stride);
+    const uint4 rv = load_row16(p.planes + img.c[2].plane_off + (size_t)y * img.c[2].stride, g, img.c[2].stride);
     const unsigned bw[4] = {bv.x, bv.y, bv.z, bv.w}, rw[4] = {rv.x, rv.y, rv.z, rv.w};
     int cb[16], cr[16];
 #pragma unroll
@@ -339,7 +369,22 @@ __global__ void __launch_bounds__(128) k2_ycbcr444(K2Params p, unsigned first, u
         cb[k] = (int)prmt(bw[k >> 2], 0u, 0x4440u | (unsigned)(k & 3));
         cr[k] = (int)prmt(rw[k >> 2], 0u, 0x4440u | (unsigned)(k & 3));
     }
-    ycbcr_store16(yv, cb, cr, p.out + img.out_off + ((size_t)y * W + g * 16u) * 3u, make_ycc_regs(p.sixteen, true));
+    ycbcr_store16(yv, cb, cr, p.out + img.out_off + ((size_t)y * W + g * 16u) * 3u, make_ycc_regs(p.sixteen, true), min(16u, W - g * 16u));
+}
+
+// ---------------------------------------------------------------------------------------------
+// 1-component images: compact the plane from stride block_w*dct_scale to `width` (src/decoder.rs:1310-1332).
+// Thread = 16 bytes of one row.  grid = (ceil(ceil(W/16)/128), height, images)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k2_gray_crop(K2Params p, unsigned first) {
+    const DevImage& img = p.images[first + blockIdx.z];
+    if (img.path != K2_PATH_GRAY) return;
+    const unsigned g = blockIdx.x * 128u + threadIdx.x, y = blockIdx.y;
+    const unsigned W = img.width;
+    if (y >= img.height || g * 16u >= W) return;
+    const uint4 v = load_row16(p.planes + img.c[0].plane_off + (size_t)y * img.c[0].stride, g, img.c[0].stride);
+    const unsigned ow[4] = {v.x, v.y, v.z, v.w};
+    store_words<4>(p.out + img.out_off + (size_t)y * W + g * 16u, ow, min(16u, W - g * 16u));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -361,7 +406,7 @@ cudaError_t launch_k2_420(const K2Params& p, unsigned first, unsigned count, uns
         mode = g_k2_mode = e ? atoi(e) : (int)K2_RP_DEFAULT;
     }
     const unsigned rp = mode == 4 ? 4u : 1u;
-    dim3 grid((max_w / 16u + 127u) / 128u, (npairs + rp - 1u) / rp, count);
+    dim3 grid(((max_w + 15u) / 16u + 127u) / 128u, (npairs + rp - 1u) / rp, count);
     if (rp == 4) k2_ycbcr420<4, 5><<<grid, 128, 0, stream>>>(p, first);
     else k2_ycbcr420<1, 8><<<grid, 128, 0, stream>>>(p, first);
     return cudaGetLastError();
@@ -369,9 +414,15 @@ cudaError_t launch_k2_420(const K2Params& p, unsigned first, unsigned count, uns
 cudaError_t launch_k2_444(const K2Params& p, unsigned first, unsigned count, unsigned max_w, unsigned max_h,
                           cudaStream_t stream) {
     if (count == 0 || max_w == 0 || max_h == 0) return cudaSuccess;
-    const unsigned gchunks = (max_w / 16u + 127u) / 128u;
+    const unsigned gchunks = ((max_w + 15u) / 16u + 127u) / 128u;
     dim3 grid(gchunks * max_h, count);
     k2_ycbcr444<<<grid, 128, 0, stream>>>(p, first, gchunks);
+    return cudaGetLastError();
+}
+cudaError_t launch_k2_gray(const K2Params& p, unsigned first, unsigned count, unsigned max_w, unsigned max_h, cudaStream_t stream) {
+    if (count == 0 || max_w == 0 || max_h == 0) return cudaSuccess;
+    dim3 grid(((max_w + 15u) / 16u + 127u) / 128u, max_h, count);
+    k2_gray_crop<<<grid, 128, 0, stream>>>(p, first);
     return cudaGetLastError();
 }
 

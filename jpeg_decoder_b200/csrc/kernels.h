@@ -46,6 +46,8 @@ cudaError_t launch_k2_420(const K2Params& p, unsigned first, unsigned count, uns
 cudaError_t launch_k2_444(const K2Params& p, unsigned first, unsigned count, unsigned max_w, unsigned max_h,
                           cudaStream_t stream);
 
+cudaError_t launch_k2_gray(const K2Params& p, unsigned first, unsigned count, unsigned max_w, unsigned max_h, cudaStream_t stream);
+
 extern int g_k1_mode, g_k2_mode;  // profiling knobs, see b200jpg_debug_set_kernel_modes
 
 }  // namespace b200jpg

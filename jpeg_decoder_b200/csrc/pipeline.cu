@@ -202,8 +202,8 @@ struct b200jpg_batch {
     b200jpg_batch_info info{};
     bool all_scale8 = true;
     bool k1_tma_aligned = true;
-    unsigned path_max_w[3] = {0, 0, 0}, path_max_h[3] = {0, 0, 0};
-    bool path_used[3] = {false, false, false};
+    unsigned path_max_w[K2_NPATHS] = {0, 0, 0, 0}, path_max_h[K2_NPATHS] = {0, 0, 0, 0};
+    bool path_used[K2_NPATHS] = {false, false, false, false};
     // device copies of the tables
     DevComp* d_comps = nullptr;
     DevTile* d_tiles = nullptr;
@@ -358,14 +358,17 @@ static int plan_image(const b200jpg_ctx* ctx, const b200jpg_image_desc& d, DevIm
     }
     // kernel choice
     img->path = K2_PATH_GENERIC;
-    if (ctx->k2_kernel != B200JPG_KERNEL_GENERIC && img->cc == CC_YCBCR && img->ssse3_pixels == 0 && d.width % 16 == 0) {
+    if (ctx->k2_kernel != B200JPG_KERNEL_GENERIC && img->cc == CC_GRAY && img->c[0].stride % 8 == 0) img->path = K2_PATH_GRAY;
+    if (ctx->k2_kernel != B200JPG_KERNEL_GENERIC && img->cc == CC_YCBCR && img->ssse3_pixels == 0) {
         const DevUpComp* u = img->c;
+        const unsigned groups = (d.width + 15u) / 16u;
         if (u[0].kind == UP_H1V1 && u[1].kind == UP_H2V2 && u[2].kind == UP_H2V2 && u[0].stride % 16 == 0 &&
             u[1].stride % 8 == 0 && u[2].stride % 8 == 0 && u[1].in_w == u[2].in_w && u[1].in_h == u[2].in_h &&
-            u[1].in_w * 2 == d.width)
+            u[1].in_w == (d.width + 1u) / 2u && groups * 16u <= u[0].stride && groups * 8u <= u[1].stride &&
+            groups * 8u <= u[2].stride)
             img->path = K2_PATH_420;
-        else if (u[0].kind == UP_H1V1 && u[1].kind == UP_H1V1 && u[2].kind == UP_H1V1 && u[0].stride % 16 == 0 &&
-                 u[1].stride % 16 == 0 && u[2].stride % 16 == 0)
+        else if (u[0].kind == UP_H1V1 && u[1].kind == UP_H1V1 && u[2].kind == UP_H1V1 && u[0].stride % 8 == 0 &&
+                 u[1].stride % 8 == 0 && u[2].stride % 8 == 0)
             img->path = K2_PATH_444;
     }
     return B200JPG_OK;
@@ -484,7 +487,7 @@ static int batch_create_impl(b200jpg_ctx* ctx, const b200jpg_image_desc* imgs, s
         out_off += L.out_len;
         b->info.n_pixels += (size_t)d.width * d.height;
         b->info.k2_algorithmic_bytes += L.out_len;
-        if (img.path < 3) {
+        if (img.path < K2_NPATHS) {
             b->path_used[img.path] = true;
             b->path_max_w[img.path] = std::max(b->path_max_w[img.path], img.width);
             b->path_max_h[img.path] = std::max(b->path_max_h[img.path], img.height);
@@ -584,10 +587,11 @@ static int batch_launch(b200jpg_batch* b, const void* d_coefs, void* d_planes, v
             return fail(ctx, B200JPG_ERR_INTERNAL, "k2_kernel=FAST requested but some image needs the generic kernel");
         for (unsigned first = img_first; first < img_first + img_count; first += 65535u) {
             const unsigned count = std::min(65535u, img_first + img_count - first);
-            for (int path = 0; path < 3; path++) {
+            for (int path = 0; path < (int)K2_NPATHS; path++) {
                 if (!b->path_used[path]) continue;
                 cudaError_t e = cudaSuccess;
-                if (path == K2_PATH_GENERIC) e = launch_k2_generic(p, first, count, b->path_max_w[path], b->path_max_h[path], stream);
+                if (path == K2_PATH_GRAY) e = launch_k2_gray(p, first, count, b->path_max_w[path], b->path_max_h[path], stream);
+                else if (path == K2_PATH_GENERIC) e = launch_k2_generic(p, first, count, b->path_max_w[path], b->path_max_h[path], stream);
                 else if (path == K2_PATH_420) e = launch_k2_420(p, first, count, b->path_max_w[path], b->path_max_h[path], stream);
                 else e = launch_k2_444(p, first, count, b->path_max_w[path], b->path_max_h[path], stream);
                 if (e != cudaSuccess) return cuda_fail(ctx, e, "K2 launch");

@@ -421,3 +421,32 @@ def test_progressive_x_many(J, oracle_mod, ctxs):
     assert st == [0] * 16
     for o in outs:
         assert np.array_equal(o, want)
+
+
+def test_decode_files_batch(J, oracle_mod, ctxs):
+    """b200jpg_decode_files: multi-threaded host Huffman + GPU worker path over every reference fixture, with broken
+    files mixed in; per-image statuses, pixels bit-exact vs the oracle."""
+    import glob
+    ctx = ctxs[("scalar", "auto")]
+    paths = reftest_files(include_disabled=True) + bench_files()
+    paths += sorted(glob.glob(os.path.join(GOLDEN, "crashtest", "*.jpg")))[:6]
+    files = [open(p, "rb").read() for p in paths]
+    wants = []
+    for data in files:
+        try:
+            wants.append(oracle_mod.Decoder(data).decode())
+        except oracle_mod.OracleError as e:
+            wants.append(-e.code)
+    for nthreads in (1, 5):
+        outs, st, infos = J.decode_files(ctx, files, nthreads=nthreads)
+        for p, o, s_, w in zip(paths, outs, st, wants):
+            if isinstance(w, int):
+                assert s_ == w, (p, s_, w)
+            else:
+                assert s_ == 0, (p, s_)
+                assert np.array_equal(o, w), p
+    # many copies of one file: exercises chunking and the double-buffered arenas
+    data = open(os.path.join(GOLDEN, "benches", "tower.jpg"), "rb").read()
+    want = oracle_mod.Decoder(data).decode()
+    outs, st, _ = J.decode_files(ctx, [data] * 70, nthreads=3)
+    assert st == [0] * 70 and all(np.array_equal(o, want) for o in outs)

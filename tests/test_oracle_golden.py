@@ -153,3 +153,22 @@ def test_buffer_limit(oracle_mod, J):
     pd2 = J.Decoder(data)
     pd2.set_max_decoding_buffer_size(8 * 8 * 3)
     pd2.entropy_decode()
+
+
+def test_read_info_files(oracle_mod, J):
+    """b200jpg_read_info_files (host only): same ImageInfo as the oracle's read_info for every fixture."""
+    paths = reftest_files(include_disabled=True) + bench_files()
+    files = [open(p, "rb").read() for p in paths]
+    res = J.read_info_files(files, nthreads=3)
+    assert len(res) == len(files)
+    for p, data, (st, info, out_len) in zip(paths, files, res):
+        od = oracle_mod.Decoder(data)
+        try:
+            od.read_info()
+            oi = od.info()
+        except oracle_mod.OracleError as e:
+            assert st == -e.code, p
+            continue
+        assert st == 0, p
+        assert (info.width, info.height, info.pixel_format, info.coding_process) == (oi.width, oi.height, oi.pixel_format, oi.coding_process)
+        assert out_len == info.width * info.height * {0: 1, 1: 1, 2: 3, 3: 4}[info.pixel_format]
