@@ -1,0 +1,37 @@
+// context.h -- the context object shared by pipeline.cu and files_api.cpp (not part of the C ABI).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <mutex>
+#include <string>
+
+typedef CUresult (*PFN_tensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                             const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                             CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                             CUtensorMapFloatOOBfill);
+
+struct b200jpg_ctx {
+    int device = 0;
+    int arith = B200JPG_ARITH_SCALAR;
+    int k1_kernel = B200JPG_KERNEL_AUTO;
+    int k2_kernel = B200JPG_KERNEL_AUTO;
+    cudaStream_t stream = nullptr;   // main stream (caller's or ours)
+    cudaStream_t stream2 = nullptr;  // second stream of the host pipeline
+    bool own_stream = false;
+    int num_sms = 148;
+    uint64_t launches = 0;
+    PFN_tensorMapEncodeTiled encode = nullptr;
+    std::string err;
+    // grow-only caches so that repeated batches / file chunks do not pay cudaMalloc / cudaHostAlloc each time
+    struct Buf {
+        void* p = nullptr;
+        size_t cap = 0;
+    };
+    std::mutex mu;
+    Buf scratch[3];  // device: coefficient, plane and pixel slabs of the host pipeline
+    bool scratch_busy = false;
+    Buf pinned[2];   // host: page-locked coefficient arenas of b200jpg_decode_files
+};
+

@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "../../include/b200jpg.h"
+#include "context.h"
 #include "host_decoder.h"
 
 using b200jpg::HostDecoder;
@@ -56,8 +57,7 @@ void fill_info(const HostDecoder& hd, b200jpg_file_job* job) {
 }
 
 struct Slot {  // one chunk in flight
-    int16_t* arena = nullptr;  // page-locked
-    size_t cap = 0;            // in int16
+    int16_t* arena = nullptr;  // page-locked, owned by the context
     std::vector<std::unique_ptr<HostDecoder>> decs;
     std::vector<b200jpg_image_desc> descs;
     std::vector<size_t> job_of_desc;
@@ -84,7 +84,7 @@ int b200jpg_read_info_files(b200jpg_file_job* jobs, size_t n, int nthreads) {
 int b200jpg_decode_files(b200jpg_ctx* ctx, b200jpg_file_job* jobs, size_t n, int nthreads) {
     if (!ctx || (!jobs && n)) return B200JPG_ERR_INTERNAL;
     if (nthreads < 1) nthreads = (int)std::max(1u, std::thread::hardware_concurrency());
-    const size_t chunk = (size_t)std::max(8, 4 * nthreads);
+    const size_t chunk = (size_t)std::max(8, 2 * nthreads);
     Slot slots[2];
     std::mutex gpu_mutex;  // one chunk at a time on the context's streams (the batch path pipelines internally)
     int result = B200JPG_OK;
@@ -118,17 +118,21 @@ int b200jpg_decode_files(b200jpg_ctx* ctx, b200jpg_file_job* jobs, size_t n, int
             for (const auto& c : s.decs[i - i0]->frame().comps) total += ((size_t)c.block_w * c.block_h * 64 + 511) / 512 * 512;
         }
         off[i1 - i0] = total;
-        if (total > s.cap) {
-            if (s.arena) cudaFreeHost(s.arena);
-            s.arena = nullptr;
-            s.cap = 0;
-            const size_t want = total + total / 4;
-            if (cudaHostAlloc((void**)&s.arena, want * sizeof(int16_t), cudaHostAllocDefault) != cudaSuccess) {
-                cudaGetLastError();
-                result = B200JPG_ERR_INTERNAL;
-                break;
+        {   // the page-locked arena lives in the context (grow-only): pinning memory costs ~0.3 s per GB
+            b200jpg_ctx::Buf& pa = ctx->pinned[which];
+            if (total * sizeof(int16_t) > pa.cap) {
+                if (pa.p) cudaFreeHost(pa.p);
+                pa.p = nullptr;
+                pa.cap = 0;
+                const size_t want = (total + total / 4) * sizeof(int16_t);
+                if (cudaHostAlloc(&pa.p, want, cudaHostAllocDefault) != cudaSuccess) {
+                    cudaGetLastError();
+                    result = B200JPG_ERR_INTERNAL;
+                    break;
+                }
+                pa.cap = want;
             }
-            s.cap = want;
+            s.arena = (int16_t*)pa.p;
         }
         // phase 1: entropy decoding straight into the arena
         parallel_for(i0, i1, nthreads, [&](size_t i) {
@@ -194,7 +198,6 @@ int b200jpg_decode_files(b200jpg_ctx* ctx, b200jpg_file_job* jobs, size_t n, int
     for (auto& s : slots) {
         if (s.gpu.joinable()) s.gpu.join();
         if (s.rc != B200JPG_OK) result = s.rc;
-        if (s.arena) cudaFreeHost(s.arena);
     }
     return result;
 }

@@ -285,9 +285,20 @@ struct ChromaRow {  // one chroma row segment: samples i0..i0+7 plus the clamped
     unsigned lo, hi, L, R;
 };
 
-__device__ __forceinline__ ChromaRow load_chroma_row(const uint8_t* row, unsigned i0, unsigned iL, unsigned iR) {
+// in_w = samples in the row: in the last group of a ragged row the bytes at i >= in_w (block padding) are replaced by
+// the last valid sample, which is exactly the reference's edge rule (out[2 in_w - 1] uses t[in_w-1] alone)
+__device__ __forceinline__ ChromaRow load_chroma_row(const uint8_t* row, unsigned i0, unsigned iL, unsigned iR, unsigned in_w) {
     ChromaRow c;
-    const uint2 v = __ldg(reinterpret_cast<const uint2*>(row + i0));
+    uint2 v = __ldg(reinterpret_cast<const uint2*>(row + i0));
+    if (i0 + 8u > in_w) {
+        const unsigned nvalid = in_w - i0;  // 1..7
+        unsigned long long w = ((unsigned long long)v.y << 32) | v.x;
+        const unsigned long long last = (w >> (8u * (nvalid - 1u))) & 0xffull;
+        const unsigned long long keep = (1ull << (8u * nvalid)) - 1ull;
+        w = (w & keep) | ((last * 0x0101010101010101ull) & ~keep);
+        v.x = (unsigned)w;
+        v.y = (unsigned)(w >> 32);
+    }
     c.lo = v.x;
     c.hi = v.y;
     c.L = __ldg(row + iL);
@@ -318,14 +329,14 @@ __global__ void __launch_bounds__(128, MINB) k2_ycbcr420(K2Params p, unsigned fi
 
     // chroma row A of the first pair
     const unsigned rA0 = p0 > 0 ? p0 - 1 : 0;
-    ChromaRow ba = load_chroma_row(bplane + (size_t)rA0 * sb, i0, iL, iR);
-    ChromaRow ra = load_chroma_row(rplane + (size_t)rA0 * sr, i0, iL, iR);
+    ChromaRow ba = load_chroma_row(bplane + (size_t)rA0 * sb, i0, iL, iR, in_w);
+    ChromaRow ra = load_chroma_row(rplane + (size_t)rA0 * sr, i0, iL, iR, in_w);
     for (unsigned pr = p0; pr < p1; pr++) {
         const unsigned rB = min(pr, in_h - 1);
         // all loads of the iteration up front (independent, clamped rows) so their latencies overlap
         const unsigned y_odd = pr > 0 ? 2 * pr - 1 : 0, y_even = min(2 * pr, H - 1);
-        const ChromaRow bb = load_chroma_row(bplane + (size_t)rB * sb, i0, iL, iR);
-        const ChromaRow rb = load_chroma_row(rplane + (size_t)rB * sr, i0, iL, iR);
+        const ChromaRow bb = load_chroma_row(bplane + (size_t)rB * sb, i0, iL, iR, in_w);
+        const ChromaRow rb = load_chroma_row(rplane + (size_t)rB * sr, i0, iL, iR, in_w);
         const uint4 yv_odd = __ldg(reinterpret_cast<const uint4*>(yplane + (size_t)y_odd * sy));
         const uint4 yv_even = __ldg(reinterpret_cast<const uint4*>(yplane + (size_t)y_even * sy));
         Chroma16 cb, cr;

@@ -25,24 +25,7 @@ using namespace b200jpg;
 // ---------------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------------
-typedef CUresult (*PFN_tensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                             const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
-                                             CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                             CUtensorMapFloatOOBfill);
-
-struct b200jpg_ctx {
-    int device = 0;
-    int arith = B200JPG_ARITH_SCALAR;
-    int k1_kernel = B200JPG_KERNEL_AUTO;
-    int k2_kernel = B200JPG_KERNEL_AUTO;
-    cudaStream_t stream = nullptr;   // main stream (caller's or ours)
-    cudaStream_t stream2 = nullptr;  // second stream of the host pipeline
-    bool own_stream = false;
-    int num_sms = 148;
-    uint64_t launches = 0;
-    PFN_tensorMapEncodeTiled encode = nullptr;
-    std::string err;
-};
+#include "context.h"
 
 static int fail(b200jpg_ctx* ctx, int code, const std::string& msg) {
     if (ctx) ctx->err = msg;
@@ -109,6 +92,8 @@ void b200jpg_destroy(b200jpg_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    for (auto& sc : ctx->scratch) cudaFree(sc.p);
+    for (auto& pa : ctx->pinned) if (pa.p) cudaFreeHost(pa.p);
     delete ctx;
 }
 const char* b200jpg_last_error(const b200jpg_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
@@ -218,6 +203,7 @@ struct b200jpg_batch {
     void* d_planes = nullptr;
     void* d_out = nullptr;
     bool planes_absolute = false;  // plane_off holds absolute device addresses (worker path)
+    bool slabs_borrowed = false;   // d_coefs/d_planes/d_out belong to the context's scratch cache
 };
 
 struct PlanOverrides {
@@ -381,9 +367,15 @@ static void batch_release_device(b200jpg_batch* b) {
     cudaFree(b->d_images);
     cudaFree(b->d_qtabs);
     cudaFree(b->d_qpack);
-    cudaFree(b->d_coefs);
-    cudaFree(b->d_planes);
-    cudaFree(b->d_out);
+    if (b->slabs_borrowed) {
+        std::lock_guard<std::mutex> lock(b->ctx->mu);
+        b->ctx->scratch_busy = false;
+        b->slabs_borrowed = false;
+    } else {
+        cudaFree(b->d_coefs);
+        cudaFree(b->d_planes);
+        cudaFree(b->d_out);
+    }
     b->d_comps = nullptr; b->d_tiles = nullptr; b->d_images = nullptr; b->d_qtabs = nullptr; b->d_qpack = nullptr;
     b->d_coefs = nullptr; b->d_planes = nullptr; b->d_out = nullptr;
 }
@@ -650,6 +642,40 @@ int b200jpg_batch_run_host(b200jpg_batch* b, const b200jpg_image_desc* imgs, uin
     if (!b || !imgs || !outs) return B200JPG_ERR_INTERNAL;
     b200jpg_ctx* ctx = b->ctx;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
+    if (!b->d_coefs && !b->d_planes && !b->d_out) {
+        // internal slabs: borrow the context's grow-only scratch buffers when they are free (repeated batches then
+        // cost no cudaMalloc/cudaFree), otherwise allocate private ones
+        const size_t need[3] = {b->info.coef_bytes, b->info.plane_bytes, b->info.out_bytes};
+        bool borrowed = false;
+        {
+            std::lock_guard<std::mutex> lock(ctx->mu);
+            if (!ctx->scratch_busy) {
+                ctx->scratch_busy = true;
+                borrowed = true;
+            }
+        }
+        if (borrowed) {
+            for (int k = 0; k < 3; k++)
+                if (ctx->scratch[k].cap < need[k]) {
+                    cudaFree(ctx->scratch[k].p);
+                    ctx->scratch[k].p = nullptr;
+                    ctx->scratch[k].cap = 0;
+                    const size_t want = need[k] + need[k] / 8;
+                    cudaError_t e = cudaMalloc(&ctx->scratch[k].p, want);
+                    if (e != cudaSuccess) {
+                        std::lock_guard<std::mutex> lock(ctx->mu);
+                        ctx->scratch_busy = false;
+                        return cuda_fail(ctx, e, "scratch slab allocation");
+                    }
+                    ctx->scratch[k].cap = want;
+                }
+            b->d_coefs = ctx->scratch[0].p;
+            b->d_planes = ctx->scratch[1].p;
+            b->d_out = ctx->scratch[2].p;
+            b->slabs_borrowed = true;
+            b->tmap_base = nullptr;
+        }
+    }
     if (!b->d_coefs && b->info.coef_bytes) CU_TRY(ctx, cudaMalloc(&b->d_coefs, b->info.coef_bytes));
     if (!b->d_planes && b->info.plane_bytes) CU_TRY(ctx, cudaMalloc(&b->d_planes, b->info.plane_bytes));
     if (!b->d_out && b->info.out_bytes) CU_TRY(ctx, cudaMalloc(&b->d_out, b->info.out_bytes));
