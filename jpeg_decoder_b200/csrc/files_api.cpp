@@ -103,8 +103,9 @@ int b200jpg_decode_files(b200jpg_ctx* ctx, b200jpg_file_job* jobs, size_t n, int
             jobs[i].out_len = 0;
             if (jobs[i].status == B200JPG_OK) {
                 fill_info(*hd, &jobs[i]);
-                if (hd->frame().coding_process == B200JPG_CP_LOSSLESS) jobs[i].status = B200JPG_ERR_UNSUPPORTED;
-                else if (jobs[i].out && jobs[i].out_cap < jobs[i].out_len) jobs[i].status = B200JPG_ERR_INTERNAL;
+                // (lossless files are rejected by entropy_decode at their first scan, after the same header checks
+                //  the reference performs, so the error class matches)
+                if (jobs[i].out && jobs[i].out_cap < jobs[i].out_len) jobs[i].status = B200JPG_ERR_INTERNAL;
                 else if (!jobs[i].out) jobs[i].status = B200JPG_ERR_INTERNAL;
             }
             s.decs[i - i0] = std::move(hd);

@@ -285,20 +285,29 @@ struct ChromaRow {  // one chroma row segment: samples i0..i0+7 plus the clamped
     unsigned lo, hi, L, R;
 };
 
+// selector that keeps bytes 0..m-1 of a word and replicates byte m-1 into the rest (m = 1..4)
+__device__ __forceinline__ unsigned keep_sel(unsigned m) {
+    return (0x3210u & ((1u << (4u * m)) - 1u)) | ((((m - 1u) * 0x1111u) << (4u * m)) & 0xffffu);
+}
+
+// bytes nvalid..7 of the 8-byte window := byte nvalid-1 (nvalid = 1..7): two PRMTs with computed selectors
+__device__ __forceinline__ uint2 replicate_last_sample(uint2 v, unsigned nvalid) {
+    if (nvalid <= 4u) {
+        v.x = prmt(v.x, 0u, keep_sel(nvalid));
+        v.y = prmt(v.x, 0u, (nvalid - 1u) * 0x1111u);
+    } else {
+        v.y = prmt(v.y, 0u, keep_sel(nvalid - 4u));
+    }
+    return v;
+}
+
 // in_w = samples in the row: in the last group of a ragged row the bytes at i >= in_w (block padding) are replaced by
 // the last valid sample, which is exactly the reference's edge rule (out[2 in_w - 1] uses t[in_w-1] alone)
+template <bool RAGGED>
 __device__ __forceinline__ ChromaRow load_chroma_row(const uint8_t* row, unsigned i0, unsigned iL, unsigned iR, unsigned in_w) {
     ChromaRow c;
     uint2 v = __ldg(reinterpret_cast<const uint2*>(row + i0));
-    if (i0 + 8u > in_w) {
-        const unsigned nvalid = in_w - i0;  // 1..7
-        unsigned long long w = ((unsigned long long)v.y << 32) | v.x;
-        const unsigned long long last = (w >> (8u * (nvalid - 1u))) & 0xffull;
-        const unsigned long long keep = (1ull << (8u * nvalid)) - 1ull;
-        w = (w & keep) | ((last * 0x0101010101010101ull) & ~keep);
-        v.x = (unsigned)w;
-        v.y = (unsigned)(w >> 32);
-    }
+    if (RAGGED && i0 + 8u > in_w) v = replicate_last_sample(v, in_w - i0);  // last group of a ragged row only
     c.lo = v.x;
     c.hi = v.y;
     c.L = __ldg(row + iL);
@@ -306,10 +315,12 @@ __device__ __forceinline__ ChromaRow load_chroma_row(const uint8_t* row, unsigne
     return c;
 }
 
-template <unsigned K2_RP, int MINB>
+// RAGGED: images whose chroma width is not a multiple of 8 (the last 8-sample window of a row then needs the
+// edge sample replicated); a separate instantiation so that the common case keeps 64 registers / 8 CTAs per SM.
+template <unsigned K2_RP, int MINB, bool RAGGED>
 __global__ void __launch_bounds__(128, MINB) k2_ycbcr420(K2Params p, unsigned first) {
     const DevImage& img = p.images[first + blockIdx.z];
-    if (img.path != K2_PATH_420) return;
+    if (img.path != (RAGGED ? K2_PATH_420R : K2_PATH_420)) return;
     const unsigned g = blockIdx.x * 128u + threadIdx.x;
     const unsigned W = img.width, H = img.height;
     const unsigned npairs = H / 2 + 1;
@@ -329,14 +340,14 @@ __global__ void __launch_bounds__(128, MINB) k2_ycbcr420(K2Params p, unsigned fi
 
     // chroma row A of the first pair
     const unsigned rA0 = p0 > 0 ? p0 - 1 : 0;
-    ChromaRow ba = load_chroma_row(bplane + (size_t)rA0 * sb, i0, iL, iR, in_w);
-    ChromaRow ra = load_chroma_row(rplane + (size_t)rA0 * sr, i0, iL, iR, in_w);
+    ChromaRow ba = load_chroma_row<RAGGED>(bplane + (size_t)rA0 * sb, i0, iL, iR, in_w);
+    ChromaRow ra = load_chroma_row<RAGGED>(rplane + (size_t)rA0 * sr, i0, iL, iR, in_w);
     for (unsigned pr = p0; pr < p1; pr++) {
         const unsigned rB = min(pr, in_h - 1);
         // all loads of the iteration up front (independent, clamped rows) so their latencies overlap
         const unsigned y_odd = pr > 0 ? 2 * pr - 1 : 0, y_even = min(2 * pr, H - 1);
-        const ChromaRow bb = load_chroma_row(bplane + (size_t)rB * sb, i0, iL, iR, in_w);
-        const ChromaRow rb = load_chroma_row(rplane + (size_t)rB * sr, i0, iL, iR, in_w);
+        const ChromaRow bb = load_chroma_row<RAGGED>(bplane + (size_t)rB * sb, i0, iL, iR, in_w);
+        const ChromaRow rb = load_chroma_row<RAGGED>(rplane + (size_t)rB * sr, i0, iL, iR, in_w);
         const uint4 yv_odd = __ldg(reinterpret_cast<const uint4*>(yplane + (size_t)y_odd * sy));
         const uint4 yv_even = __ldg(reinterpret_cast<const uint4*>(yplane + (size_t)y_even * sy));
         Chroma16 cb, cr;
@@ -407,7 +418,7 @@ cudaError_t launch_k2_generic(const K2Params& p, unsigned first, unsigned count,
     k2_generic<<<grid, 256, 0, stream>>>(p, first, xchunks);
     return cudaGetLastError();
 }
-cudaError_t launch_k2_420(const K2Params& p, unsigned first, unsigned count, unsigned max_w, unsigned max_h,
+cudaError_t launch_k2_420(const K2Params& p, unsigned first, unsigned count, unsigned max_w, unsigned max_h, bool ragged,
                           cudaStream_t stream) {
     if (count == 0 || max_w == 0 || max_h == 0) return cudaSuccess;
     const unsigned npairs = max_h / 2u + 1u;
@@ -418,8 +429,9 @@ cudaError_t launch_k2_420(const K2Params& p, unsigned first, unsigned count, uns
     }
     const unsigned rp = mode == 4 ? 4u : 1u;
     dim3 grid(((max_w + 15u) / 16u + 127u) / 128u, (npairs + rp - 1u) / rp, count);
-    if (rp == 4) k2_ycbcr420<4, 5><<<grid, 128, 0, stream>>>(p, first);
-    else k2_ycbcr420<1, 8><<<grid, 128, 0, stream>>>(p, first);
+    if (ragged) k2_ycbcr420<1, 7, true><<<dim3(grid.x, npairs, count), 128, 0, stream>>>(p, first);
+    else if (rp == 4) k2_ycbcr420<4, 5, false><<<grid, 128, 0, stream>>>(p, first);
+    else k2_ycbcr420<1, 8, false><<<grid, 128, 0, stream>>>(p, first);
     return cudaGetLastError();
 }
 cudaError_t launch_k2_444(const K2Params& p, unsigned first, unsigned count, unsigned max_w, unsigned max_h,

@@ -41,7 +41,7 @@ cudaError_t launch_k1_tma(const CUtensorMap& tmap, const K1QCache& qc, const K1P
 // skipped by it, so a heterogeneous batch is covered by one launch per path in use.
 cudaError_t launch_k2_generic(const K2Params& p, unsigned first, unsigned count, unsigned max_w, unsigned max_h,
                               cudaStream_t stream);
-cudaError_t launch_k2_420(const K2Params& p, unsigned first, unsigned count, unsigned max_w, unsigned max_h,
+cudaError_t launch_k2_420(const K2Params& p, unsigned first, unsigned count, unsigned max_w, unsigned max_h, bool ragged,
                           cudaStream_t stream);
 cudaError_t launch_k2_444(const K2Params& p, unsigned first, unsigned count, unsigned max_w, unsigned max_h,
                           cudaStream_t stream);

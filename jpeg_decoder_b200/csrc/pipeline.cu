@@ -187,8 +187,8 @@ struct b200jpg_batch {
     b200jpg_batch_info info{};
     bool all_scale8 = true;
     bool k1_tma_aligned = true;
-    unsigned path_max_w[K2_NPATHS] = {0, 0, 0, 0}, path_max_h[K2_NPATHS] = {0, 0, 0, 0};
-    bool path_used[K2_NPATHS] = {false, false, false, false};
+    unsigned path_max_w[K2_NPATHS] = {}, path_max_h[K2_NPATHS] = {};
+    bool path_used[K2_NPATHS] = {};
     // device copies of the tables
     DevComp* d_comps = nullptr;
     DevTile* d_tiles = nullptr;
@@ -352,7 +352,7 @@ static int plan_image(const b200jpg_ctx* ctx, const b200jpg_image_desc& d, DevIm
             u[1].stride % 8 == 0 && u[2].stride % 8 == 0 && u[1].in_w == u[2].in_w && u[1].in_h == u[2].in_h &&
             u[1].in_w == (d.width + 1u) / 2u && groups * 16u <= u[0].stride && groups * 8u <= u[1].stride &&
             groups * 8u <= u[2].stride)
-            img->path = K2_PATH_420;
+            img->path = u[1].in_w % 8u == 0 ? K2_PATH_420 : K2_PATH_420R;
         else if (u[0].kind == UP_H1V1 && u[1].kind == UP_H1V1 && u[2].kind == UP_H1V1 && u[0].stride % 8 == 0 &&
                  u[1].stride % 8 == 0 && u[2].stride % 8 == 0)
             img->path = K2_PATH_444;
@@ -584,7 +584,8 @@ static int batch_launch(b200jpg_batch* b, const void* d_coefs, void* d_planes, v
                 cudaError_t e = cudaSuccess;
                 if (path == K2_PATH_GRAY) e = launch_k2_gray(p, first, count, b->path_max_w[path], b->path_max_h[path], stream);
                 else if (path == K2_PATH_GENERIC) e = launch_k2_generic(p, first, count, b->path_max_w[path], b->path_max_h[path], stream);
-                else if (path == K2_PATH_420) e = launch_k2_420(p, first, count, b->path_max_w[path], b->path_max_h[path], stream);
+                else if (path == K2_PATH_420 || path == K2_PATH_420R)
+                    e = launch_k2_420(p, first, count, b->path_max_w[path], b->path_max_h[path], path == K2_PATH_420R, stream);
                 else e = launch_k2_444(p, first, count, b->path_max_w[path], b->path_max_h[path], stream);
                 if (e != cudaSuccess) return cuda_fail(ctx, e, "K2 launch");
                 ctx->launches++;
