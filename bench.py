@@ -57,56 +57,49 @@ def load_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """SM clock and throttle reasons sampled every few milliseconds through NVML while kernels run (the timed
+    region is tens of milliseconds long: far too short for `nvidia-smi -lms`)."""
 
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
-        self.samples = []
+        self.samples = []      # (time, sm_mhz, reasons bitmask)
+        self.windows = []      # (t0, t1) of the timed regions
+        self.max_mhz = None
         self.stop_flag = False
-        self.proc = None
+        self.ok = False
 
     def run(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            for line in self.proc.stdout:
-                if self.stop_flag:
-                    break
-                self.samples.append(line.strip())
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            self.ok = True
+            while not self.stop_flag:
+                self.samples.append((time.perf_counter(), float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), int(get_reasons(h))))
+                time.sleep(0.002)
         except Exception:
-            pass
+            self.ok = False
 
     def stop(self):
         self.stop_flag = True
-        if self.proc:
-            try:
-                self.proc.terminate()
-            except Exception:
-                pass
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
-            f = [x.strip() for x in s.split(",")]
-            if len(f) < 6:
-                continue
-            try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for name, v in zip(names, f[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        inside = [s for s in self.samples if any(t0 <= s[0] <= t1 for t0, t1 in self.windows)]
+        use = inside if inside else self.samples
+        if not use:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        mask = 0
+        for s_ in use:
+            mask |= s_[2]
+        reasons = sorted(name for bit, name in self.REASONS.items() if mask & bit)
+        return {"sm_mhz": float(np.median([s_[1] for s_ in use])), "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(use), "source": "nvml, 2 ms period, samples inside the CUDA-event timed regions"}
 
 
 def bind_to_gpu_numa_node(torch, index):
@@ -275,21 +268,22 @@ def main():
     def timed(stages, steps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
+        t0 = time.perf_counter()
         e0.record(stream)
         for _ in range(steps):
             run(stages)
         e1.record(stream)
         torch.cuda.synchronize()
+        sampler.windows.append((t0, time.perf_counter()))
         return e0.elapsed_time(e1)
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         run()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    time.sleep(0.3)
     launches0 = ctx.launch_count
     ms = timed(3, args.steps)
     launches = ctx.launch_count - launches0
@@ -380,11 +374,19 @@ def main():
         flist = [jpegs[j % len(jpegs)] for j in range(Bf)]
         f_out = torch.empty(Bf * out_per_img, dtype=torch.uint8, pin_memory=True).numpy()
         f_outs = [f_out[j * out_per_img:(j + 1) * out_per_img] for j in range(Bf)]
-        J.decode_files(ctx, flist[:2 * nthreads], nthreads=nthreads, outs=f_outs[:2 * nthreads])   # warm-up
+        # the job array is built outside the timed region; the timed call is the C entry point itself
+        import ctypes as C
+        fbufs = [np.frombuffer(j, dtype=np.uint8) for j in jpegs]
+        jobs = (J.FileJob * Bf)()
+        for j in range(Bf):
+            jobs[j].data, jobs[j].len = fbufs[j % len(jpegs)].ctypes.data, fbufs[j % len(jpegs)].size
+            jobs[j].out, jobs[j].out_cap = f_outs[j].ctypes.data, f_outs[j].size
+        ctx.check(J.lib().b200jpg_decode_files(ctx._h, jobs, Bf, nthreads))   # warm-up (allocates the cached arenas)
         t0 = time.perf_counter()
-        _, fst, _ = J.decode_files(ctx, flist, nthreads=nthreads, outs=f_outs)
+        ctx.check(J.lib().b200jpg_decode_files(ctx._h, jobs, Bf, nthreads))
         f_dt = time.perf_counter() - t0
-        assert all(s == 0 for s in fst)
+        assert all(jobs[j].status == 0 for j in range(Bf))
+        assert bool(np.array_equal(f_outs[0], ref0))
         files_e2e = {"value": Bf * W * H / 1e6 / f_dt, "unit": "MP/s", "images": Bf, "host_threads": nthreads,
                      "jpeg_bytes_per_image": int(np.mean([len(j) for j in jpegs])),
                      "api": "b200jpg_decode_files (JPEG bytes -> pixels; Huffman on the host, worker path on the GPU)"}

@@ -21,7 +21,7 @@ from ._native import (ARITH_SCALAR, ARITH_SSSE3, CP_DCT_PROGRESSIVE, CP_DCT_SEQU
                       ERR_FORMAT, ERR_INTERNAL, ERR_IO, ERR_UNSUPPORTED, KERNEL_AUTO, KERNEL_FAST, KERNEL_GENERIC, OK,
                       PF_CMYK32, PF_L8, PF_L16, PF_RGB24, BatchInfo, Component, FileJob, ImageDesc, ImageInfo, Options, lib)
 
-__all__ = ["Context", "Worker", "Batch", "Decoder", "B200JpgError", "make_components", "make_image_desc",
+__all__ = ["Context", "Worker", "Batch", "Decoder", "B200JpgError", "FileJob", "make_components", "make_image_desc",
            "compute_image", "decode_batch", "decode_files", "read_info_files", "Component", "ImageDesc"]
 
 

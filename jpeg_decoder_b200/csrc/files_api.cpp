@@ -7,7 +7,11 @@
 // chunk through the batch path (one H2D, K1, K2, D2H into the callers' buffers) while the host threads
 // already decode the next chunk.
 #include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <chrono>
 
 #include <algorithm>
 #include <atomic>
@@ -85,6 +89,9 @@ int b200jpg_decode_files(b200jpg_ctx* ctx, b200jpg_file_job* jobs, size_t n, int
     if (!ctx || (!jobs && n)) return B200JPG_ERR_INTERNAL;
     if (nthreads < 1) nthreads = (int)std::max(1u, std::thread::hardware_concurrency());
     const size_t chunk = (size_t)std::max(8, 2 * nthreads);
+    const bool trace = getenv("B200JPG_TRACE") != nullptr;  // phase timings on stderr
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_start = now();
     Slot slots[2];
     std::mutex gpu_mutex;  // one chunk at a time on the context's streams (the batch path pipelines internally)
     int result = B200JPG_OK;
@@ -92,7 +99,9 @@ int b200jpg_decode_files(b200jpg_ctx* ctx, b200jpg_file_job* jobs, size_t n, int
     for (size_t i0 = 0; i0 < n; i0 += chunk, which ^= 1) {
         const size_t i1 = std::min(n, i0 + chunk);
         Slot& s = slots[which];
+        const double t_c0 = now();
         if (s.gpu.joinable()) s.gpu.join();  // the slot's previous chunk has left the GPU
+        const double t_c1 = now();
         if (s.rc != B200JPG_OK) result = s.rc;
         s.decs.clear();
         s.decs.resize(i1 - i0);
@@ -110,6 +119,7 @@ int b200jpg_decode_files(b200jpg_ctx* ctx, b200jpg_file_job* jobs, size_t n, int
             }
             s.decs[i - i0] = std::move(hd);
         });
+        const double t_c2 = now();
         // arena layout: components of one image back to back, 1 KiB aligned like the device slab
         std::vector<size_t> off(i1 - i0 + 1, 0);
         size_t total = 0;
@@ -135,6 +145,7 @@ int b200jpg_decode_files(b200jpg_ctx* ctx, b200jpg_file_job* jobs, size_t n, int
             }
             s.arena = (int16_t*)pa.p;
         }
+        const double t_c3 = now();
         // phase 1: entropy decoding straight into the arena
         parallel_for(i0, i1, nthreads, [&](size_t i) {
             if (jobs[i].status != B200JPG_OK) return;
@@ -147,6 +158,10 @@ int b200jpg_decode_files(b200jpg_ctx* ctx, b200jpg_file_job* jobs, size_t n, int
             }
             jobs[i].status = hd.entropy_decode();
         });
+        const double t_c4 = now();
+        if (trace)
+            fprintf(stderr, "[b200jpg] chunk %zu..%zu: wait-gpu %.1f ms, headers %.1f ms, arena %.1f ms, huffman %.1f ms (t=%.1f)\n", i0, i1,
+                    t_c1 - t_c0, t_c2 - t_c1, t_c3 - t_c2, t_c4 - t_c3, t_c4 - t_start);
         // phase 2: hand the chunk to the GPU on a submitter thread
         s.descs.clear();
         s.job_of_desc.clear();
@@ -175,10 +190,11 @@ int b200jpg_decode_files(b200jpg_ctx* ctx, b200jpg_file_job* jobs, size_t n, int
             s.job_of_desc.push_back(i);
         }
         s.rc = B200JPG_OK;
-        s.gpu = std::thread([&s, &gpu_mutex, ctx, jobs] {
+        s.gpu = std::thread([&s, &gpu_mutex, ctx, jobs, trace, now, t_start] {
             const size_t m = s.descs.size();
             if (m == 0) return;
             std::lock_guard<std::mutex> lock(gpu_mutex);
+            const double t_g0 = now();
             std::vector<uint8_t*> outs(m);
             std::vector<size_t> caps(m);
             std::vector<int> st(m, 0);
@@ -187,6 +203,7 @@ int b200jpg_decode_files(b200jpg_ctx* ctx, b200jpg_file_job* jobs, size_t n, int
                 caps[k] = jobs[s.job_of_desc[k]].out_cap;
             }
             const int rc = b200jpg_decode_batch(ctx, s.descs.data(), m, outs.data(), caps.data(), st.data());
+            if (trace) fprintf(stderr, "[b200jpg] gpu chunk of %zu images: %.1f ms (t=%.1f)\n", m, now() - t_g0, now() - t_start);
             for (size_t k = 0; k < m; k++) jobs[s.job_of_desc[k]].status = st[k];
             bool any_image_error = false;
             for (int v : st) any_image_error = any_image_error || v != 0;
