@@ -71,20 +71,55 @@ class ClockSampler(threading.Thread):
         self.max_mhz = None
         self.stop_flag = False
         self.ok = False
+        self.error = None
 
     def run(self):
         try:
             import pynvml
             pynvml.nvmlInit()
             h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
-            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            try:
+                self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            except Exception as e:  # noqa: BLE001
+                self.error = "max clock: %r" % (e,)
+
+            def reasons():
+                for name in ("nvmlDeviceGetCurrentClocksEventReasons", "nvmlDeviceGetCurrentClocksThrottleReasons"):
+                    fn = getattr(pynvml, name, None)
+                    if fn is not None:
+                        try:
+                            return int(fn(h))
+                        except Exception:  # noqa: BLE001
+                            continue
+                return 0
             self.ok = True
             while not self.stop_flag:
-                self.samples.append((time.perf_counter(), float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), int(get_reasons(h))))
+                self.samples.append((time.perf_counter(), float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), reasons()))
                 time.sleep(0.002)
-        except Exception:
+        except Exception as e:  # noqa: BLE001
+            self.error = repr(e)
             self.ok = False
+        if not self.samples:
+            self.run_smi()
+
+    def run_smi(self):
+        """Fallback: nvidia-smi in a loop (coarser: ~20 ms per query)."""
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        bits = [0x8, 0x40, 0x20, 0x4]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().splitlines()[0]
+                f = [x.strip() for x in out.split(",")]
+                mask = 0
+                for b, v in zip(bits, f[2:6]):
+                    if v.lower().startswith("active"):
+                        mask |= b
+                self.max_mhz = float(f[1])
+                self.samples.append((time.perf_counter(), float(f[0]), mask))
+            except Exception as e:  # noqa: BLE001
+                self.error = repr(e)
+                time.sleep(0.05)
 
     def stop(self):
         self.stop_flag = True
@@ -93,13 +128,14 @@ class ClockSampler(threading.Thread):
         inside = [s for s in self.samples if any(t0 <= s[0] <= t1 for t0, t1 in self.windows)]
         use = inside if inside else self.samples
         if not use:
-            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0, "error": self.error}
         mask = 0
         for s_ in use:
             mask |= s_[2]
         reasons = sorted(name for bit, name in self.REASONS.items() if mask & bit)
         return {"sm_mhz": float(np.median([s_[1] for s_ in use])), "sm_max_mhz": self.max_mhz, "reasons": reasons,
-                "samples": len(use), "source": "nvml, 2 ms period, samples inside the CUDA-event timed regions"}
+                "samples": len(use), "samples_inside_timed_regions": len(inside),
+                "source": "NVML polled every 2 ms (nvidia-smi loop as fallback) while the CUDA-event timed regions run"}
 
 
 def bind_to_gpu_numa_node(torch, index):

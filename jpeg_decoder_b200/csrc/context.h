@@ -32,6 +32,6 @@ struct b200jpg_ctx {
     std::mutex mu;
     Buf scratch[3];  // device: coefficient, plane and pixel slabs of the host pipeline
     bool scratch_busy = false;
-    Buf pinned[2];   // host: page-locked coefficient arenas of b200jpg_decode_files
+    Buf pinned[3];   // host: page-locked coefficient arenas of b200jpg_decode_files
 };
 

@@ -92,11 +92,12 @@ int b200jpg_decode_files(b200jpg_ctx* ctx, b200jpg_file_job* jobs, size_t n, int
     const bool trace = getenv("B200JPG_TRACE") != nullptr;  // phase timings on stderr
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_start = now();
-    Slot slots[2];
+    constexpr size_t NSLOTS = 3;
+    Slot slots[NSLOTS];
     std::mutex gpu_mutex;  // one chunk at a time on the context's streams (the batch path pipelines internally)
     int result = B200JPG_OK;
     size_t which = 0;
-    for (size_t i0 = 0; i0 < n; i0 += chunk, which ^= 1) {
+    for (size_t i0 = 0; i0 < n; i0 += chunk, which = (which + 1) % NSLOTS) {
         const size_t i1 = std::min(n, i0 + chunk);
         Slot& s = slots[which];
         const double t_c0 = now();

@@ -824,6 +824,7 @@ int HostDecoder::decode_scan(const ScanInfo& scan, const bool finished[4], bool*
     // where each scan component's blocks go: the progressive store, the final buffer (worker::start
     // zero-fills, src/decoder.rs:848-861, 874-880), or a dummy block
     int16_t* target[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool zero_per_block[4] = {false, false, false, false};
     int16_t dummy[64];
     for (int i = 0; i < nc; i++) {
         const int ci = scan.comp_index[i];
@@ -833,13 +834,17 @@ int HostDecoder::decode_scan(const ScanInfo& scan, const bool finished[4], bool*
             target[i] = work_[ci].data();
         } else if (finished[i]) {
             have_final_[ci] = false;
+            // An interleaved scan visits every block of the component exactly once, so each block is zeroed right
+            // before it is decoded (cache-hot, one pass over the buffer instead of two); otherwise zero up front.
             if (ext_[ci]) {
-                memset(ext_[ci], 0, count * sizeof(int16_t));
+                if (!is_interleaved) memset(ext_[ci], 0, count * sizeof(int16_t));
                 target[i] = ext_[ci];
             } else {
-                final_[ci].assign(count, 0);
+                if (is_interleaved) final_[ci].resize(count);
+                else final_[ci].assign(count, 0);
                 target[i] = final_[ci].data();
             }
+            zero_per_block[i] = is_interleaved;
         }
     }
     bits_ = 0;
@@ -896,6 +901,7 @@ int HostDecoder::decode_scan(const ScanInfo& scan, const bool finished[4], bool*
                         if (target[i]) {
                             const size_t block_y = (size_t)mcu_y * mv[i] + v_pos, block_x = (size_t)mcu_x * mh[i] + h_pos;
                             c = target[i] + (block_y * comp.block_w + block_x) * 64;
+                            if (zero_per_block[i]) memset(c, 0, 128);
                         } else {
                             c = dummy;
                             if (scan.ah == 0) memset(dummy, 0, sizeof dummy);
