@@ -404,7 +404,9 @@ def main():
     # ---- whole files: JPEG bytes -> pixels (host Huffman on the NUMA-local cores + GPU worker path) ----
     files_e2e = None
     if rank == 0 and world == 1:
-        nthreads = len(os.sched_getaffinity(0))
+        # host threads = the CPUs of the GPU's NUMA node (this process is bound to them): measured faster than using
+        # both sockets (profiles/r01_files_trace.txt)
+        nthreads = max(1, len(os.sched_getaffinity(0)))
         Bf = min(512, max(64, 8 * nthreads))
         jpegs = [workload.synth_jpeg(W, H, cfg["seed"] + k, cfg["subsampling"]) for k in range(min(U, 4))]
         flist = [jpegs[j % len(jpegs)] for j in range(Bf)]

@@ -839,12 +839,11 @@ int HostDecoder::decode_scan(const ScanInfo& scan, const bool finished[4], bool*
             if (ext_[ci]) {
                 if (!is_interleaved) memset(ext_[ci], 0, count * sizeof(int16_t));
                 target[i] = ext_[ci];
+                zero_per_block[i] = is_interleaved;
             } else {
-                if (is_interleaved) final_[ci].resize(count);
-                else final_[ci].assign(count, 0);
+                final_[ci].assign(count, 0);
                 target[i] = final_[ci].data();
             }
-            zero_per_block[i] = is_interleaved;
         }
     }
     bits_ = 0;

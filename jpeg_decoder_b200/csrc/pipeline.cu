@@ -9,9 +9,11 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <map>
 #include <string>
 #include <vector>
@@ -761,11 +763,17 @@ int b200jpg_batch_run_host(b200jpg_batch* b, const b200jpg_image_desc* imgs, uin
 
 int b200jpg_decode_batch(b200jpg_ctx* ctx, const b200jpg_image_desc* imgs, size_t n, uint8_t* const* outs,
                          const size_t* out_caps, int* statuses) {
+    const bool trace = getenv("B200JPG_TRACE") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
     b200jpg_batch* b = nullptr;
     int rc = b200jpg_batch_create(ctx, imgs, n, statuses, &b);
     if (rc) return rc;
+    const double t1 = now();
     rc = b200jpg_batch_run_host(b, imgs, outs, out_caps, statuses);
+    const double t2 = now();
     b200jpg_batch_free(b);
+    if (trace) fprintf(stderr, "[b200jpg] decode_batch(%zu): plan %.1f ms, run_host %.1f ms, free %.1f ms\n", n, t1 - t0, t2 - t1, now() - t2);
     return rc;
 }
 
