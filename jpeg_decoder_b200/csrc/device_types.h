@@ -37,7 +37,7 @@ struct __align__(16) DevTile {
 
 enum : unsigned { UP_H1V1 = 0, UP_H2V1 = 1, UP_H1V2 = 2, UP_H2V2 = 3, UP_GENERIC = 4 };
 enum : unsigned { CC_NOCONVERT = 0, CC_RGB = 1, CC_YCBCR = 2, CC_CMYK = 3, CC_YCCK = 4, CC_GRAY = 5 };
-enum : unsigned { K2_PATH_GENERIC = 0, K2_PATH_420 = 1, K2_PATH_444 = 2, K2_PATH_GRAY = 3, K2_PATH_420R = 4, K2_NPATHS = 5 };
+enum : unsigned { K2_PATH_GENERIC = 0, K2_PATH_420 = 1, K2_PATH_444 = 2, K2_PATH_GRAY = 3, K2_PATH_420R = 4, K2_PATH_420T = 5, K2_NPATHS = 6 };
 
 struct DevUpComp {
     unsigned long long plane_off;
@@ -57,6 +57,14 @@ struct __align__(16) DevImage {
     unsigned ssse3_pixels;       // pixels per row converted with the SSSE3 formula (0 in scalar mode)
     unsigned path;               // K2_PATH_* the planner chose for this image
     DevUpComp c[4];
+};
+
+// One per (image on the bulk-copy 4:2:0 path, 2048-pixel strip): the flattened work list of k2_ycbcr420_tma.
+struct __align__(16) K2Strip {
+    unsigned image;       // index into DevImage[]
+    unsigned x0;          // first pixel of the strip
+    unsigned first_item;  // index of the strip's first row pair in the flattened (strip, row pair) sequence
+    unsigned npairs;      // height / 2 + 1
 };
 
 }  // namespace b200jpg

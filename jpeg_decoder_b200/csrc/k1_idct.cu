@@ -20,6 +20,7 @@
 
 #include "device_types.h"
 #include "kernels.h"
+#include "ptx.cuh"
 
 #define K1_DEFAULT_MODE 5
 
@@ -287,48 +288,6 @@ __global__ void __launch_bounds__(K1_TILE) k1_idct_generic(K1Params p, int arith
 }
 
 // ---------------------------------------------------------------------------------------------
-// mbarrier / TMA helpers (PTX; SASS: SYNCS.*, UTMALDG)
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
-    unsigned ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
-    while (!mbar_try_wait(bar, parity)) {
-    }
-}
-__device__ __forceinline__ uint4 lds128(unsigned addr) {
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* map, int x, int y, unsigned bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-        ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(bar)
-        : "memory");
-}
-
-// ---------------------------------------------------------------------------------------------
 // The hot kernel.
 // ---------------------------------------------------------------------------------------------
 constexpr int K1_STAGE_BYTES = K1_TILE * 128;
@@ -400,8 +359,7 @@ k1_idct8_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ K
             mbar_init(smem_u32(&full_bar[st]), 1);
             mbar_init(smem_u32(&empty_bar[st]), K1_TILE / 32);
         }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_fence_init();
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
         for (unsigned it = 0; it < (unsigned)K1_STAGES && it < n; it++) {
             const unsigned bar = smem_u32(&full_bar[it]);

@@ -24,6 +24,7 @@
 
 #include "device_types.h"
 #include "kernels.h"
+#include "ptx.cuh"
 
 namespace b200jpg {
 
@@ -278,7 +279,6 @@ __device__ __forceinline__ void ycbcr_store16(const uint4 yv, const int* cb, con
 // but halves the occupancy -- profiles/sweep_*.jsonl).
 // grid = (ceil(G/128), ceil(P/K2_RP), images), G = width/16, P = height/2 + 1
 // ---------------------------------------------------------------------------------------------
-constexpr unsigned K2_RP_DEFAULT = 1;
 int g_k2_mode = -1;
 
 struct ChromaRow {  // one chroma row segment: samples i0..i0+7 plus the clamped halo samples
@@ -320,7 +320,7 @@ __device__ __forceinline__ ChromaRow load_chroma_row(const uint8_t* row, unsigne
 template <unsigned K2_RP, int MINB, bool RAGGED>
 __global__ void __launch_bounds__(128, MINB) k2_ycbcr420(K2Params p, unsigned first) {
     const DevImage& img = p.images[first + blockIdx.z];
-    if (img.path != (RAGGED ? K2_PATH_420R : K2_PATH_420)) return;
+    if (RAGGED ? img.path != K2_PATH_420R : (img.path != K2_PATH_420 && !(img.path == K2_PATH_420T && (p.flags & K2_FLAG_LDG_TAKES_420T)))) return;
     const unsigned g = blockIdx.x * 128u + threadIdx.x;
     const unsigned W = img.width, H = img.height;
     const unsigned npairs = H / 2 + 1;
@@ -364,6 +364,150 @@ __global__ void __launch_bounds__(128, MINB) k2_ycbcr420(K2Params p, unsigned fi
 // 4:4:4 YCbCr fast path: thread = 16 pixels of one row.
 // grid.x = ceil(G/128) * height, grid.y = image
 // ---------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------
+// 4:2:0 YCbCr, bulk-copy fed (the default for aligned images).  Same arithmetic as k2_ycbcr420; what changes
+// is how bytes reach the SM.  The load-compute-store kernel above has ~64 B of loads in flight per thread and only
+// while the thread waits for them, which leaves it latency bound at ~0.78 of the HBM roofline with 32 warps/SM.
+// Here persistent 4-warp CTAs each own a contiguous run of row pairs of 2048-pixel strips; thread 0 keeps a
+// K2T_STAGES-deep shared-memory ring full with 1-D bulk copies (cp.async.bulk + mbarrier complete_tx): per row
+// pair the two luma rows and ONE new chroma row per component -- the other chroma row is the previous pair's,
+// still in the ring (its slot is released one iteration late).  Tens of KiB per SM are in flight regardless of
+// what the warps are doing.
+// ---------------------------------------------------------------------------------------------
+constexpr unsigned K2T_STAGES = 6;
+constexpr unsigned K2T_STRIP = 2048;                      // pixels per strip = 128 threads x 16
+constexpr unsigned K2T_CROW = K2T_STRIP / 2 + 32;         // chroma row buffer: 16 B pad | 1024 samples | 16 B pad
+constexpr unsigned K2T_OFF_Y0 = 0, K2T_OFF_Y1 = K2T_STRIP, K2T_OFF_BB = 2 * K2T_STRIP, K2T_OFF_RB = K2T_OFF_BB + K2T_CROW,
+                   K2T_OFF_BA = K2T_OFF_RB + K2T_CROW, K2T_OFF_RA = K2T_OFF_BA + K2T_CROW;
+constexpr unsigned K2T_STAGE_BYTES = (K2T_OFF_RA + K2T_CROW + 127u) / 128u * 128u;
+
+struct K2TCursor {  // position in the flattened (strip, row pair) sequence
+    unsigned strip;   // index into K2Strip[]
+    unsigned pair;    // row pair inside the strip
+    unsigned npairs;  // row pairs of the current strip
+};
+
+__global__ void __launch_bounds__(128, 4) k2_ycbcr420_tma(K2Params p, const K2Strip* __restrict__ strips, unsigned nstrips,
+                                                          unsigned item_base, unsigned total_items) {
+    extern __shared__ __align__(128) uint8_t k2t_smem[];
+    __shared__ __align__(8) unsigned long long full_bar[K2T_STAGES];
+    __shared__ __align__(8) unsigned long long empty_bar[K2T_STAGES];
+    const unsigned smem = smem_u32(k2t_smem);
+    const unsigned tid = threadIdx.x, lane = tid & 31;
+    const unsigned w_begin = item_base + (unsigned)(((unsigned long long)blockIdx.x * total_items) / gridDim.x);
+    const unsigned w_end = item_base + (unsigned)(((unsigned long long)(blockIdx.x + 1) * total_items) / gridDim.x);
+    const unsigned n = w_end - w_begin;
+    if (n == 0) return;
+
+    if (tid == 0) {
+        for (unsigned st = 0; st < K2T_STAGES; st++) {
+            mbar_init(smem_u32(&full_bar[st]), 1);
+            mbar_init(smem_u32(&empty_bar[st]), 4);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    // strip containing item w_begin: binary search on first_item
+    unsigned lo = 0, hi = nstrips - 1;
+    while (lo < hi) {
+        const unsigned mid = (lo + hi + 1) / 2;
+        if (__ldg(&strips[mid].first_item) <= w_begin) lo = mid; else hi = mid - 1;
+    }
+    K2TCursor cons;
+    cons.strip = lo;
+    cons.pair = w_begin - __ldg(&strips[lo].first_item);
+    cons.npairs = __ldg(&strips[lo].npairs);
+    K2TCursor prod = cons;  // thread 0 only
+
+    // Issues the copies of tile `j` (the producer cursor points at it) into slot j % STAGES and advances the cursor.
+    auto issue = [&](unsigned j) {
+        const K2Strip sp = strips[prod.strip];
+        const DevImage& img = p.images[sp.image];
+        const unsigned pr = prod.pair, H = img.height, W = img.width;
+        const unsigned wpx = min(K2T_STRIP, W - sp.x0);
+        const unsigned ybytes = (wpx + 15u) & ~15u;
+        const unsigned cs = sp.x0 / 2u, in_h = img.c[1].in_h;
+        const unsigned c_lo = cs >= 16u ? cs - 16u : 0u;
+        const unsigned c_hi = min(img.c[1].stride, cs + K2T_STRIP / 2u + 16u);
+        const unsigned cbytes = c_hi - c_lo, cdst = c_lo + 16u - cs;
+        const bool need_a = pr > 0 && j == 0;  // first tile of this CTA: chroma row p-1 is not in the ring
+        const unsigned slot = smem + (j % K2T_STAGES) * K2T_STAGE_BYTES;
+        const unsigned bar = smem_u32(&full_bar[j % K2T_STAGES]);
+        unsigned tx = 2u * cbytes;
+        if (pr > 0) tx += ybytes;
+        if (2u * pr < H) tx += ybytes;
+        if (need_a) tx += 2u * cbytes;
+        mbar_expect_tx(bar, tx);
+        const uint8_t* yp = p.planes + img.c[0].plane_off + sp.x0;
+        if (pr > 0) bulk_load_1d(slot + K2T_OFF_Y0, yp + (size_t)(2u * pr - 1u) * img.c[0].stride, ybytes, bar);
+        if (2u * pr < H) bulk_load_1d(slot + K2T_OFF_Y1, yp + (size_t)(2u * pr) * img.c[0].stride, ybytes, bar);
+        const unsigned rB = min(pr, in_h - 1u);
+        bulk_load_1d(slot + K2T_OFF_BB + cdst, p.planes + img.c[1].plane_off + (size_t)rB * img.c[1].stride + c_lo, cbytes, bar);
+        bulk_load_1d(slot + K2T_OFF_RB + cdst, p.planes + img.c[2].plane_off + (size_t)rB * img.c[2].stride + c_lo, cbytes, bar);
+        if (need_a) {
+            bulk_load_1d(slot + K2T_OFF_BA + cdst, p.planes + img.c[1].plane_off + (size_t)(pr - 1u) * img.c[1].stride + c_lo, cbytes, bar);
+            bulk_load_1d(slot + K2T_OFF_RA + cdst, p.planes + img.c[2].plane_off + (size_t)(pr - 1u) * img.c[2].stride + c_lo, cbytes, bar);
+        }
+        if (++prod.pair == prod.npairs) {
+            prod.pair = 0;
+            if (++prod.strip < nstrips) prod.npairs = __ldg(&strips[prod.strip].npairs);
+        }
+    };
+    if (tid == 0)
+        for (unsigned j = 0; j < K2T_STAGES && j < n; j++) issue(j);
+
+    const YccRegs ycc = make_ycc_regs(p.sixteen, true);
+    for (unsigned it = 0; it < n; it++) {
+        const unsigned stage = it % K2T_STAGES, round = it / K2T_STAGES;
+        // refill: slot (it-2) was released at the end of iteration it-1 (one iteration late, see below)
+        if (tid == 0 && it >= 2 && it - 2 + K2T_STAGES < n) {
+            const unsigned ps = (it - 2) % K2T_STAGES;
+            mbar_wait(smem_u32(&empty_bar[ps]), ((it - 2) / K2T_STAGES) & 1);
+            issue(it - 2 + K2T_STAGES);
+        }
+        const K2Strip sp = strips[cons.strip];
+        const DevImage& img = p.images[sp.image];
+        const unsigned pr = cons.pair, H = img.height, W = img.width;
+        const unsigned wpx = min(K2T_STRIP, W - sp.x0);
+        const bool active = tid * 16u < wpx;
+        const unsigned slot = smem + stage * K2T_STAGE_BYTES;
+        // chroma row A (= max(p-1,0)): row B of this slot when p == 0, this slot's A buffers for the CTA's first tile,
+        // otherwise row B of the previous pair, which still sits in the previous slot
+        const unsigned prev = smem + ((it + K2T_STAGES - 1u) % K2T_STAGES) * K2T_STAGE_BYTES;
+        const unsigned a_b = pr == 0 ? slot + K2T_OFF_BB : (it == 0 ? slot + K2T_OFF_BA : prev + K2T_OFF_BB);
+        const unsigned a_r = pr == 0 ? slot + K2T_OFF_RB : (it == 0 ? slot + K2T_OFF_RA : prev + K2T_OFF_RB);
+        mbar_wait(smem_u32(&full_bar[stage]), round & 1);
+        if (active) {
+            const unsigned cs = sp.x0 / 2u, in_w = img.c[1].in_w;
+            const unsigned li = tid * 8u, gi = cs + li;                          // local / global chroma sample index
+            const unsigned oL = 16u + (gi > 0 ? li - 1u : li);                    // buffer offsets of the clamped halo samples
+            const unsigned oR = 16u + (min(gi + 8u, in_w - 1u) - cs);
+            const unsigned oM = 16u + li;
+            Chroma16 cb, cr;
+            {
+                const uint2 av = lds64(a_b + oM), bv = lds64(slot + K2T_OFF_BB + oM);
+                h2v2_16(av.x, av.y, lds8(a_b + oL), lds8(a_b + oR), bv.x, bv.y, lds8(slot + K2T_OFF_BB + oL), lds8(slot + K2T_OFF_BB + oR), cb);
+            }
+            {
+                const uint2 av = lds64(a_r + oM), bv = lds64(slot + K2T_OFF_RB + oM);
+                h2v2_16(av.x, av.y, lds8(a_r + oL), lds8(a_r + oR), bv.x, bv.y, lds8(slot + K2T_OFF_RB + oL), lds8(slot + K2T_OFF_RB + oR), cr);
+            }
+            const unsigned npx = min(16u, wpx - tid * 16u);
+            uint8_t* out = p.out + img.out_off + ((size_t)sp.x0 + tid * 16u) * 3u;
+            if (pr > 0) ycbcr_store16(lds128(slot + K2T_OFF_Y0 + tid * 16u), cb.odd, cr.odd, out + (size_t)(2u * pr - 1u) * W * 3u, ycc, npx);
+            if (2u * pr < H) ycbcr_store16(lds128(slot + K2T_OFF_Y1 + tid * 16u), cb.even, cr.even, out + (size_t)(2u * pr) * W * 3u, ycc, npx);
+        }
+        // release the PREVIOUS slot: its chroma rows were this iteration's row A
+        __syncwarp();
+        if (lane == 0 && it > 0) mbar_arrive(smem_u32(&empty_bar[(it - 1) % K2T_STAGES]));
+        if (++cons.pair == cons.npairs) {
+            cons.pair = 0;
+            if (++cons.strip < nstrips) cons.npairs = __ldg(&strips[cons.strip].npairs);
+        }
+    }
+}
+
 // 16 bytes of a plane row whose stride is a multiple of 8 (not necessarily 16): two aligned 8-byte loads, the
 // second only when it still lies inside the row
 __device__ __forceinline__ uint4 load_row16(const uint8_t* row, unsigned g, unsigned stride) {
@@ -418,20 +562,37 @@ cudaError_t launch_k2_generic(const K2Params& p, unsigned first, unsigned count,
     k2_generic<<<grid, 256, 0, stream>>>(p, first, xchunks);
     return cudaGetLastError();
 }
+int k2_mode() {  // experiment knob (profiling only): 0 = default, 1 = load/store kernels only, 4 = 4 row pairs per thread
+    if (g_k2_mode < 0) {
+        const char* e = getenv("B200JPG_K2_MODE");
+        g_k2_mode = e ? atoi(e) : 0;
+    }
+    return g_k2_mode;
+}
 cudaError_t launch_k2_420(const K2Params& p, unsigned first, unsigned count, unsigned max_w, unsigned max_h, bool ragged,
                           cudaStream_t stream) {
     if (count == 0 || max_w == 0 || max_h == 0) return cudaSuccess;
     const unsigned npairs = max_h / 2u + 1u;
-    int mode = g_k2_mode;  // experiment knob (profiling only): row pairs per thread
-    if (mode < 0) {
-        const char* e = getenv("B200JPG_K2_MODE");
-        mode = g_k2_mode = e ? atoi(e) : (int)K2_RP_DEFAULT;
-    }
-    const unsigned rp = mode == 4 ? 4u : 1u;
+    const unsigned rp = k2_mode() == 4 ? 4u : 1u;
     dim3 grid(((max_w + 15u) / 16u + 127u) / 128u, (npairs + rp - 1u) / rp, count);
     if (ragged) k2_ycbcr420<1, 7, true><<<dim3(grid.x, npairs, count), 128, 0, stream>>>(p, first);
     else if (rp == 4) k2_ycbcr420<4, 5, false><<<grid, 128, 0, stream>>>(p, first);
     else k2_ycbcr420<1, 8, false><<<grid, 128, 0, stream>>>(p, first);
+    return cudaGetLastError();
+}
+cudaError_t launch_k2_420_tma(const K2Params& p, const K2Strip* strips, unsigned nstrips, unsigned item_base, unsigned total_items,
+                              int num_sms, cudaStream_t stream) {
+    if (nstrips == 0 || total_items == 0) return cudaSuccess;
+    const size_t smem_bytes = (size_t)K2T_STAGES * K2T_STAGE_BYTES;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k2_ycbcr420_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    unsigned grid = (unsigned)num_sms * 4u;
+    if (grid > total_items) grid = total_items;
+    k2_ycbcr420_tma<<<grid, 128, smem_bytes, stream>>>(p, strips, nstrips, item_base, total_items);
     return cudaGetLastError();
 }
 cudaError_t launch_k2_444(const K2Params& p, unsigned first, unsigned count, unsigned max_w, unsigned max_h,

@@ -24,6 +24,7 @@ struct K2Params {
     const uint8_t* planes;
     uint8_t* out;
     unsigned nimages;
+    unsigned flags;  // K2_FLAG_*
     int3 sixteen;  // (16, 16, 16), see ycbcr_scalar_y16 in k2_color.cu
 };
 
@@ -46,6 +47,10 @@ cudaError_t launch_k2_420(const K2Params& p, unsigned first, unsigned count, uns
 cudaError_t launch_k2_444(const K2Params& p, unsigned first, unsigned count, unsigned max_w, unsigned max_h,
                           cudaStream_t stream);
 
+cudaError_t launch_k2_420_tma(const K2Params& p, const K2Strip* strips, unsigned nstrips, unsigned item_base, unsigned total_items,
+                              int num_sms, cudaStream_t stream);
+int k2_mode();
+constexpr unsigned K2_FLAG_LDG_TAKES_420T = 1u;  // K2Params::flags: the load/store 4:2:0 kernel also takes the bulk-copy path's images
 cudaError_t launch_k2_gray(const K2Params& p, unsigned first, unsigned count, unsigned max_w, unsigned max_h, cudaStream_t stream);
 
 extern int g_k1_mode, g_k2_mode;  // profiling knobs, see b200jpg_debug_set_kernel_modes

@@ -191,6 +191,10 @@ struct b200jpg_batch {
     bool k1_tma_aligned = true;
     unsigned path_max_w[K2_NPATHS] = {}, path_max_h[K2_NPATHS] = {};
     bool path_used[K2_NPATHS] = {};
+    std::vector<K2Strip> strips;         // work list of the bulk-copy 4:2:0 kernel (images on K2_PATH_420T)
+    std::vector<unsigned> strip_first;   // per image: index of its first strip (n + 1 entries)
+    unsigned strip_items = 0;
+    K2Strip* d_strips = nullptr;
     // device copies of the tables
     DevComp* d_comps = nullptr;
     DevTile* d_tiles = nullptr;
@@ -369,6 +373,7 @@ static void batch_release_device(b200jpg_batch* b) {
     cudaFree(b->d_images);
     cudaFree(b->d_qtabs);
     cudaFree(b->d_qpack);
+    cudaFree(b->d_strips);
     if (b->slabs_borrowed) {
         std::lock_guard<std::mutex> lock(b->ctx->mu);
         b->ctx->scratch_busy = false;
@@ -378,7 +383,7 @@ static void batch_release_device(b200jpg_batch* b) {
         cudaFree(b->d_planes);
         cudaFree(b->d_out);
     }
-    b->d_comps = nullptr; b->d_tiles = nullptr; b->d_images = nullptr; b->d_qtabs = nullptr; b->d_qpack = nullptr;
+    b->d_comps = nullptr; b->d_tiles = nullptr; b->d_images = nullptr; b->d_qtabs = nullptr; b->d_qpack = nullptr; b->d_strips = nullptr;
     b->d_coefs = nullptr; b->d_planes = nullptr; b->d_out = nullptr;
 }
 
@@ -400,6 +405,7 @@ static int batch_create_impl(b200jpg_ctx* ctx, const b200jpg_image_desc* imgs, s
     for (size_t i = 0; i < n; i++) {
         const b200jpg_image_desc& d = imgs[i];
         ImageLayout& L = b->layout[i];
+        b->strip_first.push_back((unsigned)b->strips.size());
         std::string err;
         int rc = plan_image(ctx, d, &b->images[i], &err);
         for (int k = 0; rc == B200JPG_OK && k < d.ncomp; k++)
@@ -481,6 +487,17 @@ static int batch_create_impl(b200jpg_ctx* ctx, const b200jpg_image_desc* imgs, s
         out_off += L.out_len;
         b->info.n_pixels += (size_t)d.width * d.height;
         b->info.k2_algorithmic_bytes += L.out_len;
+        // bulk-copy fed 4:2:0 kernel: every row it copies must start on a 16-byte boundary (cp.async.bulk)
+        if (img.path == K2_PATH_420 && img.c[1].stride % 16 == 0 && img.c[1].stride == img.c[2].stride &&
+            img.c[0].plane_off % 16 == 0 && img.c[1].plane_off % 16 == 0 && img.c[2].plane_off % 16 == 0)
+            img.path = K2_PATH_420T;
+        if (img.path == K2_PATH_420T) {
+            const unsigned npairs = img.height / 2u + 1u;
+            for (unsigned x0 = 0; x0 < img.width; x0 += 2048u) {
+                b->strips.push_back(K2Strip{(unsigned)i, x0, b->strip_items, npairs});
+                b->strip_items += npairs;
+            }
+        }
         if (img.path < K2_NPATHS) {
             b->path_used[img.path] = true;
             b->path_max_w[img.path] = std::max(b->path_max_w[img.path], img.width);
@@ -509,6 +526,8 @@ static int batch_create_impl(b200jpg_ctx* ctx, const b200jpg_image_desc* imgs, s
     if (e == cudaSuccess) e = upload((void**)&b->d_images, b->images.data(), b->images.size() * sizeof(DevImage));
     if (e == cudaSuccess) e = upload((void**)&b->d_qtabs, b->qtabs.data(), b->qtabs.size() * sizeof(unsigned));
     if (e == cudaSuccess) e = upload((void**)&b->d_qpack, b->qpack.data(), b->qpack.size() * sizeof(unsigned));
+    if (e == cudaSuccess) e = upload((void**)&b->d_strips, b->strips.data(), b->strips.size() * sizeof(K2Strip));
+    b->strip_first.push_back((unsigned)b->strips.size());
     memset(&b->qcache, 0, sizeof b->qcache);
     for (size_t t = 0; t < 4 && t < b->qt_is8.size(); t++)
         memcpy(b->qcache.b[t], b->qpack.data() + 32 * t, 32 * sizeof(unsigned));
@@ -577,18 +596,36 @@ static int batch_launch(b200jpg_batch* b, const void* d_coefs, void* d_planes, v
         p.out = (uint8_t*)d_out;
         p.nimages = (unsigned)b->n;
         p.sixteen = make_int3(16, 16, 16);
+        const bool bulk = k2_mode() == 0 && ((uintptr_t)d_planes % 16 == 0);
+        p.flags = bulk ? 0u : K2_FLAG_LDG_TAKES_420T;
+        if (bulk && b->path_used[K2_PATH_420T]) {
+            const unsigned s0 = b->strip_first[img_first], s1 = b->strip_first[img_first + img_count];
+            if (s1 > s0) {
+                const unsigned base = b->strips[s0].first_item;
+                const unsigned end = s1 < b->strips.size() ? b->strips[s1].first_item : b->strip_items;
+                cudaError_t e = launch_k2_420_tma(p, b->d_strips + s0, s1 - s0, base, end - base, ctx->num_sms, stream);
+                if (e != cudaSuccess) return cuda_fail(ctx, e, "K2 launch");
+                ctx->launches++;
+            }
+        }
         if (ctx->k2_kernel == B200JPG_KERNEL_FAST && b->path_used[K2_PATH_GENERIC])
             return fail(ctx, B200JPG_ERR_INTERNAL, "k2_kernel=FAST requested but some image needs the generic kernel");
         for (unsigned first = img_first; first < img_first + img_count; first += 65535u) {
             const unsigned count = std::min(65535u, img_first + img_count - first);
             for (int path = 0; path < (int)K2_NPATHS; path++) {
-                if (!b->path_used[path]) continue;
+                if (path == K2_PATH_420T) continue;
+                unsigned max_w = b->path_used[path] ? b->path_max_w[path] : 0, max_h = b->path_used[path] ? b->path_max_h[path] : 0;
+                if (path == K2_PATH_420 && !bulk && b->path_used[K2_PATH_420T]) {  // the load/store kernel takes those images too
+                    max_w = std::max(max_w, b->path_max_w[K2_PATH_420T]);
+                    max_h = std::max(max_h, b->path_max_h[K2_PATH_420T]);
+                }
+                if (max_w == 0 || max_h == 0) continue;
                 cudaError_t e = cudaSuccess;
-                if (path == K2_PATH_GRAY) e = launch_k2_gray(p, first, count, b->path_max_w[path], b->path_max_h[path], stream);
-                else if (path == K2_PATH_GENERIC) e = launch_k2_generic(p, first, count, b->path_max_w[path], b->path_max_h[path], stream);
+                if (path == K2_PATH_GRAY) e = launch_k2_gray(p, first, count, max_w, max_h, stream);
+                else if (path == K2_PATH_GENERIC) e = launch_k2_generic(p, first, count, max_w, max_h, stream);
                 else if (path == K2_PATH_420 || path == K2_PATH_420R)
-                    e = launch_k2_420(p, first, count, b->path_max_w[path], b->path_max_h[path], path == K2_PATH_420R, stream);
-                else e = launch_k2_444(p, first, count, b->path_max_w[path], b->path_max_h[path], stream);
+                    e = launch_k2_420(p, first, count, max_w, max_h, path == K2_PATH_420R, stream);
+                else e = launch_k2_444(p, first, count, max_w, max_h, stream);
                 if (e != cudaSuccess) return cuda_fail(ctx, e, "K2 launch");
                 ctx->launches++;
             }

@@ -51,7 +51,7 @@ for kernels in ("auto", "generic"):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / steps
 
-    modes = [(0, 1), (5, 1), (5, 4)] if kernels == "auto" else [(-1, -1)]
+    modes = [(5, 0), (5, 1), (5, 4), (0, 0)] if kernels == "auto" else [(-1, -1)]
     for k1m, k2m in modes:
         J.lib().b200jpg_debug_set_kernel_modes(k1m, k2m)
         d_planes.zero_()

@@ -395,6 +395,65 @@ def test_full_size_batch_properties(J, oracle_mod, ctxs, k1):
     batch.close()
 
 
+BULK_SIZES = [(32, 1), (32, 2), (32, 37), (64, 9), (96, 200), (2048, 5), (2080, 4), (4096, 3), (4128, 37), (6176, 11), (1920, 1080)]
+
+
+@pytest.mark.parametrize("k2_mode", [0, 1, 4])
+def test_k2_420_bulk_copy_kernel_geometries(J, oracle_mod, ctxs, k2_mode):
+    """The bulk-copy fed 4:2:0 kernel (k2_ycbcr420_tma: strips of 2048 pixels, row pairs chained through the shared
+    memory ring) against the oracle at the geometries that stress it: one row, fewer row pairs than ring stages, several
+    strips with a short last strip, odd heights; the load/store kernels (modes 1 and 4) must give the same bytes."""
+    ctx = ctxs[("scalar", "auto")]
+    rng = np.random.default_rng(420)
+    J.lib().b200jpg_debug_set_kernel_modes(-1, k2_mode)
+    try:
+        for (w, h) in BULK_SIZES:
+            comps, _ = J.make_components(w, h, SAMPLINGS["420"])
+            ocomps, _ = oracle_mod.make_components(w, h, SAMPLINGS["420"])
+            planes = random_planes(rng, comps)
+            got = J.compute_image(ctx, comps, planes, w, h, J.CT_YCBCR)
+            want = oracle_mod.compute_image(ocomps, planes, w, h, oracle_mod.CT_YCBCR)
+            assert np.array_equal(got, want), (w, h, k2_mode)
+    finally:
+        J.lib().b200jpg_debug_set_kernel_modes(-1, -1)
+
+
+def test_k2_420_bulk_copy_mixed_batch(J, oracle_mod, ctxs):
+    """One batch mixing images on the bulk-copy path with ragged / 4:4:4 / gray ones: the strip table only lists the
+    eligible images and the per-CTA ranges cross image boundaries."""
+    from jpeg_decoder_b200 import workload
+    ctx = ctxs[("scalar", "auto")]
+    datas = [workload.synth_jpeg(w, h, 3000 + i, sub) for i, (w, h, sub) in enumerate(
+        [(64, 40, 2), (2080, 36, 2), (50, 30, 2), (96, 64, 0), (4128, 20, 2), (32, 2, 2), (640, 480, 2)])]
+    descs, keep = [], []
+    for d in datas:
+        dec = J.Decoder(d)
+        keep.append(dec)
+        descs.append(dec.entropy_decode())
+    outs, st = J.decode_batch(ctx, descs * 3)
+    assert st == [0] * (3 * len(datas))
+    wants = [oracle_mod.Decoder(d).decode() for d in datas]
+    for j, o in enumerate(outs):
+        assert np.array_equal(o, wants[j % len(datas)]), j
+
+
+def test_k1_more_than_four_quant_tables(J, oracle_mod, ctxs):
+    """Only the first four 8-bit tables of a batch ride in the kernel-parameter constant bank; later ones are read
+    from the packed table in global memory (qflags slot 0xff).  Six images with distinct tables."""
+    from jpeg_decoder_b200 import workload
+    ctx = ctxs[("scalar", "auto")]
+    datas = [workload.synth_jpeg(160, 96, 100 + q, 2, quality=q) for q in (35, 50, 65, 75, 85, 92)]
+    descs, keep = [], []
+    for d in datas:
+        dec = J.Decoder(d)
+        keep.append(dec)
+        descs.append(dec.entropy_decode())
+    outs, st = J.decode_batch(ctx, descs)
+    assert st == [0] * len(datas)
+    for d, o in zip(datas, outs):
+        assert np.array_equal(o, oracle_mod.Decoder(d).decode())
+
+
 def copy_ocomps(oracle_mod, comps):
     arr = (oracle_mod.Component * len(comps))()
     for i, c in enumerate(comps):
