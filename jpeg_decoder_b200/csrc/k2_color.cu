@@ -366,32 +366,38 @@ __global__ void __launch_bounds__(128, MINB) k2_ycbcr420(K2Params p, unsigned fi
 // ---------------------------------------------------------------------------------------------
 // ---------------------------------------------------------------------------------------------
 // 4:2:0 YCbCr, bulk-copy fed (the default for aligned images).  Same arithmetic as k2_ycbcr420; what changes
-// is how bytes reach the SM.  The load-compute-store kernel above has ~64 B of loads in flight per thread and only
-// while the thread waits for them, which leaves it latency bound at ~0.78 of the HBM roofline with 32 warps/SM.
-// Here persistent 4-warp CTAs each own a contiguous run of row pairs of 2048-pixel strips; thread 0 keeps a
-// K2T_STAGES-deep shared-memory ring full with 1-D bulk copies (cp.async.bulk + mbarrier complete_tx): per row
-// pair the two luma rows and ONE new chroma row per component -- the other chroma row is the previous pair's,
-// still in the ring (its slot is released one iteration late).  Tens of KiB per SM are in flight regardless of
-// what the warps are doing.
+// is how bytes reach the SM.  Persistent CTAs each own a contiguous run of row pairs of 2048-pixel strips (work list
+// K2Strip[] built by the planner, so heterogeneous batches cost no empty CTAs).  Warp 4 keeps a K2T_STAGES-deep
+// shared-memory ring full with 1-D bulk copies (cp.async.bulk + mbarrier complete_tx): per row pair the two luma
+// rows and ONE new chroma row per component -- the other chroma row is the previous pair's, still in the ring (its
+// slot is released one iteration late).  Warps 0-3 convert out of shared memory.
+// Measured on B200 (profiles/r01_k2_bulk_vs_ldg.md): 0.917 ms vs 0.923 ms per 512 images for the load/store kernel --
+// both sit at ~68 % ALU-pipe and ~70 % FMA-heavy-pipe utilisation, i.e. the conversion is bound by integer issue,
+// not by how the bytes arrive.
 // ---------------------------------------------------------------------------------------------
 constexpr unsigned K2T_STAGES = 6;
+constexpr unsigned K2T_THREADS = 160;                     // warps 0-3 convert, warp 4 feeds the ring
 constexpr unsigned K2T_STRIP = 2048;                      // pixels per strip = 128 threads x 16
 constexpr unsigned K2T_CROW = K2T_STRIP / 2 + 32;         // chroma row buffer: 16 B pad | 1024 samples | 16 B pad
 constexpr unsigned K2T_OFF_Y0 = 0, K2T_OFF_Y1 = K2T_STRIP, K2T_OFF_BB = 2 * K2T_STRIP, K2T_OFF_RB = K2T_OFF_BB + K2T_CROW,
                    K2T_OFF_BA = K2T_OFF_RB + K2T_CROW, K2T_OFF_RA = K2T_OFF_BA + K2T_CROW;
 constexpr unsigned K2T_STAGE_BYTES = (K2T_OFF_RA + K2T_CROW + 127u) / 128u * 128u;
 
-struct K2TCursor {  // position in the flattened (strip, row pair) sequence
-    unsigned strip;   // index into K2Strip[]
-    unsigned pair;    // row pair inside the strip
-    unsigned npairs;  // row pairs of the current strip
+struct K2TProd {  // what the producer needs per strip; lives in shared memory, touched by one thread only
+    const uint8_t* y;   // luma row 0 at the strip's first pixel
+    const uint8_t* cb;  // chroma rows 0 at the first copied sample (c_lo)
+    const uint8_t* cr;
+    unsigned sy, sc;    // plane strides
+    unsigned H, in_h;
+    unsigned ybytes, cbytes, cdst;  // bytes per luma / chroma row copy, offset of the chroma copy in its row buffer
 };
 
-__global__ void __launch_bounds__(128, 4) k2_ycbcr420_tma(K2Params p, const K2Strip* __restrict__ strips, unsigned nstrips,
-                                                          unsigned item_base, unsigned total_items) {
+__global__ void __launch_bounds__(K2T_THREADS, 4) k2_ycbcr420_tma(K2Params p, const K2Strip* __restrict__ strips, unsigned nstrips,
+                                                                  unsigned item_base, unsigned total_items) {
     extern __shared__ __align__(128) uint8_t k2t_smem[];
     __shared__ __align__(8) unsigned long long full_bar[K2T_STAGES];
     __shared__ __align__(8) unsigned long long empty_bar[K2T_STAGES];
+    __shared__ K2TProd prod_state;
     const unsigned smem = smem_u32(k2t_smem);
     const unsigned tid = threadIdx.x, lane = tid & 31;
     const unsigned w_begin = item_base + (unsigned)(((unsigned long long)blockIdx.x * total_items) / gridDim.x);
@@ -414,96 +420,122 @@ __global__ void __launch_bounds__(128, 4) k2_ycbcr420_tma(K2Params p, const K2St
         const unsigned mid = (lo + hi + 1) / 2;
         if (__ldg(&strips[mid].first_item) <= w_begin) lo = mid; else hi = mid - 1;
     }
-    K2TCursor cons;
-    cons.strip = lo;
-    cons.pair = w_begin - __ldg(&strips[lo].first_item);
-    cons.npairs = __ldg(&strips[lo].npairs);
-    K2TCursor prod = cons;  // thread 0 only
+    const unsigned first_pair = w_begin - __ldg(&strips[lo].first_item);
 
-    // Issues the copies of tile `j` (the producer cursor points at it) into slot j % STAGES and advances the cursor.
-    auto issue = [&](unsigned j) {
-        const K2Strip sp = strips[prod.strip];
-        const DevImage& img = p.images[sp.image];
-        const unsigned pr = prod.pair, H = img.height, W = img.width;
-        const unsigned wpx = min(K2T_STRIP, W - sp.x0);
-        const unsigned ybytes = (wpx + 15u) & ~15u;
-        const unsigned cs = sp.x0 / 2u, in_h = img.c[1].in_h;
-        const unsigned c_lo = cs >= 16u ? cs - 16u : 0u;
-        const unsigned c_hi = min(img.c[1].stride, cs + K2T_STRIP / 2u + 16u);
-        const unsigned cbytes = c_hi - c_lo, cdst = c_lo + 16u - cs;
-        const bool need_a = pr > 0 && j == 0;  // first tile of this CTA: chroma row p-1 is not in the ring
-        const unsigned slot = smem + (j % K2T_STAGES) * K2T_STAGE_BYTES;
-        const unsigned bar = smem_u32(&full_bar[j % K2T_STAGES]);
-        unsigned tx = 2u * cbytes;
-        if (pr > 0) tx += ybytes;
-        if (2u * pr < H) tx += ybytes;
-        if (need_a) tx += 2u * cbytes;
-        mbar_expect_tx(bar, tx);
-        const uint8_t* yp = p.planes + img.c[0].plane_off + sp.x0;
-        if (pr > 0) bulk_load_1d(slot + K2T_OFF_Y0, yp + (size_t)(2u * pr - 1u) * img.c[0].stride, ybytes, bar);
-        if (2u * pr < H) bulk_load_1d(slot + K2T_OFF_Y1, yp + (size_t)(2u * pr) * img.c[0].stride, ybytes, bar);
-        const unsigned rB = min(pr, in_h - 1u);
-        bulk_load_1d(slot + K2T_OFF_BB + cdst, p.planes + img.c[1].plane_off + (size_t)rB * img.c[1].stride + c_lo, cbytes, bar);
-        bulk_load_1d(slot + K2T_OFF_RB + cdst, p.planes + img.c[2].plane_off + (size_t)rB * img.c[2].stride + c_lo, cbytes, bar);
-        if (need_a) {
-            bulk_load_1d(slot + K2T_OFF_BA + cdst, p.planes + img.c[1].plane_off + (size_t)(pr - 1u) * img.c[1].stride + c_lo, cbytes, bar);
-            bulk_load_1d(slot + K2T_OFF_RA + cdst, p.planes + img.c[2].plane_off + (size_t)(pr - 1u) * img.c[2].stride + c_lo, cbytes, bar);
+    if (tid >= 128) {
+        // ---- producer (lane 0 of warp 4): cursor + per-strip state, refreshed only when the cursor enters a new strip.
+        // A consumer warp doing this on the side was measured 1.5x slower than its siblings, which then idled. ----
+        if (lane != 0) return;
+        unsigned p_strip = lo, p_pair = first_pair, p_npairs = 0;
+        bool p_new = true;
+        unsigned slot_index = 0, e_phase = 0;
+        for (unsigned j = 0; j < n; j++) {
+            // tile j replaces tile j - STAGES, which is released one iteration late (end of iteration j - STAGES + 1)
+            if (j >= K2T_STAGES) mbar_wait(smem_u32(&empty_bar[slot_index]), e_phase);
+            if (p_new) {
+                const K2Strip sp = strips[p_strip];
+                const DevImage& img = p.images[sp.image];
+                const unsigned wpx = min(K2T_STRIP, img.width - sp.x0);
+                const unsigned cs = sp.x0 / 2u;
+                const unsigned c_lo = cs >= 16u ? cs - 16u : 0u;
+                const unsigned c_hi = min(img.c[1].stride, cs + K2T_STRIP / 2u + 16u);
+                prod_state.y = p.planes + img.c[0].plane_off + sp.x0;
+                prod_state.cb = p.planes + img.c[1].plane_off + c_lo;
+                prod_state.cr = p.planes + img.c[2].plane_off + c_lo;
+                prod_state.sy = img.c[0].stride;
+                prod_state.sc = img.c[1].stride;
+                prod_state.H = img.height;
+                prod_state.in_h = img.c[1].in_h;
+                prod_state.ybytes = (wpx + 15u) & ~15u;
+                prod_state.cbytes = c_hi - c_lo;
+                prod_state.cdst = c_lo + 16u - cs;
+                p_npairs = sp.npairs;
+                p_new = false;
+            }
+            const unsigned pr = p_pair, ybytes = prod_state.ybytes, cbytes = prod_state.cbytes, sc = prod_state.sc;
+            const bool need_a = pr > 0 && j == 0;  // first tile of this CTA: chroma row p-1 is not in the ring
+            const bool has_even = 2u * pr < prod_state.H;
+            const unsigned slot = smem + slot_index * K2T_STAGE_BYTES;
+            const unsigned bar = smem_u32(&full_bar[slot_index]);
+            mbar_expect_tx(bar, (need_a ? 4u : 2u) * cbytes + (pr > 0 ? ybytes : 0u) + (has_even ? ybytes : 0u));
+            const uint8_t* yp = prod_state.y + (size_t)(2u * pr) * prod_state.sy;
+            if (pr > 0) bulk_load_1d(slot + K2T_OFF_Y0, yp - prod_state.sy, ybytes, bar);
+            if (has_even) bulk_load_1d(slot + K2T_OFF_Y1, yp, ybytes, bar);
+            const size_t rb = (size_t)min(pr, prod_state.in_h - 1u) * sc;
+            const unsigned cdst = slot + prod_state.cdst;
+            bulk_load_1d(cdst + K2T_OFF_BB, prod_state.cb + rb, cbytes, bar);
+            bulk_load_1d(cdst + K2T_OFF_RB, prod_state.cr + rb, cbytes, bar);
+            if (need_a) {
+                const size_t ra = (size_t)(pr - 1u) * sc;
+                bulk_load_1d(cdst + K2T_OFF_BA, prod_state.cb + ra, cbytes, bar);
+                bulk_load_1d(cdst + K2T_OFF_RA, prod_state.cr + ra, cbytes, bar);
+            }
+            if (++p_pair == p_npairs) {
+                p_pair = 0;
+                p_strip++;
+                p_new = true;
+            }
+            if (++slot_index == K2T_STAGES) {
+                slot_index = 0;
+                if (j >= K2T_STAGES) e_phase ^= 1u;
+            }
         }
-        if (++prod.pair == prod.npairs) {
-            prod.pair = 0;
-            if (++prod.strip < nstrips) prod.npairs = __ldg(&strips[prod.strip].npairs);
-        }
-    };
-    if (tid == 0)
-        for (unsigned j = 0; j < K2T_STAGES && j < n; j++) issue(j);
+        return;
+    }
 
+    // ---- consumers (warps 0-3): cursor + per-strip constants of this thread, refreshed only on a strip change ----
+    unsigned c_strip = lo, c_pair = first_pair, c_npairs = 0, c_H = 0, c_row_bytes = 0, c_npx = 0, c_oL = 0, c_oR = 0;
+    uint8_t* c_out = nullptr;
+    bool c_new = true;
+    const unsigned oM = 16u + tid * 8u;
     const YccRegs ycc = make_ycc_regs(p.sixteen, true);
+    unsigned stage = 0, phase = 0;  // slot / parity of the tile being consumed
     for (unsigned it = 0; it < n; it++) {
-        const unsigned stage = it % K2T_STAGES, round = it / K2T_STAGES;
-        // refill: slot (it-2) was released at the end of iteration it-1 (one iteration late, see below)
-        if (tid == 0 && it >= 2 && it - 2 + K2T_STAGES < n) {
-            const unsigned ps = (it - 2) % K2T_STAGES;
-            mbar_wait(smem_u32(&empty_bar[ps]), ((it - 2) / K2T_STAGES) & 1);
-            issue(it - 2 + K2T_STAGES);
+        if (c_new) {
+            const K2Strip sp = strips[c_strip];
+            const DevImage& img = p.images[sp.image];
+            const unsigned W = img.width, wpx = min(K2T_STRIP, W - sp.x0);
+            const unsigned cs = sp.x0 / 2u, gi = cs + tid * 8u;  // global index of this thread's first chroma sample
+            c_H = img.height;
+            c_row_bytes = W * 3u;
+            c_npx = tid * 16u < wpx ? min(16u, wpx - tid * 16u) : 0u;
+            c_oL = gi > 0 ? oM - 1u : oM;                                   // clamped halo samples, as buffer offsets
+            c_oR = 16u + (min(gi + 8u, img.c[1].in_w - 1u) - cs);
+            c_out = p.out + img.out_off + ((size_t)sp.x0 + tid * 16u) * 3u;
+            c_npairs = sp.npairs;
+            c_new = false;
         }
-        const K2Strip sp = strips[cons.strip];
-        const DevImage& img = p.images[sp.image];
-        const unsigned pr = cons.pair, H = img.height, W = img.width;
-        const unsigned wpx = min(K2T_STRIP, W - sp.x0);
-        const bool active = tid * 16u < wpx;
+        const unsigned pr = c_pair;
         const unsigned slot = smem + stage * K2T_STAGE_BYTES;
         // chroma row A (= max(p-1,0)): row B of this slot when p == 0, this slot's A buffers for the CTA's first tile,
         // otherwise row B of the previous pair, which still sits in the previous slot
-        const unsigned prev = smem + ((it + K2T_STAGES - 1u) % K2T_STAGES) * K2T_STAGE_BYTES;
+        const unsigned prev_stage = stage == 0 ? K2T_STAGES - 1u : stage - 1u;
+        const unsigned prev = smem + prev_stage * K2T_STAGE_BYTES;
         const unsigned a_b = pr == 0 ? slot + K2T_OFF_BB : (it == 0 ? slot + K2T_OFF_BA : prev + K2T_OFF_BB);
-        const unsigned a_r = pr == 0 ? slot + K2T_OFF_RB : (it == 0 ? slot + K2T_OFF_RA : prev + K2T_OFF_RB);
-        mbar_wait(smem_u32(&full_bar[stage]), round & 1);
-        if (active) {
-            const unsigned cs = sp.x0 / 2u, in_w = img.c[1].in_w;
-            const unsigned li = tid * 8u, gi = cs + li;                          // local / global chroma sample index
-            const unsigned oL = 16u + (gi > 0 ? li - 1u : li);                    // buffer offsets of the clamped halo samples
-            const unsigned oR = 16u + (min(gi + 8u, in_w - 1u) - cs);
-            const unsigned oM = 16u + li;
+        const unsigned a_r = a_b + K2T_CROW;
+        mbar_wait(smem_u32(&full_bar[stage]), phase);
+        if (c_npx) {
             Chroma16 cb, cr;
             {
                 const uint2 av = lds64(a_b + oM), bv = lds64(slot + K2T_OFF_BB + oM);
-                h2v2_16(av.x, av.y, lds8(a_b + oL), lds8(a_b + oR), bv.x, bv.y, lds8(slot + K2T_OFF_BB + oL), lds8(slot + K2T_OFF_BB + oR), cb);
+                h2v2_16(av.x, av.y, lds8(a_b + c_oL), lds8(a_b + c_oR), bv.x, bv.y, lds8(slot + K2T_OFF_BB + c_oL), lds8(slot + K2T_OFF_BB + c_oR), cb);
             }
             {
                 const uint2 av = lds64(a_r + oM), bv = lds64(slot + K2T_OFF_RB + oM);
-                h2v2_16(av.x, av.y, lds8(a_r + oL), lds8(a_r + oR), bv.x, bv.y, lds8(slot + K2T_OFF_RB + oL), lds8(slot + K2T_OFF_RB + oR), cr);
+                h2v2_16(av.x, av.y, lds8(a_r + c_oL), lds8(a_r + c_oR), bv.x, bv.y, lds8(slot + K2T_OFF_RB + c_oL), lds8(slot + K2T_OFF_RB + c_oR), cr);
             }
-            const unsigned npx = min(16u, wpx - tid * 16u);
-            uint8_t* out = p.out + img.out_off + ((size_t)sp.x0 + tid * 16u) * 3u;
-            if (pr > 0) ycbcr_store16(lds128(slot + K2T_OFF_Y0 + tid * 16u), cb.odd, cr.odd, out + (size_t)(2u * pr - 1u) * W * 3u, ycc, npx);
-            if (2u * pr < H) ycbcr_store16(lds128(slot + K2T_OFF_Y1 + tid * 16u), cb.even, cr.even, out + (size_t)(2u * pr) * W * 3u, ycc, npx);
+            uint8_t* row = c_out + (size_t)(2u * pr) * c_row_bytes;
+            if (pr > 0) ycbcr_store16(lds128(slot + K2T_OFF_Y0 + tid * 16u), cb.odd, cr.odd, row - c_row_bytes, ycc, c_npx);
+            if (2u * pr < c_H) ycbcr_store16(lds128(slot + K2T_OFF_Y1 + tid * 16u), cb.even, cr.even, row, ycc, c_npx);
         }
         // release the PREVIOUS slot: its chroma rows were this iteration's row A
         __syncwarp();
-        if (lane == 0 && it > 0) mbar_arrive(smem_u32(&empty_bar[(it - 1) % K2T_STAGES]));
-        if (++cons.pair == cons.npairs) {
-            cons.pair = 0;
-            if (++cons.strip < nstrips) cons.npairs = __ldg(&strips[cons.strip].npairs);
+        if (lane == 0 && it > 0) mbar_arrive(smem_u32(&empty_bar[prev_stage]));
+        if (++stage == K2T_STAGES) { stage = 0; phase ^= 1u; }
+        if (++c_pair == c_npairs) {
+            c_pair = 0;
+            c_strip++;
+            c_new = true;
         }
     }
 }
@@ -592,7 +624,7 @@ cudaError_t launch_k2_420_tma(const K2Params& p, const K2Strip* strips, unsigned
     }
     unsigned grid = (unsigned)num_sms * 4u;
     if (grid > total_items) grid = total_items;
-    k2_ycbcr420_tma<<<grid, 128, smem_bytes, stream>>>(p, strips, nstrips, item_base, total_items);
+    k2_ycbcr420_tma<<<grid, K2T_THREADS, smem_bytes, stream>>>(p, strips, nstrips, item_base, total_items);
     return cudaGetLastError();
 }
 cudaError_t launch_k2_444(const K2Params& p, unsigned first, unsigned count, unsigned max_w, unsigned max_h,

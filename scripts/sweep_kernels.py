@@ -24,7 +24,7 @@ for i in range(B):
     u = uniq[i % len(uniq)]
     descs.append(J.make_image_desc(u.width, u.height, u.components, u.qts, u.coefs, u.color_transform, keep))
 ref_sum = None
-for kernels in ("auto", "generic"):
+for kernels in (("auto",) if os.environ.get("SWEEP_ONLY_AUTO") else ("auto", "generic")):
     k = J.KERNEL_AUTO if kernels == "auto" else J.KERNEL_GENERIC
     ctx = J.Context(device=0, k1_kernel=k, k2_kernel=k, stream=stream.cuda_stream)
     batch = J.Batch(ctx, descs)
@@ -52,6 +52,8 @@ for kernels in ("auto", "generic"):
         return e0.elapsed_time(e1) / steps
 
     modes = [(5, 0), (5, 1), (5, 4), (0, 0)] if kernels == "auto" else [(-1, -1)]
+    if os.environ.get("SWEEP_ONLY_AUTO"):
+        modes = [(-1, -1)]  # whatever B200JPG_K1_MODE / B200JPG_K2_MODE say (profiling runs)
     for k1m, k2m in modes:
         J.lib().b200jpg_debug_set_kernel_modes(k1m, k2m)
         d_planes.zero_()
