@@ -242,6 +242,37 @@ B200JPG_API int b200jpg_decoder_xmp_data(const b200jpg_decoder *d, const uint8_t
 B200JPG_API int b200jpg_decoder_entropy_decode(b200jpg_decoder *d, b200jpg_image_desc *desc);
 
 /* ============================================================================================
+ * Sparse block streams ("sparse coefficient wire format").  The dense Vec<i16> the
+ * reference pushes through Worker::append_row (src/worker/mod.rs:26, src/decoder.rs:962-983) is 128 B per
+ * block of mostly zeros; a stream carries, per block, a 63-bit map of the non-zero AC coefficients (zig-zag
+ * order), the DC coefficient, and the non-zero values as int8 / int16 -- what Huffman decoding produced
+ * (csrc/sbs.h has the byte layout).  Kernel K0 rebuilds the dense slab on the device, bit for bit.
+ * ========================================================================================== */
+enum { B200JPG_SBS_PLANAR = 0, B200JPG_SBS_INTERLEAVED = 1 }; /* block order inside a stream */
+typedef struct {
+    const uint8_t *data; /* host memory, ideally page-locked */
+    size_t len;
+    int order;           /* B200JPG_SBS_* */
+} b200jpg_sbs_stream;
+/* upper bound of the stream length of an image with `nblocks` 8x8 blocks over all components */
+B200JPG_API size_t b200jpg_sbs_worst_bytes(size_t nblocks);
+/* number of 8x8 blocks over all components (sum of block_w*block_h); reads the headers if necessary */
+B200JPG_API int b200jpg_decoder_total_blocks(b200jpg_decoder *d, size_t *nblocks);
+/* Like b200jpg_decoder_entropy_decode, but the coefficients are written as a sparse stream into buf (cap >=
+ * b200jpg_sbs_worst_bytes); desc->coefs stay NULL.  Host only. */
+B200JPG_API int b200jpg_decoder_entropy_decode_sbs(b200jpg_decoder *d, uint8_t *buf, size_t cap,
+                                                   b200jpg_image_desc *desc, b200jpg_sbs_stream *stream);
+/* b200jpg_decode_batch with the coefficients given as streams: H2D -> K0 expand -> K1 -> K2 -> D2H,
+ * pipelined over three CUDA streams in groups of 32 images.  Streams are validated before use. */
+B200JPG_API int b200jpg_decode_batch_sbs(b200jpg_ctx *ctx, const b200jpg_image_desc *imgs,
+                                         const b200jpg_sbs_stream *streams, size_t n, uint8_t *const *outs,
+                                         const size_t *out_caps, int *statuses);
+/* test hook: runs one image through the stream path and copies the dense slab K0 produced back to the host
+ * (dense_out[c]: block_w*block_h*64 int16 of component c, or NULL to skip) */
+B200JPG_API int b200jpg_debug_expand_sbs(b200jpg_ctx *ctx, const b200jpg_image_desc *img,
+                                         const b200jpg_sbs_stream *stream, int16_t *const dense_out[4]);
+
+/* ============================================================================================
  * Whole-file batches: what an outer par_iter over Decoder::decode() gives a
  * user of the reference, with the host threads doing only marker parsing + Huffman decoding
  * (src/parser.rs, src/huffman.rs, src/decoder.rs:794-1298) and the worker path on the GPU.

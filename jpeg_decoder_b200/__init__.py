@@ -19,10 +19,12 @@ import numpy as np
 from ._native import (ARITH_SCALAR, ARITH_SSSE3, CP_DCT_PROGRESSIVE, CP_DCT_SEQUENTIAL, CP_LOSSLESS, CT_CMYK,
                       CT_GRAYSCALE, CT_JCS_BG_RGB, CT_JCS_BG_YCC, CT_NONE, CT_RGB, CT_UNKNOWN, CT_YCBCR, CT_YCCK,
                       ERR_FORMAT, ERR_INTERNAL, ERR_IO, ERR_UNSUPPORTED, KERNEL_AUTO, KERNEL_FAST, KERNEL_GENERIC, OK,
-                      PF_CMYK32, PF_L8, PF_L16, PF_RGB24, BatchInfo, Component, FileJob, ImageDesc, ImageInfo, Options, lib)
+                      PF_CMYK32, PF_L8, PF_L16, PF_RGB24, SBS_INTERLEAVED, SBS_PLANAR, BatchInfo, Component, FileJob, ImageDesc,
+                      ImageInfo, Options, SbsStream, lib)
 
 __all__ = ["Context", "Worker", "Batch", "Decoder", "B200JpgError", "FileJob", "make_components", "make_image_desc",
-           "compute_image", "decode_batch", "decode_files", "read_info_files", "Component", "ImageDesc"]
+           "compute_image", "decode_batch", "decode_batch_sbs", "expand_sbs", "decode_files", "read_info_files", "Component",
+           "ImageDesc", "SbsStream"]
 
 
 class B200JpgError(Exception):
@@ -222,6 +224,33 @@ def decode_batch(ctx, descs):
     return outs, list(st)
 
 
+def decode_batch_sbs(ctx, descs, streams):
+    """b200jpg_decode_batch_sbs: coefficients as sparse block streams [(uint8 array, order)] -> (pixels, statuses)."""
+    n = len(descs)
+    arr = (ImageDesc * n)(*descs)
+    ss = (SbsStream * n)()
+    for s, (buf, order) in zip(ss, streams):
+        s.data, s.len, s.order = buf.ctypes.data, buf.size, order
+    outs = [np.zeros(int(d.width) * int(d.height) * int(d.ncomp), dtype=np.uint8) for d in descs]
+    op = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
+    caps = (C.c_size_t * n)(*[o.size for o in outs])
+    st = (C.c_int * n)()
+    rc = lib().b200jpg_decode_batch_sbs(ctx._h, arr, ss, n, op, caps, st)
+    if rc and all(s == 0 for s in st):
+        ctx.check(rc)
+    return outs, list(st)
+
+
+def expand_sbs(ctx, desc, buf, order):
+    """b200jpg_debug_expand_sbs: the dense coefficient arrays kernel K0 rebuilds from one stream."""
+    s = SbsStream()
+    s.data, s.len, s.order = buf.ctypes.data, buf.size, order
+    dense = [np.zeros(int(desc.comps[c].block_w) * int(desc.comps[c].block_h) * 64, dtype=np.int16) for c in range(desc.ncomp)]
+    ptrs = (C.c_void_p * 4)(*([d.ctypes.data for d in dense] + [None] * (4 - len(dense))))
+    ctx.check(lib().b200jpg_debug_expand_sbs(ctx._h, C.byref(desc), C.byref(s), ptrs))
+    return dense
+
+
 def read_info_files(files, nthreads=0):
     """b200jpg_read_info_files: [(status, ImageInfo, out_len)] for a list of bytes objects."""
     n = len(files)
@@ -302,6 +331,15 @@ class Decoder:
         d = ImageDesc()
         self._check(lib().b200jpg_decoder_entropy_decode(self._h, C.byref(d)))
         return d
+
+    def entropy_decode_sbs(self):
+        """Host half only, coefficients as a sparse block stream: (ImageDesc, uint8 stream, order)."""
+        nb = C.c_size_t()
+        self._check(lib().b200jpg_decoder_total_blocks(self._h, C.byref(nb)))
+        buf = np.zeros(lib().b200jpg_sbs_worst_bytes(nb.value), dtype=np.uint8)
+        d, s = ImageDesc(), SbsStream()
+        self._check(lib().b200jpg_decoder_entropy_decode_sbs(self._h, buf.ctypes.data, buf.size, C.byref(d), C.byref(s)))
+        return d, buf[:s.len], s.order
 
     def coefficients(self, desc, i):
         c = desc.comps[i]

@@ -48,6 +48,13 @@ class FileJob(C.Structure):
                 ("info", ImageInfo), ("out_len", C.c_size_t), ("status", C.c_int)]
 
 
+class SbsStream(C.Structure):
+    """b200jpg_sbs_stream: one image's sparse block stream (csrc/sbs.h)"""
+    _fields_ = [("data", C.c_void_p), ("len", C.c_size_t), ("order", C.c_int)]
+
+
+SBS_PLANAR, SBS_INTERLEAVED = 0, 1
+
 # every symbol include/b200jpg.h declares (tests/test_abi.py checks the two lists agree)
 EXPORTS = {
     "b200jpg_default_options": (None, [C.POINTER(Options)]),
@@ -97,6 +104,12 @@ EXPORTS = {
     "b200jpg_decoder_exif_data": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "b200jpg_decoder_xmp_data": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "b200jpg_decoder_entropy_decode": (C.c_int, [C.c_void_p, C.POINTER(ImageDesc)]),
+    "b200jpg_sbs_worst_bytes": (C.c_size_t, [C.c_size_t]),
+    "b200jpg_decoder_total_blocks": (C.c_int, [C.c_void_p, C.POINTER(C.c_size_t)]),
+    "b200jpg_decoder_entropy_decode_sbs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(ImageDesc), C.POINTER(SbsStream)]),
+    "b200jpg_decode_batch_sbs": (C.c_int, [C.c_void_p, C.POINTER(ImageDesc), C.POINTER(SbsStream), C.c_size_t,
+                                           C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_int)]),
+    "b200jpg_debug_expand_sbs": (C.c_int, [C.c_void_p, C.POINTER(ImageDesc), C.POINTER(SbsStream), C.POINTER(C.c_void_p)]),
     "b200jpg_read_info_files": (C.c_int, [C.POINTER(FileJob), C.c_size_t, C.c_int]),
     "b200jpg_decode_files": (C.c_int, [C.c_void_p, C.POINTER(FileJob), C.c_size_t, C.c_int]),
 }

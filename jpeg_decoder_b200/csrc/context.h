@@ -32,6 +32,11 @@ struct b200jpg_ctx {
     std::mutex mu;
     Buf scratch[3];  // device: coefficient, plane and pixel slabs of the host pipeline
     bool scratch_busy = false;
-    Buf pinned[3];   // host: page-locked coefficient arenas of b200jpg_decode_files
+    // the sparse-stream pipeline and the whole-file engine built on it (sbs_pipeline.h, files_api.cpp), created on
+    // first use and destroyed with the context
+    void* sbs_pipeline = nullptr;
+    void (*sbs_pipeline_free)(void*) = nullptr;
+    void* files_engine = nullptr;
+    void (*files_engine_free)(void*) = nullptr;
 };
 

@@ -86,6 +86,42 @@ int b200jpg_decoder_entropy_decode(b200jpg_decoder* d, b200jpg_image_desc* desc)
     }
     return fill_desc(d, desc);
 }
+int b200jpg_decoder_total_blocks(b200jpg_decoder* d, size_t* nblocks) {
+    if (!d || !nblocks) return B200JPG_ERR_INTERNAL;
+    const int rc = d->host.read_info();
+    if (rc) {
+        d->err = d->host.error();
+        return rc;
+    }
+    *nblocks = d->host.total_blocks();
+    return B200JPG_OK;
+}
+int b200jpg_decoder_entropy_decode_sbs(b200jpg_decoder* d, uint8_t* buf, size_t cap, b200jpg_image_desc* desc,
+                                       b200jpg_sbs_stream* stream) {
+    if (!d || !buf || !desc || !stream) return B200JPG_ERR_INTERNAL;
+    int rc = d->host.read_info();
+    if (rc) {
+        d->err = d->host.error();
+        return rc;
+    }
+    if (cap < b200jpg_sbs_worst_bytes(d->host.total_blocks())) {
+        d->err = "internal: sparse block stream buffer is smaller than b200jpg_sbs_worst_bytes()";
+        return B200JPG_ERR_INTERNAL;
+    }
+    d->host.set_sbs_sink(buf);
+    rc = d->host.entropy_decode();
+    if (rc) {
+        d->err = d->host.error();
+        return rc;
+    }
+    rc = fill_desc(d, desc);
+    if (rc) return rc;
+    for (int i = 0; i < 4; i++) desc->coefs[i] = nullptr;  // the coefficients are in the stream
+    stream->data = buf;
+    stream->len = d->host.sbs_length();
+    stream->order = (int)d->host.sbs_order();
+    return B200JPG_OK;
+}
 int b200jpg_decoder_decode(b200jpg_decoder* d, const uint8_t** pixels, size_t* len) {
     if (!d || !pixels || !len) return B200JPG_ERR_INTERNAL;
     b200jpg_image_desc desc;

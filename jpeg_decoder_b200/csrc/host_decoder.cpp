@@ -624,10 +624,37 @@ int HostDecoder::decode_block(int16_t* c, const HuffTable& dc, const HuffTable& 
     return 0;
 }
 
+// Where decode_block_seq puts what it decodes: the dense block of the reference (natural order,
+// src/decoder.rs:1137-1172) or one block of the sparse stream (zig-zag order, sbs.h).
+namespace {
+struct DenseSink {
+    int16_t* c;
+    inline void dc(int16_t v) { c[0] = v; }
+    inline void ac(unsigned k, int16_t v) { c[UNZIGZAG[k]] = v; }
+    inline void done() {}
+};
+struct SbsSink {
+    SbsWriter* w;
+    uint64_t bits = 0;
+    unsigned n = 0, acc = 0;
+    int16_t dcv = 0;
+    alignas(16) int16_t v[64 + 16];
+    explicit SbsSink(SbsWriter* wr) : w(wr) {}
+    inline void dc(int16_t x) { dcv = x; }
+    inline void ac(unsigned k, int16_t x) {
+        v[n++] = x;
+        bits |= (uint64_t)1 << k;
+        acc |= (unsigned)(x + 128);  // > 255 as soon as one value is outside int8
+    }
+    inline void done() { w->put(bits, dcv, v, n, acc > 255u); }
+};
+}  // namespace
+
 // decode_block for sequential scans (ss = 0..63, al = 0), the hot loop of every baseline JPEG: identical
 // decisions and refill thresholds (16 bits before a code, 8 before the fast-AC probe, `count` before
 // receive_extend -- src/huffman.rs:31-96), with the bit buffer kept in locals.
-int HostDecoder::decode_block_seq(int16_t* c, const HuffTable& dc, const HuffTable& ac, uint16_t* eob_run, int16_t* pred) {
+template <class Sink>
+int HostDecoder::decode_block_seq(Sink& sink, const HuffTable& dc, const HuffTable& ac, uint16_t* eob_run, int16_t* pred) {
     uint64_t bits = bits_;
     unsigned nb = num_bits_;
 #define SEQ_REFILL()                   \
@@ -668,12 +695,13 @@ int HostDecoder::decode_block_seq(int16_t* c, const HuffTable& dc, const HuffTab
             diff = extend(u, value);
         }
         *pred = (int16_t)((uint16_t)*pred + (uint16_t)diff);
-        c[0] = *pred;
+        sink.dc(*pred);
     }
     if (*eob_run > 0) {
         *eob_run -= 1;
         bits_ = bits;
         num_bits_ = (uint8_t)nb;
+        sink.done();
         return 0;
     }
     unsigned index = 1;
@@ -686,7 +714,7 @@ int HostDecoder::decode_block_seq(int16_t* c, const HuffTable& dc, const HuffTab
             nb -= (rs & 0x0f);
             index += rs >> 4;
             if (index >= 64) break;
-            c[UNZIGZAG[index]] = ac.ac_value[idx];
+            sink.ac(index, ac.ac_value[idx]);
             index++;
             continue;
         }
@@ -722,12 +750,13 @@ int HostDecoder::decode_block_seq(int16_t* c, const HuffTable& dc, const HuffTab
             const uint16_t u = (uint16_t)(bits >> (64 - sz));
             bits <<= sz;
             nb -= sz;
-            c[UNZIGZAG[index]] = extend(u, (uint8_t)sz);
+            sink.ac(index, extend(u, (uint8_t)sz));
             index++;
         }
     }
     bits_ = bits;
     num_bits_ = (uint8_t)nb;
+    sink.done();
     return 0;
 #undef SEQ_REFILL
 #undef SEQ_SLOW_CODE
@@ -821,6 +850,12 @@ int HostDecoder::decode_scan(const ScanInfo& scan, const bool finished[4], bool*
     const bool is_progressive = frame.coding_process == B200JPG_CP_DCT_PROGRESSIVE;
     const bool is_interleaved = nc > 1;
     const bool sequential = scan.ss_start == 0 && scan.ss_end == 64 && scan.al == 0 && scan.ah == 0;
+    // Sparse stream straight from the Huffman loop: only when this one scan delivers every block of every
+    // component, in an order K0 can map back to raster positions (interleaved MCUs, or a lone 1x1 component).
+    bool direct = sbs_base_ != nullptr && sequential && !is_progressive && !sbs_direct_ && nc == (int)frame.comps.size() &&
+                  (is_interleaved || (comps[0].h == 1 && comps[0].v == 1));
+    for (int i = 0; i < nc; i++) direct = direct && finished[i] && scan.comp_index[i] == i;
+    if (direct) sbs_.begin(sbs_base_, total_blocks());
     // where each scan component's blocks go: the progressive store, the final buffer (worker::start
     // zero-fills, src/decoder.rs:848-861, 874-880), or a dummy block
     int16_t* target[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -832,6 +867,8 @@ int HostDecoder::decode_scan(const ScanInfo& scan, const bool finished[4], bool*
         if (finished[i]) memcpy(final_qt_[ci], qt_[comps[i].tq], 128);  // RowData.quantization_table
         if (is_progressive) {
             target[i] = work_[ci].data();
+        } else if (finished[i] && direct) {
+            have_final_[ci] = false;
         } else if (finished[i]) {
             have_final_[ci] = false;
             // An interleaved scan visits every block of the component exactly once, so each block is zeroed right
@@ -896,6 +933,11 @@ int HostDecoder::decode_scan(const ScanInfo& scan, const bool finished[4], bool*
                 const b200jpg_component& comp = comps[i];
                 for (uint32_t v_pos = 0; v_pos < mv[i]; v_pos++)
                     for (uint32_t h_pos = 0; h_pos < mh[i]; h_pos++) {
+                        if (direct) {
+                            SbsSink sink(&sbs_);
+                            TRY(decode_block_seq(sink, dc_[scan.dc_table[i]], ac_[scan.ac_table[i]], &eob_run, &dc_predictors[i]));
+                            continue;
+                        }
                         int16_t* c;
                         if (target[i]) {
                             const size_t block_y = (size_t)mcu_y * mv[i] + v_pos, block_x = (size_t)mcu_x * mh[i] + h_pos;
@@ -905,9 +947,10 @@ int HostDecoder::decode_scan(const ScanInfo& scan, const bool finished[4], bool*
                             c = dummy;
                             if (scan.ah == 0) memset(dummy, 0, sizeof dummy);
                         }
-                        if (sequential)
-                            TRY(decode_block_seq(c, dc_[scan.dc_table[i]], ac_[scan.ac_table[i]], &eob_run, &dc_predictors[i]));
-                        else if (scan.ah == 0)
+                        if (sequential) {
+                            DenseSink sink{c};
+                            TRY(decode_block_seq(sink, dc_[scan.dc_table[i]], ac_[scan.ac_table[i]], &eob_run, &dc_predictors[i]));
+                        } else if (scan.ah == 0)
                             TRY(decode_block(c, dc_[scan.dc_table[i]], ac_[scan.ac_table[i]], scan, &eob_run, &dc_predictors[i]));
                         else
                             TRY(decode_block_sa(c, ac_[scan.ac_table[i]], scan, &eob_run));
@@ -937,6 +980,26 @@ int HostDecoder::decode_scan(const ScanInfo& scan, const bool finished[4], bool*
             }
             have_final_[ci] = true;
         }
+    if (direct) sbs_direct_ = true;
+    return 0;
+}
+
+// Ends the sparse stream: a directly written one is padded; otherwise the dense per-component buffers the
+// scans produced are compacted in planar order (the reference's worker would receive exactly these blocks).
+int HostDecoder::finish_sbs() {
+    sbs_len_ = 0;
+    if (!sbs_base_) return 0;
+    for (size_t i = 0; i < frame_.comps.size(); i++)
+        if (!have_final_[i]) return 0;  // "not all components have data": reported by the caller
+    if (!sbs_direct_) {
+        sbs_.begin(sbs_base_, total_blocks());
+        for (size_t i = 0; i < frame_.comps.size(); i++) {
+            const size_t n = (size_t)frame_.comps[i].block_w * frame_.comps[i].block_h;
+            const int16_t* c = coefficients((int)i);
+            for (size_t b = 0; b < n; b++) sbs_.put_dense(c + 64 * b);
+        }
+    }
+    sbs_len_ = sbs_.finish();
     return 0;
 }
 
@@ -1041,7 +1104,7 @@ int HostDecoder::decode_internal(bool stop_after_metadata) {
             else final_[i] = work_[i];
             have_final_[i] = true;
         }
-    return 0;
+    return finish_sbs();
 }
 
 bool HostDecoder::buffer_limit_exceeded() const {

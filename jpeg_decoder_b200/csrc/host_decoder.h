@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "../../include/b200jpg.h"
+#include "sbs.h"
 
 namespace b200jpg {
 
@@ -73,6 +74,18 @@ public:
     // Optional: caller-owned destination (e.g. page-locked memory) for component i's final coefficients,
     // block_w*block_h*64 int16; must be set after read_info() and before entropy_decode().
     void set_external_buffer(int i, int16_t* p) { if (i >= 0 && i < 4) ext_[i] = p; }
+    // Optional: sparse block stream destination (sbs.h) of at least SbsLayout::make(total blocks).worst_bytes()
+    // bytes; must be set after read_info() and before entropy_decode().  A single-scan sequential image is
+    // written straight from the Huffman loop in scan order; anything else (progressive, several scans) is decoded
+    // densely as usual and compacted at the end, component by component.
+    void set_sbs_sink(uint8_t* base) { sbs_base_ = base; }
+    size_t sbs_length() const { return sbs_len_; }    // valid after a successful entropy_decode()
+    unsigned sbs_order() const { return sbs_direct_ ? SBS_INTERLEAVED : SBS_PLANAR; }
+    size_t total_blocks() const {
+        size_t n = 0;
+        for (const auto& c : frame_.comps) n += (size_t)c.block_w * c.block_h;
+        return n;
+    }
     // quantisation table captured when the component was handed to the worker (RowData, src/decoder.rs:850-857)
     const uint16_t* component_qtable(int i) const { return final_qt_[i]; }
     bool buffer_limit_exceeded() const;
@@ -106,7 +119,9 @@ private:
     int huff_decode(const HuffTable& t, uint8_t* out);
     int take_marker(bool* has, uint8_t* m);
     int decode_block(int16_t* c, const HuffTable& dc, const HuffTable& ac, const ScanInfo& s, uint16_t* eob_run, int16_t* pred);
-    int decode_block_seq(int16_t* c, const HuffTable& dc, const HuffTable& ac, uint16_t* eob_run, int16_t* pred);
+    template <class Sink>
+    int decode_block_seq(Sink& sink, const HuffTable& dc, const HuffTable& ac, uint16_t* eob_run, int16_t* pred);
+    int finish_sbs();
     int decode_block_sa(int16_t* c, const HuffTable& ac, const ScanInfo& s, uint16_t* eob_run);
     int refine_non_zeroes(int16_t* c, uint8_t start, uint8_t end, uint8_t zrl, int16_t bit, uint8_t* ret);
 
@@ -135,6 +150,11 @@ private:
     int16_t* ext_[4] = {nullptr, nullptr, nullptr, nullptr};
     bool have_final_[4] = {false, false, false, false};
     uint16_t final_qt_[4][64];
+    // sparse block stream output
+    uint8_t* sbs_base_ = nullptr;
+    SbsWriter sbs_;
+    bool sbs_direct_ = false;
+    size_t sbs_len_ = 0;
     // bit reader (src/huffman.rs:14-18)
     uint64_t bits_ = 0;
     uint8_t num_bits_ = 0;

@@ -1,0 +1,112 @@
+// k0_expand.cu -- K0: sparse block stream -> dense coefficient slab (sm_100a).
+//
+// The reference hands the worker one dense Vec<i16> per MCU row (Worker::append_row,
+// src/worker/mod.rs:26, filled at src/decoder.rs:962-983).  Over PCIe that is 128 B per block of mostly
+// zeros, so the host ships the stream of sbs.h instead and this kernel rebuilds, in HBM, exactly the dense
+// raster-order slab K1 consumes (device_types.h): same bytes as if the dense buffers had been uploaded.
+//
+// One warp = one group of 32 scan-order blocks.  Lane l owns block 32g+l for the bookkeeping (bitmap, byte
+// count, warp scan for its value offset, destination row); the expansion itself is cooperative: for every
+// block of the group lane l produces zig-zag positions l and l+32 (rank of the position among the bitmap's
+// set bits = index of its value), so value bytes are read by neighbouring lanes and every one of the 64
+// natural-order slots is written exactly once (no zero fill).  A 4 KB shared-memory tile per warp turns the
+// scatter into 16-byte row stores: 128 contiguous bytes per block, blocks of a group are (nearly) adjacent.
+//
+// Roofline: HBM write of the slab (128 B / block) + stream read (~25 B / block); it runs only on the
+// host-fed paths, which are PCIe / host bound by two orders of magnitude.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.h"
+#include "sbs.h"
+
+namespace b200jpg {
+
+__constant__ unsigned char c_unzigzag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,
+                                             12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6,  7,  14, 21, 28,
+                                             35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51,
+                                             58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+
+constexpr int K0_WARPS = 8;
+
+__global__ void __launch_bounds__(K0_WARPS * 32) k0_expand(const K0Image* __restrict__ images, const uint8_t* __restrict__ streams,
+                                                           short* __restrict__ slab) {
+    __shared__ __align__(16) short tile[K0_WARPS][32][64];
+    const K0Image& im = images[blockIdx.y];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const unsigned g = blockIdx.x * K0_WARPS + warp;
+    const unsigned nb = im.nb;
+    if (g * 32u >= nb) return;
+    const unsigned nb_pad = (nb + 31u) & ~31u;
+    const uint8_t* s = streams + im.stream_off;
+    const unsigned t = g * 32u + lane;
+    const unsigned long long bm = ((const unsigned long long*)s)[t];
+    const int dcv = ((const short*)(s + 8ull * nb_pad))[t];
+    const unsigned base = ((const unsigned*)(s + 10ull * nb_pad))[g];
+    const uint8_t* vals = s + ((10ull * nb_pad + 4ull * (nb_pad / 32u + 1u) + 15ull) & ~15ull);
+
+    // byte offset of this lane's values: exclusive scan of the per-block byte counts
+    const unsigned bytes = (unsigned)__popcll(bm >> 1) << (unsigned)(bm & 1ull);
+    unsigned incl = bytes;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (unsigned)d) incl += o;
+    }
+    const unsigned off = base + incl - bytes;
+
+    // destination row of this lane's block inside the dense slab
+    unsigned row = 0xffffffffu;
+    if (t < nb) {
+        if (im.order == SBS_PLANAR) {
+            const unsigned c = (t >= im.first[1]) + (t >= im.first[2]) + (t >= im.first[3]);
+            row = im.slab_row[c] + (t - im.first[c]);
+        } else {
+            const unsigned mcu = t / im.bpm, j = t - mcu * im.bpm;
+            const unsigned c = im.mcu_comp[j];
+            const unsigned my = mcu / im.mcu_w, mx = mcu - my * im.mcu_w;
+            row = im.slab_row[c] + (my * im.v[c] + im.mcu_vy[j]) * im.block_w[c] + mx * im.h[c] + im.mcu_hx[j];
+        }
+    }
+
+    const unsigned p0 = c_unzigzag[lane], p1 = c_unzigzag[lane + 32u];
+    const unsigned long long below0 = ((1ull << lane) - 1ull) & ~1ull, below1 = ((1ull << (lane + 32u)) - 1ull) & ~1ull;
+#pragma unroll 4
+    for (int b = 0; b < 32; b++) {
+        const unsigned long long m = __shfl_sync(0xffffffffu, bm, b);
+        const unsigned o = __shfl_sync(0xffffffffu, off, b);
+        const int d = __shfl_sync(0xffffffffu, dcv, b);
+        const bool wide = (m & 1ull) != 0;
+        int v0 = 0, v1 = 0;
+        if (lane == 0) {
+            v0 = d;
+        } else if ((m >> lane) & 1ull) {
+            const unsigned r = (unsigned)__popcll(m & below0);
+            v0 = wide ? (int)(short)((unsigned)vals[o + 2u * r] | ((unsigned)vals[o + 2u * r + 1u] << 8)) : (int)(signed char)vals[o + r];
+        }
+        if ((m >> (lane + 32u)) & 1ull) {
+            const unsigned r = (unsigned)__popcll(m & below1);
+            v1 = wide ? (int)(short)((unsigned)vals[o + 2u * r] | ((unsigned)vals[o + 2u * r + 1u] << 8)) : (int)(signed char)vals[o + r];
+        }
+        tile[warp][b][p0] = (short)v0;
+        tile[warp][b][p1] = (short)v1;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const unsigned b = (unsigned)i * 4u + (lane >> 3), chunk = lane & 7u;
+        const unsigned r = __shfl_sync(0xffffffffu, row, (int)b);
+        if (r != 0xffffffffu) *(int4*)(slab + (size_t)r * 64u + chunk * 8u) = *(const int4*)&tile[warp][b][chunk * 8u];
+    }
+}
+
+cudaError_t launch_k0_expand(const K0Image* d_images, unsigned nimages, unsigned max_blocks, const uint8_t* d_streams, short* d_slab,
+                             cudaStream_t stream) {
+    if (nimages == 0 || max_blocks == 0) return cudaSuccess;
+    const unsigned groups = (max_blocks + 31u) / 32u;
+    dim3 grid((groups + K0_WARPS - 1) / K0_WARPS, nimages);
+    k0_expand<<<grid, K0_WARPS * 32, 0, stream>>>(d_images, d_streams, d_slab);
+    return cudaGetLastError();
+}
+
+}  // namespace b200jpg

@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include "device_types.h"
+#include "sbs.h"
 
 namespace b200jpg {
 
@@ -33,6 +34,9 @@ struct K1QCache {
     unsigned b[4][32];
 };
 
+// K0: sparse block streams -> dense coefficient slab; max_blocks = largest K0Image::nb of the launch
+cudaError_t launch_k0_expand(const K0Image* d_images, unsigned nimages, unsigned max_blocks, const uint8_t* d_streams, short* d_slab,
+                             cudaStream_t stream);
 cudaError_t launch_k1_generic(const K1Params& p, int arith, cudaStream_t stream);
 size_t k1_tma_smem_bytes();
 cudaError_t launch_k1_tma(const CUtensorMap& tmap, const K1QCache& qc, const K1Params& p, int num_sms, cudaStream_t stream);

@@ -18,29 +18,20 @@
 #include <string>
 #include <vector>
 
-#include "../../include/b200jpg.h"
-#include "device_types.h"
-#include "kernels.h"
-
-using namespace b200jpg;
+#include "batch_internal.h"
 
 // ---------------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------------
-#include "context.h"
-
-static int fail(b200jpg_ctx* ctx, int code, const std::string& msg) {
+int b200jpg_fail(b200jpg_ctx* ctx, int code, const std::string& msg) {
     if (ctx) ctx->err = msg;
     return code;
 }
-static int cuda_fail(b200jpg_ctx* ctx, cudaError_t e, const char* what) {
-    return fail(ctx, B200JPG_ERR_INTERNAL, std::string(what) + ": " + cudaGetErrorString(e));
+int b200jpg_cuda_fail(b200jpg_ctx* ctx, cudaError_t e, const char* what) {
+    return b200jpg_fail(ctx, B200JPG_ERR_INTERNAL, std::string(what) + ": " + cudaGetErrorString(e));
 }
-#define CU_TRY(ctx, call)                                            \
-    do {                                                             \
-        cudaError_t e_ = (call);                                     \
-        if (e_ != cudaSuccess) return cuda_fail((ctx), e_, #call);   \
-    } while (0)
+static inline int fail(b200jpg_ctx* ctx, int code, const std::string& msg) { return b200jpg_fail(ctx, code, msg); }
+static inline int cuda_fail(b200jpg_ctx* ctx, cudaError_t e, const char* what) { return b200jpg_cuda_fail(ctx, e, what); }
 
 extern "C" {
 
@@ -92,10 +83,11 @@ int b200jpg_create(const b200jpg_options* opt, b200jpg_ctx** out) {
 void b200jpg_destroy(b200jpg_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    if (ctx->files_engine && ctx->files_engine_free) ctx->files_engine_free(ctx->files_engine);
+    if (ctx->sbs_pipeline && ctx->sbs_pipeline_free) ctx->sbs_pipeline_free(ctx->sbs_pipeline);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     for (auto& sc : ctx->scratch) cudaFree(sc.p);
-    for (auto& pa : ctx->pinned) if (pa.p) cudaFreeHost(pa.p);
     delete ctx;
 }
 const char* b200jpg_last_error(const b200jpg_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
@@ -164,58 +156,6 @@ int b200jpg_choose_idct_size(uint16_t full_w, uint16_t full_h, uint16_t req_w, u
 // ---------------------------------------------------------------------------------------------
 // batch plan
 // ---------------------------------------------------------------------------------------------
-static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
-
-struct ImageLayout {
-    size_t coef_off[4] = {0, 0, 0, 0};
-    size_t plane_off[4] = {0, 0, 0, 0};
-    size_t coef_bytes[4] = {0, 0, 0, 0};
-    size_t out_off = 0, out_len = 0;
-    unsigned tile_first = 0, tile_count = 0;
-    int status = B200JPG_OK;
-};
-
-struct b200jpg_batch {
-    b200jpg_ctx* ctx = nullptr;
-    size_t n = 0;
-    std::vector<ImageLayout> layout;
-    std::vector<DevComp> comps;
-    std::vector<DevTile> tiles;
-    std::vector<DevImage> images;
-    std::vector<unsigned> qtabs;  // 64 per table
-    std::vector<unsigned> qpack;  // 32 per table (8-bit tables: {q[2j], 0, 0, q[2j+1]})
-    std::vector<unsigned char> qt_is8;
-    K1QCache qcache;
-    b200jpg_batch_info info{};
-    bool all_scale8 = true;
-    bool k1_tma_aligned = true;
-    unsigned path_max_w[K2_NPATHS] = {}, path_max_h[K2_NPATHS] = {};
-    bool path_used[K2_NPATHS] = {};
-    std::vector<K2Strip> strips;         // work list of the bulk-copy 4:2:0 kernel (images on K2_PATH_420T)
-    std::vector<unsigned> strip_first;   // per image: index of its first strip (n + 1 entries)
-    unsigned strip_items = 0;
-    K2Strip* d_strips = nullptr;
-    // device copies of the tables
-    DevComp* d_comps = nullptr;
-    DevTile* d_tiles = nullptr;
-    DevImage* d_images = nullptr;
-    unsigned* d_qtabs = nullptr;
-    unsigned* d_qpack = nullptr;
-    // tensor map cache (one slab pointer at a time)
-    const void* tmap_base = nullptr;
-    CUtensorMap tmap;
-    // internal slabs for the host pipeline
-    void* d_coefs = nullptr;
-    void* d_planes = nullptr;
-    void* d_out = nullptr;
-    bool planes_absolute = false;  // plane_off holds absolute device addresses (worker path)
-    bool slabs_borrowed = false;   // d_coefs/d_planes/d_out belong to the context's scratch cache
-};
-
-struct PlanOverrides {
-    const unsigned long long (*plane_addr)[4] = nullptr;  // per image absolute device addresses of the planes
-};
-
 // choose_upsampler, src/upsampler.rs:76-105
 static int choose_upsampler(uint8_t h, uint8_t v, uint8_t hmax, uint8_t vmax, uint16_t out_w, uint16_t out_h,
                             DevUpComp* u, std::string* err) {
@@ -366,14 +306,16 @@ static int plan_image(const b200jpg_ctx* ctx, const b200jpg_image_desc& d, DevIm
     return B200JPG_OK;
 }
 
-static void batch_release_device(b200jpg_batch* b) {
+void batch_release_device(b200jpg_batch* b) {
     if (!b) return;
-    cudaFree(b->d_comps);
-    cudaFree(b->d_tiles);
-    cudaFree(b->d_images);
-    cudaFree(b->d_qtabs);
-    cudaFree(b->d_qpack);
-    cudaFree(b->d_strips);
+    if (!b->tables_borrowed) {
+        cudaFree(b->d_comps);
+        cudaFree(b->d_tiles);
+        cudaFree(b->d_images);
+        cudaFree(b->d_qtabs);
+        cudaFree(b->d_qpack);
+        cudaFree(b->d_strips);
+    }
     if (b->slabs_borrowed) {
         std::lock_guard<std::mutex> lock(b->ctx->mu);
         b->ctx->scratch_busy = false;
@@ -387,8 +329,8 @@ static void batch_release_device(b200jpg_batch* b) {
     b->d_coefs = nullptr; b->d_planes = nullptr; b->d_out = nullptr;
 }
 
-static int batch_create_impl(b200jpg_ctx* ctx, const b200jpg_image_desc* imgs, size_t n, int* statuses,
-                             const PlanOverrides& ov, b200jpg_batch** out) {
+int batch_create_impl(b200jpg_ctx* ctx, const b200jpg_image_desc* imgs, size_t n, int* statuses, const PlanOverrides& ov,
+                      b200jpg_batch** out) {
     if (!ctx || !out || (!imgs && n)) return B200JPG_ERR_INTERNAL;
     *out = nullptr;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
@@ -513,13 +455,24 @@ static int batch_create_impl(b200jpg_ctx* ctx, const b200jpg_image_desc* imgs, s
     b->info.out_bytes = align_up(out_off, 256);
     if (first_error) ctx->err = first_msg;
 
+    cudaStream_t up_stream = ov.upload_stream ? ov.upload_stream : ctx->stream;
+    size_t arena_used = 0;
+    b->tables_borrowed = ov.arena != nullptr;
     auto upload = [&](void** dptr, const void* src, size_t bytes) -> cudaError_t {
         *dptr = nullptr;
         if (bytes == 0) return cudaSuccess;
+        if (ov.arena) {
+            const size_t at = align_up(arena_used, 256);
+            if (at + bytes > ov.arena->bytes) return cudaErrorMemoryAllocation;
+            memcpy(ov.arena->h + at, src, bytes);
+            *dptr = ov.arena->d + at;
+            arena_used = at + bytes;
+            return cudaSuccess;
+        }
         cudaError_t e = cudaMalloc(dptr, bytes);
         if (e != cudaSuccess) return e;
         // pageable source: the copy is staged before the call returns, so the vectors may be reused
-        return cudaMemcpyAsync(*dptr, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+        return cudaMemcpyAsync(*dptr, src, bytes, cudaMemcpyHostToDevice, up_stream);
     };
     cudaError_t e = upload((void**)&b->d_comps, b->comps.data(), b->comps.size() * sizeof(DevComp));
     if (e == cudaSuccess) e = upload((void**)&b->d_tiles, b->tiles.data(), b->tiles.size() * sizeof(DevTile));
@@ -527,6 +480,9 @@ static int batch_create_impl(b200jpg_ctx* ctx, const b200jpg_image_desc* imgs, s
     if (e == cudaSuccess) e = upload((void**)&b->d_qtabs, b->qtabs.data(), b->qtabs.size() * sizeof(unsigned));
     if (e == cudaSuccess) e = upload((void**)&b->d_qpack, b->qpack.data(), b->qpack.size() * sizeof(unsigned));
     if (e == cudaSuccess) e = upload((void**)&b->d_strips, b->strips.data(), b->strips.size() * sizeof(K2Strip));
+    if (e == cudaSuccess && ov.arena && arena_used)
+        e = cudaMemcpyAsync(ov.arena->d, ov.arena->h, arena_used, cudaMemcpyHostToDevice, up_stream);
+    b->table_bytes = arena_used;
     b->strip_first.push_back((unsigned)b->strips.size());
     memset(&b->qcache, 0, sizeof b->qcache);
     for (size_t t = 0; t < 4 && t < b->qt_is8.size(); t++)
@@ -562,7 +518,7 @@ static int ensure_tensor_map(b200jpg_batch* b, const void* d_coefs) {
 }
 
 // K1 over tiles [tile_first, tile_first+tile_count), K2 over images [img_first, img_first+img_count)
-static int batch_launch(b200jpg_batch* b, const void* d_coefs, void* d_planes, void* d_out, int stages, unsigned tile_first,
+int batch_launch(b200jpg_batch* b, const void* d_coefs, void* d_planes, void* d_out, int stages, unsigned tile_first,
                         unsigned tile_count, unsigned img_first, unsigned img_count, cudaStream_t stream) {
     b200jpg_ctx* ctx = b->ctx;
     if ((stages & 1) && tile_count) {

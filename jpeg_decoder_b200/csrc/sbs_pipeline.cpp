@@ -1,0 +1,283 @@
+// sbs_pipeline.cpp -- see sbs_pipeline.h.
+#include "sbs_pipeline.h"
+
+#include <string.h>
+
+#include <algorithm>
+
+namespace b200jpg {
+
+static inline size_t up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+SbsPipeline::SbsPipeline(b200jpg_ctx* ctx, int nslots) : ctx_(ctx) {
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return;
+    if (cudaStreamCreateWithFlags(&s_in_, cudaStreamNonBlocking) != cudaSuccess) return;
+    if (cudaStreamCreateWithFlags(&s_comp_, cudaStreamNonBlocking) != cudaSuccess) return;
+    if (cudaStreamCreateWithFlags(&s_out_, cudaStreamNonBlocking) != cudaSuccess) return;
+    slots_.resize((size_t)std::max(2, nslots));
+    for (auto& s : slots_) {
+        if (cudaEventCreateWithFlags(&s.e_h2d, cudaEventDisableTiming) != cudaSuccess) return;
+        if (cudaEventCreateWithFlags(&s.e_comp, cudaEventDisableTiming) != cudaSuccess) return;
+        if (cudaEventCreateWithFlags(&s.e_done, cudaEventDisableTiming) != cudaSuccess) return;
+    }
+    ok_ = true;
+}
+
+SbsPipeline::~SbsPipeline() {
+    cudaSetDevice(ctx_->device);
+    drain();
+    for (auto& s : slots_) {
+        cudaFree(s.d_streams.p);
+        cudaFree(s.d_coefs.p);
+        cudaFree(s.d_planes.p);
+        cudaFree(s.d_out.p);
+        cudaFree(s.d_tables.p);
+        if (s.h_tables.p) cudaFreeHost(s.h_tables.p);
+        if (s.e_h2d) cudaEventDestroy(s.e_h2d);
+        if (s.e_comp) cudaEventDestroy(s.e_comp);
+        if (s.e_done) cudaEventDestroy(s.e_done);
+    }
+    if (s_in_) cudaStreamDestroy(s_in_);
+    if (s_comp_) cudaStreamDestroy(s_comp_);
+    if (s_out_) cudaStreamDestroy(s_out_);
+}
+
+int SbsPipeline::grow_device(Buf& b, size_t need) {
+    if (need <= b.cap) return B200JPG_OK;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+    const size_t want = up(need + need / 4, 1 << 20);
+    CU_TRY(ctx_, cudaMalloc(&b.p, want));
+    b.cap = want;
+    return B200JPG_OK;
+}
+int SbsPipeline::grow_pinned(Buf& b, size_t need) {
+    if (need <= b.cap) return B200JPG_OK;
+    if (b.p) cudaFreeHost(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+    const size_t want = up(need + need / 4, 1 << 16);
+    CU_TRY(ctx_, cudaHostAlloc(&b.p, want, cudaHostAllocDefault));
+    b.cap = want;
+    return B200JPG_OK;
+}
+
+// Fires the callbacks of a slot whose work has completed (or waits for it) and frees its plan.
+void SbsPipeline::retire(Slot& s, bool wait) {
+    if (!s.busy) return;
+    if (!s.h2d_reported) {
+        if (wait) cudaEventSynchronize(s.e_h2d);
+        else if (cudaEventQuery(s.e_h2d) != cudaSuccess) return;
+        s.h2d_reported = true;
+        if (on_h2d) on_h2d(s.group);
+    }
+    if (wait) {
+        if (cudaEventSynchronize(s.e_done) != cudaSuccess && error_ == B200JPG_OK)
+            error_ = b200jpg_cuda_fail(ctx_, cudaGetLastError(), "sparse-stream pipeline");
+    } else if (cudaEventQuery(s.e_done) != cudaSuccess) {
+        return;
+    }
+    if (on_done) on_done(s.group);
+    if (s.batch) {
+        batch_release_device(s.batch);
+        delete s.batch;
+        s.batch = nullptr;
+    }
+    s.group.items.clear();
+    s.busy = false;
+}
+
+void SbsPipeline::poll() {
+    while (oldest_ < next_) {
+        Slot& s = slots_[oldest_ % slots_.size()];
+        retire(s, false);
+        if (s.busy) break;  // callbacks fire in submission order
+        oldest_++;
+    }
+}
+
+int SbsPipeline::drain() {
+    while (oldest_ < next_) {
+        retire(slots_[oldest_ % slots_.size()], true);
+        oldest_++;
+    }
+    const int e = error_;
+    error_ = B200JPG_OK;
+    return e;
+}
+
+static void fill_k0(const b200jpg_image_desc& d, const ImageLayout& L, unsigned order, size_t stream_off, K0Image* k) {
+    memset(k, 0, sizeof *k);
+    k->stream_off = stream_off;
+    k->order = order;
+    unsigned nb = 0, j = 0;
+    for (int c = 0; c < d.ncomp; c++) {
+        k->slab_row[c] = (unsigned)(L.coef_off[c] / 128);
+        k->block_w[c] = d.comps[c].block_w;
+        k->first[c] = nb;
+        k->h[c] = d.comps[c].h;
+        k->v[c] = d.comps[c].v;
+        nb += (unsigned)d.comps[c].block_w * d.comps[c].block_h;
+        if (order == SBS_INTERLEAVED)
+            for (unsigned vy = 0; vy < d.comps[c].v; vy++)
+                for (unsigned hx = 0; hx < d.comps[c].h; hx++)
+                    if (j < 12) {
+                        k->mcu_comp[j] = (unsigned char)c;
+                        k->mcu_hx[j] = (unsigned char)hx;
+                        k->mcu_vy[j] = (unsigned char)vy;
+                        j++;
+                    }
+    }
+    for (int c = d.ncomp; c < 4; c++) k->first[c] = 0xffffffffu;  // never reached by the planar search
+    k->nb = nb;
+    k->bpm = j ? j : 1;
+    k->mcu_w = d.comps[0].h ? d.comps[0].block_w / d.comps[0].h : 1;
+    if (k->mcu_w == 0) k->mcu_w = 1;
+}
+
+int SbsPipeline::submit(std::vector<SbsItem>&& items) {
+    if (!ok_) return b200jpg_fail(ctx_, B200JPG_ERR_INTERNAL, "sparse-stream pipeline could not be created");
+    if (items.empty()) return B200JPG_OK;
+    CU_TRY(ctx_, cudaSetDevice(ctx_->device));
+    if (next_ - oldest_ >= slots_.size()) {  // the slot we are about to reuse is still in flight
+        retire(slots_[oldest_ % slots_.size()], true);
+        oldest_++;
+    }
+    Slot& s = slots_[next_ % slots_.size()];
+    s.group.items = std::move(items);
+    const int rc = enqueue(s);
+    if (rc != B200JPG_OK) {  // leave the slot reusable: nothing of this group may still be running
+        cudaStreamSynchronize(s_in_);
+        cudaStreamSynchronize(s_comp_);
+        cudaStreamSynchronize(s_out_);
+        if (s.batch) {
+            batch_release_device(s.batch);
+            delete s.batch;
+            s.batch = nullptr;
+        }
+        s.group.items.clear();
+        return rc;
+    }
+    last_coefs_ = s.d_coefs.p;
+    s.busy = true;
+    s.h2d_reported = false;
+    next_++;
+    return B200JPG_OK;
+}
+
+int SbsPipeline::enqueue(Slot& s) {
+    const size_t n = s.group.items.size();
+    s.group.statuses.assign(n, B200JPG_OK);
+    const std::vector<SbsItem>& it = s.group.items;
+
+    // bound of the plan's tables (see batch_create_impl): per component 32 B + two tables, per 128 blocks 16 B, ...
+    std::vector<b200jpg_image_desc> descs(n);
+    size_t tbound = 8 * 256 + n * (sizeof(DevImage) + sizeof(K0Image) + 64);
+    for (size_t i = 0; i < n; i++) {
+        descs[i] = it[i].desc;
+        for (int c = 0; c < 4; c++) descs[i].coefs[c] = nullptr;
+        for (int c = 0; c < descs[i].ncomp && c < 4; c++)
+            tbound += sizeof(DevComp) + 96 * sizeof(unsigned) + ((size_t)descs[i].comps[c].block_w * descs[i].comps[c].block_h / K1_TILE + 1) * sizeof(DevTile);
+        tbound += ((size_t)descs[i].width / 2048 + 1) * sizeof(K2Strip);
+    }
+    int rc = grow_device(s.d_tables, tbound);
+    if (rc == B200JPG_OK) rc = grow_pinned(s.h_tables, tbound);
+    if (rc) return rc;
+
+    TableArena arena;
+    arena.d = (char*)s.d_tables.p;
+    arena.h = (char*)s.h_tables.p;
+    arena.bytes = tbound - n * sizeof(K0Image) - 256;
+    PlanOverrides ov;
+    ov.arena = &arena;
+    ov.upload_stream = s_in_;
+    rc = batch_create_impl(ctx_, descs.data(), n, s.group.statuses.data(), ov, &s.batch);
+    if (rc) return rc;
+    b200jpg_batch* b = s.batch;
+
+    // K0 descriptors + stream placement for the images the planner accepted
+    const size_t k0_at = up(b->table_bytes, 256);
+    K0Image* h_k0 = (K0Image*)(arena.h + k0_at);
+    const K0Image* d_k0 = (const K0Image*)(arena.d + k0_at);
+    size_t nk0 = 0, stream_bytes = 0;
+    unsigned max_nb = 0;
+    for (size_t i = 0; i < n; i++) {
+        if (s.group.statuses[i]) continue;
+        if (!it[i].out || it[i].out_cap < b->layout[i].out_len || !it[i].stream) {
+            s.group.statuses[i] = B200JPG_ERR_INTERNAL;
+            b200jpg_fail(ctx_, B200JPG_ERR_INTERNAL, "output buffer too small");
+            continue;
+        }
+        fill_k0(descs[i], b->layout[i], it[i].order, stream_bytes, &h_k0[nk0]);
+        const SbsLayout lay = SbsLayout::make(h_k0[nk0].nb);
+        if (it[i].len < lay.off_vals || it[i].len > lay.worst_bytes() || it[i].len % 16 != 0) {
+            s.group.statuses[i] = B200JPG_ERR_INTERNAL;
+            b200jpg_fail(ctx_, B200JPG_ERR_INTERNAL, "malformed sparse block stream");
+            continue;
+        }
+        max_nb = std::max(max_nb, h_k0[nk0].nb);
+        stream_bytes += it[i].len;
+        nk0++;
+    }
+    rc = grow_device(s.d_streams, stream_bytes + 256);
+    if (rc == B200JPG_OK) rc = grow_device(s.d_coefs, b->info.coef_bytes + K1_TILE * 128);
+    if (rc == B200JPG_OK) rc = grow_device(s.d_planes, b->info.plane_bytes + 256);
+    if (rc == B200JPG_OK) rc = grow_device(s.d_out, b->info.out_bytes + 256);
+    if (rc) return rc;
+
+    // copy-in
+    {
+        size_t k = 0;
+        const char* run_src = nullptr;
+        size_t run_dst = 0, run_bytes = 0;
+        for (size_t i = 0; i < n; i++) {
+            if (s.group.statuses[i]) continue;
+            const size_t dst = (size_t)h_k0[k++].stream_off;
+            const char* src = (const char*)it[i].stream;
+            if (run_bytes && run_src + run_bytes == src && run_dst + run_bytes == dst) {
+                run_bytes += it[i].len;
+            } else {
+                if (run_bytes) CU_TRY(ctx_, cudaMemcpyAsync((char*)s.d_streams.p + run_dst, run_src, run_bytes, cudaMemcpyHostToDevice, s_in_));
+                run_src = src;
+                run_dst = dst;
+                run_bytes = it[i].len;
+            }
+        }
+        if (run_bytes) CU_TRY(ctx_, cudaMemcpyAsync((char*)s.d_streams.p + run_dst, run_src, run_bytes, cudaMemcpyHostToDevice, s_in_));
+        if (nk0) CU_TRY(ctx_, cudaMemcpyAsync((void*)d_k0, h_k0, nk0 * sizeof(K0Image), cudaMemcpyHostToDevice, s_in_));
+        CU_TRY(ctx_, cudaEventRecord(s.e_h2d, s_in_));
+    }
+    // compute
+    CU_TRY(ctx_, cudaStreamWaitEvent(s_comp_, s.e_h2d, 0));
+    if (nk0) {
+        CU_TRY(ctx_, launch_k0_expand(d_k0, (unsigned)nk0, max_nb, (const uint8_t*)s.d_streams.p, (short*)s.d_coefs.p, s_comp_));
+        ctx_->launches++;
+        rc = batch_launch(b, s.d_coefs.p, s.d_planes.p, s.d_out.p, 3, 0, (unsigned)b->tiles.size(), 0, (unsigned)n, s_comp_);
+        if (rc) return rc;
+    }
+    CU_TRY(ctx_, cudaEventRecord(s.e_comp, s_comp_));
+    // copy-out
+    CU_TRY(ctx_, cudaStreamWaitEvent(s_out_, s.e_comp, 0));
+    {
+        char* out_dst = nullptr;
+        size_t out_src = 0, out_bytes = 0;
+        for (size_t i = 0; i < n; i++) {
+            if (s.group.statuses[i]) continue;
+            const ImageLayout& L = b->layout[i];
+            if (out_bytes && out_dst + out_bytes == (char*)it[i].out && out_src + out_bytes == L.out_off) {
+                out_bytes += L.out_len;
+            } else {
+                if (out_bytes) CU_TRY(ctx_, cudaMemcpyAsync(out_dst, (char*)s.d_out.p + out_src, out_bytes, cudaMemcpyDeviceToHost, s_out_));
+                out_dst = (char*)it[i].out;
+                out_src = L.out_off;
+                out_bytes = L.out_len;
+            }
+        }
+        if (out_bytes) CU_TRY(ctx_, cudaMemcpyAsync(out_dst, (char*)s.d_out.p + out_src, out_bytes, cudaMemcpyDeviceToHost, s_out_));
+        CU_TRY(ctx_, cudaEventRecord(s.e_done, s_out_));
+    }
+    return B200JPG_OK;
+}
+
+}  // namespace b200jpg

@@ -1,0 +1,80 @@
+// sbs_pipeline.h -- the sparse-stream host pipeline: groups of images whose coefficients arrive as sparse block
+// streams (sbs.h) flow through three CUDA streams,
+//     copy-in : H2D of the streams + the plan's tables          (event h2d)
+//     compute : K0 expand -> K1 dequant+IDCT -> K2 colour        (event comp)
+//     copy-out: D2H of the pixels into the callers' buffers      (event done)
+// so that group k+1 uploads while group k computes and group k-1 downloads.  A ring of slots owns the device
+// buffers (grow-only: nothing is cudaMalloc'ed or cudaFree'd in steady state, both would serialise the device).
+// Single-threaded: one submitter thread drives submit()/poll()/drain().  Not part of the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include <functional>
+#include <vector>
+
+#include "../../include/b200jpg.h"
+#include "batch_internal.h"
+#include "sbs.h"
+
+namespace b200jpg {
+
+struct SbsItem {
+    b200jpg_image_desc desc;  // geometry, tables, colour transform; desc.coefs is ignored
+    const uint8_t* stream = nullptr;  // host (ideally page-locked) sparse stream, valid until on_h2d
+    size_t len = 0;
+    unsigned order = SBS_PLANAR;
+    uint8_t* out = nullptr;  // host pixels (ideally page-locked)
+    size_t out_cap = 0;
+    size_t job = 0;        // caller's cookie
+    int thread = 0;        // caller's cookie
+    uint64_t ring_end = 0; // caller's cookie
+};
+
+class SbsPipeline {
+public:
+    struct Group {
+        std::vector<SbsItem> items;
+        std::vector<int> statuses;
+    };
+    SbsPipeline(b200jpg_ctx* ctx, int nslots);
+    ~SbsPipeline();
+    bool ok() const { return ok_; }
+    // called from poll()/drain()/submit() on the submitter thread, in submission order
+    std::function<void(const Group&)> on_h2d;   // the streams of this group have left host memory
+    std::function<void(const Group&)> on_done;  // pixels are in the callers' buffers, statuses are final
+
+    int submit(std::vector<SbsItem>&& items);  // B200JPG_OK or a device-level error
+    void poll();                               // fire callbacks of whatever has completed
+    int drain();                               // wait for everything in flight
+    // optional: keep dense slab copies for debugging (tests): after drain(), the last group's coefficient slab
+    const void* last_coef_slab() const { return last_coefs_; }
+
+private:
+    struct Buf {
+        void* p = nullptr;
+        size_t cap = 0;
+    };
+    struct Slot {
+        Buf d_streams, d_coefs, d_planes, d_out, d_tables, h_tables;
+        cudaEvent_t e_h2d = nullptr, e_comp = nullptr, e_done = nullptr;
+        bool busy = false, h2d_reported = false;
+        b200jpg_batch* batch = nullptr;
+        Group group;
+    };
+    int grow_device(Buf& b, size_t need);
+    int grow_pinned(Buf& b, size_t need);
+    void retire(Slot& s, bool wait);
+    int enqueue(Slot& s);
+
+    b200jpg_ctx* ctx_;
+    bool ok_ = false;
+    cudaStream_t s_in_ = nullptr, s_comp_ = nullptr, s_out_ = nullptr;
+    std::vector<Slot> slots_;
+    size_t next_ = 0, oldest_ = 0;  // tickets: slot = ticket % nslots
+    const void* last_coefs_ = nullptr;
+    int error_ = B200JPG_OK;
+};
+
+}  // namespace b200jpg

@@ -509,3 +509,85 @@ def test_decode_files_batch(J, oracle_mod, ctxs):
     want = oracle_mod.Decoder(data).decode()
     outs, st, _ = J.decode_files(ctx, [data] * 70, nthreads=3)
     assert st == [0] * 70 and all(np.array_equal(o, want) for o in outs)
+
+
+# ---------------------------------------------------------------------------------------------
+# K0: sparse block streams (csrc/sbs.h, csrc/k0_expand.cu)
+# ---------------------------------------------------------------------------------------------
+def test_k0_expand_rebuilds_the_dense_slab(J, ctxs):
+    """Kernel K0 turns the host decoder's sparse stream back into exactly the dense coefficients the reference pushes
+    through Worker::append_row -- for every fixture (planar and interleaved order, wide blocks, odd geometries)."""
+    from jpeg_decoder_b200 import workload
+    ctx = ctxs[("scalar", "auto")]
+    datas = [open(p, "rb").read() for p in reftest_files() + bench_files()]
+    datas += [workload.synth_jpeg(w, h, seed=3, subsampling=s, progressive=pr)
+              for (w, h, s, pr) in [(1920, 1080, 2, False), (97, 61, 2, False), (640, 360, 0, False), (320, 200, 1, False), (200, 120, 2, True)]]
+    orders = set()
+    for data in datas:
+        ref = J.Decoder(data)
+        try:
+            d0 = ref.entropy_decode()
+        except J.B200JpgError:
+            continue
+        if any(not d0.coefs[c] for c in range(d0.ncomp)):
+            continue
+        d1, buf, order = J.Decoder(data).entropy_decode_sbs()
+        orders.add(order)
+        dense = J.expand_sbs(ctx, d1, buf, order)
+        for c in range(d0.ncomp):
+            assert np.array_equal(dense[c], ref.coefficients(d0, c)), (len(data), c)
+    assert orders == {0, 1}
+
+
+@pytest.mark.parametrize("variant", [("scalar", "auto"), ("ssse3", "auto")])
+def test_decode_batch_sbs_bit_exact(J, oracle_mod, ctxs, variant):
+    """Streams in, pixels out (H2D -> K0 -> K1 -> K2 -> D2H over three CUDA streams): bit-exact vs the oracle, more
+    images than one group, a malformed stream is rejected without poisoning the batch."""
+    from jpeg_decoder_b200 import workload
+    ctx = ctxs[variant]
+    datas = [open(p, "rb").read() for p in bench_files()]
+    datas += [workload.synth_jpeg(w, h, seed=21 + i, subsampling=s) for i, (w, h, s) in enumerate([(256, 144, 2), (130, 70, 0), (48, 48, 1)])]
+    datas = datas * 6  # > 32 images: several groups
+    descs, streams, wants, keep = [], [], [], []
+    for data in datas:
+        dec = J.Decoder(data)
+        d, buf, order = dec.entropy_decode_sbs()
+        keep.append(dec)
+        descs.append(d)
+        streams.append((buf, order))
+        wants.append(oracle_mod.Decoder(data, oarith(oracle_mod, variant[0])).decode())
+    bad = streams[5][0].copy()
+    bad[0] ^= 0x10  # a bitmap bit without a value: offsets no longer add up
+    streams[5] = (bad, streams[5][1])
+    outs, st = J.decode_batch_sbs(ctx, descs, streams)
+    for i, (o, s_, w) in enumerate(zip(outs, st, wants)):
+        if i == 5:
+            assert s_ == J.ERR_INTERNAL
+        else:
+            assert s_ == 0 and np.array_equal(o, w), i
+
+
+def test_decode_files_streaming_engine(J, oracle_mod, ctxs):
+    """The whole-file engine under load: many 1080p-class images over few and many host threads (ring wrap-around,
+    ring growth when a larger image follows smaller ones, more threads than images), results bit-exact."""
+    from jpeg_decoder_b200 import workload
+    ctx = ctxs[("scalar", "auto")]
+    small = [workload.synth_jpeg(320, 240, seed=40 + i, subsampling=2) for i in range(3)]
+    big = [workload.synth_jpeg(1920, 1080, seed=50 + i, subsampling=2) for i in range(2)]
+    prog = workload.synth_jpeg(640, 480, seed=60, subsampling=0, progressive=True)
+    files = (small * 5 + big + [prog] + small + big * 9 + [prog] * 3 + [b"\xff\xd8\xff\xd9"] + small * 4)
+    cache = {}
+    for f in files:
+        if f not in cache:
+            try:
+                cache[f] = oracle_mod.Decoder(f).decode()
+            except oracle_mod.OracleError as e:
+                cache[f] = -e.code
+    for nthreads in (1, 3, 16, 200):
+        outs, st, _ = J.decode_files(ctx, files, nthreads=nthreads)
+        for i, (f, o, s_) in enumerate(zip(files, outs, st)):
+            w = cache[f]
+            if isinstance(w, int):
+                assert s_ == w, (nthreads, i, s_, w)
+            else:
+                assert s_ == 0 and np.array_equal(o, w), (nthreads, i, s_)
