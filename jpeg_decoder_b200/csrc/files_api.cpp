@@ -27,6 +27,7 @@
 #include "../../include/b200jpg.h"
 #include "context.h"
 #include "host_decoder.h"
+#include "ring_book.h"
 #include "sbs_pipeline.h"
 
 using b200jpg::HostDecoder;
@@ -75,13 +76,11 @@ int default_threads() {
     return (int)std::max(1u, std::thread::hardware_concurrency());
 }
 
-// One host thread's page-locked ring.  head/tail are monotonic byte counters; a region is handed out
-// contiguous (a request that would straddle the end skips to the start) and returned in allocation order.
+// One host thread's page-locked ring: memory + the bookkeeping of ring_book.h (regions are released by the
+// submitter once their upload has completed).
 struct Ring {
     uint8_t* base = nullptr;
-    size_t cap = 0;
-    uint64_t head = 0;               // owner thread only
-    std::atomic<uint64_t> tail{0};   // advanced by the submitter when an upload has completed
+    b200jpg::RingBook book;
 };
 
 // Persistent per-context state: the rings (pinning memory costs ~0.3 s per GB) and the device pipeline.
@@ -216,16 +215,16 @@ int b200jpg_decode_files(b200jpg_ctx* ctx, b200jpg_file_job* jobs, size_t n, int
                 continue;
             }
             // a contiguous worst-case region in this thread's ring
-            if (ring.cap < need) {  // (re)allocate once everything handed out earlier has been uploaded
-                const double w0 = now_ms();
-                {
+            if (ring.book.cap() < need) {  // (re)allocate once everything handed out earlier has been uploaded
+                if (!ring.book.empty()) {
+                    const double w0 = now_ms();
                     std::unique_lock<std::mutex> lk(cs.mu);
-                    cs.space_cv.wait(lk, [&] { return ring.tail.load() == ring.head; });
+                    cs.space_cv.wait(lk, [&] { return ring.book.empty(); });
+                    cs.ring_wait_us += (uint64_t)((now_ms() - w0) * 1e3);
                 }
-                cs.ring_wait_us += (uint64_t)((now_ms() - w0) * 1e3);
                 if (ring.base) cudaFreeHost(ring.base);
                 ring.base = nullptr;
-                ring.cap = 0;
+                ring.book.reset(0);
                 const size_t want = std::max(kMinRing, need * 2 + need / 2);
                 void* p = nullptr;
                 if (cudaHostAlloc(&p, want, cudaHostAllocDefault) != cudaSuccess) {
@@ -234,19 +233,13 @@ int b200jpg_decode_files(b200jpg_ctx* ctx, b200jpg_file_job* jobs, size_t n, int
                     continue;
                 }
                 ring.base = (uint8_t*)p;
-                ring.cap = want;
-                ring.head = 0;
-                ring.tail.store(0);
+                ring.book.reset(want);
             }
-            size_t pos = (size_t)(ring.head % ring.cap);
-            if (pos + need > ring.cap) {  // skip the end of the ring
-                ring.head += ring.cap - pos;
-                pos = 0;
-            }
-            if (ring.head + need - ring.tail.load() > ring.cap) {
+            size_t pos = 0;
+            if (!ring.book.try_reserve(need, &pos)) {
                 const double w0 = now_ms();
                 std::unique_lock<std::mutex> lk(cs.mu);
-                cs.space_cv.wait(lk, [&] { return ring.head + need - ring.tail.load() <= ring.cap; });
+                cs.space_cv.wait(lk, [&] { return ring.book.try_reserve(need, &pos); });
                 cs.ring_wait_us += (uint64_t)((now_ms() - w0) * 1e3);
             }
             hd.set_sbs_sink(ring.base + pos);
@@ -282,8 +275,7 @@ int b200jpg_decode_files(b200jpg_ctx* ctx, b200jpg_file_job* jobs, size_t n, int
             item.out_cap = job.out_cap;
             item.job = i;
             item.thread = tid;
-            ring.head += (len + extra + 255) / 256 * 256;
-            item.ring_end = ring.head;
+            item.ring_end = ring.book.commit((len + extra + 255) / 256 * 256);
             cs.decode_us += (uint64_t)((now_ms() - t0) * 1e3);
             {
                 std::lock_guard<std::mutex> lk(cs.mu);
@@ -300,7 +292,7 @@ int b200jpg_decode_files(b200jpg_ctx* ctx, b200jpg_file_job* jobs, size_t n, int
 
     SbsPipeline& pipe = *eng->pipe;
     pipe.on_h2d = [&](const SbsPipeline::Group& g) {
-        for (const SbsItem& it : g.items) eng->rings[(size_t)it.thread]->tail.store(it.ring_end);
+        for (const SbsItem& it : g.items) eng->rings[(size_t)it.thread]->book.release(it.ring_end);
         {
             std::lock_guard<std::mutex> lk(cs.mu);
         }
@@ -351,7 +343,7 @@ int b200jpg_decode_files(b200jpg_ctx* ctx, b200jpg_file_job* jobs, size_t n, int
                     result = rc;
                     for (const SbsItem& it : copy) {
                         jobs[it.job].status = rc;
-                        eng->rings[(size_t)it.thread]->tail.store(it.ring_end);
+                        eng->rings[(size_t)it.thread]->book.release(it.ring_end);
                     }
                     {
                         std::lock_guard<std::mutex> lk(cs.mu);
