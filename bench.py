@@ -40,6 +40,8 @@ def parse_args():
     ap.add_argument("--arith", default="scalar", choices=["scalar", "ssse3"])
     ap.add_argument("--k1", default="auto", choices=["auto", "generic"], help="K1 kernel variant (profiling)")
     ap.add_argument("--k2", default="auto", choices=["auto", "generic"], help="K2 kernel variant (profiling)")
+    ap.add_argument("--host-compact", default="auto", choices=["auto", "on", "off"],
+                    help="b200jpg_batch_run_host: compact the dense coefficients into sparse block streams on host threads")
     ap.add_argument("--no-numa-bind", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the CPU baseline sample")
@@ -279,7 +281,9 @@ def main():
     arith = J.ARITH_SSSE3 if args.arith == "ssse3" else J.ARITH_SCALAR
     kmap = {"auto": J.KERNEL_AUTO, "generic": J.KERNEL_GENERIC}
     assert stream.cuda_stream != 0
-    ctx = J.Context(device=local_rank, arith=arith, k1_kernel=kmap[args.k1], k2_kernel=kmap[args.k2], stream=stream.cuda_stream)
+    cmap = {"auto": J.COMPACT_AUTO, "on": J.COMPACT_ON, "off": J.COMPACT_OFF}
+    ctx = J.Context(device=local_rank, arith=arith, k1_kernel=kmap[args.k1], k2_kernel=kmap[args.k2], stream=stream.cuda_stream,
+                    host_compact=cmap[args.host_compact])
     keep = []
     descs = []
     for i in range(lo, hi):
@@ -397,6 +401,20 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e_dt = float(t.item())
     e2e_value = world * Be * W * H / 1e6 * e_steps / e_dt
+    # the same call with the dense buffers uploaded as they are (host_compact = off), for comparison
+    dense_upload = None
+    if rank == 0 and world == 1 and args.host_compact != "off":
+        ctx_d = J.Context(device=local_rank, arith=arith, k1_kernel=kmap[args.k1], k2_kernel=kmap[args.k2], host_compact=J.COMPACT_OFF)
+        d_batch = J.Batch(ctx_d, e_descs)
+        for _ in range(2):
+            d_batch.run_host(outs)
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            d_batch.run_host(outs)
+        d_dt = time.perf_counter() - t0
+        dense_upload = {"value": Be * W * H / 1e6 * e_steps / d_dt, "unit": "MP/s", "gbs_each_direction": Be * coef_per_img * e_steps / d_dt / 1e9}
+        d_batch.close()
+        ctx_d.close()
     # cheap end-to-end sanity: the host result of image 0 equals the device-resident result
     ref0 = d_out[batch.layout(0)["out_off"]:batch.layout(0)["out_off"] + out_per_img].cpu().numpy()
     same = bool(np.array_equal(ref0, h_out.numpy()[:out_per_img]))
@@ -452,9 +470,11 @@ def main():
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": Be * coef_per_img, "d2h_bytes_per_step": Be * out_per_img,
                     "images_per_step": Be, "steps": e_steps, "host_result_equals_device_result": same,
-                    "api": "b200jpg_batch_run_host (pinned host coefficient buffers -> pinned host pixels)",
+                    "api": "b200jpg_batch_run_host (pinned host dense coefficient buffers -> pinned host pixels)",
+                    "host_compact": args.host_compact, "dense_upload": dense_upload,
+                    "note": "h2d_bytes_per_step = the dense input the call is given; with host compaction the link carries the sparse streams",
                     "pcie_gbs_measured": pcie, "numa_bind": numa, "files": files_e2e,
-                    "gbs_each_direction": Be * coef_per_img * e_steps / e_dt / 1e9},
+                    "d2h_gbs": Be * out_per_img * e_steps / e_dt / 1e9},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }

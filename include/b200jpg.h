@@ -63,6 +63,12 @@ enum {
                                  the reference runs by default, emulated bit-exactly            */
 };
 
+/* b200jpg_batch_run_host takes dense coefficient buffers (the reference's Worker::append_row payload).  They are
+ * mostly zeros, so host threads can compact them into sparse block streams (see "Sparse block streams" below)
+ * before the upload: PCIe then carries ~1/5 of the bytes and the download of the pixels gets the link to itself.
+ * AUTO compacts when the host has >= 8 CPUs for it and a sample of the batch is < 35 % non-zero. */
+enum { B200JPG_COMPACT_AUTO = 0, B200JPG_COMPACT_OFF = 1, B200JPG_COMPACT_ON = 2 };
+
 /* kernel selection, for tests and profiling (0 = pick the fastest applicable kernel) */
 enum { B200JPG_KERNEL_AUTO = 0, B200JPG_KERNEL_GENERIC = 1, B200JPG_KERNEL_FAST = 2 };
 
@@ -83,7 +89,9 @@ typedef struct {
     int k1_kernel;    /* B200JPG_KERNEL_* for dequant+IDCT                                 */
     int k2_kernel;    /* B200JPG_KERNEL_* for upsample+colour                              */
     void *stream;     /* cudaStream_t to enqueue on; NULL = the context creates its own    */
-    int reserved[4];
+    int host_compact; /* b200jpg_batch_run_host: B200JPG_COMPACT_* (0 = decide per batch)   */
+    int host_threads; /* host threads of the host-fed paths; 0 = one per CPU of the process */
+    int reserved[2];
 } b200jpg_options;
 
 typedef struct b200jpg_ctx b200jpg_ctx;
@@ -187,10 +195,11 @@ B200JPG_API int b200jpg_batch_image_layout(const b200jpg_batch *b, size_t i, siz
  * context's stream (no synchronisation).  stages: bit0 = K1, bit1 = K2. */
 B200JPG_API int b200jpg_batch_run_device(b200jpg_batch *b, const void *d_coefs, void *d_planes, void *d_out,
                                          int stages);
-/* Host-to-host run through internal device slabs: H2D of the coefficients named in the descs,
- * K1, K2, D2H of the pixels into outs[i] (out_caps[i] bytes), chunked and double-buffered over
- * two streams.  pinned: non-zero if the caller's buffers are page-locked (then copies are truly
- * asynchronous). */
+/* Host-to-host run: the coefficients named in the descs -> pixels in outs[i] (out_caps[i] bytes).  Either the
+ * dense buffers are uploaded as they are (H2D, K1, K2, D2H, chunked and double-buffered over two streams through
+ * internal device slabs), or -- b200jpg_options.host_compact -- host threads first compact them into sparse block
+ * streams (H2D of the streams, K0, K1, K2, D2H over three streams).  Same pixels either way.  Page-locked caller
+ * buffers make the copies truly asynchronous. */
 B200JPG_API int b200jpg_batch_run_host(b200jpg_batch *b, const b200jpg_image_desc *imgs, uint8_t *const *outs,
                                        const size_t *out_caps, int *statuses);
 /* convenience: create + run_host + free */
@@ -248,7 +257,11 @@ B200JPG_API int b200jpg_decoder_entropy_decode(b200jpg_decoder *d, b200jpg_image
  * order), the DC coefficient, and the non-zero values as int8 / int16 -- what Huffman decoding produced
  * (csrc/sbs.h has the byte layout).  Kernel K0 rebuilds the dense slab on the device, bit for bit.
  * ========================================================================================== */
-enum { B200JPG_SBS_PLANAR = 0, B200JPG_SBS_INTERLEAVED = 1 }; /* block order inside a stream */
+enum {
+    B200JPG_SBS_PLANAR = 0,      /* blocks: component by component, raster order                          */
+    B200JPG_SBS_INTERLEAVED = 1, /* blocks: MCU by MCU as in an interleaved scan (src/decoder.rs:978-983) */
+    B200JPG_SBS_NATURAL = 2      /* flag: bitmaps / values in natural coefficient order, not zig-zag      */
+};
 typedef struct {
     const uint8_t *data; /* host memory, ideally page-locked */
     size_t len;
@@ -262,6 +275,10 @@ B200JPG_API int b200jpg_decoder_total_blocks(b200jpg_decoder *d, size_t *nblocks
  * b200jpg_sbs_worst_bytes); desc->coefs stay NULL.  Host only. */
 B200JPG_API int b200jpg_decoder_entropy_decode_sbs(b200jpg_decoder *d, uint8_t *buf, size_t cap,
                                                    b200jpg_image_desc *desc, b200jpg_sbs_stream *stream);
+/* Host only: compacts the dense coefficients desc->coefs of one image into a stream (PLANAR | NATURAL) in buf
+ * (cap >= b200jpg_sbs_worst_bytes) -- what b200jpg_batch_run_host does on its host threads when compacting. */
+B200JPG_API int b200jpg_sbs_from_dense(const b200jpg_image_desc *img, uint8_t *buf, size_t cap,
+                                       b200jpg_sbs_stream *stream);
 /* b200jpg_decode_batch with the coefficients given as streams: H2D -> K0 expand -> K1 -> K2 -> D2H,
  * pipelined over three CUDA streams in groups of 32 images.  Streams are validated before use. */
 B200JPG_API int b200jpg_decode_batch_sbs(b200jpg_ctx *ctx, const b200jpg_image_desc *imgs,

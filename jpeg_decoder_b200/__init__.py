@@ -16,14 +16,14 @@ import ctypes as C
 
 import numpy as np
 
-from ._native import (ARITH_SCALAR, ARITH_SSSE3, CP_DCT_PROGRESSIVE, CP_DCT_SEQUENTIAL, CP_LOSSLESS, CT_CMYK,
+from ._native import (ARITH_SCALAR, ARITH_SSSE3, COMPACT_AUTO, COMPACT_OFF, COMPACT_ON, CP_DCT_PROGRESSIVE, CP_DCT_SEQUENTIAL, CP_LOSSLESS, CT_CMYK,
                       CT_GRAYSCALE, CT_JCS_BG_RGB, CT_JCS_BG_YCC, CT_NONE, CT_RGB, CT_UNKNOWN, CT_YCBCR, CT_YCCK,
                       ERR_FORMAT, ERR_INTERNAL, ERR_IO, ERR_UNSUPPORTED, KERNEL_AUTO, KERNEL_FAST, KERNEL_GENERIC, OK,
-                      PF_CMYK32, PF_L8, PF_L16, PF_RGB24, SBS_INTERLEAVED, SBS_PLANAR, BatchInfo, Component, FileJob, ImageDesc,
+                      PF_CMYK32, PF_L8, PF_L16, PF_RGB24, SBS_INTERLEAVED, SBS_NATURAL, SBS_PLANAR, BatchInfo, Component, FileJob, ImageDesc,
                       ImageInfo, Options, SbsStream, lib)
 
 __all__ = ["Context", "Worker", "Batch", "Decoder", "B200JpgError", "FileJob", "make_components", "make_image_desc",
-           "compute_image", "decode_batch", "decode_batch_sbs", "expand_sbs", "decode_files", "read_info_files", "Component",
+           "compute_image", "decode_batch", "decode_batch_sbs", "expand_sbs", "sbs_from_dense", "decode_files", "read_info_files", "Component",
            "ImageDesc", "SbsStream"]
 
 
@@ -80,11 +80,13 @@ def make_image_desc(width, height, components, qts, coefs, color_transform, keep
 class Context:
     """b200jpg_ctx: one per device/stream."""
 
-    def __init__(self, device=0, arith=ARITH_SCALAR, k1_kernel=KERNEL_AUTO, k2_kernel=KERNEL_AUTO, stream=None):
+    def __init__(self, device=0, arith=ARITH_SCALAR, k1_kernel=KERNEL_AUTO, k2_kernel=KERNEL_AUTO, stream=None,
+                 host_compact=COMPACT_AUTO, host_threads=0):
         opt = Options()
         lib().b200jpg_default_options(C.byref(opt))
         opt.device, opt.arith, opt.k1_kernel, opt.k2_kernel = device, arith, k1_kernel, k2_kernel
         opt.stream = stream
+        opt.host_compact, opt.host_threads = host_compact, host_threads
         h = C.c_void_p()
         rc = lib().b200jpg_create(C.byref(opt), C.byref(h))
         if rc:
@@ -239,6 +241,17 @@ def decode_batch_sbs(ctx, descs, streams):
     if rc and all(s == 0 for s in st):
         ctx.check(rc)
     return outs, list(st)
+
+
+def sbs_from_dense(desc):
+    """b200jpg_sbs_from_dense: (uint8 stream, order) of an ImageDesc whose coefs point to dense coefficients."""
+    nb = sum(int(desc.comps[c].block_w) * int(desc.comps[c].block_h) for c in range(desc.ncomp))
+    buf = np.zeros(lib().b200jpg_sbs_worst_bytes(nb), dtype=np.uint8)
+    s = SbsStream()
+    rc = lib().b200jpg_sbs_from_dense(C.byref(desc), buf.ctypes.data, buf.size, C.byref(s))
+    if rc:
+        raise B200JpgError(rc, "b200jpg_sbs_from_dense failed")
+    return buf[:s.len], s.order
 
 
 def expand_sbs(ctx, desc, buf, order):

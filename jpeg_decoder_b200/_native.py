@@ -24,7 +24,7 @@ class Component(C.Structure):
 
 class Options(C.Structure):
     _fields_ = [("device", C.c_int), ("arith", C.c_int), ("k1_kernel", C.c_int), ("k2_kernel", C.c_int),
-                ("stream", C.c_void_p), ("reserved", C.c_int * 4)]
+                ("stream", C.c_void_p), ("host_compact", C.c_int), ("host_threads", C.c_int), ("reserved", C.c_int * 2)]
 
 
 class ImageDesc(C.Structure):
@@ -53,7 +53,8 @@ class SbsStream(C.Structure):
     _fields_ = [("data", C.c_void_p), ("len", C.c_size_t), ("order", C.c_int)]
 
 
-SBS_PLANAR, SBS_INTERLEAVED = 0, 1
+SBS_PLANAR, SBS_INTERLEAVED, SBS_NATURAL = 0, 1, 2
+COMPACT_AUTO, COMPACT_OFF, COMPACT_ON = 0, 1, 2
 
 # every symbol include/b200jpg.h declares (tests/test_abi.py checks the two lists agree)
 EXPORTS = {
@@ -107,6 +108,7 @@ EXPORTS = {
     "b200jpg_sbs_worst_bytes": (C.c_size_t, [C.c_size_t]),
     "b200jpg_decoder_total_blocks": (C.c_int, [C.c_void_p, C.POINTER(C.c_size_t)]),
     "b200jpg_decoder_entropy_decode_sbs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(ImageDesc), C.POINTER(SbsStream)]),
+    "b200jpg_sbs_from_dense": (C.c_int, [C.POINTER(ImageDesc), C.c_void_p, C.c_size_t, C.POINTER(SbsStream)]),
     "b200jpg_decode_batch_sbs": (C.c_int, [C.c_void_p, C.POINTER(ImageDesc), C.POINTER(SbsStream), C.c_size_t,
                                            C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_int)]),
     "b200jpg_debug_expand_sbs": (C.c_int, [C.c_void_p, C.POINTER(ImageDesc), C.POINTER(SbsStream), C.POINTER(C.c_void_p)]),

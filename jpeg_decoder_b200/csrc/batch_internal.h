@@ -63,6 +63,7 @@ struct b200jpg_batch {
     bool slabs_borrowed = false;   // d_coefs/d_planes/d_out belong to the context's scratch cache
     bool tables_borrowed = false;  // the d_* tables live in a caller's TableArena
     size_t table_bytes = 0;        // bytes of that arena in use
+    int compact_decision = -1;     // b200jpg_batch_run_host: -1 undecided, 0 dense upload, 1 host compaction
 };
 
 // Caller-provided home of a plan's device tables: `bytes` of device memory at `d` mirrored by page-locked host

@@ -17,6 +17,8 @@ struct b200jpg_ctx {
     int arith = B200JPG_ARITH_SCALAR;
     int k1_kernel = B200JPG_KERNEL_AUTO;
     int k2_kernel = B200JPG_KERNEL_AUTO;
+    int host_compact = B200JPG_COMPACT_AUTO;
+    int host_threads = 0;
     cudaStream_t stream = nullptr;   // main stream (caller's or ours)
     cudaStream_t stream2 = nullptr;  // second stream of the host pipeline
     bool own_stream = false;

@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(K0_WARPS * 32) k0_expand(const K0Image* __rest
     // destination row of this lane's block inside the dense slab
     unsigned row = 0xffffffffu;
     if (t < nb) {
-        if (im.order == SBS_PLANAR) {
+        if ((im.order & SBS_INTERLEAVED) == 0) {
             const unsigned c = (t >= im.first[1]) + (t >= im.first[2]) + (t >= im.first[3]);
             row = im.slab_row[c] + (t - im.first[c]);
         } else {
@@ -69,7 +69,8 @@ __global__ void __launch_bounds__(K0_WARPS * 32) k0_expand(const K0Image* __rest
         }
     }
 
-    const unsigned p0 = c_unzigzag[lane], p1 = c_unzigzag[lane + 32u];
+    const bool natural = (im.order & SBS_NATURAL) != 0;
+    const unsigned p0 = natural ? lane : c_unzigzag[lane], p1 = natural ? lane + 32u : c_unzigzag[lane + 32u];
     const unsigned long long below0 = ((1ull << lane) - 1ull) & ~1ull, below1 = ((1ull << (lane + 32u)) - 1ull) & ~1ull;
 #pragma unroll 4
     for (int b = 0; b < 32; b++) {

@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "batch_internal.h"
+#include "stream_engine.h"
 
 // ---------------------------------------------------------------------------------------------
 // context
@@ -56,6 +57,8 @@ int b200jpg_create(const b200jpg_options* opt, b200jpg_ctx** out) {
     ctx->arith = o.arith;
     ctx->k1_kernel = o.k1_kernel;
     ctx->k2_kernel = o.k2_kernel;
+    ctx->host_compact = o.host_compact;
+    ctx->host_threads = o.host_threads;
     if (cudaSetDevice(o.device) != cudaSuccess) { delete ctx; return B200JPG_ERR_INTERNAL; }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, o.device) != cudaSuccess) { delete ctx; return B200JPG_ERR_INTERNAL; }
@@ -638,6 +641,17 @@ int b200jpg_batch_run_host(b200jpg_batch* b, const b200jpg_image_desc* imgs, uin
     if (!b || !imgs || !outs) return B200JPG_ERR_INTERNAL;
     b200jpg_ctx* ctx = b->ctx;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
+    if (b->compact_decision < 0) {
+        const int cpus = ctx->host_threads > 0 ? ctx->host_threads : stream_engine_default_threads();
+        b->compact_decision = ctx->host_compact == B200JPG_COMPACT_ON ||
+                              (ctx->host_compact == B200JPG_COMPACT_AUTO && b->n >= 4 && cpus >= 8 &&
+                               stream_engine_sample_density(imgs, b->n) < 0.35);
+    }
+    if (b->compact_decision == 1) {
+        std::vector<int> plan(b->n);
+        for (size_t m = 0; m < b->n; m++) plan[m] = b->layout[m].status;
+        return stream_engine_run_dense(ctx, imgs, b->n, plan.data(), outs, out_caps, statuses, ctx->host_threads);
+    }
     if (!b->d_coefs && !b->d_planes && !b->d_out) {
         // internal slabs: borrow the context's grow-only scratch buffers when they are free (repeated batches then
         // cost no cudaMalloc/cudaFree), otherwise allocate private ones

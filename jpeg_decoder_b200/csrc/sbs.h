@@ -14,18 +14,26 @@
 // nb_pad = nb rounded up to 32; padding blocks are all-zero.  Scan order is either
 //   SBS_PLANAR      component 0's blocks in raster order, then component 1's, ...
 //   SBS_INTERLEAVED MCU by MCU, inside an MCU component by component, v then h (src/decoder.rs:978-983)
+// optionally or-ed with
+//   SBS_NATURAL     bit k of bm / the order of a block's values refer to NATURAL coefficient positions instead of
+//                   zig-zag indices (what compacting an already dense block produces without a permutation)
 #pragma once
 #include <stddef.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #if !defined(__CUDACC__)
 #include <emmintrin.h>
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+#define B200JPG_SBS_AVX512 1
+#endif
 #endif
 
 namespace b200jpg {
 
-enum : unsigned { SBS_PLANAR = 0, SBS_INTERLEAVED = 1 };
+enum : unsigned { SBS_PLANAR = 0, SBS_INTERLEAVED = 1, SBS_NATURAL = 2 };
 
 struct SbsLayout {
     size_t nb = 0, nb_pad = 0, off_dc = 0, off_voff = 0, off_vals = 0;
@@ -138,6 +146,51 @@ public:
         for (uint64_t m = zm; m; m &= m - 1) v[n++] = byk[__builtin_ctzll(m)];
         put(zm, c[0], v, n, acc > 255u);
     }
+    // one block from dense coefficients in natural order, for SBS_NATURAL streams: bitmap and values stay in
+    // natural order, so this is one SIMD zero test and one pass over the set bits
+    inline void put_dense_natural(const int16_t* c) {
+        const __m128i z = _mm_setzero_si128(), k128 = _mm_set1_epi16(128);
+        uint64_t nz = 0;
+        __m128i hi = z;
+        for (int r = 0; r < 4; r++) {
+            __m128i a = _mm_loadu_si128((const __m128i*)(c + 16 * r));
+            const __m128i b = _mm_loadu_si128((const __m128i*)(c + 16 * r + 8));
+            const unsigned m = (unsigned)_mm_movemask_epi8(_mm_packs_epi16(_mm_cmpeq_epi16(a, z), _mm_cmpeq_epi16(b, z)));
+            nz |= (uint64_t)(~m & 0xffffu) << (16 * r);
+            if (r == 0) a = _mm_and_si128(a, _mm_set_epi16(-1, -1, -1, -1, -1, -1, -1, 0));  // DC travels separately
+            hi = _mm_or_si128(hi, _mm_or_si128(_mm_srli_epi16(_mm_add_epi16(a, k128), 8), _mm_srli_epi16(_mm_add_epi16(b, k128), 8)));
+        }
+        nz &= ~(uint64_t)1;
+        if ((t_ & 31) == 0) voff_[t_ >> 5] = (uint32_t)vpos_;
+        const bool wide = _mm_movemask_epi8(_mm_cmpeq_epi16(hi, z)) != 0xffff;  // some (v + 128) >> 8 != 0
+        bm_[t_] = nz | (wide ? 1u : 0u);
+        dc_[t_] = c[0];
+        t_++;
+        uint8_t* o = vals_ + vpos_;
+        if (!wide) {
+            for (uint64_t m = nz; m; m &= m - 1) *o++ = (uint8_t)c[__builtin_ctzll(m)];
+        } else {
+            for (uint64_t m = nz; m; m &= m - 1) {
+                const uint16_t v = (uint16_t)c[__builtin_ctzll(m)];
+                *o++ = (uint8_t)v;
+                *o++ = (uint8_t)(v >> 8);
+            }
+        }
+        vpos_ = (size_t)(o - vals_);
+    }
+    // `count` consecutive dense blocks (natural order) -> SBS_NATURAL blocks; picks the AVX-512 VBMI2 body when the
+    // CPU has it (one vpcompressb per block instead of a loop over the set bits)
+    void put_dense_natural_run(const int16_t* c, size_t count) {
+#ifdef B200JPG_SBS_AVX512
+        static const bool vbmi2 = __builtin_cpu_supports("avx512vbmi2") && __builtin_cpu_supports("avx512bw") &&
+                                  !getenv("B200JPG_NO_AVX512");  // (the variable exists for the tests of the SSE2 body)
+        if (vbmi2) {
+            put_dense_natural_run_avx512(c, count);
+            return;
+        }
+#endif
+        for (size_t b = 0; b < count; b++) put_dense_natural(c + 64 * b);
+    }
     // pads the tables to nb_pad and returns the stream length (multiple of 16)
     size_t finish() {
         while (t_ < lay_.nb_pad) put_zero();
@@ -148,6 +201,33 @@ public:
     }
 
 private:
+#ifdef B200JPG_SBS_AVX512
+    __attribute__((target("avx512f,avx512bw,avx512vbmi2"))) void put_dense_natural_run_avx512(const int16_t* c, size_t count) {
+        for (size_t b = 0; b < count; b++, c += 64) {
+            const __m512i lo = _mm512_loadu_si512(c), hi = _mm512_loadu_si512(c + 32);
+            const uint64_t nz = (((uint64_t)_mm512_test_epi16_mask(hi, hi) << 32) | (uint64_t)_mm512_test_epi16_mask(lo, lo)) & ~(uint64_t)1;
+            // saturating narrow + widen back: differs exactly where a value is outside int8
+            const __m256i nlo = _mm512_cvtsepi16_epi8(lo), nhi = _mm512_cvtsepi16_epi8(hi);
+            const uint64_t out8 = (((uint64_t)_mm512_cmpneq_epi16_mask(_mm512_cvtepi8_epi16(nhi), hi) << 32) |
+                                   (uint64_t)_mm512_cmpneq_epi16_mask(_mm512_cvtepi8_epi16(nlo), lo)) & ~(uint64_t)1;
+            if ((t_ & 31) == 0) voff_[t_ >> 5] = (uint32_t)vpos_;
+            bm_[t_] = nz | (out8 ? 1u : 0u);
+            dc_[t_] = c[0];
+            t_++;
+            uint8_t* o = vals_ + vpos_;
+            if (!out8) {
+                const __m512i bytes = _mm512_inserti64x4(_mm512_castsi256_si512(nlo), nhi, 1);
+                _mm512_storeu_si512(o, _mm512_maskz_compress_epi8((__mmask64)nz, bytes));
+                vpos_ += (size_t)__builtin_popcountll(nz);
+            } else {
+                const unsigned nlo16 = (unsigned)__builtin_popcountll(nz & 0xffffffffull);
+                _mm512_storeu_si512(o, _mm512_maskz_compress_epi16((__mmask32)nz, lo));
+                _mm512_storeu_si512(o + 2 * nlo16, _mm512_maskz_compress_epi16((__mmask32)(nz >> 32), hi));
+                vpos_ += 2 * (size_t)__builtin_popcountll(nz);
+            }
+        }
+    }
+#endif
     SbsLayout lay_;
     uint8_t* base_ = nullptr;
     uint64_t* bm_ = nullptr;

@@ -61,6 +61,24 @@ extern "C" {
 
 size_t b200jpg_sbs_worst_bytes(size_t nblocks) { return SbsLayout::make(nblocks).worst_bytes(); }
 
+int b200jpg_sbs_from_dense(const b200jpg_image_desc* img, uint8_t* buf, size_t cap, b200jpg_sbs_stream* stream) {
+    if (!img || !buf || !stream || img->ncomp < 1 || img->ncomp > 4) return B200JPG_ERR_INTERNAL;
+    const size_t nb = desc_blocks(*img);
+    if (nb == 0 || cap < SbsLayout::make(nb).worst_bytes()) return B200JPG_ERR_INTERNAL;
+    for (int c = 0; c < img->ncomp; c++)
+        if (!img->coefs[c]) return B200JPG_ERR_FORMAT;
+    SbsWriter w;
+    w.begin(buf, nb);
+    for (int c = 0; c < img->ncomp; c++) {
+        const size_t cnt = (size_t)img->comps[c].block_w * img->comps[c].block_h;
+        w.put_dense_natural_run(img->coefs[c], cnt);
+    }
+    stream->data = buf;
+    stream->len = w.finish();
+    stream->order = (int)(SBS_PLANAR | SBS_NATURAL);
+    return B200JPG_OK;
+}
+
 int b200jpg_decode_batch_sbs(b200jpg_ctx* ctx, const b200jpg_image_desc* imgs, const b200jpg_sbs_stream* streams, size_t n,
                              uint8_t* const* outs, const size_t* out_caps, int* statuses) {
     if (!ctx || (n && (!imgs || !streams || !outs || !out_caps))) return B200JPG_ERR_INTERNAL;
@@ -78,7 +96,7 @@ int b200jpg_decode_batch_sbs(b200jpg_ctx* ctx, const b200jpg_image_desc* imgs, c
     for (size_t i0 = 0; i0 < n; i0 += group_max) {
         std::vector<SbsItem> items;
         for (size_t i = i0; i < n && i < i0 + group_max; i++) {
-            if (streams[i].order != SBS_PLANAR && streams[i].order != SBS_INTERLEAVED) {
+            if (streams[i].order < 0 || streams[i].order > (int)(SBS_INTERLEAVED | SBS_NATURAL)) {
                 local[i] = B200JPG_ERR_INTERNAL;
                 continue;
             }

@@ -119,7 +119,7 @@ static void fill_k0(const b200jpg_image_desc& d, const ImageLayout& L, unsigned 
         k->h[c] = d.comps[c].h;
         k->v[c] = d.comps[c].v;
         nb += (unsigned)d.comps[c].block_w * d.comps[c].block_h;
-        if (order == SBS_INTERLEAVED)
+        if (order & SBS_INTERLEAVED)
             for (unsigned vy = 0; vy < d.comps[c].v; vy++)
                 for (unsigned hx = 0; hx < d.comps[c].h; hx++)
                     if (j < 12) {

@@ -591,3 +591,49 @@ def test_decode_files_streaming_engine(J, oracle_mod, ctxs):
                 assert s_ == w, (nthreads, i, s_, w)
             else:
                 assert s_ == 0 and np.array_equal(o, w), (nthreads, i, s_)
+
+
+def test_run_host_compaction_equals_dense_upload(J, oracle_mod):
+    """b200jpg_batch_run_host gives the same pixels whether the dense coefficients are uploaded as they are
+    (COMPACT_OFF) or compacted into sparse block streams by host threads first (COMPACT_ON): mixed geometries, a
+    grey image, a progressive one, an image the planner rejects and one with a missing component."""
+    from jpeg_decoder_b200 import workload
+    jobs = [workload.synth_jpeg(320, 176, 1, 2), workload.synth_jpeg(96, 64, 2, 0), workload.synth_jpeg(161, 99, 3, 1),
+            open(os.path.join(GOLDEN, "benches", "tower_grayscale.jpg"), "rb").read(), workload.synth_jpeg(640, 368, 4, 2, progressive=True),
+            workload.synth_jpeg(1920, 1080, 5, 2)]
+    decs, descs, wants = [], [], []
+    for data in jobs * 9:
+        d = J.Decoder(data)
+        decs.append(d)
+        descs.append(d.entropy_decode())
+        wants.append(oracle_mod.Decoder(data).decode())
+    bad = J.ImageDesc()
+    for f, _ in J.ImageDesc._fields_:
+        setattr(bad, f, getattr(descs[0], f))
+    bad.color_transform = J.CT_CMYK          # 3 components + CMYK: Format error
+    descs.insert(2, bad)
+    wants.insert(2, J.ERR_FORMAT)
+    hole = J.ImageDesc()
+    for f, _ in J.ImageDesc._fields_:
+        setattr(hole, f, getattr(descs[1], f))
+    hole.coefs[1] = None                     # "not all components have data"
+    descs.insert(7, hole)
+    wants.insert(7, J.ERR_FORMAT)
+    results = []
+    for mode, threads in ((J.COMPACT_OFF, 0), (J.COMPACT_ON, 0), (J.COMPACT_ON, 1), (J.COMPACT_ON, 5)):
+        ctx = J.Context(device=0, host_compact=mode, host_threads=threads)
+        try:
+            batch = J.Batch(ctx, descs)
+            outs = [np.zeros(int(d.width) * int(d.height) * int(d.ncomp), dtype=np.uint8) for d in descs]
+            try:
+                st = batch.run_host(outs)
+            except J.B200JpgError:
+                st = list(batch.statuses)
+            for i, (o, s_, w) in enumerate(zip(outs, st, wants)):
+                if isinstance(w, int):
+                    assert s_ == w, (mode, i, s_)
+                else:
+                    assert s_ == 0 and np.array_equal(o, w), (mode, threads, i, s_)
+            batch.close()
+        finally:
+            ctx.close()

@@ -27,7 +27,7 @@ def expand_stream(desc, buf, order):
     dense = [np.zeros((n, 64), dtype=np.int16) for n in nbs]
     # scan-order block -> (component, raster block)
     where = []
-    if order == 0:
+    if order & 1 == 0:
         for c, n in enumerate(nbs):
             where += [(c, b) for b in range(n)]
     else:
@@ -40,6 +40,7 @@ def expand_stream(desc, buf, order):
                         for hx in range(int(cp.h)):
                             where.append((c, (my * int(cp.v) + vy) * int(cp.block_w) + mx * int(cp.h) + hx))
     assert len(where) == nb
+    natural = bool(order & 2)
     at = 0
     for t in range(nb_pad):
         if t % 32 == 0:
@@ -59,7 +60,7 @@ def expand_stream(desc, buf, order):
                 else:
                     v = np.int8(vals[at])
                     at += 1
-                dense[c][b, UNZIGZAG[k]] = v
+                dense[c][b, k if natural else UNZIGZAG[k]] = v
     assert voff[nb_pad // 32] == at and off_vals + at <= buf.size
     return [d.reshape(-1) for d in dense]
 
@@ -118,3 +119,51 @@ def test_wide_values_and_grey(J):
         bm = buf[:8 * ((nb + 31) // 32 * 32)].view(np.uint64)
         assert (bm & np.uint64(1)).any()  # some block is wide
         check(J, data, want_order=1)
+
+
+def test_compacted_dense_buffers(J):
+    """b200jpg_sbs_from_dense (what b200jpg_batch_run_host's host threads do): PLANAR | NATURAL streams of real and of
+    adversarial coefficient buffers expand to the same coefficients."""
+    from jpeg_decoder_b200 import workload
+    for data in [workload.synth_jpeg(200, 120, seed=2, subsampling=2), open(bench_files()[0], "rb").read()]:
+        dec = J.Decoder(data)
+        d = dec.entropy_decode()
+        buf, order = J.sbs_from_dense(d)
+        assert order == 2
+        got = expand_stream(d, buf, order)
+        for c in range(d.ncomp):
+            assert np.array_equal(got[c], dec.coefficients(d, c))
+    # adversarial: every value class next to each other (zero, int8 limits, just beyond them, int16 limits)
+    rng = np.random.default_rng(9)
+    comps, _ = J.make_components(64, 48, [(1, 1)] * 3)
+    keep = []
+    coefs = [rng.choice(np.array([0, 0, 0, 1, -1, 127, -128, 128, -129, 32767, -32768], dtype=np.int16), 48 * 64) for _ in range(3)]
+    coefs[1][:64 * 10] = 0  # all-zero blocks
+    qts = [np.full(64, 1, dtype=np.uint16)] * 3
+    d = J.make_image_desc(64, 48, comps, qts, coefs, J.CT_YCBCR, keep)
+    buf, order = J.sbs_from_dense(d)
+    got = expand_stream(d, buf, order)
+    for c in range(3):
+        assert np.array_equal(got[c], coefs[c])
+
+
+def test_compaction_sse2_body_matches_avx512_body():
+    """The two bodies of SbsWriter::put_dense_natural_run write identical streams (B200JPG_NO_AVX512 selects SSE2)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys, zlib, numpy as np; sys.path.insert(0, %r); import jpeg_decoder_b200 as J; from jpeg_decoder_b200 import workload;"
+            "rng = np.random.default_rng(3); out = [];\n"
+            "for data in [workload.synth_jpeg(300, 200, seed=8, subsampling=2), workload.synth_jpeg(64, 64, seed=9, subsampling=0)]:\n"
+            "    dec = J.Decoder(data); d = dec.entropy_decode(); buf, order = J.sbs_from_dense(d); out.append(zlib.crc32(buf.tobytes()))\n"
+            "comps, _ = J.make_components(64, 48, [(1, 1)] * 3); keep = []\n"
+            "coefs = [rng.choice(np.array([0, 0, 0, 1, -1, 127, -128, 128, -129, 32767, -32768], dtype=np.int16), 48 * 64) for _ in range(3)]\n"
+            "d = J.make_image_desc(64, 48, comps, [np.full(64, 1, dtype=np.uint16)] * 3, coefs, J.CT_YCBCR, keep)\n"
+            "buf, order = J.sbs_from_dense(d); out.append(zlib.crc32(buf.tobytes())); print(out)") % root
+    runs = []
+    for env_extra in ({}, {"B200JPG_NO_AVX512": "1"}):
+        env = dict(os.environ, **env_extra)
+        runs.append(subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300))
+        assert runs[-1].returncode == 0, runs[-1].stderr
+    assert runs[0].stdout == runs[1].stdout and runs[0].stdout.startswith("[")
