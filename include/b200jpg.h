@@ -66,7 +66,10 @@ enum {
 /* b200jpg_batch_run_host takes dense coefficient buffers (the reference's Worker::append_row payload).  They are
  * mostly zeros, so host threads can compact them into sparse block streams (see "Sparse block streams" below)
  * before the upload: PCIe then carries ~1/5 of the bytes and the download of the pixels gets the link to itself.
- * AUTO compacts when the host has >= 8 CPUs for it and a sample of the batch is < 35 % non-zero. */
+ * Whether that pays depends on what bounds the host side: PCIe (it does) or host DRAM bandwidth (it does not: the
+ * CPU then reads what the DMA engine would have read).  AUTO therefore measures: a batch object that is run
+ * repeatedly uploads densely on runs 1-2, compacts on runs 3-4 (only with >= 8 CPUs and a sample of the batch
+ * < 35 % non-zero) and keeps whichever second run was faster. */
 enum { B200JPG_COMPACT_AUTO = 0, B200JPG_COMPACT_OFF = 1, B200JPG_COMPACT_ON = 2 };
 
 /* kernel selection, for tests and profiling (0 = pick the fastest applicable kernel) */

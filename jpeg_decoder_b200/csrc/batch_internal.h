@@ -63,7 +63,12 @@ struct b200jpg_batch {
     bool slabs_borrowed = false;   // d_coefs/d_planes/d_out belong to the context's scratch cache
     bool tables_borrowed = false;  // the d_* tables live in a caller's TableArena
     size_t table_bytes = 0;        // bytes of that arena in use
-    int compact_decision = -1;     // b200jpg_batch_run_host: -1 undecided, 0 dense upload, 1 host compaction
+    // b200jpg_batch_run_host, host_compact = AUTO: whether compaction pays depends on what bounds the host side
+    // (PCIe: it does; host DRAM bandwidth: it does not -- the CPU then reads what the DMA engine would have read), so
+    // a batch that is run repeatedly times its second dense run and its second compacted run and keeps the faster.
+    int compact_decision = -1;     // -1 undecided, 0 dense upload, 1 host compaction
+    int compact_trials = 0;
+    double compact_ms[2] = {0, 0};
 };
 
 // Caller-provided home of a plan's device tables: `bytes` of device memory at `d` mirrored by page-locked host

@@ -641,16 +641,33 @@ int b200jpg_batch_run_host(b200jpg_batch* b, const b200jpg_image_desc* imgs, uin
     if (!b || !imgs || !outs) return B200JPG_ERR_INTERNAL;
     b200jpg_ctx* ctx = b->ctx;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    bool use_compaction = b->compact_decision == 1;
+    bool trial = false;
     if (b->compact_decision < 0) {
         const int cpus = ctx->host_threads > 0 ? ctx->host_threads : stream_engine_default_threads();
-        b->compact_decision = ctx->host_compact == B200JPG_COMPACT_ON ||
-                              (ctx->host_compact == B200JPG_COMPACT_AUTO && b->n >= 4 && cpus >= 8 &&
-                               stream_engine_sample_density(imgs, b->n) < 0.35);
+        if (ctx->host_compact == B200JPG_COMPACT_ON) b->compact_decision = 1;
+        else if (ctx->host_compact == B200JPG_COMPACT_OFF || b->n < 4 || cpus < 8 || b->d_coefs) b->compact_decision = 0;
+        else if (b->compact_trials == 0 && stream_engine_sample_density(imgs, b->n) >= 0.35) b->compact_decision = 0;
+        use_compaction = b->compact_decision == 1;
+        if (b->compact_decision < 0) {  // AUTO: runs 1-2 dense, runs 3-4 compacted, then whichever second run was faster
+            trial = true;
+            use_compaction = b->compact_trials >= 2;
+        }
     }
-    if (b->compact_decision == 1) {
+    const double t_run0 = now();
+    if (use_compaction) {
         std::vector<int> plan(b->n);
         for (size_t m = 0; m < b->n; m++) plan[m] = b->layout[m].status;
-        return stream_engine_run_dense(ctx, imgs, b->n, plan.data(), outs, out_caps, statuses, ctx->host_threads);
+        const int rc = stream_engine_run_dense(ctx, imgs, b->n, plan.data(), outs, out_caps, statuses, ctx->host_threads);
+        if (trial && ++b->compact_trials == 4) {  // (the first run of each kind pays for allocations and page-locking)
+            b->compact_ms[1] = now() - t_run0;
+            b->compact_decision = b->compact_ms[1] < b->compact_ms[0] ? 1 : 0;
+            if (getenv("B200JPG_TRACE"))
+                fprintf(stderr, "[b200jpg] run_host auto: dense upload %.1f ms, host compaction %.1f ms -> %s\n", b->compact_ms[0],
+                        b->compact_ms[1], b->compact_decision ? "compaction" : "dense upload");
+        }
+        return rc;
     }
     if (!b->d_coefs && !b->d_planes && !b->d_out) {
         // internal slabs: borrow the context's grow-only scratch buffers when they are free (repeated batches then
@@ -765,6 +782,10 @@ int b200jpg_batch_run_host(b200jpg_batch* b, const b200jpg_image_desc* imgs, uin
     }
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream2));
+    if (trial) {
+        b->compact_ms[0] = now() - t_run0;
+        b->compact_trials++;
+    }
     return result;
 }
 
