@@ -1,0 +1,256 @@
+// entropy_dev.h -- Huffman entropy decoding of baseline scans ON THE DEVICE ("the step
+// before the path").  The reference decodes a scan with one sequential loop per image (src/decoder.rs:794-1172,
+// src/huffman.rs:20-161); the position of every code word depends on all code words before it.  What makes the
+// stream parallel anyway is that Huffman codes self-synchronise: a decoder started at a wrong bit position falls
+// into step with the true code-word boundaries after a few dozen symbols.  So the scan is cut into fixed
+// subsequences of ENT_SUB_BITS bits, one thread each:
+//
+//   cold  : every thread decodes its subsequence from the guess (bit 0 of the subsequence, block start) and
+//           publishes where it ended: state = (bit position p, zig-zag index k, block-in-MCU b, blocks completed)
+//   sync  : thread i re-decodes subsequence i from the state thread i-1 published; repeated while any published
+//           state still changes (only threads whose predecessor changed do work).  Subsequence 0 starts from the
+//           true state, so a pass without changes means state[i] = f_i(state[i-1]) for every i: the chain IS the
+//           sequential decode
+//   prefix: exclusive sum of "blocks completed" -> the index of the block every subsequence starts in
+//   write : every thread decodes once more from its predecessor's state and stores the coefficients it meets at
+//           their final place in the dense slab (the layout K1 reads); it re-checks state[i] = f_i(state[i-1]),
+//           so a stream that did not converge (or is malformed in any way) is detected, never mis-decoded
+//   dc    : DC differences -> DC values, a wrapping int16 prefix sum per component in scan order
+//
+// Anything the device flags goes back to the host decoder, which reproduces the reference's behaviour for
+// broken streams exactly.  This header is shared by the kernels (ke_entropy.cu), the host code that prepares
+// the payload (entropy_host.h) and a CPU emulation used by the tests (tests/cpp/entropy_emul.cpp).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define ENT_HD __host__ __device__ __forceinline__
+#else
+#define ENT_HD inline
+#endif
+
+namespace b200jpg {
+
+constexpr unsigned ENT_SUB_BITS = 1024;            // one thread's share of the scan
+constexpr unsigned ENT_SUB_BYTES = ENT_SUB_BITS / 8;
+constexpr unsigned ENT_LUT_BITS = 9;               // code words up to this length resolve with one table probe
+constexpr unsigned ENT_MAX_SLOTS = 4;              // Huffman tables per image (baseline: 2 DC + 2 AC)
+constexpr unsigned ENT_TAIL_SLACK_BITS = 2048;     // zero bits the last subsequence may read past the end of the scan
+constexpr unsigned ENT_MAGIC = 0x544e4542u;        // "BENT"
+
+// Anomalies: reasons the device result of an image is discarded and the image is decoded on the host instead.
+enum : unsigned {
+    ENT_BAD_SYMBOL = 1,    // no code word matches / DC category > 11 / EOBn in a sequential scan
+    ENT_BAD_RUN = 2,       // a run that leaves the block (src/decoder.rs:1149-1153 ends the block silently)
+    ENT_BAD_CHAIN = 4,     // state[i] != f_i(state[i-1]): the synchronisation passes did not converge
+    ENT_INCOMPLETE = 8,    // the scan ended before every block was decoded
+    ENT_BAD_PAYLOAD = 16,  // header / geometry mismatch
+};
+
+// One table entry: bits 0..4 code length (0 = not resolved by this probe), bits 5..8 number of value bits that
+// follow the code, bits 9..15 how far the zig-zag index advances (run + 1; 64 = end of block; 0 = anomaly).
+ENT_HD uint32_t ent_entry(unsigned len, unsigned s, unsigned adv) { return len | (s << 5) | (adv << 9); }
+
+// Decoding tables of one Huffman table ("slot").  Built on the host, copied to shared memory by the kernels.
+struct EntTables {
+    uint16_t lut[1u << ENT_LUT_BITS];  // indexed by the next ENT_LUT_BITS bits
+    uint32_t maxl[8];                  // lengths 10..16: (last code of that length + 1) << (16 - length), 0 if none
+    int32_t off[8];                    // lengths 10..16: canonical index of a code = code + off
+    uint16_t syment[256];              // by canonical index: entry without the length
+};
+static_assert(sizeof(EntTables) == 1600, "EntTables layout");
+
+// What the host writes in front of the unstuffed scan bytes.  All offsets are relative to the payload start.
+struct alignas(16) EntHeader {
+    uint32_t magic;
+    uint32_t scan_bytes;    // unstuffed entropy-coded bytes that follow the tables
+    uint32_t data_off;      // where they start (16-byte aligned); readable, zero-filled, up to payload_len
+    uint32_t payload_len;   // multiple of 16
+    uint32_t total_blocks;  // blocks the scan must deliver
+    uint32_t nslots;
+    uint8_t bpm;            // blocks per MCU
+    uint8_t pad_[3];
+    uint8_t dcslot[12], acslot[12];  // table slot of MCU block j
+    uint32_t tables_off;    // EntTables[nslots]
+    uint32_t reserved_[2];
+};
+static_assert(sizeof(EntHeader) == 64, "EntHeader layout");
+
+// Per-image descriptor of the kernels (built by the submitter from EntHeader + the image geometry).
+struct alignas(16) EntImage {
+    unsigned long long payload_off;  // byte offset of the payload inside the device stream buffer
+    unsigned data_off, scan_bits, nwords, nsub, sub0, total_blocks, mcu_w, nslots, tables_off;
+    unsigned slab_row[4];   // first 128-byte row of each component inside the coefficient slab
+    unsigned block_w[4];    // blocks per block row
+    unsigned comp_blocks[4];  // block_w * block_h, 0 for absent components
+    unsigned char bpm, ncomp;
+    unsigned char dec_bpm;  // period of the table pattern the decoder tracks as `b`: bpm, or 1 when every block of an MCU uses the
+                            // same tables (b then never influences decoding and would only delay synchronisation)
+    unsigned char pad_;
+    unsigned char h[4], v[4];
+    unsigned char mcu_comp[12], mcu_hx[12], mcu_vy[12], dcslot[12], acslot[12];
+    unsigned pad2_[3];
+};
+static_assert(sizeof(EntImage) % 16 == 0, "EntImage layout");
+
+// Published per subsequence.  Two states are "equal" for synchronisation purposes when p, k and b agree.
+struct EntState {
+    uint32_t p;   // bit position of the next code word (relative to the scan start)
+    uint32_t k;   // zig-zag index the next code word writes (0 = the next code word is a DC code)
+    uint32_t b;   // index of the current block inside its MCU
+    uint32_t nb;  // blocks completed while decoding the subsequence
+};
+ENT_HD uint64_t ent_pack(const EntState& s) {
+    return (uint64_t)s.p | ((uint64_t)(s.k & 127u) << 32) | ((uint64_t)(s.b & 31u) << 39) | ((uint64_t)(s.nb & 0xfffffu) << 44);
+}
+ENT_HD EntState ent_unpack(uint64_t v) {
+    EntState s;
+    s.p = (uint32_t)v;
+    s.k = (uint32_t)(v >> 32) & 127u;
+    s.b = (uint32_t)(v >> 39) & 31u;
+    s.nb = (uint32_t)(v >> 44) & 0xfffffu;
+    return s;
+}
+constexpr uint64_t ENT_SYNC_MASK = ((uint64_t)1 << 44) - 1;  // p, k, b
+
+ENT_HD uint32_t ent_bswap(uint32_t w) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(w, 0u, 0x0123u);
+#else
+    return __builtin_bswap32(w);
+#endif
+}
+// big-endian word i of the scan; zero beyond the end (the reference feeds zero bits once the data is exhausted,
+// src/huffman.rs:126-160)
+ENT_HD uint32_t ent_word(const uint32_t* words, uint32_t nwords, uint32_t i) { return i < nwords ? ent_bswap(words[i]) : 0u; }
+
+// code words longer than ENT_LUT_BITS bits (rare by construction: they are the improbable symbols)
+ENT_HD uint32_t ent_slow(const EntTables& T, uint32_t peek16) {
+#pragma unroll
+    for (unsigned i = 0; i < 7; i++) {
+        if (peek16 < T.maxl[i]) {
+            const unsigned len = 10 + i;
+            const int idx = (int)(peek16 >> (16 - len)) + T.off[i];
+            return (uint32_t)T.syment[idx & 255] | len;
+        }
+    }
+    return ent_entry(1, 0, 0);  // no code word matches: anomaly, skip one bit
+}
+
+// Sinks: what happens to decoded coefficients.
+struct EntNullSink {
+    ENT_HD void store(unsigned, int) {}
+    ENT_HD bool block_done() { return false; }
+};
+
+// Decodes code words starting at state `st` while they start before bit `end_bit`.  Returns the state after the
+// last one (nb = blocks completed here).  The function is deterministic in (st, end_bit) whatever the bits are:
+// that is all the synchronisation passes need from it.
+template <class Sink>
+ENT_HD EntState ent_decode_range(const uint32_t* words, uint32_t nwords, const EntTables* tabs, const uint8_t* dcslot,
+                                 const uint8_t* acslot, unsigned bpm, EntState st, uint32_t end_bit, Sink& sink, unsigned* anomaly) {
+    uint32_t p = st.p, k = st.k, b = st.b, nb = 0;
+    uint32_t wi = p >> 5;
+    uint32_t hi = ent_word(words, nwords, wi), lo = ent_word(words, nwords, wi + 1);
+    unsigned bad = 0;
+    while (p < end_bit) {
+        const uint32_t sh = p & 31u;
+#if defined(__CUDA_ARCH__)
+        const uint32_t win = __funnelshift_l(lo, hi, sh);
+#else
+        const uint32_t win = sh ? (hi << sh) | (lo >> (32u - sh)) : hi;
+#endif
+        const EntTables& T = tabs[k == 0 ? dcslot[b] : acslot[b]];
+        uint32_t e = T.lut[win >> (32u - ENT_LUT_BITS)];
+        if ((e & 31u) == 0) e = ent_slow(T, win >> 16);
+        const uint32_t len = e & 31u, s = (e >> 5) & 15u;
+        uint32_t adv = e >> 9;
+        if (adv == 0) {
+            bad |= ENT_BAD_SYMBOL;
+            adv = 1;
+        }
+        if (s) {
+            const uint32_t pos = k + adv - 1;
+            const uint32_t u = (win << len) >> (32u - s);
+            // extend(), src/huffman.rs:98-... / Figure F.12
+            const int v = u < (1u << (s - 1)) ? (int)u - (int)(1u << s) + 1 : (int)u;
+            if (pos <= 63u) sink.store(pos, v);
+            else bad |= ENT_BAD_RUN;
+        }
+        p += len + s;
+        k += adv;
+        const uint32_t nwi = p >> 5;
+        if (nwi != wi) {  // len + s <= 31: at most one word further
+            hi = lo;
+            lo = ent_word(words, nwords, nwi + 1);
+            wi = nwi;
+        }
+        if (k >= 64u) {
+            k = 0;
+            nb++;
+            b = b + 1 == bpm ? 0 : b + 1;
+            if (sink.block_done()) break;
+        }
+    }
+    if (bad) *anomaly |= bad;
+    EntState r;
+    r.p = p;
+    r.k = k;
+    r.b = b;
+    r.nb = nb;
+    return r;
+}
+
+// The write pass: coefficients go to their place in the dense slab (blocks of 64 int16 in natural order, per
+// component in raster order -- what Worker::append_row receives, src/decoder.rs:962-983).  DC code words store
+// the DIFFERENCE at position 0; the dc pass turns differences into values.
+struct EntWriteSink {
+    int16_t* coefs;
+    const EntImage* im;
+    const uint8_t* unzz;  // zig-zag index -> natural position
+    uint32_t B, j, mx, my;
+    int16_t* cur;
+    ENT_HD void locate() {
+        const unsigned c = im->mcu_comp[j];
+        const unsigned bx = mx * im->h[c] + im->mcu_hx[j], by = my * im->v[c] + im->mcu_vy[j];
+        cur = coefs + ((size_t)im->slab_row[c] + (size_t)by * im->block_w[c] + bx) * 64;
+    }
+    ENT_HD void begin(int16_t* slab, const EntImage* image, const uint8_t* unzigzag, uint32_t first_block) {
+        coefs = slab;
+        im = image;
+        unzz = unzigzag;
+        B = first_block;
+        const uint32_t m = B / im->bpm;
+        j = B % im->bpm;
+        mx = m % im->mcu_w;
+        my = m / im->mcu_w;
+        cur = slab;
+        if (B < im->total_blocks) locate();
+    }
+    ENT_HD void store(unsigned pos, int v) {
+        if (B < im->total_blocks) cur[unzz[pos]] = (int16_t)v;
+    }
+    ENT_HD bool block_done() {
+        B++;
+        if (++j == im->bpm) {
+            j = 0;
+            if (++mx == im->mcu_w) {
+                mx = 0;
+                my++;
+            }
+        }
+        if (B >= im->total_blocks) return true;
+        locate();
+        return false;
+    }
+};
+
+// where subsequence i of an image ends (the last one ends with the scan)
+ENT_HD uint32_t ent_sub_end(uint32_t i, uint32_t nsub, uint32_t scan_bits) { return i + 1 < nsub ? (i + 1) * ENT_SUB_BITS : scan_bits; }
+
+// zig-zag index -> natural position, src/decoder.rs:27-36
+#define ENT_UNZIGZAG_INIT                                                                                                      \
+    {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6,  7,  14, 21, 28, \
+     35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63}
+
+}  // namespace b200jpg

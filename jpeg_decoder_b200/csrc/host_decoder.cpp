@@ -984,6 +984,26 @@ int HostDecoder::decode_scan(const ScanInfo& scan, const bool finished[4], bool*
     return 0;
 }
 
+// The conditions under which decode_scan would take its `direct` route with nothing left to go wrong before the
+// first code word: every check decode_scan makes up front holds, so the host would start decoding here.
+bool HostDecoder::device_scan_ok(const ScanInfo& scan) const {
+    const FrameInfo& f = frame_;
+    if (f.coding_process != B200JPG_CP_DCT_SEQUENTIAL || f.precision != 8 || is_mjpeg_ || restart_interval_ != 0) return false;
+    if (scan.n != (int)f.comps.size() || scan.ss_start != 0 || scan.ss_end != 64 || scan.al != 0 || scan.ah != 0) return false;
+    if (scan.n == 1 && (f.comps[0].h != 1 || f.comps[0].v != 1)) return false;
+    unsigned bpm = 0;
+    for (int i = 0; i < scan.n; i++) {
+        if (scan.comp_index[i] != i || finished_mask_[i] != 0) return false;
+        if (!has_qt_[f.comps[(size_t)i].tq] || !dc_[scan.dc_table[i]].present || !ac_[scan.ac_table[i]].present) return false;
+        bpm += (unsigned)f.comps[(size_t)i].h * f.comps[(size_t)i].v;
+    }
+    if (bpm > 10 || buffer_limit_exceeded()) return false;
+    return true;
+}
+void HostDecoder::capture_final_qtables() {
+    for (size_t i = 0; i < frame_.comps.size() && i < 4; i++) memcpy(final_qt_[i], qt_[frame_.comps[i].tq], 128);
+}
+
 // Ends the sparse stream: a directly written one is padded; otherwise the dense per-component buffers the
 // scans produced are compacted in planar order (the reference's worker would receive exactly these blocks).
 int HostDecoder::finish_sbs() {
@@ -1042,6 +1062,13 @@ int HostDecoder::decode_internal(bool stop_after_metadata) {
             }
             if (frame.coding_process == B200JPG_CP_LOSSLESS)
                 return fail(B200JPG_ERR_UNSUPPORTED, "lossless JPEG (SOF3) bypasses the worker path and is not built (SURVEY section 2)");
+            if (probe_device_ && scans_processed == 0 && device_scan_ok(scan)) {
+                device_scan_.eligible = true;
+                device_scan_.scan_begin = pos_;
+                device_scan_.scan = scan;
+                capture_final_qtables();
+                return B200JPG_INTERNAL_DEVICE_SCAN;
+            }
             bool finished[4] = {false, false, false, false};
             if (scan.al == 0)
                 for (int k = 0; k < scan.n; k++) {

@@ -48,6 +48,17 @@ struct ScanInfo {  // src/parser.rs:64-74
     uint8_t ss_start = 0, ss_end = 0, ah = 0, al = 0;
 };
 
+// Filled at the first SOS when probing for device entropy decoding (entropy_dev.h): the scan is a complete
+// sequential single-scan image (every component, in frame order, interleaved or a lone 1x1 component, no restart
+// interval, all tables present) -- the case HostDecoder would write straight into a sparse stream.
+struct DeviceScan {
+    bool eligible = false;
+    size_t scan_begin = 0;  // offset of the first entropy-coded byte in the file
+    ScanInfo scan;
+};
+// positive (not an error): entropy_decode() stopped at the first SOS because the scan qualifies for the device
+enum { B200JPG_INTERNAL_DEVICE_SCAN = 1 };
+
 struct IccChunk {
     uint8_t num_markers, seq_no;
     std::vector<uint8_t> data;
@@ -63,6 +74,15 @@ public:
     // all scans up to EOI; afterwards coefficients(i) are what the worker boundary receives
     int entropy_decode() { return decode_internal(false); }
     int scale(uint16_t req_w, uint16_t req_h, uint16_t* w, uint16_t* h);
+
+    // Optional: entropy_decode() returns B200JPG_INTERNAL_DEVICE_SCAN at the first SOS of a qualifying scan instead of
+    // decoding it; device_scan() then says where the entropy-coded bytes start.  Otherwise nothing changes.
+    void probe_device_scan(bool on) { probe_device_ = on; }
+    const DeviceScan& device_scan() const { return device_scan_; }
+    const HuffTable& dc_table(int i) const { return dc_[i & 3]; }
+    const HuffTable& ac_table(int i) const { return ac_[i & 3]; }
+    // what decode_scan records for the worker when a component is finished by the (only) scan
+    void capture_final_qtables();
 
     bool has_frame() const { return has_frame_; }
     const FrameInfo& frame() const { return frame_; }
@@ -155,6 +175,9 @@ private:
     SbsWriter sbs_;
     bool sbs_direct_ = false;
     size_t sbs_len_ = 0;
+    bool probe_device_ = false;
+    DeviceScan device_scan_;
+    bool device_scan_ok(const ScanInfo& scan) const;
     // bit reader (src/huffman.rs:14-18)
     uint64_t bits_ = 0;
     uint8_t num_bits_ = 0;

@@ -1,0 +1,243 @@
+// entropy_emul.cpp -- CPU emulation of the device entropy decoder (csrc/entropy_dev.h), pass by pass, with the very
+// functions the kernels call (ent_decode_range, EntWriteSink, ent_build_tables, ent_build_payload, ent_fill_image).
+// For each JPEG file given:
+//   * decodes it with the host decoder (the reference's sequential Huffman loop) -> dense coefficients
+//   * runs cold / sync* / prefix / write / dc exactly as the kernels do (Jacobi passes, predecessor-changed flags)
+//   * requires: device result accepted  =>  host decode succeeded and every coefficient is identical
+// With --corrupt N SEED the same is repeated for N corrupted copies of each file (random byte edits inside the
+// scan): the device path must either flag the image or agree with the host bit for bit.
+// Test infrastructure only (tests/test_entropy_emul.py builds it with g++).
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <random>
+#include <string>
+#include <vector>
+
+#include "../../jpeg_decoder_b200/csrc/entropy_host.h"
+
+using namespace b200jpg;
+
+static const uint8_t UNZZ[64] = ENT_UNZIGZAG_INIT;
+
+struct EmulResult {
+    bool eligible = false;
+    unsigned status = 0;  // anomaly bits
+    unsigned passes = 0, nsub = 0;
+    std::vector<int16_t> coefs;  // all components back to back
+};
+
+static EmulResult emulate(const std::vector<uint8_t>& file, const HostDecoder& probe, const b200jpg_image_desc& d, int max_passes) {
+    EmulResult r;
+    std::vector<uint8_t> payload(ent_payload_bound(file.size()) + 64);
+    const size_t plen = ent_build_payload(probe, file.data(), file.size(), payload.data(), payload.size());
+    if (!plen) return r;
+    EntHeader h;
+    memcpy(&h, payload.data(), sizeof h);
+    size_t coef_off[4] = {0, 0, 0, 0}, total = 0;
+    for (int c = 0; c < d.ncomp; c++) {
+        coef_off[c] = total;
+        total += (size_t)d.comps[c].block_w * d.comps[c].block_h * 128;
+    }
+    EntImage im;
+    if (!ent_fill_image(h, d, coef_off, 0, 0, &im)) return r;
+    r.eligible = true;
+    r.nsub = im.nsub;
+    r.coefs.assign(total / 2, 0);
+    const uint32_t* words = (const uint32_t*)(payload.data() + im.data_off);
+    const EntTables* tabs = (const EntTables*)(payload.data() + im.tables_off);
+    const unsigned n = im.nsub;
+    std::vector<uint64_t> state(n);
+    std::vector<uint8_t> chA(n, 1), chB(n, 0);
+    unsigned dummy = 0;
+    // cold
+    for (unsigned i = 0; i < n; i++) {
+        EntNullSink sink;
+        EntState st{i * ENT_SUB_BITS, 0, 0, 0};
+        state[i] = ent_pack(ent_decode_range(words, im.nwords, tabs, im.dcslot, im.acslot, im.dec_bpm, st, ent_sub_end(i, n, im.scan_bits), sink, &dummy));
+    }
+    // sync: Jacobi on a snapshot (the kernels read/write in place; any interleaving is covered by "repeat until a
+    // pass changes nothing")
+    uint8_t *cin = chA.data(), *cout = chB.data();
+    for (int pass = 0; pass < max_passes; pass++) {
+        std::vector<uint64_t> snap = state;
+        unsigned nchanged = 0;
+        for (unsigned i = 0; i < n; i++) {
+            cout[i] = 0;
+            if (i == 0 || !cin[i - 1]) continue;
+            EntNullSink sink;
+            const EntState st = ent_unpack(snap[i - 1]);
+            const uint64_t v = ent_pack(ent_decode_range(words, im.nwords, tabs, im.dcslot, im.acslot, im.dec_bpm, EntState{st.p, st.k, st.b, 0},
+                                                         ent_sub_end(i, n, im.scan_bits), sink, &dummy));
+            if ((v ^ snap[i]) & ENT_SYNC_MASK) {
+                cout[i] = 1;
+                nchanged++;
+            }
+            state[i] = v;
+        }
+        std::swap(cin, cout);
+        r.passes++;
+        if (!nchanged) break;
+    }
+    // prefix
+    std::vector<uint32_t> first(n);
+    uint32_t acc = 0;
+    for (unsigned i = 0; i < n; i++) {
+        first[i] = acc;
+        acc += ent_unpack(state[i]).nb;
+    }
+    // write
+    bool completed = false;
+    for (unsigned i = 0; i < n; i++) {
+        if (first[i] >= im.total_blocks) continue;
+        EntState st{0, 0, 0, 0};
+        if (i) {
+            st = ent_unpack(state[i - 1]);
+            st.nb = 0;
+        }
+        EntWriteSink sink;
+        sink.begin(r.coefs.data(), &im, UNZZ, first[i]);
+        const bool last = i + 1 == n;
+        const uint32_t end = last ? im.scan_bits + ENT_TAIL_SLACK_BITS : ent_sub_end(i, n, im.scan_bits);
+        unsigned bad = 0;
+        const EntState e = ent_decode_range(words, im.nwords, tabs, im.dcslot, im.acslot, im.dec_bpm, st, end, sink, &bad);
+        if (sink.B >= im.total_blocks) completed = true;
+        else if (last) bad |= ENT_INCOMPLETE;
+        else if (ent_pack(e) != state[i]) bad |= ENT_BAD_CHAIN;
+        r.status |= bad;
+    }
+    if (!completed) r.status |= ENT_INCOMPLETE;
+    // dc: differences -> values, per component in scan order
+    for (int c = 0; c < d.ncomp; c++) {
+        const unsigned hv = (unsigned)im.h[c] * im.v[c];
+        uint16_t pred = 0;
+        for (unsigned q = 0; q < im.comp_blocks[c]; q++) {
+            const unsigned m = q / hv, rr = q % hv, vy = rr / im.h[c], hx = rr % im.h[c];
+            const unsigned mx = m % im.mcu_w, my = m / im.mcu_w;
+            int16_t* blk = r.coefs.data() + ((size_t)im.slab_row[c] + (size_t)(my * im.v[c] + vy) * im.block_w[c] + mx * im.h[c] + hx) * 64;
+            pred = (uint16_t)(pred + (uint16_t)blk[0]);
+            blk[0] = (int16_t)pred;
+        }
+    }
+    return r;
+}
+
+struct HostResult {
+    int status = 0;
+    bool complete = false;
+    std::vector<int16_t> coefs;
+    b200jpg_image_desc desc;
+};
+
+static HostResult host_decode(const std::vector<uint8_t>& file) {
+    HostResult r;
+    memset(&r.desc, 0, sizeof r.desc);
+    HostDecoder hd(file.data(), file.size());
+    r.status = hd.entropy_decode();
+    if (r.status != B200JPG_OK) return r;
+    r.complete = true;
+    for (size_t c = 0; c < hd.frame().comps.size(); c++) {
+        if (!hd.component_has_data((int)c)) r.complete = false;
+        else {
+            const size_t n = (size_t)hd.frame().comps[c].block_w * hd.frame().comps[c].block_h * 64;
+            r.coefs.insert(r.coefs.end(), hd.coefficients((int)c), hd.coefficients((int)c) + n);
+        }
+    }
+    return r;
+}
+
+// 0 = fine, 1 = mismatch
+static int check(const std::vector<uint8_t>& file, const char* name, int max_passes, bool verbose, unsigned* n_device, unsigned* n_flagged) {
+    HostDecoder probe(file.data(), file.size());
+    probe.probe_device_scan(true);
+    const int st = probe.entropy_decode();
+    if (st != B200JPG_INTERNAL_DEVICE_SCAN) {
+        if (verbose) printf("%s: host path (status %d)\n", name, st);
+        return 0;
+    }
+    b200jpg_image_desc d;
+    memset(&d, 0, sizeof d);
+    d.ncomp = (uint8_t)probe.frame().comps.size();
+    for (int c = 0; c < d.ncomp; c++) d.comps[c] = probe.frame().comps[(size_t)c];
+    const EmulResult e = emulate(file, probe, d, max_passes);
+    if (!e.eligible) {
+        if (verbose) printf("%s: host path (scan does not qualify)\n", name);
+        return 0;
+    }
+    if (e.status) {
+        (*n_flagged)++;
+        if (verbose) printf("%s: flagged 0x%x after %u passes (%u subsequences) -> host\n", name, e.status, e.passes, e.nsub);
+        return 0;
+    }
+    (*n_device)++;
+    const HostResult h = host_decode(file);
+    if (h.status != B200JPG_OK || !h.complete) {
+        printf("%s: MISMATCH device accepted, host status %d complete %d\n", name, h.status, (int)h.complete);
+        return 1;
+    }
+    if (h.coefs.size() != e.coefs.size() || memcmp(h.coefs.data(), e.coefs.data(), h.coefs.size() * 2) != 0) {
+        size_t k = 0;
+        while (k < h.coefs.size() && k < e.coefs.size() && h.coefs[k] == e.coefs[k]) k++;
+        printf("%s: MISMATCH at coefficient %zu (block %zu pos %zu): host %d device %d\n", name, k, k / 64, k % 64, k < h.coefs.size() ? h.coefs[k] : -1,
+               k < e.coefs.size() ? e.coefs[k] : -1);
+        return 1;
+    }
+    if (verbose) printf("%s: device == host, %u subsequences, %u sync passes\n", name, e.nsub, e.passes);
+    return 0;
+}
+
+int main(int argc, char** argv) {
+    int ncorrupt = 0, max_passes = 64;
+    unsigned seed = 1;
+    std::vector<std::string> files;
+    for (int i = 1; i < argc; i++) {
+        if (!strcmp(argv[i], "--corrupt") && i + 2 < argc) {
+            ncorrupt = atoi(argv[i + 1]);
+            seed = (unsigned)atoi(argv[i + 2]);
+            i += 2;
+        } else if (!strcmp(argv[i], "--passes") && i + 1 < argc) {
+            max_passes = atoi(argv[++i]);
+        } else {
+            files.push_back(argv[i]);
+        }
+    }
+    int bad = 0;
+    unsigned n_device = 0, n_flagged = 0;
+    for (const auto& path : files) {
+        FILE* f = fopen(path.c_str(), "rb");
+        if (!f) {
+            printf("cannot open %s\n", path.c_str());
+            return 2;
+        }
+        std::vector<uint8_t> data;
+        uint8_t buf[65536];
+        size_t got;
+        while ((got = fread(buf, 1, sizeof buf, f)) > 0) data.insert(data.end(), buf, buf + got);
+        fclose(f);
+        bad += check(data, path.c_str(), max_passes, true, &n_device, &n_flagged);
+        if (ncorrupt > 0) {
+            // locate the scan so that the edits land in entropy-coded data
+            HostDecoder probe(data.data(), data.size());
+            probe.probe_device_scan(true);
+            if (probe.entropy_decode() != B200JPG_INTERNAL_DEVICE_SCAN) continue;
+            const size_t begin = probe.device_scan().scan_begin;
+            if (begin + 4 >= data.size()) continue;
+            std::mt19937 rng(seed);
+            for (int t = 0; t < ncorrupt; t++) {
+                std::vector<uint8_t> c = data;
+                const int kind = (int)(rng() % 4);
+                const size_t at = begin + rng() % (c.size() - begin - 2);
+                if (kind == 0) c[at] ^= (uint8_t)(1u << (rng() % 8));                      // one bit
+                else if (kind == 1) c[at] = (uint8_t)rng();                                // one byte
+                else if (kind == 2) c.erase(c.begin() + (long)at, c.begin() + (long)std::min(c.size() - 2, at + 1 + rng() % 64));  // drop a run
+                else for (size_t q = at; q < std::min(c.size() - 2, at + 1 + rng() % 32); q++) c[q] = (uint8_t)rng();       // scramble a run
+                char name[512];
+                snprintf(name, sizeof name, "%s#%d", path.c_str(), t);
+                bad += check(c, name, max_passes, false, &n_device, &n_flagged);
+            }
+        }
+    }
+    printf("%s %u decoded on the emulated device, %u flagged for the host\n", bad ? "FAILED" : "ok", n_device, n_flagged);
+    return bad ? 1 : 0;
+}

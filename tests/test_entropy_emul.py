@@ -1,0 +1,77 @@
+"""Device entropy decoding (csrc/entropy_dev.h), emulated on the CPU pass by pass with the functions the kernels
+call (tests/cpp/entropy_emul.cpp): cold start, synchronisation passes, block prefix, write pass, DC prefix.
+
+The property under test is the one the product relies on: whenever the device path ACCEPTS an image, its dense
+coefficients equal what the host decoder -- the restatement of the reference's sequential Huffman loop,
+src/huffman.rs + src/decoder.rs:1086-1172 -- produces, bit for bit; everything else is flagged and goes to the host.
+Checked on every reftest / bench fixture, on synthetic BASELINE-shaped files and on ~1500 corrupted scans.
+CPU only (the GPU kernels themselves are covered by tests/test_gpu_entropy.py)."""
+import glob
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "jpeg_decoder_b200")
+
+
+@pytest.fixture(scope="module")
+def emul(tmp_path_factory):
+    from jpeg_decoder_b200 import build
+    build.build()
+    exe = str(tmp_path_factory.mktemp("emul") / "entropy_emul")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "cpp", "entropy_emul.cpp"),
+                           os.path.join(PKG, "csrc", "host_decoder.cpp"), "-L" + PKG, "-lb200jpg", "-Wl,-rpath," + PKG])
+    return exe
+
+
+def run(exe, args):
+    out = subprocess.run([exe, *args], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-4000:] + out.stderr[-2000:]
+    last = out.stdout.strip().splitlines()[-1]
+    assert last.startswith("ok "), last
+    return out.stdout
+
+
+def test_fixtures_decode_identically(emul):
+    files = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "reftest", "**", "*.jpg"), recursive=True))
+    files += sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "benches", "*.jpg")))
+    assert len(files) > 30
+    text = run(emul, files)
+    # the baseline fixtures really take the device route (not merely "nothing mismatched because nothing ran")
+    for name in ("tower.jpg", "rgb.jpg", "jpg-size-33x33.jpg", "jpg-cmyk-1.jpg", "grayscale_large.jpg", "16bit-qtables.jpg"):
+        line = [l for l in text.splitlines() if l.split(":")[0].endswith(name)]
+        assert line and "device == host" in line[0], (name, line)
+    # progressive / restart-interval / non-interleaved files stay with the host decoder
+    for name in ("tower_progressive.jpg", "restarts.jpg", "non-interleaved-mcu.jpg", "mjpeg.jpg"):
+        line = [l for l in text.splitlines() if l.split(":")[0].endswith(name)]
+        assert line and "host path" in line[0], (name, line)
+
+
+def test_crashtest_files_never_mismatch(emul):
+    files = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "crashtest", "**", "*.jpg"), recursive=True))
+    assert len(files) > 50
+    run(emul, files)
+
+
+@pytest.mark.parametrize("shape", [(1920, 1080, 2), (640, 480, 0), (333, 217, 1), (48, 1000, 2)])
+def test_synthetic_baseline_shapes(emul, tmp_path, shape):
+    from jpeg_decoder_b200 import workload
+    w, h, ss = shape
+    p = tmp_path / "s.jpg"
+    p.write_bytes(workload.synth_jpeg(w, h, seed=1234, subsampling=ss))
+    assert "device == host" in run(emul, [str(p)])
+
+
+def test_corrupted_scans_are_flagged_or_identical(emul, tmp_path):
+    from jpeg_decoder_b200 import workload
+    p = tmp_path / "s.jpg"
+    p.write_bytes(workload.synth_jpeg(333, 217, seed=5, subsampling=2))
+    g = os.path.join(ROOT, "tests", "golden")
+    text = run(emul, ["--corrupt", "300", "7", str(p), os.path.join(g, "benches", "tower.jpg"),
+                      os.path.join(g, "reftest", "mozilla", "jpg-size-33x33.jpg"), os.path.join(g, "reftest", "mozilla", "jpg-cmyk-1.jpg"),
+                      os.path.join(g, "reftest", "grayscale_large.jpg")])
+    last = text.strip().splitlines()[-1].split()
+    decoded, flagged = int(last[1]), int(last[7])
+    assert decoded > 300 and flagged > 100, last  # both outcomes occur
