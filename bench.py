@@ -438,18 +438,30 @@ def main():
         for j in range(Bf):
             jobs[j].data, jobs[j].len = fbufs[j % len(jpegs)].ctypes.data, fbufs[j % len(jpegs)].size
             jobs[j].out, jobs[j].out_cap = f_outs[j].ctypes.data, f_outs[j].size
-        ctx.check(J.lib().b200jpg_decode_files(ctx._h, jobs, Bf, nthreads))   # warm-up (allocates the cached arenas)
-        f_reps = 3
-        t0 = time.perf_counter()
-        for _ in range(f_reps):
-            ctx.check(J.lib().b200jpg_decode_files(ctx._h, jobs, Bf, nthreads))
-        f_dt = (time.perf_counter() - t0) / f_reps
-        assert all(jobs[j].status == 0 for j in range(Bf))
-        assert bool(np.array_equal(f_outs[0], ref0))
-        files_e2e = {"value": Bf * W * H / 1e6 / f_dt, "unit": "MP/s", "images": Bf, "host_threads": nthreads,
+        def time_files(c):
+            c.check(J.lib().b200jpg_decode_files(c._h, jobs, Bf, nthreads))   # warm-up (allocates the cached arenas)
+            reps = 3
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                c.check(J.lib().b200jpg_decode_files(c._h, jobs, Bf, nthreads))
+            dt = (time.perf_counter() - t0) / reps
+            assert all(jobs[j].status == 0 for j in range(Bf))
+            assert bool(np.array_equal(f_outs[0], ref0))
+            return Bf * W * H / 1e6 / dt, reps
+        # Huffman decoding on the device (the default for complete baseline scans), then forced onto the host threads
+        f_value, f_reps = time_files(ctx)
+        scans = ctx.device_scan_counts
+        f_out[:] = 0
+        ctx_h = J.Context(device=local_rank, arith=arith, k1_kernel=kmap[args.k1], k2_kernel=kmap[args.k2], entropy=J.ENTROPY_HOST)
+        fh_value, _ = time_files(ctx_h)
+        ctx_h.close()
+        files_e2e = {"value": f_value, "unit": "MP/s", "images": Bf, "host_threads": nthreads,
                      "jpeg_bytes_per_image": int(np.mean([len(j) for j in jpegs])),
-                     "calls": f_reps,
-                     "api": "b200jpg_decode_files (JPEG bytes -> pixels; Huffman on the host -> sparse block streams -> K0/K1/K2 on the GPU)"}
+                     "calls": f_reps, "scans_decoded_on_device": int(scans[0]), "scans_handed_back_to_host": int(scans[1]),
+                     "host_entropy": {"value": fh_value, "unit": "MP/s",
+                                      "api": "same call with B200JPG_ENTROPY_HOST: Huffman on the host threads -> sparse block streams -> K0/K1/K2"},
+                     "api": "b200jpg_decode_files (JPEG bytes -> pinned host pixels; host threads parse markers and copy the scan, "
+                            "Huffman decoding + K1 + K2 on the GPU)"}
     pcie = pcie_probe(torch, dev) if rank == 0 else None
     os.sched_setaffinity(0, all_cpus)   # the CPU baseline uses every core
     cpu_baseline = None

@@ -72,6 +72,13 @@ enum {
  * < 35 % non-zero) and keeps whichever second run was faster. */
 enum { B200JPG_COMPACT_AUTO = 0, B200JPG_COMPACT_OFF = 1, B200JPG_COMPACT_ON = 2 };
 
+/* Where the Huffman entropy decoding of b200jpg_decode_files happens.  The reference decodes a scan with one
+ * sequential loop per image (src/huffman.rs, src/decoder.rs:1086-1172).  DEVICE: complete baseline single-scan images
+ * without restart intervals are decoded by the GPU (self-synchronising parallel Huffman decoding, csrc/entropy_dev.h);
+ * host threads then only parse markers and copy the scan bytes.  Every other image, and every image whose scan the
+ * device flags as irregular in any way, is decoded by the host loop, so results and errors never differ. */
+enum { B200JPG_ENTROPY_AUTO = 0, B200JPG_ENTROPY_HOST = 1, B200JPG_ENTROPY_DEVICE = 2 };
+
 /* kernel selection, for tests and profiling (0 = pick the fastest applicable kernel) */
 enum { B200JPG_KERNEL_AUTO = 0, B200JPG_KERNEL_GENERIC = 1, B200JPG_KERNEL_FAST = 2 };
 
@@ -94,7 +101,8 @@ typedef struct {
     void *stream;     /* cudaStream_t to enqueue on; NULL = the context creates its own    */
     int host_compact; /* b200jpg_batch_run_host: B200JPG_COMPACT_* (0 = decide per batch)   */
     int host_threads; /* host threads of the host-fed paths; 0 = one per CPU of the process */
-    int reserved[2];
+    int entropy;      /* b200jpg_decode_files: B200JPG_ENTROPY_* (0 = device where it applies)    */
+    int reserved[1];
 } b200jpg_options;
 
 typedef struct b200jpg_ctx b200jpg_ctx;
@@ -108,6 +116,9 @@ B200JPG_API const char *b200jpg_version(void);
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */
 B200JPG_API uint64_t b200jpg_launch_count(const b200jpg_ctx *ctx);
 B200JPG_API int b200jpg_synchronize(b200jpg_ctx *ctx);
+/* b200jpg_decode_files since creation: scans whose Huffman decoding ran on the device, and how many of those the
+ * device flagged and handed back to the host loop (see B200JPG_ENTROPY_*) */
+B200JPG_API void b200jpg_device_scan_counts(const b200jpg_ctx *ctx, uint64_t *decoded, uint64_t *retried);
 
 /* parser::update_component_sizes, src/parser.rs:292-310: fills size_* / block_* of comps[] from the
  * sampling factors and dct_scale already set in them. */

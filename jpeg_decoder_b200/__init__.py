@@ -16,7 +16,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._native import (ARITH_SCALAR, ARITH_SSSE3, COMPACT_AUTO, COMPACT_OFF, COMPACT_ON, CP_DCT_PROGRESSIVE, CP_DCT_SEQUENTIAL, CP_LOSSLESS, CT_CMYK,
+from ._native import (ARITH_SCALAR, ARITH_SSSE3, ENTROPY_AUTO, ENTROPY_DEVICE, ENTROPY_HOST, COMPACT_AUTO, COMPACT_OFF, COMPACT_ON, CP_DCT_PROGRESSIVE, CP_DCT_SEQUENTIAL, CP_LOSSLESS, CT_CMYK,
                       CT_GRAYSCALE, CT_JCS_BG_RGB, CT_JCS_BG_YCC, CT_NONE, CT_RGB, CT_UNKNOWN, CT_YCBCR, CT_YCCK,
                       ERR_FORMAT, ERR_INTERNAL, ERR_IO, ERR_UNSUPPORTED, KERNEL_AUTO, KERNEL_FAST, KERNEL_GENERIC, OK,
                       PF_CMYK32, PF_L8, PF_L16, PF_RGB24, SBS_INTERLEAVED, SBS_NATURAL, SBS_PLANAR, BatchInfo, Component, FileJob, ImageDesc,
@@ -81,12 +81,13 @@ class Context:
     """b200jpg_ctx: one per device/stream."""
 
     def __init__(self, device=0, arith=ARITH_SCALAR, k1_kernel=KERNEL_AUTO, k2_kernel=KERNEL_AUTO, stream=None,
-                 host_compact=COMPACT_AUTO, host_threads=0):
+                 host_compact=COMPACT_AUTO, host_threads=0, entropy=0):
         opt = Options()
         lib().b200jpg_default_options(C.byref(opt))
         opt.device, opt.arith, opt.k1_kernel, opt.k2_kernel = device, arith, k1_kernel, k2_kernel
         opt.stream = stream
         opt.host_compact, opt.host_threads = host_compact, host_threads
+        opt.entropy = entropy  # ENTROPY_AUTO / ENTROPY_HOST / ENTROPY_DEVICE
         h = C.c_void_p()
         rc = lib().b200jpg_create(C.byref(opt), C.byref(h))
         if rc:
@@ -111,6 +112,13 @@ class Context:
     @property
     def launch_count(self):
         return lib().b200jpg_launch_count(self._h)
+
+    @property
+    def device_scan_counts(self):
+        """(scans Huffman-decoded on the GPU, scans the GPU handed back to the host) by decode_files so far."""
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        lib().b200jpg_device_scan_counts(self._h, C.byref(a), C.byref(b))
+        return a.value, b.value
 
 
 class Worker:

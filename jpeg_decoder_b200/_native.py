@@ -24,7 +24,7 @@ class Component(C.Structure):
 
 class Options(C.Structure):
     _fields_ = [("device", C.c_int), ("arith", C.c_int), ("k1_kernel", C.c_int), ("k2_kernel", C.c_int),
-                ("stream", C.c_void_p), ("host_compact", C.c_int), ("host_threads", C.c_int), ("reserved", C.c_int * 2)]
+                ("stream", C.c_void_p), ("host_compact", C.c_int), ("host_threads", C.c_int), ("entropy", C.c_int), ("reserved", C.c_int * 1)]
 
 
 class ImageDesc(C.Structure):
@@ -55,6 +55,7 @@ class SbsStream(C.Structure):
 
 SBS_PLANAR, SBS_INTERLEAVED, SBS_NATURAL = 0, 1, 2
 COMPACT_AUTO, COMPACT_OFF, COMPACT_ON = 0, 1, 2
+ENTROPY_AUTO, ENTROPY_HOST, ENTROPY_DEVICE = 0, 1, 2
 
 # every symbol include/b200jpg.h declares (tests/test_abi.py checks the two lists agree)
 EXPORTS = {
@@ -64,6 +65,7 @@ EXPORTS = {
     "b200jpg_last_error": (C.c_char_p, [C.c_void_p]),
     "b200jpg_version": (C.c_char_p, []),
     "b200jpg_launch_count": (C.c_uint64, [C.c_void_p]),
+    "b200jpg_device_scan_counts": (None, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "b200jpg_synchronize": (C.c_int, [C.c_void_p]),
     "b200jpg_update_component_sizes": (C.c_int, [C.c_uint16, C.c_uint16, C.POINTER(Component), C.c_int,
                                                  C.POINTER(C.c_uint16), C.POINTER(C.c_uint16)]),

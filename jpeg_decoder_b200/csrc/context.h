@@ -19,11 +19,13 @@ struct b200jpg_ctx {
     int k2_kernel = B200JPG_KERNEL_AUTO;
     int host_compact = B200JPG_COMPACT_AUTO;
     int host_threads = 0;
+    int entropy = B200JPG_ENTROPY_AUTO;
     cudaStream_t stream = nullptr;   // main stream (caller's or ours)
     cudaStream_t stream2 = nullptr;  // second stream of the host pipeline
     bool own_stream = false;
     int num_sms = 148;
     uint64_t launches = 0;
+    uint64_t device_scans = 0, device_scan_retries = 0;  // b200jpg_decode_files: scans Huffman-decoded on the GPU / sent back to the host
     PFN_tensorMapEncodeTiled encode = nullptr;
     std::string err;
     // grow-only caches so that repeated batches / file chunks do not pay cudaMalloc / cudaHostAlloc each time

@@ -18,6 +18,7 @@
 
 #include "../../include/b200jpg.h"
 #include "context.h"
+#include "entropy_host.h"
 #include "host_decoder.h"
 #include "stream_engine.h"
 
@@ -75,14 +76,22 @@ constexpr size_t kMaxSbsImage = (size_t)1 << 30;  // larger images take the dens
 
 class FileSource : public b200jpg::JobSource {
 public:
-    FileSource(b200jpg_ctx* ctx, b200jpg_file_job* jobs, size_t n) : ctx_(ctx), jobs_(jobs), n_(n) {}
+    // index: optional subset of jobs (the second wave: images the device sent back); device_entropy: let qualifying
+    // scans be Huffman-decoded on the GPU
+    FileSource(b200jpg_ctx* ctx, b200jpg_file_job* jobs, size_t n, const std::vector<size_t>* index, bool device_entropy)
+        : ctx_(ctx), jobs_(jobs), n_(index ? index->size() : n), index_(index), device_entropy_(device_entropy) {}
     size_t size() const override { return n_; }
+    std::vector<size_t> take_retries() {
+        std::lock_guard<std::mutex> g(mu_);
+        return std::move(retry_);
+    }
+    size_t device_scans() const { return device_scans_.load(); }
     const char* name() const override { return "decode_files"; }
 
     int prepare(size_t i, size_t* need, void** state, std::mutex* gpu_mu) override {
         *need = 0;
         *state = nullptr;
-        b200jpg_file_job& job = jobs_[i];
+        b200jpg_file_job& job = jobs_[index_ ? (*index_)[i] : i];
         std::unique_ptr<HostDecoder> hd(new HostDecoder(job.data, job.len));
         job.status = hd->read_info();
         job.out_len = 0;
@@ -106,17 +115,41 @@ public:
             job.status = rc != B200JPG_OK && st == B200JPG_OK ? rc : st;
             return job.status;
         }
-        *need = worst;
+        *need = device_entropy_ ? std::max(worst, b200jpg::ent_payload_bound(job.len)) : worst;
         *state = hd.release();
         return B200JPG_OK;
     }
 
-    int produce(size_t i, void* state, uint8_t* dst, size_t, SbsItem* item) override {
+    int produce(size_t i, void* state, uint8_t* dst, size_t need, SbsItem* item) override {
         std::unique_ptr<HostDecoder> hd((HostDecoder*)state);
-        b200jpg_file_job& job = jobs_[i];
+        b200jpg_file_job& job = jobs_[index_ ? (*index_)[i] : i];
         if (!dst) return job.status = B200JPG_ERR_INTERNAL;
         hd->set_sbs_sink(dst);
+        hd->probe_device_scan(device_entropy_);
         job.status = hd->entropy_decode();
+        if (job.status == b200jpg::B200JPG_INTERNAL_DEVICE_SCAN) {
+            // a complete baseline scan: ship the entropy-coded bytes, the GPU does the Huffman decoding
+            const size_t len = b200jpg::ent_build_payload(*hd, job.data, job.len, dst, need);
+            if (len) {
+                job.status = B200JPG_OK;
+                fill_desc(*hd, &item->desc);
+                item->len = len;
+                item->order = b200jpg::SBS_ENTROPY;
+                item->out = job.out;
+                item->out_cap = job.out_cap;
+                uint16_t* qcopy = (uint16_t*)(dst + item->len);
+                for (int k = 0; k < item->desc.ncomp && k < 4; k++) {
+                    memcpy(qcopy + 64 * k, item->desc.qt[k], 128);
+                    item->desc.qt[k] = qcopy + 64 * k;
+                }
+                device_scans_++;
+                return B200JPG_OK;
+            }
+            // markers inside the scan, a truncated file, ...: the host loop mirrors the reference there
+            hd.reset(new HostDecoder(job.data, job.len));
+            hd->set_sbs_sink(dst);
+            job.status = hd->entropy_decode();
+        }
         if (job.status != B200JPG_OK) return job.status;
         bool complete = hd->sbs_length() != 0;
         for (size_t k = 0; k < hd->frame().comps.size(); k++) complete = complete && hd->component_has_data((int)k);
@@ -134,13 +167,35 @@ public:
         }
         return B200JPG_OK;
     }
-    void finish(size_t i, int status) override { jobs_[i].status = status; }
+    void finish(size_t i, int status) override {
+        const size_t j = index_ ? (*index_)[i] : i;
+        if (status == b200jpg::B200JPG_INTERNAL_RETRY_HOST) {  // the device flagged the scan: second wave, host Huffman
+            std::lock_guard<std::mutex> g(mu_);
+            retry_.push_back(j);
+            jobs_[j].status = B200JPG_ERR_INTERNAL;  // overwritten by the second wave
+            return;
+        }
+        jobs_[j].status = status;
+    }
 
 private:
     b200jpg_ctx* ctx_;
     b200jpg_file_job* jobs_;
     size_t n_;
+    const std::vector<size_t>* index_;
+    bool device_entropy_;
+    std::mutex mu_;
+    std::vector<size_t> retry_;
+    std::atomic<size_t> device_scans_{0};
 };
+
+bool want_device_entropy(const b200jpg_ctx* ctx) {
+    if (const char* e = getenv("B200JPG_ENTROPY")) {
+        if (!strcmp(e, "host")) return false;
+        if (!strcmp(e, "device")) return true;
+    }
+    return ctx->entropy != B200JPG_ENTROPY_HOST;
+}
 
 }  // namespace
 
@@ -160,8 +215,18 @@ int b200jpg_read_info_files(b200jpg_file_job* jobs, size_t n, int nthreads) {
 
 int b200jpg_decode_files(b200jpg_ctx* ctx, b200jpg_file_job* jobs, size_t n, int nthreads) {
     if (!ctx || (!jobs && n)) return B200JPG_ERR_INTERNAL;
-    FileSource src(ctx, jobs, n);
-    return b200jpg::stream_engine_run(ctx, src, nthreads);
+    const bool device = want_device_entropy(ctx);
+    FileSource src(ctx, jobs, n, nullptr, device);
+    int rc = b200jpg::stream_engine_run(ctx, src, nthreads);
+    ctx->device_scans += src.device_scans();
+    const std::vector<size_t> retry = src.take_retries();
+    if (!retry.empty()) {  // scans the device flagged (malformed streams, or no convergence): the reference's own loop decides
+        ctx->device_scan_retries += retry.size();
+        FileSource again(ctx, jobs, n, &retry, false);
+        const int rc2 = b200jpg::stream_engine_run(ctx, again, nthreads);
+        if (rc == B200JPG_OK) rc = rc2;
+    }
+    return rc;
 }
 
 }  // extern "C"

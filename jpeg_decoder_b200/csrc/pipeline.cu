@@ -59,6 +59,7 @@ int b200jpg_create(const b200jpg_options* opt, b200jpg_ctx** out) {
     ctx->k2_kernel = o.k2_kernel;
     ctx->host_compact = o.host_compact;
     ctx->host_threads = o.host_threads;
+    ctx->entropy = o.entropy;
     if (cudaSetDevice(o.device) != cudaSuccess) { delete ctx; return B200JPG_ERR_INTERNAL; }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, o.device) != cudaSuccess) { delete ctx; return B200JPG_ERR_INTERNAL; }
@@ -95,6 +96,10 @@ void b200jpg_destroy(b200jpg_ctx* ctx) {
 }
 const char* b200jpg_last_error(const b200jpg_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
 uint64_t b200jpg_launch_count(const b200jpg_ctx* ctx) { return ctx ? ctx->launches : 0; }
+void b200jpg_device_scan_counts(const b200jpg_ctx* ctx, uint64_t* decoded, uint64_t* retried) {
+    if (decoded) *decoded = ctx ? ctx->device_scans : 0;
+    if (retried) *retried = ctx ? ctx->device_scan_retries : 0;
+}
 int b200jpg_synchronize(b200jpg_ctx* ctx) {
     if (!ctx) return B200JPG_ERR_INTERNAL;
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));

@@ -1,11 +1,23 @@
 // sbs_pipeline.cpp -- see sbs_pipeline.h.
 #include "sbs_pipeline.h"
 
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
 
+#include "entropy_host.h"
+
 namespace b200jpg {
+
+static int ent_max_passes() {
+    static const int v = [] {
+        const char* e = getenv("B200JPG_ENT_PASSES");
+        const int n = e ? atoi(e) : 0;
+        return n > 0 && n <= 1024 ? n : 24;
+    }();
+    return v;
+}
 
 static inline size_t up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -32,7 +44,9 @@ SbsPipeline::~SbsPipeline() {
         cudaFree(s.d_planes.p);
         cudaFree(s.d_out.p);
         cudaFree(s.d_tables.p);
+        cudaFree(s.d_ent.p);
         if (s.h_tables.p) cudaFreeHost(s.h_tables.p);
+        if (s.h_status.p) cudaFreeHost(s.h_status.p);
         if (s.e_h2d) cudaEventDestroy(s.e_h2d);
         if (s.e_comp) cudaEventDestroy(s.e_comp);
         if (s.e_done) cudaEventDestroy(s.e_done);
@@ -77,6 +91,12 @@ void SbsPipeline::retire(Slot& s, bool wait) {
             error_ = b200jpg_cuda_fail(ctx_, cudaGetLastError(), "sparse-stream pipeline");
     } else if (cudaEventQuery(s.e_done) != cudaSuccess) {
         return;
+    }
+    // images whose scan the device flagged (entropy_dev.h) go back to the caller for a host decode
+    for (size_t k = 0; k < s.ent_items.size(); k++) {
+        const unsigned* st = (const unsigned*)s.h_status.p + 2 * k;
+        const size_t i = s.ent_items[k];
+        if (s.group.statuses[i] == B200JPG_OK && (st[0] != 0 || st[1] != 1)) s.group.statuses[i] = B200JPG_INTERNAL_RETRY_HOST;
     }
     if (on_done) on_done(s.group);
     if (s.batch) {
@@ -173,7 +193,7 @@ int SbsPipeline::enqueue(Slot& s) {
 
     // bound of the plan's tables (see batch_create_impl): per component 32 B + two tables, per 128 blocks 16 B, ...
     std::vector<b200jpg_image_desc> descs(n);
-    size_t tbound = 8 * 256 + n * (sizeof(DevImage) + sizeof(K0Image) + 64);
+    size_t tbound = 10 * 256 + n * (sizeof(DevImage) + sizeof(K0Image) + sizeof(EntImage) + 64);
     for (size_t i = 0; i < n; i++) {
         descs[i] = it[i].desc;
         for (int c = 0; c < 4; c++) descs[i].coefs[c] = nullptr;
@@ -188,7 +208,7 @@ int SbsPipeline::enqueue(Slot& s) {
     TableArena arena;
     arena.d = (char*)s.d_tables.p;
     arena.h = (char*)s.h_tables.p;
-    arena.bytes = tbound - n * sizeof(K0Image) - 256;
+    arena.bytes = tbound - n * (sizeof(K0Image) + sizeof(EntImage)) - 3 * 256;
     PlanOverrides ov;
     ov.arena = &arena;
     ov.upload_stream = s_in_;
@@ -196,12 +216,17 @@ int SbsPipeline::enqueue(Slot& s) {
     if (rc) return rc;
     b200jpg_batch* b = s.batch;
 
-    // K0 descriptors + stream placement for the images the planner accepted
+    // K0 / entropy descriptors + stream placement for the images the planner accepted
     const size_t k0_at = up(b->table_bytes, 256);
     K0Image* h_k0 = (K0Image*)(arena.h + k0_at);
     const K0Image* d_k0 = (const K0Image*)(arena.d + k0_at);
-    size_t nk0 = 0, stream_bytes = 0;
-    unsigned max_nb = 0;
+    const size_t ent_at = up(k0_at + n * sizeof(K0Image), 256);
+    EntImage* h_ent = (EntImage*)(arena.h + ent_at);
+    const EntImage* d_ent = (const EntImage*)(arena.d + ent_at);
+    size_t nk0 = 0, nent = 0, stream_bytes = 0;
+    unsigned max_nb = 0, max_nsub = 0, total_sub = 0;
+    std::vector<size_t> soff(n, 0);
+    s.ent_items.clear();
     for (size_t i = 0; i < n; i++) {
         if (s.group.statuses[i]) continue;
         if (!it[i].out || it[i].out_cap < b->layout[i].out_len || !it[i].stream) {
@@ -209,31 +234,49 @@ int SbsPipeline::enqueue(Slot& s) {
             b200jpg_fail(ctx_, B200JPG_ERR_INTERNAL, "output buffer too small");
             continue;
         }
-        fill_k0(descs[i], b->layout[i], it[i].order, stream_bytes, &h_k0[nk0]);
-        const SbsLayout lay = SbsLayout::make(h_k0[nk0].nb);
-        if (it[i].len < lay.off_vals || it[i].len > lay.worst_bytes() || it[i].len % 16 != 0) {
-            s.group.statuses[i] = B200JPG_ERR_INTERNAL;
-            b200jpg_fail(ctx_, B200JPG_ERR_INTERNAL, "malformed sparse block stream");
-            continue;
+        if (it[i].order == SBS_ENTROPY) {  // an entropy-coded scan: Huffman decoding happens on the device
+            EntHeader h;
+            if (it[i].len >= sizeof h) memcpy(&h, it[i].stream, sizeof h);
+            if (it[i].len < sizeof h || h.payload_len != it[i].len ||
+                !ent_fill_image(h, descs[i], b->layout[i].coef_off, stream_bytes, total_sub, &h_ent[nent])) {
+                s.group.statuses[i] = B200JPG_ERR_INTERNAL;
+                b200jpg_fail(ctx_, B200JPG_ERR_INTERNAL, "malformed entropy payload");
+                continue;
+            }
+            max_nsub = std::max(max_nsub, h_ent[nent].nsub);
+            total_sub += h_ent[nent].nsub;
+            s.ent_items.push_back(i);
+            nent++;
+        } else {
+            fill_k0(descs[i], b->layout[i], it[i].order, stream_bytes, &h_k0[nk0]);
+            const SbsLayout lay = SbsLayout::make(h_k0[nk0].nb);
+            if (it[i].len < lay.off_vals || it[i].len > lay.worst_bytes() || it[i].len % 16 != 0) {
+                s.group.statuses[i] = B200JPG_ERR_INTERNAL;
+                b200jpg_fail(ctx_, B200JPG_ERR_INTERNAL, "malformed sparse block stream");
+                continue;
+            }
+            max_nb = std::max(max_nb, h_k0[nk0].nb);
+            nk0++;
         }
-        max_nb = std::max(max_nb, h_k0[nk0].nb);
+        soff[i] = stream_bytes;
         stream_bytes += it[i].len;
-        nk0++;
     }
+    const int passes = ent_max_passes();
     rc = grow_device(s.d_streams, stream_bytes + 256);
     if (rc == B200JPG_OK) rc = grow_device(s.d_coefs, b->info.coef_bytes + K1_TILE * 128);
     if (rc == B200JPG_OK) rc = grow_device(s.d_planes, b->info.plane_bytes + 256);
     if (rc == B200JPG_OK) rc = grow_device(s.d_out, b->info.out_bytes + 256);
+    if (rc == B200JPG_OK && nent) rc = grow_device(s.d_ent, ent_work_bytes(total_sub, (unsigned)nent, passes));
+    if (rc == B200JPG_OK && nent) rc = grow_pinned(s.h_status, nent * 8);
     if (rc) return rc;
 
     // copy-in
     {
-        size_t k = 0;
         const char* run_src = nullptr;
         size_t run_dst = 0, run_bytes = 0;
         for (size_t i = 0; i < n; i++) {
             if (s.group.statuses[i]) continue;
-            const size_t dst = (size_t)h_k0[k++].stream_off;
+            const size_t dst = soff[i];
             const char* src = (const char*)it[i].stream;
             if (run_bytes && run_src + run_bytes == src && run_dst + run_bytes == dst) {
                 run_bytes += it[i].len;
@@ -246,19 +289,31 @@ int SbsPipeline::enqueue(Slot& s) {
         }
         if (run_bytes) CU_TRY(ctx_, cudaMemcpyAsync((char*)s.d_streams.p + run_dst, run_src, run_bytes, cudaMemcpyHostToDevice, s_in_));
         if (nk0) CU_TRY(ctx_, cudaMemcpyAsync((void*)d_k0, h_k0, nk0 * sizeof(K0Image), cudaMemcpyHostToDevice, s_in_));
+        if (nent) CU_TRY(ctx_, cudaMemcpyAsync((void*)d_ent, h_ent, nent * sizeof(EntImage), cudaMemcpyHostToDevice, s_in_));
         CU_TRY(ctx_, cudaEventRecord(s.e_h2d, s_in_));
     }
     // compute
     CU_TRY(ctx_, cudaStreamWaitEvent(s_comp_, s.e_h2d, 0));
+    unsigned* d_status = nullptr;
+    if (nent) {
+        // the write pass stores only non-zero coefficients: the slab starts out zeroed (Worker::start, src/worker/immediate.rs:30-37)
+        CU_TRY(ctx_, cudaMemsetAsync(s.d_coefs.p, 0, b->info.coef_bytes, s_comp_));
+    }
     if (nk0) {
         CU_TRY(ctx_, launch_k0_expand(d_k0, (unsigned)nk0, max_nb, (const uint8_t*)s.d_streams.p, (short*)s.d_coefs.p, s_comp_));
         ctx_->launches++;
+    }
+    if (nent)
+        CU_TRY(ctx_, launch_entropy(d_ent, (unsigned)nent, max_nsub, total_sub, (const uint8_t*)s.d_streams.p, s.d_ent.p, passes, (short*)s.d_coefs.p,
+                                    &d_status, s_comp_, &ctx_->launches));
+    if (nk0 || nent) {
         rc = batch_launch(b, s.d_coefs.p, s.d_planes.p, s.d_out.p, 3, 0, (unsigned)b->tiles.size(), 0, (unsigned)n, s_comp_);
         if (rc) return rc;
     }
     CU_TRY(ctx_, cudaEventRecord(s.e_comp, s_comp_));
     // copy-out
     CU_TRY(ctx_, cudaStreamWaitEvent(s_out_, s.e_comp, 0));
+    if (nent) CU_TRY(ctx_, cudaMemcpyAsync(s.h_status.p, d_status, nent * 8, cudaMemcpyDeviceToHost, s_out_));
     {
         char* out_dst = nullptr;
         size_t out_src = 0, out_bytes = 0;

@@ -20,11 +20,14 @@
 
 namespace b200jpg {
 
+// positive, internal (never leaves the library): the device flagged this image's entropy-coded scan; decode it on the host
+enum { B200JPG_INTERNAL_RETRY_HOST = 2 };
+
 struct SbsItem {
     b200jpg_image_desc desc;  // geometry, tables, colour transform; desc.coefs is ignored
     const uint8_t* stream = nullptr;  // host (ideally page-locked) sparse stream, valid until on_h2d
     size_t len = 0;
-    unsigned order = SBS_PLANAR;
+    unsigned order = SBS_PLANAR;  // SBS_ENTROPY: `stream` is an entropy payload (entropy_dev.h), not a block stream
     uint8_t* out = nullptr;  // host pixels (ideally page-locked)
     size_t out_cap = 0;
     size_t job = 0;        // caller's cookie
@@ -57,7 +60,8 @@ private:
         size_t cap = 0;
     };
     struct Slot {
-        Buf d_streams, d_coefs, d_planes, d_out, d_tables, h_tables;
+        Buf d_streams, d_coefs, d_planes, d_out, d_tables, h_tables, d_ent, h_status;
+        std::vector<size_t> ent_items;  // group indices of the images whose scan is decoded on the device
         cudaEvent_t e_h2d = nullptr, e_comp = nullptr, e_done = nullptr;
         bool busy = false, h2d_reported = false;
         b200jpg_batch* batch = nullptr;

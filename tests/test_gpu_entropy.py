@@ -1,0 +1,128 @@
+"""Device entropy decoding on the GPU (csrc/entropy_dev.h, csrc/ke_entropy.cu) through b200jpg_decode_files.
+
+The host decoder is the restatement of the reference's sequential Huffman loop (src/huffman.rs, src/decoder.rs:1086-1172)
+and is itself checked against the oracle elsewhere; here the device path must give the same pixels and the same
+per-image status as the host path AND as the oracle, on fixtures, BASELINE-shaped synthetic files and corrupted scans,
+and it must really run (scan counters)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, bench_files, reftest_files
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pair(J):
+    dev = J.Context(device=0, entropy=J.ENTROPY_DEVICE)
+    host = J.Context(device=0, entropy=J.ENTROPY_HOST)
+    yield dev, host
+    dev.close()
+    host.close()
+
+
+def same(J, pair, files, nthreads=4):
+    dev, host = pair
+    o1, s1, _ = J.decode_files(dev, files, nthreads=nthreads)
+    o2, s2, _ = J.decode_files(host, files, nthreads=nthreads)
+    assert s1 == s2
+    for i, (a, b) in enumerate(zip(o1, o2)):
+        assert (a is None) == (b is None), i
+        if a is not None:
+            assert np.array_equal(a, b), i
+    return o1, s1
+
+
+def test_fixtures_device_equals_host_equals_oracle(J, oracle_mod, pair):
+    dev, host = pair
+    paths = reftest_files(include_disabled=True) + bench_files()
+    files = [open(p, "rb").read() for p in paths]
+    before = dev.device_scan_counts
+    outs, st = same(J, pair, files)
+    after = dev.device_scan_counts
+    assert after[0] - before[0] >= 20, "the baseline fixtures did not take the device route"
+    assert host.device_scan_counts == (0, 0)
+    for p, data, o, s_ in zip(paths, files, outs, st):
+        try:
+            want = oracle_mod.Decoder(data).decode()
+        except oracle_mod.OracleError as e:
+            assert s_ == -e.code, p
+            continue
+        assert s_ == 0 and np.array_equal(o, want), p
+
+
+@pytest.mark.parametrize("shape", [(1920, 1080, 2), (1920, 1080, 0), (640, 480, 1), (333, 217, 2), (8, 8, 2), (3840, 2160, 2)])
+def test_synthetic_shapes(J, oracle_mod, pair, shape):
+    from jpeg_decoder_b200 import workload
+    w, h, ss = shape
+    files = [workload.synth_jpeg(w, h, seed=900 + k, subsampling=ss) for k in range(3)]
+    dev = pair[0]
+    before = dev.device_scan_counts
+    outs, st = same(J, pair, files * 2)
+    after = dev.device_scan_counts
+    assert after[0] - before[0] == 6 and after[1] == before[1], "expected every scan to be accepted by the device"
+    assert st == [0] * 6
+    for f, o in zip(files, outs):
+        assert np.array_equal(o, oracle_mod.Decoder(f).decode())
+
+
+def test_large_batch_many_threads(J, oracle_mod, pair):
+    from jpeg_decoder_b200 import workload
+    uniq = [workload.synth_jpeg(1920, 1080, seed=1234 + k, subsampling=2) for k in range(4)]
+    wants = [oracle_mod.Decoder(f).decode() for f in uniq]
+    files = [uniq[i % 4] for i in range(96)]
+    dev = pair[0]
+    for nthreads in (2, 16):
+        outs, st, _ = J.decode_files(dev, files, nthreads=nthreads)
+        assert st == [0] * 96
+        for i, o in enumerate(outs):
+            assert np.array_equal(o, wants[i % 4]), i
+
+
+def test_corrupted_scans(J, oracle_mod, pair):
+    """Random damage inside the entropy-coded segment: whatever the host path (= the reference's behaviour) reports
+    or decodes, the device path reports or decodes the same -- by accepting only what it can prove and sending the
+    rest back to the host loop."""
+    from jpeg_decoder_b200 import workload
+    rng = np.random.default_rng(11)
+    base = [workload.synth_jpeg(333, 217, seed=5, subsampling=2), open(os.path.join(GOLDEN, "benches", "tower.jpg"), "rb").read(),
+            open(os.path.join(GOLDEN, "reftest", "mozilla", "jpg-size-33x33.jpg"), "rb").read()]
+    files = []
+    for data in base:
+        sos = data.rfind(b"\xff\xda")
+        for t in range(60):
+            b = bytearray(data)
+            at = int(rng.integers(sos + 14, len(b) - 2))
+            kind = t % 4
+            if kind == 0:
+                b[at] ^= 1 << int(rng.integers(0, 8))
+            elif kind == 1:
+                b[at] = int(rng.integers(0, 256))
+            elif kind == 2:
+                del b[at:min(len(b) - 2, at + 1 + int(rng.integers(0, 64)))]
+            else:
+                for q in range(at, min(len(b) - 2, at + 1 + int(rng.integers(0, 32)))):
+                    b[q] = int(rng.integers(0, 256))
+            files.append(bytes(b))
+    dev = pair[0]
+    before = dev.device_scan_counts
+    outs, st = same(J, pair, files, nthreads=8)
+    after = dev.device_scan_counts
+    assert after[0] > before[0] and after[1] > before[1], "expected both accepted and handed-back scans"
+    # and the oracle agrees on a sample
+    for f, o, s_ in list(zip(files, outs, st))[::7]:
+        try:
+            want = oracle_mod.Decoder(f).decode()
+        except oracle_mod.OracleError as e:
+            assert s_ == -e.code
+            continue
+        assert s_ == 0 and np.array_equal(o, want)
+
+
+def test_crashtest_files(J, pair):
+    files = [open(p, "rb").read() for p in sorted(glob.glob(os.path.join(GOLDEN, "crashtest", "**", "*.jpg"), recursive=True))]
+    assert len(files) > 50
+    same(J, pair, files)
