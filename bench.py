@@ -486,9 +486,26 @@ def main():
         ctx_h = J.Context(device=local_rank, arith=arith, k1_kernel=kmap[args.k1], k2_kernel=kmap[args.k2], entropy=J.ENTROPY_HOST)
         fh_value, _ = time_files(ctx_h)
         ctx_h.close()
+        # the same call with the pixel buffers in DEVICE memory (an on-GPU consumer, e.g. a training input pipeline): no D2H
+        d_pix = torch.empty(Bf * out_per_img, dtype=torch.uint8, device=dev)
+        for j in range(Bf):
+            jobs[j].out = d_pix.data_ptr() + j * out_per_img
+        ctx.check(J.lib().b200jpg_decode_files(ctx._h, jobs, Bf, nthreads))
+        t0 = time.perf_counter()
+        for _ in range(3):
+            ctx.check(J.lib().b200jpg_decode_files(ctx._h, jobs, Bf, nthreads))
+        torch.cuda.synchronize()
+        fd_value = Bf * W * H / 1e6 * 3 / (time.perf_counter() - t0)
+        assert all(jobs[j].status == 0 for j in range(Bf))
+        assert bool(np.array_equal(d_pix[:out_per_img].cpu().numpy(), ref0))
+        for j in range(Bf):
+            jobs[j].out = f_outs[j].ctypes.data
+        del d_pix
         files_e2e = {"value": f_value, "unit": "MP/s", "images": Bf, "host_threads": nthreads,
                      "jpeg_bytes_per_image": int(np.mean([len(j) for j in jpegs])),
                      "calls": f_reps, "scans_decoded_on_device": int(scans[0]), "scans_handed_back_to_host": int(scans[1]),
+                     "device_outputs": {"value": fd_value, "unit": "MP/s",
+                                        "api": "same call, b200jpg_file_job.out in device memory: JPEG bytes over PCIe, pixels stay in HBM"},
                      "host_entropy": {"value": fh_value, "unit": "MP/s",
                                       "api": "same call with B200JPG_ENTROPY_HOST: Huffman on the host threads -> sparse block streams -> K0/K1/K2"},
                      "api": "b200jpg_decode_files (JPEG bytes -> pinned host pixels; host threads parse markers and copy the scan, "

@@ -311,7 +311,8 @@ B200JPG_API int b200jpg_debug_expand_sbs(b200jpg_ctx *ctx, const b200jpg_image_d
 typedef struct {
     const uint8_t *data; /* in: the JPEG file                                   */
     size_t len;
-    uint8_t *out;        /* in: pixel buffer (ideally page-locked); unused by read_info_files */
+    uint8_t *out;        /* in: pixel buffer: host memory (ideally page-locked) or DEVICE memory of the context's
+                            GPU (the pixels then never cross PCIe); unused by read_info_files                  */
     size_t out_cap;
     b200jpg_image_info info; /* out */
     size_t out_len;      /* out: width*height*ncomp                              */

@@ -23,7 +23,7 @@ from ._native import (ARITH_SCALAR, ARITH_SSSE3, ENTROPY_AUTO, ENTROPY_DEVICE, E
                       ImageInfo, Options, SbsStream, lib)
 
 __all__ = ["Context", "Worker", "Batch", "Decoder", "B200JpgError", "FileJob", "make_components", "make_image_desc",
-           "compute_image", "decode_batch", "decode_batch_sbs", "expand_sbs", "sbs_from_dense", "decode_files", "read_info_files", "Component",
+           "compute_image", "decode_batch", "decode_batch_sbs", "expand_sbs", "sbs_from_dense", "decode_files", "decode_files_into", "read_info_files", "Component",
            "ImageDesc", "SbsStream"]
 
 
@@ -299,6 +299,21 @@ def decode_files(ctx, files, nthreads=0, outs=None):
     if rc and all(j.status == 0 for j in jobs):
         ctx.check(rc)
     return [o[:j.out_len] if j.status == 0 else None for j, o in zip(jobs, outs)], [j.status for j in jobs], [j.info for j in jobs]
+
+
+def decode_files_into(ctx, files, out_ptrs, out_caps, nthreads=0):
+    """b200jpg_decode_files with caller-owned pixel buffers given as raw addresses (host or device memory of the
+    context's GPU).  Returns (status codes, out_len per image)."""
+    n = len(files)
+    bufs = [np.frombuffer(bytes(f), dtype=np.uint8) for f in files]
+    jobs = (FileJob * n)()
+    for j, b, p, c in zip(jobs, bufs, out_ptrs, out_caps):
+        j.data, j.len = b.ctypes.data, b.size
+        j.out, j.out_cap = p, c
+    rc = lib().b200jpg_decode_files(ctx._h, jobs, n, nthreads)
+    if rc and all(j.status == 0 for j in jobs):
+        ctx.check(rc)
+    return [j.status for j in jobs], [j.out_len for j in jobs]
 
 
 class Decoder:

@@ -34,6 +34,8 @@ namespace b200jpg {
 constexpr unsigned ENT_SUB_BITS = 1024;            // one thread's share of the scan
 constexpr unsigned ENT_SUB_BYTES = ENT_SUB_BITS / 8;
 constexpr unsigned ENT_LUT_BITS = 9;               // code words up to this length resolve with one table probe
+constexpr unsigned ENT_SUB_LUT_BITS = 16 - ENT_LUT_BITS;  // longer ones with a second probe, indexed by the remaining bits
+constexpr unsigned ENT_MAX_SUBTABLES = 12;         // ENT_LUT_BITS-bit prefixes that continue into longer code words, per table
 constexpr unsigned ENT_MAX_SLOTS = 4;              // Huffman tables per image (baseline: 2 DC + 2 AC)
 constexpr unsigned ENT_TAIL_SLACK_BITS = 2048;     // zero bits the last subsequence may read past the end of the scan
 constexpr unsigned ENT_MAGIC = 0x544e4542u;        // "BENT"
@@ -47,18 +49,21 @@ enum : unsigned {
     ENT_BAD_PAYLOAD = 16,  // header / geometry mismatch
 };
 
-// One table entry: bits 0..4 code length (0 = not resolved by this probe), bits 5..8 number of value bits that
-// follow the code, bits 9..15 how far the zig-zag index advances (run + 1; 64 = end of block; 0 = anomaly).
+// One table entry: bits 0..4 code length, bits 5..8 number of value bits that follow the code, bits 9..15 how far
+// the zig-zag index advances (run + 1; 64 = end of block; 0 = anomaly).  Length 31 marks a first-level entry whose
+// prefix continues into longer code words: bits 5..15 then hold the index of the second-level table.
 ENT_HD uint32_t ent_entry(unsigned len, unsigned s, unsigned adv) { return len | (s << 5) | (adv << 9); }
+constexpr uint32_t ENT_LINK = 31;
 
-// Decoding tables of one Huffman table ("slot").  Built on the host, copied to shared memory by the kernels.
+// Decoding tables of one Huffman table ("slot"): two levels, so that every code word resolves with at most two
+// shared-memory probes whatever its length (a search over code lengths would make the whole warp wait for the one
+// lane that met a rare symbol).  Built on the host, copied to shared memory by the kernels.
 struct EntTables {
-    uint16_t lut[1u << ENT_LUT_BITS];  // indexed by the next ENT_LUT_BITS bits
-    uint32_t maxl[8];                  // lengths 10..16: (last code of that length + 1) << (16 - length), 0 if none
-    int32_t off[8];                    // lengths 10..16: canonical index of a code = code + off
-    uint16_t syment[256];              // by canonical index: entry without the length
+    uint16_t lut[1u << ENT_LUT_BITS];                          // indexed by the next ENT_LUT_BITS bits
+    uint16_t sub[ENT_MAX_SUBTABLES][1u << ENT_SUB_LUT_BITS];   // indexed by the ENT_SUB_LUT_BITS bits after those
 };
-static_assert(sizeof(EntTables) == 1600, "EntTables layout");
+constexpr unsigned ENT_TABLE_U16 = (unsigned)(sizeof(EntTables) / 2);
+static_assert(sizeof(EntTables) == 4096, "EntTables layout");
 
 // What the host writes in front of the unstuffed scan bytes.  All offsets are relative to the payload start.
 struct alignas(16) EntHeader {
@@ -120,22 +125,18 @@ ENT_HD uint32_t ent_bswap(uint32_t w) {
     return __builtin_bswap32(w);
 #endif
 }
-// big-endian word i of the scan; zero beyond the end (the reference feeds zero bits once the data is exhausted,
-// src/huffman.rs:126-160)
-ENT_HD uint32_t ent_word(const uint32_t* words, uint32_t nwords, uint32_t i) { return i < nwords ? ent_bswap(words[i]) : 0u; }
+// Word sources of the decoder: get(i) = big-endian word i of the scan, zero beyond the end (the reference feeds zero
+// bits once the data is exhausted, src/huffman.rs:126-160).  This one reads the payload where it lies; the kernels
+// stage their CTA's share of the scan in shared memory first (ke_entropy.cu).
+struct EntWordsGlobal {
+    const uint32_t* w;
+    uint32_t n;
+    ENT_HD uint32_t get(uint32_t i) const { return i < n ? ent_bswap(w[i]) : 0u; }
+};
 
-// code words longer than ENT_LUT_BITS bits (rare by construction: they are the improbable symbols)
-ENT_HD uint32_t ent_slow(const EntTables& T, uint32_t peek16) {
-#pragma unroll
-    for (unsigned i = 0; i < 7; i++) {
-        if (peek16 < T.maxl[i]) {
-            const unsigned len = 10 + i;
-            const int idx = (int)(peek16 >> (16 - len)) + T.off[i];
-            return (uint32_t)T.syment[idx & 255] | len;
-        }
-    }
-    return ent_entry(1, 0, 0);  // no code word matches: anomaly, skip one bit
-}
+#if defined(ENT_STATS)
+static unsigned long long ent_stats_len[32];  // emulator only: code-length histogram
+#endif
 
 // Sinks: what happens to decoded coefficients.
 struct EntNullSink {
@@ -145,13 +146,15 @@ struct EntNullSink {
 
 // Decodes code words starting at state `st` while they start before bit `end_bit`.  Returns the state after the
 // last one (nb = blocks completed here).  The function is deterministic in (st, end_bit) whatever the bits are:
-// that is all the synchronisation passes need from it.
-template <class Sink>
-ENT_HD EntState ent_decode_range(const uint32_t* words, uint32_t nwords, const EntTables* tabs, const uint8_t* dcslot,
-                                 const uint8_t* acslot, unsigned bpm, EntState st, uint32_t end_bit, Sink& sink, unsigned* anomaly) {
+// that is all the synchronisation passes need from it.  tabs = EntTables[] viewed as uint16_t; CHECK = report
+// anomalies (only the write pass decodes the true code words, only there they mean something).
+template <bool CHECK, class Words, class Sink>
+ENT_HD EntState ent_decode_range(const Words& words, const uint16_t* tabs, const uint8_t* dcslot, const uint8_t* acslot, unsigned bpm,
+                                 EntState st, uint32_t end_bit, Sink& sink, unsigned* anomaly) {
     uint32_t p = st.p, k = st.k, b = st.b, nb = 0;
     uint32_t wi = p >> 5;
-    uint32_t hi = ent_word(words, nwords, wi), lo = ent_word(words, nwords, wi + 1);
+    uint32_t hi = words.get(wi), lo = words.get(wi + 1);
+    uint32_t dc_off = dcslot[b] * ENT_TABLE_U16, ac_off = acslot[b] * ENT_TABLE_U16;  // change only at block boundaries
     unsigned bad = 0;
     while (p < end_bit) {
         const uint32_t sh = p & 31u;
@@ -160,13 +163,17 @@ ENT_HD EntState ent_decode_range(const uint32_t* words, uint32_t nwords, const E
 #else
         const uint32_t win = sh ? (hi << sh) | (lo >> (32u - sh)) : hi;
 #endif
-        const EntTables& T = tabs[k == 0 ? dcslot[b] : acslot[b]];
-        uint32_t e = T.lut[win >> (32u - ENT_LUT_BITS)];
-        if ((e & 31u) == 0) e = ent_slow(T, win >> 16);
+        const uint32_t off = k == 0 ? dc_off : ac_off;
+        uint32_t e = tabs[off + (win >> (32u - ENT_LUT_BITS))];
+        if ((e & 31u) == ENT_LINK)
+            e = tabs[off + (1u << ENT_LUT_BITS) + ((e >> 5) << ENT_SUB_LUT_BITS) + ((win >> 16) & ((1u << ENT_SUB_LUT_BITS) - 1u))];
         const uint32_t len = e & 31u, s = (e >> 5) & 15u;
         uint32_t adv = e >> 9;
+#if defined(ENT_STATS)
+        ent_stats_len[len]++;
+#endif
         if (adv == 0) {
-            bad |= ENT_BAD_SYMBOL;
+            if (CHECK) bad |= ENT_BAD_SYMBOL;
             adv = 1;
         }
         if (s) {
@@ -175,24 +182,26 @@ ENT_HD EntState ent_decode_range(const uint32_t* words, uint32_t nwords, const E
             // extend(), src/huffman.rs:98-... / Figure F.12
             const int v = u < (1u << (s - 1)) ? (int)u - (int)(1u << s) + 1 : (int)u;
             if (pos <= 63u) sink.store(pos, v);
-            else bad |= ENT_BAD_RUN;
+            else if (CHECK) bad |= ENT_BAD_RUN;
         }
         p += len + s;
         k += adv;
         const uint32_t nwi = p >> 5;
         if (nwi != wi) {  // len + s <= 31: at most one word further
             hi = lo;
-            lo = ent_word(words, nwords, nwi + 1);
+            lo = words.get(nwi + 1);
             wi = nwi;
         }
         if (k >= 64u) {
             k = 0;
             nb++;
             b = b + 1 == bpm ? 0 : b + 1;
+            dc_off = dcslot[b] * ENT_TABLE_U16;
+            ac_off = acslot[b] * ENT_TABLE_U16;
             if (sink.block_done()) break;
         }
     }
-    if (bad) *anomaly |= bad;
+    if (CHECK && bad) *anomaly |= bad;
     EntState r;
     r.p = p;
     r.k = k;
@@ -227,9 +236,8 @@ struct EntWriteSink {
         cur = slab;
         if (B < im->total_blocks) locate();
     }
-    ENT_HD void store(unsigned pos, int v) {
-        if (B < im->total_blocks) cur[unzz[pos]] = (int16_t)v;
-    }
+    // only reached with B < total_blocks: begin() is not used past the end, block_done() stops there
+    ENT_HD void store(unsigned pos, int v) { cur[unzz[pos]] = (int16_t)v; }
     ENT_HD bool block_done() {
         B++;
         if (++j == im->bpm) {

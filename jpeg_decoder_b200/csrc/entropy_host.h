@@ -13,8 +13,13 @@
 namespace b200jpg {
 
 // Decoding tables of one Huffman table.  `is_ac` selects how symbols are interpreted (run/size vs DC category).
-inline void ent_build_tables(const HuffTable& t, bool is_ac, EntTables* out) {
-    memset(out, 0, sizeof *out);
+// Returns false when the table has more long-code prefixes than ENT_MAX_SUBTABLES (such files stay on the host).
+inline bool ent_build_tables(const HuffTable& t, bool is_ac, EntTables* out) {
+    const uint16_t invalid = (uint16_t)ent_entry(1, 0, 0);  // no code word matches: anomaly, skip one bit
+    for (auto& e : out->lut) e = invalid;
+    for (auto& row : out->sub)
+        for (auto& e : row) e = invalid;
+    unsigned nsub = 0;
     int idx = 0;
     for (int len = 1; len <= 16; len++) {
         if (t.maxcode[len - 1] < 0) continue;
@@ -33,18 +38,24 @@ inline void ent_build_tables(const HuffTable& t, bool is_ac, EntTables* out) {
                 else adv = r == 0 ? 64 : (r == 15 ? 16 : 0);  // EOB, ZRL; EOBn does not occur in sequential scans
             }
             const unsigned code = (unsigned)(first + c);
+            const uint16_t entry = (uint16_t)ent_entry((unsigned)len, s, adv);
             if (len <= (int)ENT_LUT_BITS) {
                 const unsigned rem = ENT_LUT_BITS - (unsigned)len;
-                for (unsigned f = 0; f < (1u << rem); f++) out->lut[(code << rem) + f] = (uint16_t)ent_entry((unsigned)len, s, adv);
+                for (unsigned f = 0; f < (1u << rem); f++) out->lut[(code << rem) + f] = entry;
             } else {
-                out->syment[idx & 255] = (uint16_t)ent_entry(0, s, adv);
+                const unsigned prefix = code >> ((unsigned)len - ENT_LUT_BITS);
+                uint16_t& l = out->lut[prefix];
+                if ((l & 31u) != ENT_LINK) {
+                    if (nsub == ENT_MAX_SUBTABLES) return false;
+                    l = (uint16_t)(ENT_LINK | (nsub++ << 5));
+                }
+                const unsigned rem = 16 - (unsigned)len;
+                const unsigned low = (code << rem) & ((1u << ENT_SUB_LUT_BITS) - 1u);
+                for (unsigned f = 0; f < (1u << rem); f++) out->sub[l >> 5][low + f] = entry;
             }
         }
-        if (len > (int)ENT_LUT_BITS) {
-            out->maxl[len - 10] = (uint32_t)(t.maxcode[len - 1] + 1) << (16 - len);
-            out->off[len - 10] = t.delta[len - 1];
-        }
     }
+    return true;
 }
 
 inline size_t ent_payload_bound(size_t file_len) { return sizeof(EntHeader) + ENT_MAX_SLOTS * sizeof(EntTables) + file_len + 64; }
@@ -67,12 +78,12 @@ inline size_t ent_build_payload(const HostDecoder& hd, const uint8_t* file, size
         const int d = ds.scan.dc_table[i], a = ds.scan.ac_table[i];
         if (slot_dc[d] < 0) {
             if (nslots == ENT_MAX_SLOTS) return 0;
-            ent_build_tables(hd.dc_table(d), false, &tabs[nslots]);
+            if (!ent_build_tables(hd.dc_table(d), false, &tabs[nslots])) return 0;
             slot_dc[d] = (int)nslots++;
         }
         if (slot_ac[a] < 0) {
             if (nslots == ENT_MAX_SLOTS) return 0;
-            ent_build_tables(hd.ac_table(a), true, &tabs[nslots]);
+            if (!ent_build_tables(hd.ac_table(a), true, &tabs[nslots])) return 0;
             slot_ac[a] = (int)nslots++;
         }
         const b200jpg_component& c = fr.comps[(size_t)ds.scan.comp_index[i]];

@@ -1,10 +1,10 @@
 // ke_entropy.cu -- the kernels of device entropy decoding; the algorithm is described in entropy_dev.h.
 //
-//   ent_pass<COLD | SYNC | WRITE>  one thread per subsequence (ENT_SUB_BITS bits of the scan), 128 per CTA; the image's
+//   ent_pass<COLD | WRITE>, ent_sync  one thread per subsequence (ENT_SUB_BITS bits of the scan), 128 per CTA; the image's
 //                                  decoding tables (<= 6.4 KB) live in shared memory, the scan bytes are read through L1
 //                                  (every thread walks its own 128-byte line)
 //   ent_prefix                     per image: exclusive sum of the blocks each subsequence completed
-//   ent_dc                         per (image, component): DC differences -> DC values (wrapping int16 prefix sum)
+//   ent_dc_sums/_chunks/_apply     DC differences -> DC values (wrapping int16 prefix sum per component), one thread per block
 //
 // grid.y = image, grid.x covers the longest scan of the launch; CTAs past the end of their image exit at once.
 #include <cuda_runtime.h>
@@ -16,7 +16,7 @@ namespace b200jpg {
 
 namespace {
 
-constexpr int ENT_COLD = 0, ENT_SYNC = 1, ENT_WRITE = 2;
+constexpr int ENT_COLD = 0, ENT_WRITE = 2;
 constexpr unsigned ENT_THREADS = 128;
 
 struct EntShared {
@@ -27,6 +27,41 @@ struct EntShared {
 };
 
 __constant__ uint8_t c_unzigzag[64] = ENT_UNZIGZAG_INIT;
+
+// The CTA's share of the scan in shared memory: the 128 subsequences of its threads plus the few words the last code
+// word of the last one may reach into.  Staged once with coalesced 128-bit loads (every thread walking its own
+// 128-byte line through L1 thrashes it: measured 5 % hit rate), byte-swapped on the way in, and rotated by the row
+// number so that lanes sitting at the same offset of their own subsequence hit different banks.
+constexpr unsigned TILE_WORDS = ENT_THREADS * (ENT_SUB_BITS / 32);  // 4096
+constexpr unsigned TILE_EXTRA = 4;
+struct EntWordsTile {
+    const uint32_t* tile;  // shared
+    uint32_t first;        // word index of tile[0]
+    const uint32_t* w;     // the payload, for the rare read outside the tile (tail slack of the very last subsequence)
+    uint32_t n;
+    __device__ __forceinline__ static uint32_t slot(uint32_t j) { return (j & ~31u) + ((j + (j >> 5)) & 31u); }
+    __device__ __forceinline__ uint32_t get(uint32_t i) const {
+        const uint32_t j = i - first;
+        if (j < TILE_WORDS + TILE_EXTRA) return tile[slot(j)];
+        return i < n ? ent_bswap(__ldg(w + i)) : 0u;
+    }
+};
+__device__ __forceinline__ void stage_tile(uint32_t* tile, const uint32_t* words, uint32_t nwords, uint32_t first) {
+    for (unsigned q = threadIdx.x; q < (TILE_WORDS + TILE_EXTRA) / 4; q += ENT_THREADS) {
+        const uint32_t i = first + 4 * q;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (i + 3 < nwords) v = __ldg(reinterpret_cast<const uint4*>(words + i));  // payloads are 16-byte aligned and padded
+        else if (i < nwords) {
+            v.x = __ldg(words + i);
+            v.y = i + 1 < nwords ? __ldg(words + i + 1) : 0u;
+            v.z = i + 2 < nwords ? __ldg(words + i + 2) : 0u;
+        }
+        tile[EntWordsTile::slot(4 * q)] = ent_bswap(v.x);
+        tile[EntWordsTile::slot(4 * q + 1)] = ent_bswap(v.y);
+        tile[EntWordsTile::slot(4 * q + 2)] = ent_bswap(v.z);
+        tile[EntWordsTile::slot(4 * q + 3)] = ent_bswap(v.w);
+    }
+}
 
 __device__ __forceinline__ void load_shared(EntShared& sh, const EntImage& im, const uint8_t* payload) {
     const uint4* src = reinterpret_cast<const uint4*>(payload + im.tables_off);
@@ -51,10 +86,68 @@ struct EntWork {
     unsigned* status;    // per image: [anomaly bits, completed]
 };
 
+__device__ __forceinline__ unsigned long long ld_state(const unsigned long long* p) { return __ldcg(p); }  // L2: other SMs write these
+__device__ __forceinline__ void st_state(unsigned long long* p, unsigned long long v) { __stcg(p, v); }
+
+constexpr unsigned ENT_LOCAL_ITERS = 32;  // synchronisation rounds a CTA runs by itself before the next launch takes over
+
+// COLD and WRITE: one decode per thread.
 template <int MODE>
 __global__ void __launch_bounds__(ENT_THREADS) ent_pass(const EntImage* __restrict__ imgs, const uint8_t* __restrict__ streams, EntWork w,
-                                                        unsigned pass, short* __restrict__ coefs) {
-    if (MODE == ENT_SYNC && w.counters[pass - 1] == 0) return;  // converged earlier: nothing left to do
+                                                        short* __restrict__ coefs) {
+    const EntImage& im = imgs[blockIdx.y];
+    if (blockIdx.x * ENT_THREADS >= im.nsub) return;
+    const unsigned i = blockIdx.x * ENT_THREADS + threadIdx.x;
+    const bool valid = i < im.nsub;
+    const unsigned g = im.sub0 + i;
+    bool active = valid;
+    if (MODE == ENT_WRITE) {
+        active = valid && w.first_block[g] < im.total_blocks;
+        if (!__syncthreads_or(active)) return;
+    }
+    __shared__ EntShared sh;
+    __shared__ uint32_t tile[TILE_WORDS + 32];
+    const uint8_t* payload = streams + im.payload_off;
+    const uint32_t* gwords = reinterpret_cast<const uint32_t*>(payload + im.data_off);
+    stage_tile(tile, gwords, im.nwords, blockIdx.x * TILE_WORDS);
+    load_shared(sh, im, payload);  // ends with a barrier
+    if (!active) return;
+    const EntWordsTile words{tile, blockIdx.x * TILE_WORDS, gwords, im.nwords};
+    const uint16_t* tabs = reinterpret_cast<const uint16_t*>(sh.tabs);
+    EntState st;
+    st.p = i * ENT_SUB_BITS;
+    st.k = st.b = st.nb = 0;
+    unsigned bad = 0;
+    if (MODE == ENT_COLD) {
+        EntNullSink sink;
+        st_state(&w.state[g], ent_pack(ent_decode_range<false>(words, tabs, sh.dcslot, sh.acslot, im.dec_bpm, st,
+                                                               ent_sub_end(i, im.nsub, im.scan_bits), sink, &bad)));
+        w.ch[0][g] = 1;  // the first synchronisation launch looks at everybody
+        if (i == 0) w.counters[0] = 1;
+    } else {
+        if (i > 0) {
+            st = ent_unpack(ld_state(&w.state[g - 1]));
+            st.nb = 0;
+        }
+        EntWriteSink sink;
+        sink.begin(coefs, &sh.im, sh.unzz, w.first_block[g]);
+        const bool last = i + 1 == im.nsub;
+        const uint32_t end = last ? im.scan_bits + ENT_TAIL_SLACK_BITS : ent_sub_end(i, im.nsub, im.scan_bits);
+        const EntState e = ent_decode_range<true>(words, tabs, sh.dcslot, sh.acslot, im.dec_bpm, st, end, sink, &bad);
+        if (sink.B >= im.total_blocks) w.status[2 * blockIdx.y + 1] = 1;  // every block has been delivered
+        else if (last) bad |= ENT_INCOMPLETE;
+        else if (ent_pack(e) != ld_state(&w.state[g])) bad |= ENT_BAD_CHAIN;
+        if (bad) atomicOr(&w.status[2 * blockIdx.y], bad);
+    }
+}
+
+// SYNC launch number `pass` (1, 2, ...).  ch[] flags carry "my state changed and my successor has not seen it yet" from
+// one launch to the next (read from ch[(pass-1)&1], written to ch[pass&1]).  Inside a launch a CTA keeps iterating on
+// its own 128 subsequences through shared-memory flags until they are quiet; only the hand-over to the next CTA (and
+// whatever is left when ENT_LOCAL_ITERS runs out) waits for the next launch.
+__global__ void __launch_bounds__(ENT_THREADS) ent_sync(const EntImage* __restrict__ imgs, const uint8_t* __restrict__ streams, EntWork w,
+                                                        unsigned pass) {
+    if (w.counters[pass - 1] == 0) return;  // converged earlier: nothing left to do
     const EntImage& im = imgs[blockIdx.y];
     if (blockIdx.x * ENT_THREADS >= im.nsub) return;
     const unsigned i = blockIdx.x * ENT_THREADS + threadIdx.x;
@@ -62,59 +155,48 @@ __global__ void __launch_bounds__(ENT_THREADS) ent_pass(const EntImage* __restri
     const unsigned g = im.sub0 + i;
     const unsigned char* ch_in = (pass & 1u) ? w.ch[0] : w.ch[1];
     unsigned char* ch_out = (pass & 1u) ? w.ch[1] : w.ch[0];
-    bool active = valid;
-    if (MODE == ENT_SYNC) {
-        active = valid && i > 0 && ch_in[g - 1] != 0;
-        if (!__syncthreads_or(active)) {
-            if (valid) ch_out[g] = 0;
-            return;
-        }
-    }
-    if (MODE == ENT_WRITE) {
-        active = valid && w.first_block[g] < im.total_blocks;
-        if (!__syncthreads_or(active)) return;
-    }
-    __shared__ EntShared sh;
-    const uint8_t* payload = streams + im.payload_off;
-    load_shared(sh, im, payload);
-    if (!active) {
-        if (MODE == ENT_SYNC && valid) ch_out[g] = 0;
+    bool pending = valid && i > 0 && ch_in[g - 1] != 0;  // my predecessor changed and I have not re-decoded since
+    if (!__syncthreads_or(pending)) {
+        if (valid) ch_out[g] = 0;
         return;
     }
-    const uint32_t* words = reinterpret_cast<const uint32_t*>(payload + im.data_off);
-    EntState st;
-    st.p = i * ENT_SUB_BITS;
-    st.k = st.b = st.nb = 0;
-    if (MODE != ENT_COLD && i > 0) {
-        st = ent_unpack(w.state[g - 1]);
-        st.nb = 0;
-    }
-    unsigned bad = 0;
-    if (MODE != ENT_WRITE) {
-        EntNullSink sink;
-        const uint64_t v = ent_pack(ent_decode_range(words, im.nwords, sh.tabs, sh.dcslot, sh.acslot, im.dec_bpm, st,
-                                                     ent_sub_end(i, im.nsub, im.scan_bits), sink, &bad));
-        if (MODE == ENT_COLD) {
-            w.state[g] = v;
-            ch_out[g] = 1;  // pass 0 writes ch[0]; pass 1 reads it
-            if (i == 0) w.counters[0] = 1;
-        } else {
-            const bool changed = ((v ^ w.state[g]) & ENT_SYNC_MASK) != 0;
-            w.state[g] = v;
-            ch_out[g] = changed ? 1 : 0;
-            if (changed) w.counters[pass] = 1;
+    __shared__ EntShared sh;
+    __shared__ uint32_t tile[TILE_WORDS + 32];
+    __shared__ unsigned char s_changed[ENT_THREADS];
+    const uint8_t* payload = streams + im.payload_off;
+    const uint32_t* gwords = reinterpret_cast<const uint32_t*>(payload + im.data_off);
+    stage_tile(tile, gwords, im.nwords, blockIdx.x * TILE_WORDS);
+    load_shared(sh, im, payload);  // ends with a barrier
+    const EntWordsTile words{tile, blockIdx.x * TILE_WORDS, gwords, im.nwords};
+    const uint16_t* tabs = reinterpret_cast<const uint16_t*>(sh.tabs);
+    const uint32_t end = valid ? ent_sub_end(i, im.nsub, im.scan_bits) : 0u;
+    unsigned long long mine = valid ? ld_state(&w.state[g]) : 0ull;
+    bool ever = false, changed = false;
+    for (unsigned iter = 0; iter < ENT_LOCAL_ITERS; iter++) {
+        changed = false;
+        if (pending) {
+            EntState st = ent_unpack(ld_state(&w.state[g - 1]));
+            st.nb = 0;
+            EntNullSink sink;
+            unsigned bad = 0;
+            const unsigned long long v = ent_pack(ent_decode_range<false>(words, tabs, sh.dcslot, sh.acslot, im.dec_bpm, st, end, sink, &bad));
+            changed = ((v ^ mine) & ENT_SYNC_MASK) != 0;
+            if (v != mine) st_state(&w.state[g], v);  // nb may change even when (p, k, b) do not
+            mine = v;
         }
-    } else {
-        EntWriteSink sink;
-        sink.begin(coefs, &sh.im, sh.unzz, w.first_block[g]);
-        const bool last = i + 1 == im.nsub;
-        const uint32_t end = last ? im.scan_bits + ENT_TAIL_SLACK_BITS : ent_sub_end(i, im.nsub, im.scan_bits);
-        const EntState e = ent_decode_range(words, im.nwords, sh.tabs, sh.dcslot, sh.acslot, im.dec_bpm, st, end, sink, &bad);
-        if (sink.B >= im.total_blocks) w.status[2 * blockIdx.y + 1] = 1;  // every block has been delivered
-        else if (last) bad |= ENT_INCOMPLETE;
-        else if (ent_pack(e) != w.state[g]) bad |= ENT_BAD_CHAIN;
-        if (bad) atomicOr(&w.status[2 * blockIdx.y], bad);
+        ever |= changed;
+        s_changed[threadIdx.x] = changed ? 1 : 0;
+        __syncthreads();  // flags and states of this round are visible to the CTA
+        pending = valid && threadIdx.x > 0 && s_changed[threadIdx.x - 1] != 0;  // (threads past the image's end own no state)
+        if (!__syncthreads_or(pending)) {
+            changed = false;  // everything inside the CTA has been consumed
+            break;
+        }
     }
+    // for the next launch: the successor of my last thread lives in another CTA; changes of the final round are unconsumed
+    const bool flag = valid && (changed || (threadIdx.x == ENT_THREADS - 1 && ever));
+    if (valid) ch_out[g] = flag ? 1 : 0;
+    if (flag) w.counters[pass] = 1;
 }
 
 constexpr unsigned SCAN_THREADS = 512;
@@ -165,33 +247,68 @@ __device__ __forceinline__ short* dc_ptr(short* coefs, const EntImage& im, unsig
     return coefs + ((size_t)im.slab_row[c] + (size_t)(my * im.v[c] + vy) * im.block_w[c] + mx * h + hx) * 64;
 }
 
-// src/decoder.rs:1096-1110: dc_predictor = dc_predictor.wrapping_add(diff), per component, along the scan
-__global__ void __launch_bounds__(SCAN_THREADS) ent_dc(const EntImage* __restrict__ imgs, short* __restrict__ coefs) {
+// src/decoder.rs:1096-1110: dc_predictor = dc_predictor.wrapping_add(diff), per component, along the scan -- a prefix
+// sum over the DC differences the write pass stored.  One thread per block, three short launches:
+//   ent_dc_sums  : sum of every chunk of SCAN_THREADS consecutive blocks (in scan order) of a component
+//   ent_dc_chunks: exclusive prefix of the chunk sums, one CTA per (component, image)
+//   ent_dc_apply : block-wide inclusive prefix inside the chunk + the chunk's offset, written back
+// grid = (chunks of the largest component of the launch, 4 components, images)
+__global__ void __launch_bounds__(SCAN_THREADS) ent_dc_sums(const EntImage* __restrict__ imgs, const short* __restrict__ coefs,
+                                                            unsigned* __restrict__ chunk_sums, unsigned max_chunks) {
+    const EntImage& im = imgs[blockIdx.z];
+    const unsigned c = blockIdx.y;
+    if (c >= im.ncomp || blockIdx.x * SCAN_THREADS >= im.comp_blocks[c]) return;
+    const unsigned q = blockIdx.x * SCAN_THREADS + threadIdx.x;
+    const unsigned v = q < im.comp_blocks[c] ? (unsigned)(unsigned short)*dc_ptr(const_cast<short*>(coefs), im, c, q) : 0u;
+    unsigned total;
+    block_exclusive(v, &total);
+    if (threadIdx.x == 0) chunk_sums[((size_t)blockIdx.z * 4 + c) * max_chunks + blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) ent_dc_chunks(const EntImage* __restrict__ imgs, unsigned* __restrict__ chunk_sums, unsigned max_chunks) {
     const EntImage& im = imgs[blockIdx.y];
     const unsigned c = blockIdx.x;
     if (c >= im.ncomp) return;
-    const unsigned n = im.comp_blocks[c], per = (n + SCAN_THREADS - 1) / SCAN_THREADS;
-    const unsigned lo = min(n, threadIdx.x * per), hi = min(n, lo + per);
-    unsigned sum = 0;
-    for (unsigned q = lo; q < hi; q++) sum += (unsigned)(unsigned short)*dc_ptr(coefs, im, c, q);
-    unsigned total;
-    unsigned acc = block_exclusive(sum, &total);
-    for (unsigned q = lo; q < hi; q++) {
-        short* p = dc_ptr(coefs, im, c, q);
-        acc += (unsigned)(unsigned short)*p;
-        *p = (short)(unsigned short)acc;
+    unsigned* sums = chunk_sums + ((size_t)blockIdx.y * 4 + c) * max_chunks;
+    const unsigned n = (im.comp_blocks[c] + SCAN_THREADS - 1) / SCAN_THREADS;
+    unsigned carry = 0;
+    for (unsigned base = 0; base < n; base += SCAN_THREADS) {  // uniform trip count: block_exclusive has barriers
+        const unsigned k = base + threadIdx.x;
+        const unsigned v = k < n ? sums[k] : 0u;
+        unsigned total;
+        const unsigned ex = block_exclusive(v, &total);
+        if (k < n) sums[k] = carry + ex;
+        carry += total;
     }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) ent_dc_apply(const EntImage* __restrict__ imgs, short* __restrict__ coefs,
+                                                             const unsigned* __restrict__ chunk_sums, unsigned max_chunks) {
+    const EntImage& im = imgs[blockIdx.z];
+    const unsigned c = blockIdx.y;
+    if (c >= im.ncomp || blockIdx.x * SCAN_THREADS >= im.comp_blocks[c]) return;
+    const unsigned q = blockIdx.x * SCAN_THREADS + threadIdx.x;
+    const bool valid = q < im.comp_blocks[c];
+    short* p = dc_ptr(coefs, im, c, valid ? q : 0u);
+    const unsigned v = valid ? (unsigned)(unsigned short)*p : 0u;
+    unsigned total;
+    const unsigned ex = block_exclusive(v, &total);
+    if (valid) *p = (short)(unsigned short)(chunk_sums[((size_t)blockIdx.z * 4 + c) * max_chunks + blockIdx.x] + ex + v);
 }
 
 }  // namespace
 
-size_t ent_work_bytes(unsigned total_sub, unsigned nimages, int max_passes) {
+static unsigned dc_chunks(unsigned max_comp_blocks) { return (max_comp_blocks + SCAN_THREADS - 1) / SCAN_THREADS; }
+
+size_t ent_work_bytes(unsigned total_sub, unsigned nimages, unsigned max_comp_blocks, int max_passes) {
     auto up = [](size_t x) { return (x + 255) / 256 * 256; };
-    return up((size_t)total_sub * 8) + up((size_t)total_sub * 4) + 2 * up(total_sub) + up((size_t)(max_passes + 2) * 4) + up((size_t)nimages * 8);
+    return up((size_t)total_sub * 8) + up((size_t)total_sub * 4) + 2 * up(total_sub) + up((size_t)(max_passes + 2) * 4) + up((size_t)nimages * 8) +
+           up((size_t)nimages * 4 * dc_chunks(max_comp_blocks) * 4);
 }
 
-cudaError_t launch_entropy(const EntImage* d_images, unsigned nimages, unsigned max_nsub, unsigned total_sub, const uint8_t* d_streams, void* d_work,
-                           int max_passes, short* d_coefs, unsigned** d_status, cudaStream_t stream, uint64_t* launches) {
+cudaError_t launch_entropy(const EntImage* d_images, unsigned nimages, unsigned max_nsub, unsigned total_sub, unsigned max_comp_blocks,
+                           const uint8_t* d_streams, void* d_work, int max_passes, short* d_coefs, unsigned** d_status, cudaStream_t stream,
+                           uint64_t* launches) {
     if (nimages == 0 || max_nsub == 0) return cudaSuccess;
     auto up = [](size_t x) { return (x + 255) / 256 * 256; };
     char* p = (char*)d_work;
@@ -208,15 +325,19 @@ cudaError_t launch_entropy(const EntImage* d_images, unsigned nimages, unsigned 
     const size_t tail = up((size_t)(max_passes + 2) * 4) + up((size_t)nimages * 8);
     w.status = (unsigned*)(p + up((size_t)(max_passes + 2) * 4));
     *d_status = w.status;
+    unsigned* chunk_sums = (unsigned*)(p + tail);
+    const unsigned nchunks = dc_chunks(max_comp_blocks);
     cudaError_t e = cudaMemsetAsync(w.counters, 0, tail, stream);
     if (e != cudaSuccess) return e;
     const dim3 grid((max_nsub + ENT_THREADS - 1) / ENT_THREADS, nimages);
-    ent_pass<ENT_COLD><<<grid, ENT_THREADS, 0, stream>>>(d_images, d_streams, w, 0u, nullptr);
-    for (int r = 1; r <= max_passes; r++) ent_pass<ENT_SYNC><<<grid, ENT_THREADS, 0, stream>>>(d_images, d_streams, w, (unsigned)r, nullptr);
+    ent_pass<ENT_COLD><<<grid, ENT_THREADS, 0, stream>>>(d_images, d_streams, w, nullptr);
+    for (int r = 1; r <= max_passes; r++) ent_sync<<<grid, ENT_THREADS, 0, stream>>>(d_images, d_streams, w, (unsigned)r);
     ent_prefix<<<nimages, SCAN_THREADS, 0, stream>>>(d_images, w);
-    ent_pass<ENT_WRITE><<<grid, ENT_THREADS, 0, stream>>>(d_images, d_streams, w, 0u, d_coefs);
-    ent_dc<<<dim3(4, nimages), SCAN_THREADS, 0, stream>>>(d_images, d_coefs);
-    if (launches) *launches += (uint64_t)max_passes + 4;
+    ent_pass<ENT_WRITE><<<grid, ENT_THREADS, 0, stream>>>(d_images, d_streams, w, d_coefs);
+    ent_dc_sums<<<dim3(nchunks, 4, nimages), SCAN_THREADS, 0, stream>>>(d_images, d_coefs, chunk_sums, nchunks);
+    ent_dc_chunks<<<dim3(4, nimages), SCAN_THREADS, 0, stream>>>(d_images, chunk_sums, nchunks);
+    ent_dc_apply<<<dim3(nchunks, 4, nimages), SCAN_THREADS, 0, stream>>>(d_images, d_coefs, chunk_sums, nchunks);
+    if (launches) *launches += (uint64_t)max_passes + 6;
     return cudaGetLastError();
 }
 

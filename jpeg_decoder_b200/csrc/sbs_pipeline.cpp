@@ -1,6 +1,7 @@
 // sbs_pipeline.cpp -- see sbs_pipeline.h.
 #include "sbs_pipeline.h"
 
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -14,7 +15,7 @@ static int ent_max_passes() {
     static const int v = [] {
         const char* e = getenv("B200JPG_ENT_PASSES");
         const int n = e ? atoi(e) : 0;
-        return n > 0 && n <= 1024 ? n : 24;
+        return n > 0 && n <= 1024 ? n : 10;
     }();
     return v;
 }
@@ -24,7 +25,8 @@ static inline size_t up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 SbsPipeline::SbsPipeline(b200jpg_ctx* ctx, int nslots) : ctx_(ctx) {
     if (cudaSetDevice(ctx->device) != cudaSuccess) return;
     if (cudaStreamCreateWithFlags(&s_in_, cudaStreamNonBlocking) != cudaSuccess) return;
-    if (cudaStreamCreateWithFlags(&s_comp_, cudaStreamNonBlocking) != cudaSuccess) return;
+    for (auto& sc : s_comp2_)
+        if (cudaStreamCreateWithFlags(&sc, cudaStreamNonBlocking) != cudaSuccess) return;
     if (cudaStreamCreateWithFlags(&s_out_, cudaStreamNonBlocking) != cudaSuccess) return;
     slots_.resize((size_t)std::max(2, nslots));
     for (auto& s : slots_) {
@@ -52,7 +54,8 @@ SbsPipeline::~SbsPipeline() {
         if (s.e_done) cudaEventDestroy(s.e_done);
     }
     if (s_in_) cudaStreamDestroy(s_in_);
-    if (s_comp_) cudaStreamDestroy(s_comp_);
+    for (auto& sc : s_comp2_)
+        if (sc) cudaStreamDestroy(sc);
     if (s_out_) cudaStreamDestroy(s_out_);
 }
 
@@ -96,7 +99,13 @@ void SbsPipeline::retire(Slot& s, bool wait) {
     for (size_t k = 0; k < s.ent_items.size(); k++) {
         const unsigned* st = (const unsigned*)s.h_status.p + 2 * k;
         const size_t i = s.ent_items[k];
-        if (s.group.statuses[i] == B200JPG_OK && (st[0] != 0 || st[1] != 1)) s.group.statuses[i] = B200JPG_INTERNAL_RETRY_HOST;
+        if (s.group.statuses[i] == B200JPG_OK && (st[0] != 0 || st[1] != 1)) {
+            s.group.statuses[i] = B200JPG_INTERNAL_RETRY_HOST;
+            static const bool trace = getenv("B200JPG_TRACE") != nullptr;
+            if (trace)
+                fprintf(stderr, "[b200jpg] device entropy: job %zu (%ux%u) flagged 0x%x, completed %u -> host\n", s.group.items[i].job,
+                        s.group.items[i].desc.width, s.group.items[i].desc.height, st[0], st[1]);
+        }
     }
     if (on_done) on_done(s.group);
     if (s.batch) {
@@ -169,7 +178,7 @@ int SbsPipeline::submit(std::vector<SbsItem>&& items) {
     const int rc = enqueue(s);
     if (rc != B200JPG_OK) {  // leave the slot reusable: nothing of this group may still be running
         cudaStreamSynchronize(s_in_);
-        cudaStreamSynchronize(s_comp_);
+        for (auto& sc : s_comp2_) cudaStreamSynchronize(sc);
         cudaStreamSynchronize(s_out_);
         if (s.batch) {
             batch_release_device(s.batch);
@@ -224,7 +233,7 @@ int SbsPipeline::enqueue(Slot& s) {
     EntImage* h_ent = (EntImage*)(arena.h + ent_at);
     const EntImage* d_ent = (const EntImage*)(arena.d + ent_at);
     size_t nk0 = 0, nent = 0, stream_bytes = 0;
-    unsigned max_nb = 0, max_nsub = 0, total_sub = 0;
+    unsigned max_nb = 0, max_nsub = 0, total_sub = 0, max_comp_blocks = 0;
     std::vector<size_t> soff(n, 0);
     s.ent_items.clear();
     for (size_t i = 0; i < n; i++) {
@@ -244,6 +253,7 @@ int SbsPipeline::enqueue(Slot& s) {
                 continue;
             }
             max_nsub = std::max(max_nsub, h_ent[nent].nsub);
+            for (int c = 0; c < 4; c++) max_comp_blocks = std::max(max_comp_blocks, h_ent[nent].comp_blocks[c]);
             total_sub += h_ent[nent].nsub;
             s.ent_items.push_back(i);
             nent++;
@@ -266,7 +276,7 @@ int SbsPipeline::enqueue(Slot& s) {
     if (rc == B200JPG_OK) rc = grow_device(s.d_coefs, b->info.coef_bytes + K1_TILE * 128);
     if (rc == B200JPG_OK) rc = grow_device(s.d_planes, b->info.plane_bytes + 256);
     if (rc == B200JPG_OK) rc = grow_device(s.d_out, b->info.out_bytes + 256);
-    if (rc == B200JPG_OK && nent) rc = grow_device(s.d_ent, ent_work_bytes(total_sub, (unsigned)nent, passes));
+    if (rc == B200JPG_OK && nent) rc = grow_device(s.d_ent, ent_work_bytes(total_sub, (unsigned)nent, max_comp_blocks, passes));
     if (rc == B200JPG_OK && nent) rc = grow_pinned(s.h_status, nent * 8);
     if (rc) return rc;
 
@@ -293,6 +303,7 @@ int SbsPipeline::enqueue(Slot& s) {
         CU_TRY(ctx_, cudaEventRecord(s.e_h2d, s_in_));
     }
     // compute
+    cudaStream_t s_comp_ = s_comp2_[next_ & 1];
     CU_TRY(ctx_, cudaStreamWaitEvent(s_comp_, s.e_h2d, 0));
     unsigned* d_status = nullptr;
     if (nent) {
@@ -304,14 +315,14 @@ int SbsPipeline::enqueue(Slot& s) {
         ctx_->launches++;
     }
     if (nent)
-        CU_TRY(ctx_, launch_entropy(d_ent, (unsigned)nent, max_nsub, total_sub, (const uint8_t*)s.d_streams.p, s.d_ent.p, passes, (short*)s.d_coefs.p,
+        CU_TRY(ctx_, launch_entropy(d_ent, (unsigned)nent, max_nsub, total_sub, max_comp_blocks, (const uint8_t*)s.d_streams.p, s.d_ent.p, passes, (short*)s.d_coefs.p,
                                     &d_status, s_comp_, &ctx_->launches));
     if (nk0 || nent) {
         rc = batch_launch(b, s.d_coefs.p, s.d_planes.p, s.d_out.p, 3, 0, (unsigned)b->tiles.size(), 0, (unsigned)n, s_comp_);
         if (rc) return rc;
     }
     CU_TRY(ctx_, cudaEventRecord(s.e_comp, s_comp_));
-    // copy-out
+    // copy-out (cudaMemcpyDefault: the callers' pixel buffers may be host OR device memory -- unified addressing tells)
     CU_TRY(ctx_, cudaStreamWaitEvent(s_out_, s.e_comp, 0));
     if (nent) CU_TRY(ctx_, cudaMemcpyAsync(s.h_status.p, d_status, nent * 8, cudaMemcpyDeviceToHost, s_out_));
     {
@@ -323,13 +334,13 @@ int SbsPipeline::enqueue(Slot& s) {
             if (out_bytes && out_dst + out_bytes == (char*)it[i].out && out_src + out_bytes == L.out_off) {
                 out_bytes += L.out_len;
             } else {
-                if (out_bytes) CU_TRY(ctx_, cudaMemcpyAsync(out_dst, (char*)s.d_out.p + out_src, out_bytes, cudaMemcpyDeviceToHost, s_out_));
+                if (out_bytes) CU_TRY(ctx_, cudaMemcpyAsync(out_dst, (char*)s.d_out.p + out_src, out_bytes, cudaMemcpyDefault, s_out_));
                 out_dst = (char*)it[i].out;
                 out_src = L.out_off;
                 out_bytes = L.out_len;
             }
         }
-        if (out_bytes) CU_TRY(ctx_, cudaMemcpyAsync(out_dst, (char*)s.d_out.p + out_src, out_bytes, cudaMemcpyDeviceToHost, s_out_));
+        if (out_bytes) CU_TRY(ctx_, cudaMemcpyAsync(out_dst, (char*)s.d_out.p + out_src, out_bytes, cudaMemcpyDefault, s_out_));
         CU_TRY(ctx_, cudaEventRecord(s.e_done, s_out_));
     }
     return B200JPG_OK;

@@ -1,7 +1,7 @@
 // sbs_pipeline.h -- the sparse-stream host pipeline: groups of images whose coefficients arrive as sparse block
 // streams (sbs.h) flow through three CUDA streams,
 //     copy-in : H2D of the streams + the plan's tables          (event h2d)
-//     compute : K0 expand -> K1 dequant+IDCT -> K2 colour        (event comp)
+//     compute : K0 expand / device entropy decoding -> K1 dequant+IDCT -> K2 colour   (event comp)
 //     copy-out: D2H of the pixels into the callers' buffers      (event done)
 // so that group k+1 uploads while group k computes and group k-1 downloads.  A ring of slots owns the device
 // buffers (grow-only: nothing is cudaMalloc'ed or cudaFree'd in steady state, both would serialise the device).
@@ -74,7 +74,9 @@ private:
 
     b200jpg_ctx* ctx_;
     bool ok_ = false;
-    cudaStream_t s_in_ = nullptr, s_comp_ = nullptr, s_out_ = nullptr;
+    // two compute streams, alternating by group: the synchronisation rounds of device entropy decoding are latency-bound
+    // (a few lanes busy per round), so the next group's throughput-bound kernels fill the machine meanwhile
+    cudaStream_t s_in_ = nullptr, s_comp2_[2] = {nullptr, nullptr}, s_out_ = nullptr;
     std::vector<Slot> slots_;
     size_t next_ = 0, oldest_ = 0;  // tickets: slot = ticket % nslots
     const void* last_coefs_ = nullptr;

@@ -232,7 +232,7 @@ int stream_engine_run(b200jpg_ctx* ctx, JobSource& src, int nthreads) {
     eng->pool.start(nthreads, worker);
 
     // the submitter: group whatever is ready (bounded by bytes and count) and push it to the device
-    const size_t max_items = 48, max_bytes = (size_t)192 << 20;
+    const size_t max_items = 96, max_bytes = (size_t)640 << 20;
     size_t ngroups = 0, nitems = 0;
     double idle_ms = 0, submit_ms = 0;
     int result = B200JPG_OK;

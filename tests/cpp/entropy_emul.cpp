@@ -2,7 +2,7 @@
 // functions the kernels call (ent_decode_range, EntWriteSink, ent_build_tables, ent_build_payload, ent_fill_image).
 // For each JPEG file given:
 //   * decodes it with the host decoder (the reference's sequential Huffman loop) -> dense coefficients
-//   * runs cold / sync* / prefix / write / dc exactly as the kernels do (Jacobi passes, predecessor-changed flags)
+//   * runs cold / sync* / prefix / write / dc exactly as the kernels do (CTA-local rounds, predecessor-changed flags)
 //   * requires: device result accepted  =>  host decode succeeded and every coefficient is identical
 // With --corrupt N SEED the same is repeated for N corrupted copies of each file (random byte edits inside the
 // scan): the device path must either flag the image or agree with the host bit for bit.
@@ -11,6 +11,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <random>
 #include <string>
 #include <vector>
@@ -20,6 +21,8 @@
 using namespace b200jpg;
 
 static const uint8_t UNZZ[64] = ENT_UNZIGZAG_INIT;
+
+static int g_cta_order = 0;
 
 struct EmulResult {
     bool eligible = false;
@@ -45,8 +48,8 @@ static EmulResult emulate(const std::vector<uint8_t>& file, const HostDecoder& p
     r.eligible = true;
     r.nsub = im.nsub;
     r.coefs.assign(total / 2, 0);
-    const uint32_t* words = (const uint32_t*)(payload.data() + im.data_off);
-    const EntTables* tabs = (const EntTables*)(payload.data() + im.tables_off);
+    const EntWordsGlobal words{(const uint32_t*)(payload.data() + im.data_off), im.nwords};
+    const uint16_t* tabs = (const uint16_t*)(payload.data() + im.tables_off);
     const unsigned n = im.nsub;
     std::vector<uint64_t> state(n);
     std::vector<uint8_t> chA(n, 1), chB(n, 0);
@@ -55,30 +58,65 @@ static EmulResult emulate(const std::vector<uint8_t>& file, const HostDecoder& p
     for (unsigned i = 0; i < n; i++) {
         EntNullSink sink;
         EntState st{i * ENT_SUB_BITS, 0, 0, 0};
-        state[i] = ent_pack(ent_decode_range(words, im.nwords, tabs, im.dcslot, im.acslot, im.dec_bpm, st, ent_sub_end(i, n, im.scan_bits), sink, &dummy));
+        state[i] = ent_pack(ent_decode_range<false>(words, tabs, im.dcslot, im.acslot, im.dec_bpm, st, ent_sub_end(i, n, im.scan_bits), sink, &dummy));
     }
-    // sync: Jacobi on a snapshot (the kernels read/write in place; any interleaving is covered by "repeat until a
-    // pass changes nothing")
+    // sync, scheduled like ent_sync (ke_entropy.cu): per launch every CTA of 128 subsequences iterates on its own until
+    // it is quiet (flags through "shared memory"), states are read and written in place, only the hand-over between
+    // CTAs waits for the next launch.  g_cta_order: 0 = CTAs ascending, 1 = descending (the GPU runs them in any order).
     uint8_t *cin = chA.data(), *cout = chB.data();
+    const unsigned T = 128, LOCAL = 32;
     for (int pass = 0; pass < max_passes; pass++) {
-        std::vector<uint64_t> snap = state;
-        unsigned nchanged = 0;
-        for (unsigned i = 0; i < n; i++) {
-            cout[i] = 0;
-            if (i == 0 || !cin[i - 1]) continue;
-            EntNullSink sink;
-            const EntState st = ent_unpack(snap[i - 1]);
-            const uint64_t v = ent_pack(ent_decode_range(words, im.nwords, tabs, im.dcslot, im.acslot, im.dec_bpm, EntState{st.p, st.k, st.b, 0},
-                                                         ent_sub_end(i, n, im.scan_bits), sink, &dummy));
-            if ((v ^ snap[i]) & ENT_SYNC_MASK) {
-                cout[i] = 1;
-                nchanged++;
+        unsigned any = 0;
+        const unsigned nctas = (n + T - 1) / T;
+        for (unsigned cc = 0; cc < nctas; cc++) {
+            const unsigned cta = g_cta_order ? nctas - 1 - cc : cc;
+            const unsigned i0 = cta * T, cnt = std::min(T, n - i0);
+            std::vector<uint8_t> pending(cnt), changed(cnt, 0), ever(cnt, 0);
+            bool anyp = false;
+            for (unsigned t = 0; t < cnt; t++) {
+                pending[t] = (i0 + t) > 0 && cin[i0 + t - 1];
+                anyp |= pending[t];
             }
-            state[i] = v;
+            if (!anyp) {
+                for (unsigned t = 0; t < cnt; t++) cout[i0 + t] = 0;
+                continue;
+            }
+            std::vector<uint64_t> mine(state.begin() + i0, state.begin() + i0 + cnt);
+            for (unsigned iter = 0; iter < LOCAL; iter++) {
+                // threads of a CTA run concurrently: evaluate in descending order so that a thread mostly sees its
+                // predecessor's OLD state (the adversarial interleaving)
+                for (unsigned tt = 0; tt < cnt; tt++) {
+                    const unsigned t = cnt - 1 - tt, i = i0 + t;
+                    changed[t] = 0;
+                    if (!pending[t]) continue;
+                    EntNullSink sink;
+                    const EntState st = ent_unpack(state[i - 1]);
+                    const uint64_t v = ent_pack(ent_decode_range<false>(words, tabs, im.dcslot, im.acslot, im.dec_bpm,
+                                                                       EntState{st.p, st.k, st.b, 0}, ent_sub_end(i, n, im.scan_bits), sink, &dummy));
+                    changed[t] = ((v ^ mine[t]) & ENT_SYNC_MASK) != 0;
+                    state[i] = v;
+                    mine[t] = v;
+                    ever[t] |= changed[t];
+                }
+                bool more = false;
+                for (unsigned t = 0; t < cnt; t++) {
+                    pending[t] = t > 0 && changed[t - 1];
+                    more |= pending[t];
+                }
+                if (!more) {
+                    std::fill(changed.begin(), changed.end(), 0);
+                    break;
+                }
+            }
+            for (unsigned t = 0; t < cnt; t++) {
+                const bool flag = changed[t] || (t == T - 1 && ever[t]);
+                cout[i0 + t] = flag;
+                any |= flag;
+            }
         }
         std::swap(cin, cout);
         r.passes++;
-        if (!nchanged) break;
+        if (!any) break;
     }
     // prefix
     std::vector<uint32_t> first(n);
@@ -101,7 +139,7 @@ static EmulResult emulate(const std::vector<uint8_t>& file, const HostDecoder& p
         const bool last = i + 1 == n;
         const uint32_t end = last ? im.scan_bits + ENT_TAIL_SLACK_BITS : ent_sub_end(i, n, im.scan_bits);
         unsigned bad = 0;
-        const EntState e = ent_decode_range(words, im.nwords, tabs, im.dcslot, im.acslot, im.dec_bpm, st, end, sink, &bad);
+        const EntState e = ent_decode_range<true>(words, tabs, im.dcslot, im.acslot, im.dec_bpm, st, end, sink, &bad);
         if (sink.B >= im.total_blocks) completed = true;
         else if (last) bad |= ENT_INCOMPLETE;
         else if (ent_pack(e) != state[i]) bad |= ENT_BAD_CHAIN;
@@ -196,6 +234,8 @@ int main(int argc, char** argv) {
             ncorrupt = atoi(argv[i + 1]);
             seed = (unsigned)atoi(argv[i + 2]);
             i += 2;
+        } else if (!strcmp(argv[i], "--descending")) {
+            g_cta_order = 1;
         } else if (!strcmp(argv[i], "--passes") && i + 1 < argc) {
             max_passes = atoi(argv[++i]);
         } else {
@@ -238,6 +278,16 @@ int main(int argc, char** argv) {
             }
         }
     }
+#if defined(ENT_STATS)
+    {
+        unsigned long long tot = 0, acc = 0;
+        for (int i = 0; i < 32; i++) tot += ent_stats_len[i];
+        for (int i = 1; i <= 16; i++) {
+            acc += ent_stats_len[i];
+            printf("code length <= %2d: %.4f %%\n", i, 100.0 * (double)acc / (double)tot);
+        }
+    }
+#endif
     printf("%s %u decoded on the emulated device, %u flagged for the host\n", bad ? "FAILED" : "ok", n_device, n_flagged);
     return bad ? 1 : 0;
 }

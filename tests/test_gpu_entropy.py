@@ -126,3 +126,20 @@ def test_crashtest_files(J, pair):
     files = [open(p, "rb").read() for p in sorted(glob.glob(os.path.join(GOLDEN, "crashtest", "**", "*.jpg"), recursive=True))]
     assert len(files) > 50
     same(J, pair, files)
+
+
+def test_device_resident_outputs(J, oracle_mod, pair):
+    """b200jpg_file_job.out may point to device memory: the pixels stay on the GPU (no D2H), same bytes."""
+    import torch
+    from jpeg_decoder_b200 import workload
+    files = [workload.synth_jpeg(640, 480, seed=70 + k, subsampling=2) for k in range(5)] + [open(os.path.join(GOLDEN, "benches", "tower.jpg"), "rb").read()]
+    wants = [oracle_mod.Decoder(f).decode() for f in files]
+    d_outs = [torch.zeros(w.size, dtype=torch.uint8, device="cuda:0") for w in wants]
+    for ctx in pair:
+        for t in d_outs:
+            t.zero_()
+        st, lens = J.decode_files_into(ctx, files, [t.data_ptr() for t in d_outs], [t.numel() for t in d_outs], nthreads=3)
+        torch.cuda.synchronize()
+        assert st == [0] * len(files) and lens == [w.size for w in wants]
+        for t, w in zip(d_outs, wants):
+            assert np.array_equal(t.cpu().numpy(), w)
