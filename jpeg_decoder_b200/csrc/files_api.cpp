@@ -86,6 +86,14 @@ public:
         return std::move(retry_);
     }
     size_t device_scans() const { return device_scans_.load(); }
+    bool outputs_on_device() const override {
+        if (n_ == 0) return false;
+        const b200jpg_file_job& job = jobs_[index_ ? (*index_)[0] : 0];
+        cudaPointerAttributes pa;
+        const bool dev = job.out && cudaPointerGetAttributes(&pa, job.out) == cudaSuccess && pa.type == cudaMemoryTypeDevice;
+        cudaGetLastError();
+        return dev;
+    }
     const char* name() const override { return "decode_files"; }
 
     int prepare(size_t i, size_t* need, void** state, std::mutex* gpu_mu) override {

@@ -63,8 +63,9 @@ int SbsPipeline::grow_device(Buf& b, size_t need) {
     if (need <= b.cap) return B200JPG_OK;
     if (b.p) cudaFree(b.p);
     b.p = nullptr;
+    // doubling: cudaFree / cudaMalloc synchronise the device, so a buffer should regrow a handful of times in its life
+    const size_t want = up(std::max(need + need / 4, 2 * b.cap), 1 << 20);
     b.cap = 0;
-    const size_t want = up(need + need / 4, 1 << 20);
     CU_TRY(ctx_, cudaMalloc(&b.p, want));
     b.cap = want;
     return B200JPG_OK;
@@ -303,7 +304,20 @@ int SbsPipeline::enqueue(Slot& s) {
         CU_TRY(ctx_, cudaEventRecord(s.e_h2d, s_in_));
     }
     // compute
-    cudaStream_t s_comp_ = s_comp2_[next_ & 1];
+    // Pixels that leave over PCIe: one compute stream, first in first out, so that the oldest group finishes (and starts
+    // downloading) as early as possible.  Pixels that stay in device memory: nothing downstream is waiting, and two
+    // alternating streams let the next group's kernels fill the SMs during the latency-bound synchronisation rounds.
+    bool device_outs = true;
+    for (size_t i = 0; i < n && device_outs; i++) {
+        cudaPointerAttributes pa;
+        if (!it[i].out || cudaPointerGetAttributes(&pa, it[i].out) != cudaSuccess || pa.type != cudaMemoryTypeDevice) device_outs = false;
+    }
+    cudaGetLastError();
+    cudaStream_t s_comp_ = s_comp2_[device_outs ? (next_ & 1) : 0];
+    if (device_outs != last_device_outs_) {  // switching modes: do not let the two streams' groups race each other's events
+        for (auto& sc : s_comp2_) CU_TRY(ctx_, cudaStreamSynchronize(sc));
+        last_device_outs_ = device_outs;
+    }
     CU_TRY(ctx_, cudaStreamWaitEvent(s_comp_, s.e_h2d, 0));
     unsigned* d_status = nullptr;
     if (nent) {

@@ -79,6 +79,7 @@ private:
     cudaStream_t s_in_ = nullptr, s_comp2_[2] = {nullptr, nullptr}, s_out_ = nullptr;
     std::vector<Slot> slots_;
     size_t next_ = 0, oldest_ = 0;  // tickets: slot = ticket % nslots
+    bool last_device_outs_ = false;
     const void* last_coefs_ = nullptr;
     int error_ = B200JPG_OK;
 };

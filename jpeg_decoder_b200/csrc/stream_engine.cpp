@@ -232,7 +232,10 @@ int stream_engine_run(b200jpg_ctx* ctx, JobSource& src, int nthreads) {
     eng->pool.start(nthreads, worker);
 
     // the submitter: group whatever is ready (bounded by bytes and count) and push it to the device
-    const size_t max_items = 96, max_bytes = (size_t)640 << 20;
+    // groups: small enough that the first download starts early and the last one is short when pixels go back over PCIe,
+    // larger when they stay on the device (per-group latencies amortise over more images)
+    const bool dev_out = src.outputs_on_device();
+    const size_t max_items = dev_out ? 96 : 32, max_bytes = (size_t)(dev_out ? 640 : 160) << 20;
     size_t ngroups = 0, nitems = 0;
     double idle_ms = 0, submit_ms = 0;
     int result = B200JPG_OK;

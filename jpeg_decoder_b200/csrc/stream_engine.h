@@ -30,6 +30,8 @@ public:
     // Submitter thread: final status of a job that went through the device.
     virtual void finish(size_t i, int status) = 0;
     virtual const char* name() const = 0;
+    // hint: the jobs' pixel buffers are device memory (no download to wait for: larger groups amortise better)
+    virtual bool outputs_on_device() const { return false; }
 };
 
 // Runs every job of `src` with `nthreads` host threads (< 1: one per CPU this process may run on).
