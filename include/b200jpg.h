@@ -74,7 +74,7 @@ enum { B200JPG_COMPACT_AUTO = 0, B200JPG_COMPACT_OFF = 1, B200JPG_COMPACT_ON = 2
 
 /* Where the Huffman entropy decoding of b200jpg_decode_files happens.  The reference decodes a scan with one
  * sequential loop per image (src/huffman.rs, src/decoder.rs:1086-1172).  DEVICE: complete baseline single-scan images
- * without restart intervals are decoded by the GPU (self-synchronising parallel Huffman decoding, csrc/entropy_dev.h);
+ * (with or without restart intervals) are decoded by the GPU (self-synchronising parallel Huffman decoding, csrc/entropy_dev.h);
  * host threads then only parse markers and copy the scan bytes.  Every other image, and every image whose scan the
  * device flags as irregular in any way, is decoded by the host loop, so results and errors never differ. */
 enum { B200JPG_ENTROPY_AUTO = 0, B200JPG_ENTROPY_HOST = 1, B200JPG_ENTROPY_DEVICE = 2 };

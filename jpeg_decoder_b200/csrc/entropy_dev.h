@@ -47,6 +47,7 @@ enum : unsigned {
     ENT_BAD_CHAIN = 4,     // state[i] != f_i(state[i-1]): the synchronisation passes did not converge
     ENT_INCOMPLETE = 8,    // the scan ended before every block was decoded
     ENT_BAD_PAYLOAD = 16,  // header / geometry mismatch
+    ENT_BAD_TAIL = 32,     // whole bytes left between the last MCU of a restart interval and its RSTn marker
 };
 
 // One table entry: bits 0..4 code length, bits 5..8 number of value bits that follow the code, bits 9..15 how far
@@ -66,10 +67,17 @@ constexpr unsigned ENT_TABLE_U16 = (unsigned)(sizeof(EntTables) / 2);
 static_assert(sizeof(EntTables) == 4096, "EntTables layout");
 
 // What the host writes in front of the unstuffed scan bytes.  All offsets are relative to the payload start.
+// A scan with restart intervals (DRI, src/decoder.rs:910-931) is a sequence of independently decodable pieces: every
+// interval starts byte-aligned with fresh predictors, so each one is handed to the kernels as a scan of its own
+// (a free synchronisation point); without DRI there is one interval, the whole scan.
+struct EntInterval {
+    uint32_t data_off;  // 16-byte aligned; followed by >= 16 zero bytes
+    uint32_t nbytes;    // unstuffed entropy-coded bytes of the interval
+};
 struct alignas(16) EntHeader {
     uint32_t magic;
-    uint32_t scan_bytes;    // unstuffed entropy-coded bytes that follow the tables
-    uint32_t data_off;      // where they start (16-byte aligned); readable, zero-filled, up to payload_len
+    uint32_t scan_bytes;    // unstuffed entropy-coded bytes of all intervals
+    uint32_t data_off;      // first interval's bytes
     uint32_t payload_len;   // multiple of 16
     uint32_t total_blocks;  // blocks the scan must deliver
     uint32_t nslots;
@@ -77,26 +85,33 @@ struct alignas(16) EntHeader {
     uint8_t pad_[3];
     uint8_t dcslot[12], acslot[12];  // table slot of MCU block j
     uint32_t tables_off;    // EntTables[nslots]
-    uint32_t reserved_[2];
+    uint32_t nintervals;    // >= 1
+    uint32_t intervals_off; // EntInterval[nintervals]
+    uint32_t restart_interval;  // MCUs per interval; 0 = no DRI
+    uint32_t reserved_[3];
 };
-static_assert(sizeof(EntHeader) == 64, "EntHeader layout");
+static_assert(sizeof(EntHeader) == 80, "EntHeader layout");
 
-// Per-image descriptor of the kernels (built by the submitter from EntHeader + the image geometry).
+// Per-interval descriptor of the kernels (built by the submitter from the payload + the image geometry); "image" in
+// the kernels' vocabulary, since an interval is decoded exactly like a small scan.
 struct alignas(16) EntImage {
     unsigned long long payload_off;  // byte offset of the payload inside the device stream buffer
     unsigned data_off, scan_bits, nwords, nsub, sub0, total_blocks, mcu_w, nslots, tables_off;
     unsigned slab_row[4];   // first 128-byte row of each component inside the coefficient slab
     unsigned block_w[4];    // blocks per block row
-    unsigned comp_blocks[4];  // block_w * block_h, 0 for absent components
+    unsigned comp_blocks[4];  // blocks of each component inside this interval, 0 for absent components
     unsigned char bpm, ncomp;
     unsigned char dec_bpm;  // period of the table pattern the decoder tracks as `b`: bpm, or 1 when every block of an MCU uses the
                             // same tables (b then never influences decoding and would only delay synchronisation)
-    unsigned char pad_;
+    unsigned char tight_end;  // 1: the interval is followed by an RSTn marker, which the reference only finds when no whole byte is
+                              // left after the interval's last MCU (take_marker looks no further than its bit buffer,
+                              // src/huffman.rs:98-124); after the LAST interval extra bytes are skipped (src/decoder.rs:961-970)
     unsigned char h[4], v[4];
     unsigned char mcu_comp[12], mcu_hx[12], mcu_vy[12], dcslot[12], acslot[12];
-    unsigned pad2_[3];
+    unsigned mcu0;    // index of the interval's first MCU in the scan
+    unsigned pad2_[2];
 };
-static_assert(sizeof(EntImage) % 16 == 0, "EntImage layout");
+static_assert(sizeof(EntImage) == 176, "EntImage layout");
 
 // Published per subsequence.  Two states are "equal" for synchronisation purposes when p, k and b agree.
 struct EntState {
@@ -217,7 +232,8 @@ struct EntWriteSink {
     int16_t* coefs;
     const EntImage* im;
     const uint8_t* unzz;  // zig-zag index -> natural position
-    uint32_t B, j, mx, my;
+    uint32_t B;           // blocks of the interval delivered so far (index of the current block inside the interval)
+    uint32_t j, mx, my;
     int16_t* cur;
     ENT_HD void locate() {
         const unsigned c = im->mcu_comp[j];
@@ -229,13 +245,14 @@ struct EntWriteSink {
         im = image;
         unzz = unzigzag;
         B = first_block;
-        const uint32_t m = B / im->bpm;
+        const uint32_t m = im->mcu0 + B / im->bpm;
         j = B % im->bpm;
         mx = m % im->mcu_w;
         my = m / im->mcu_w;
         cur = slab;
         if (B < im->total_blocks) locate();
     }
+    ENT_HD bool complete() const { return B >= im->total_blocks; }
     // only reached with B < total_blocks: begin() is not used past the end, block_done() stops there
     ENT_HD void store(unsigned pos, int v) { cur[unzz[pos]] = (int16_t)v; }
     ENT_HD bool block_done() {

@@ -58,11 +58,15 @@ inline bool ent_build_tables(const HuffTable& t, bool is_ac, EntTables* out) {
     return true;
 }
 
-inline size_t ent_payload_bound(size_t file_len) { return sizeof(EntHeader) + ENT_MAX_SLOTS * sizeof(EntTables) + file_len + 64; }
+inline size_t ent_payload_bound(size_t file_len) {
+    return sizeof(EntHeader) + ENT_MAX_SLOTS * sizeof(EntTables) + file_len + file_len / 4 + 4096;
+}
+constexpr size_t ENT_MIN_INTERVAL_BYTES = 256;  // scans cut into smaller pieces than this (on average) stay on the host
 
 // Writes the payload of a qualifying scan (HostDecoder::device_scan()) to dst.  Returns its length, or 0 when the
-// entropy-coded segment turns out not to qualify: anything but stuffed bytes up to an EOI marker (restart or
-// other markers, fill bytes, a truncated file) stays with the host decoder, which mirrors the reference there.
+// entropy-coded segment turns out not to qualify: anything but stuffed bytes and the expected restart markers up to
+// an EOI marker (other markers, fill bytes, a truncated file, a wrong number or order of RSTn) stays with the host
+// decoder, which mirrors the reference there.
 inline size_t ent_build_payload(const HostDecoder& hd, const uint8_t* file, size_t file_len, uint8_t* dst, size_t cap) {
     const DeviceScan& ds = hd.device_scan();
     if (!ds.eligible || cap < ent_payload_bound(file_len) || ds.scan_begin > file_len) return 0;
@@ -97,92 +101,141 @@ inline size_t ent_build_payload(const HostDecoder& hd, const uint8_t* file, size
     h.bpm = (uint8_t)j;
     h.nslots = nslots;
     h.tables_off = (uint32_t)sizeof(EntHeader);
-    h.data_off = (uint32_t)(sizeof(EntHeader) + nslots * sizeof(EntTables));
     h.total_blocks = (uint32_t)hd.total_blocks();
-    // unstuff: FF 00 -> FF; FF D9 ends the scan; anything else disqualifies
+    // intervals: ceil(MCUs / restart interval) of them, separated by RST0..7 in cyclic order (src/decoder.rs:910-931)
+    const size_t total_mcus = h.total_blocks / h.bpm;
+    h.restart_interval = ds.restart_interval;
+    const size_t nint = ds.restart_interval ? (total_mcus + ds.restart_interval - 1) / ds.restart_interval : 1;
+    if (nint == 0 || nint > ((size_t)1 << 24)) return 0;
+    h.nintervals = (uint32_t)nint;
+    h.intervals_off = (uint32_t)(sizeof(EntHeader) + nslots * sizeof(EntTables));
+    size_t at = (h.intervals_off + nint * sizeof(EntInterval) + 15) / 16 * 16;
+    if (at + 64 > cap) return 0;
+    EntInterval* iv = (EntInterval*)(dst + h.intervals_off);
+    h.data_off = (uint32_t)at;
+    // unstuff: FF 00 -> FF; FF D0+n closes an interval; FF D9 ends the scan; anything else disqualifies
     const uint8_t* s = file + ds.scan_begin;
     const uint8_t* const end = file + file_len;
-    uint8_t* const data = dst + h.data_off;
-    uint8_t* o = data;
+    uint8_t* o = dst + at;
+    size_t cur = 0, total = 0;
     bool done = false;
+    auto close_interval = [&]() -> bool {  // records interval `cur`, pads it, opens the next one
+        const size_t nbytes = (size_t)(o - (dst + at));
+        iv[cur].data_off = (uint32_t)at;
+        iv[cur].nbytes = (uint32_t)nbytes;
+        total += nbytes;
+        const size_t next = (at + nbytes + 15) / 16 * 16 + 16;
+        if (next + 64 > cap) return false;
+        memset(o, 0, next - (at + nbytes));
+        at = next;
+        o = dst + at;
+        cur++;
+        return true;
+    };
     while (s < end) {
         const uint8_t* f = (const uint8_t*)memchr(s, 0xFF, (size_t)(end - s));
         if (!f || f + 1 >= end) return 0;
+        if ((size_t)(o - dst) + (size_t)(f - s) + 64 > cap) return 0;
         memcpy(o, s, (size_t)(f - s));
         o += f - s;
-        if (f[1] == 0x00) {
+        const uint8_t m = f[1];
+        if (m == 0x00) {
             *o++ = 0xFF;
             s = f + 2;
-        } else if (f[1] == 0xD9) {
+        } else if (m == 0xD9) {
+            if (cur + 1 != nint || !close_interval()) return 0;
             done = true;
             break;
+        } else if (m >= 0xD0 && m <= 0xD7 && ds.restart_interval && cur + 1 < nint && (unsigned)(m - 0xD0) == (cur & 7u)) {
+            if (!close_interval()) return 0;
+            s = f + 2;
         } else {
             return 0;
         }
     }
-    if (!done || o == data || (size_t)(o - data) >= ((size_t)1 << 28)) return 0;
-    h.scan_bytes = (uint32_t)(o - data);
-    size_t total = h.data_off + h.scan_bytes;
-    const size_t padded = (total + 15) / 16 * 16 + 16;
-    memset(dst + total, 0, padded - total);
-    h.payload_len = (uint32_t)padded;
+    if (!done || total == 0 || total >= ((size_t)1 << 28) || total / nint < (nint > 1 ? ENT_MIN_INTERVAL_BYTES : 1)) return 0;
+    h.scan_bytes = (uint32_t)total;
+    h.payload_len = (uint32_t)at;  // `at` is already padded and 16-byte aligned
     memcpy(dst, &h, sizeof h);
-    return padded;
+    return at;
 }
 
-// Kernel descriptor of one image from its payload header and geometry.  coef_off[c] = byte offset of component
-// c's blocks inside the coefficient slab (multiple of 128), sub0 = index of its first subsequence in the group's
-// state arrays.  Returns false when header and geometry disagree.
-inline bool ent_fill_image(const EntHeader& h, const b200jpg_image_desc& d, const size_t coef_off[4], unsigned long long payload_off,
-                           unsigned sub0, EntImage* im) {
-    memset(im, 0, sizeof *im);
-    if (h.magic != ENT_MAGIC || h.nslots == 0 || h.nslots > ENT_MAX_SLOTS || h.bpm == 0 || h.bpm > 12 || h.scan_bytes == 0) return false;
-    if (h.data_off % 16 != 0 || h.payload_len % 16 != 0 || (size_t)h.data_off + h.scan_bytes + 16 > h.payload_len) return false;
-    if (h.tables_off + h.nslots * sizeof(EntTables) > h.data_off || h.tables_off % 16 != 0) return false;
-    im->payload_off = payload_off;
-    im->data_off = h.data_off;
-    im->scan_bits = h.scan_bytes * 8u;
-    im->nwords = (h.payload_len - h.data_off) / 4u;
-    im->nsub = (im->scan_bits + ENT_SUB_BITS - 1) / ENT_SUB_BITS;
-    im->sub0 = sub0;
-    im->nslots = h.nslots;
-    im->tables_off = h.tables_off;
-    im->bpm = h.bpm;
-    im->ncomp = d.ncomp;
-    unsigned j = 0, nb = 0;
+// Kernel descriptors of one image -- one per interval -- from its payload and geometry.  coef_off[c] = byte offset of
+// component c's blocks inside the coefficient slab (multiple of 128), sub0 = index of the first subsequence in the
+// group's state arrays.  Returns the number of descriptors written (header.nintervals), 0 when payload and geometry
+// disagree or `cap` is too small; *nsub_total = subsequences over all intervals.
+inline unsigned ent_fill_images(const uint8_t* payload, size_t payload_len, const b200jpg_image_desc& d, const size_t coef_off[4],
+                                unsigned long long payload_off, unsigned sub0, EntImage* out, size_t cap, unsigned* nsub_total) {
+    EntHeader h;
+    if (payload_len < sizeof h) return 0;
+    memcpy(&h, payload, sizeof h);
+    if (h.magic != ENT_MAGIC || h.payload_len != payload_len || h.nslots == 0 || h.nslots > ENT_MAX_SLOTS || h.bpm == 0 || h.bpm > 12) return 0;
+    if (h.payload_len % 16 != 0 || h.tables_off % 16 != 0 || h.tables_off + h.nslots * sizeof(EntTables) > h.intervals_off) return 0;
+    if (h.nintervals == 0 || h.nintervals > cap || (size_t)h.intervals_off + (size_t)h.nintervals * sizeof(EntInterval) > h.payload_len) return 0;
+    EntImage base;
+    memset(&base, 0, sizeof base);
+    base.payload_off = payload_off;
+    base.nslots = h.nslots;
+    base.tables_off = h.tables_off;
+    base.bpm = h.bpm;
+    base.ncomp = d.ncomp;
+    unsigned j = 0, nb = 0, hv[4] = {0, 0, 0, 0};
     for (int c = 0; c < d.ncomp && c < 4; c++) {
         const b200jpg_component& k = d.comps[c];
-        if (k.h == 0 || k.v == 0 || coef_off[c] % 128 != 0) return false;
-        im->slab_row[c] = (unsigned)(coef_off[c] / 128);
-        im->block_w[c] = k.block_w;
-        im->comp_blocks[c] = (unsigned)k.block_w * k.block_h;
-        im->h[c] = k.h;
-        im->v[c] = k.v;
-        nb += im->comp_blocks[c];
+        if (k.h == 0 || k.v == 0 || coef_off[c] % 128 != 0) return 0;
+        base.slab_row[c] = (unsigned)(coef_off[c] / 128);
+        base.block_w[c] = k.block_w;
+        base.h[c] = k.h;
+        base.v[c] = k.v;
+        hv[c] = (unsigned)k.h * k.v;
+        nb += (unsigned)k.block_w * k.block_h;
         for (unsigned vy = 0; vy < k.v; vy++)
             for (unsigned hx = 0; hx < k.h; hx++, j++)
                 if (j < 12) {
-                    im->mcu_comp[j] = (unsigned char)c;
-                    im->mcu_hx[j] = (unsigned char)hx;
-                    im->mcu_vy[j] = (unsigned char)vy;
+                    base.mcu_comp[j] = (unsigned char)c;
+                    base.mcu_hx[j] = (unsigned char)hx;
+                    base.mcu_vy[j] = (unsigned char)vy;
                 }
     }
     if (d.ncomp == 1) {  // a lone component is not interleaved: one block per MCU, raster order (src/decoder.rs:895-905)
         j = 1;
-        im->h[0] = im->v[0] = 1;
+        base.h[0] = base.v[0] = 1;
+        hv[0] = 1;
     }
-    if (j != h.bpm || nb != h.total_blocks || nb == 0) return false;
-    im->total_blocks = nb;
-    im->mcu_w = d.comps[0].block_w / im->h[0];
-    if (im->mcu_w == 0) return false;
+    if (j != h.bpm || nb != h.total_blocks || nb == 0) return 0;
+    base.mcu_w = d.comps[0].block_w / base.h[0];
+    if (base.mcu_w == 0) return 0;
     bool uniform = true;
     for (unsigned q = 0; q < 12; q++) {
-        im->dcslot[q] = h.dcslot[q] < h.nslots ? h.dcslot[q] : 0;
-        im->acslot[q] = h.acslot[q] < h.nslots ? h.acslot[q] : 0;
-        if (q < h.bpm && (im->dcslot[q] != im->dcslot[0] || im->acslot[q] != im->acslot[0])) uniform = false;
+        base.dcslot[q] = h.dcslot[q] < h.nslots ? h.dcslot[q] : 0;
+        base.acslot[q] = h.acslot[q] < h.nslots ? h.acslot[q] : 0;
+        if (q < h.bpm && (base.dcslot[q] != base.dcslot[0] || base.acslot[q] != base.acslot[0])) uniform = false;
     }
-    im->dec_bpm = uniform ? 1 : h.bpm;
-    return true;
+    base.dec_bpm = uniform ? 1 : h.bpm;
+    const unsigned total_mcus = nb / h.bpm;
+    const unsigned ri = h.restart_interval ? h.restart_interval : total_mcus;
+    if ((total_mcus + ri - 1) / ri != h.nintervals) return 0;
+    const EntInterval* iv = (const EntInterval*)(payload + h.intervals_off);
+    unsigned nsub = 0;
+    for (unsigned r = 0; r < h.nintervals; r++) {
+        EntImage& im = out[r];
+        im = base;
+        if (iv[r].data_off % 16 != 0 || (size_t)iv[r].data_off + iv[r].nbytes + 16 > h.payload_len || iv[r].nbytes >= (1u << 28)) return 0;
+        const unsigned mcus = r + 1 < h.nintervals ? ri : total_mcus - r * ri;
+        im.data_off = iv[r].data_off;
+        im.scan_bits = iv[r].nbytes * 8u;
+        im.nwords = (iv[r].nbytes + 3u) / 4u;  // the bytes after the interval are zero up to the next 16-byte boundary and beyond
+        im.nsub = (im.scan_bits + ENT_SUB_BITS - 1) / ENT_SUB_BITS;
+        if (im.nsub == 0) im.nsub = 1;  // an empty interval still has to deliver its blocks (from zero bits, like the reference)
+        im.sub0 = sub0 + nsub;
+        im.mcu0 = r * ri;
+        im.tight_end = r + 1 < h.nintervals ? 1 : 0;
+        im.total_blocks = mcus * h.bpm;
+        for (int c = 0; c < d.ncomp && c < 4; c++) im.comp_blocks[c] = mcus * hv[c];
+        nsub += im.nsub;
+    }
+    *nsub_total = nsub;
+    return h.nintervals;
 }
 
 }  // namespace b200jpg

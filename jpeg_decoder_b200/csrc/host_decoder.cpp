@@ -988,7 +988,7 @@ int HostDecoder::decode_scan(const ScanInfo& scan, const bool finished[4], bool*
 // first code word: every check decode_scan makes up front holds, so the host would start decoding here.
 bool HostDecoder::device_scan_ok(const ScanInfo& scan) const {
     const FrameInfo& f = frame_;
-    if (f.coding_process != B200JPG_CP_DCT_SEQUENTIAL || f.precision != 8 || is_mjpeg_ || restart_interval_ != 0) return false;
+    if (f.coding_process != B200JPG_CP_DCT_SEQUENTIAL || f.precision != 8 || is_mjpeg_) return false;
     if (scan.n != (int)f.comps.size() || scan.ss_start != 0 || scan.ss_end != 64 || scan.al != 0 || scan.ah != 0) return false;
     if (scan.n == 1 && (f.comps[0].h != 1 || f.comps[0].v != 1)) return false;
     unsigned bpm = 0;
@@ -1066,6 +1066,7 @@ int HostDecoder::decode_internal(bool stop_after_metadata) {
                 device_scan_.eligible = true;
                 device_scan_.scan_begin = pos_;
                 device_scan_.scan = scan;
+                device_scan_.restart_interval = restart_interval_;
                 capture_final_qtables();
                 return B200JPG_INTERNAL_DEVICE_SCAN;
             }

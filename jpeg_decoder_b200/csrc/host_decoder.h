@@ -49,11 +49,12 @@ struct ScanInfo {  // src/parser.rs:64-74
 };
 
 // Filled at the first SOS when probing for device entropy decoding (entropy_dev.h): the scan is a complete
-// sequential single-scan image (every component, in frame order, interleaved or a lone 1x1 component, no restart
-// interval, all tables present) -- the case HostDecoder would write straight into a sparse stream.
+// sequential single-scan image (every component, in frame order, interleaved or a lone 1x1 component, all tables
+// present) -- the case HostDecoder would write straight into a sparse stream.
 struct DeviceScan {
     bool eligible = false;
     size_t scan_begin = 0;  // offset of the first entropy-coded byte in the file
+    unsigned restart_interval = 0;  // MCUs between RSTn markers (DRI), 0 = none
     ScanInfo scan;
 };
 // positive (not an error): entropy_decode() stopped at the first SOS because the scan qualifies for the device

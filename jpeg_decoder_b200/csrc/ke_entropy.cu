@@ -134,7 +134,10 @@ __global__ void __launch_bounds__(ENT_THREADS) ent_pass(const EntImage* __restri
         const bool last = i + 1 == im.nsub;
         const uint32_t end = last ? im.scan_bits + ENT_TAIL_SLACK_BITS : ent_sub_end(i, im.nsub, im.scan_bits);
         const EntState e = ent_decode_range<true>(words, tabs, sh.dcslot, sh.acslot, im.dec_bpm, st, end, sink, &bad);
-        if (sink.B >= im.total_blocks) w.status[2 * blockIdx.y + 1] = 1;  // every block has been delivered
+        if (sink.complete()) {
+            w.status[2 * blockIdx.y + 1] = 1;  // every block of the interval has been delivered
+            if (im.tight_end && e.p + 7 < im.scan_bits) bad |= ENT_BAD_TAIL;
+        }
         else if (last) bad |= ENT_INCOMPLETE;
         else if (ent_pack(e) != ld_state(&w.state[g])) bad |= ENT_BAD_CHAIN;
         if (bad) atomicOr(&w.status[2 * blockIdx.y], bad);
@@ -239,10 +242,11 @@ __global__ void __launch_bounds__(SCAN_THREADS) ent_prefix(const EntImage* __res
     }
 }
 
-// coefficient 0 of the q-th block of component c in scan order (MCU by MCU, v then h inside an MCU)
+// coefficient 0 of the q-th block of component c of the interval, in scan order (MCU by MCU, v then h inside an MCU)
 __device__ __forceinline__ short* dc_ptr(short* coefs, const EntImage& im, unsigned c, unsigned q) {
     const unsigned h = im.h[c], hv = h * im.v[c];
-    const unsigned m = q / hv, r = q - m * hv, vy = r / h, hx = r - vy * h;
+    const unsigned ml = q / hv, r = q - ml * hv, vy = r / h, hx = r - vy * h;
+    const unsigned m = im.mcu0 + ml;
     const unsigned my = m / im.mcu_w, mx = m - my * im.mcu_w;
     return coefs + ((size_t)im.slab_row[c] + (size_t)(my * im.v[c] + vy) * im.block_w[c] + mx * h + hx) * 64;
 }
@@ -329,15 +333,28 @@ cudaError_t launch_entropy(const EntImage* d_images, unsigned nimages, unsigned 
     const unsigned nchunks = dc_chunks(max_comp_blocks);
     cudaError_t e = cudaMemsetAsync(w.counters, 0, tail, stream);
     if (e != cudaSuccess) return e;
-    const dim3 grid((max_nsub + ENT_THREADS - 1) / ENT_THREADS, nimages);
-    ent_pass<ENT_COLD><<<grid, ENT_THREADS, 0, stream>>>(d_images, d_streams, w, nullptr);
-    for (int r = 1; r <= max_passes; r++) ent_sync<<<grid, ENT_THREADS, 0, stream>>>(d_images, d_streams, w, (unsigned)r);
-    ent_prefix<<<nimages, SCAN_THREADS, 0, stream>>>(d_images, w);
-    ent_pass<ENT_WRITE><<<grid, ENT_THREADS, 0, stream>>>(d_images, d_streams, w, d_coefs);
-    ent_dc_sums<<<dim3(nchunks, 4, nimages), SCAN_THREADS, 0, stream>>>(d_images, d_coefs, chunk_sums, nchunks);
-    ent_dc_chunks<<<dim3(4, nimages), SCAN_THREADS, 0, stream>>>(d_images, chunk_sums, nchunks);
-    ent_dc_apply<<<dim3(nchunks, 4, nimages), SCAN_THREADS, 0, stream>>>(d_images, d_coefs, chunk_sums, nchunks);
-    if (launches) *launches += (uint64_t)max_passes + 6;
+    const dim3 sub_grid((max_nsub + ENT_THREADS - 1) / ENT_THREADS, 1);
+    // "images" are restart intervals: a group can hold more of them than grid.y / grid.z allow
+    for (unsigned base = 0; base < nimages; base += 65535u) {
+        const unsigned cnt = min(65535u, nimages - base);
+        const EntImage* imgs = d_images + base;
+        EntWork wc = w;
+        wc.status = w.status + 2 * (size_t)base;
+        unsigned* sums = chunk_sums + (size_t)base * 4 * nchunks;
+        if (base) {
+            e = cudaMemsetAsync(w.counters, 0, up((size_t)(max_passes + 2) * 4), stream);
+            if (e != cudaSuccess) return e;
+        }
+        const dim3 grid(sub_grid.x, cnt);
+        ent_pass<ENT_COLD><<<grid, ENT_THREADS, 0, stream>>>(imgs, d_streams, wc, nullptr);
+        for (int r = 1; r <= max_passes; r++) ent_sync<<<grid, ENT_THREADS, 0, stream>>>(imgs, d_streams, wc, (unsigned)r);
+        ent_prefix<<<cnt, SCAN_THREADS, 0, stream>>>(imgs, wc);
+        ent_pass<ENT_WRITE><<<grid, ENT_THREADS, 0, stream>>>(imgs, d_streams, wc, d_coefs);
+        ent_dc_sums<<<dim3(nchunks, 4, cnt), SCAN_THREADS, 0, stream>>>(imgs, d_coefs, sums, nchunks);
+        ent_dc_chunks<<<dim3(4, cnt), SCAN_THREADS, 0, stream>>>(imgs, sums, nchunks);
+        ent_dc_apply<<<dim3(nchunks, 4, cnt), SCAN_THREADS, 0, stream>>>(imgs, d_coefs, sums, nchunks);
+        if (launches) *launches += (uint64_t)max_passes + 6;
+    }
     return cudaGetLastError();
 }
 

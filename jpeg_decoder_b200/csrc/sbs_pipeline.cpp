@@ -203,14 +203,20 @@ int SbsPipeline::enqueue(Slot& s) {
 
     // bound of the plan's tables (see batch_create_impl): per component 32 B + two tables, per 128 blocks 16 B, ...
     std::vector<b200jpg_image_desc> descs(n);
-    size_t tbound = 10 * 256 + n * (sizeof(DevImage) + sizeof(K0Image) + sizeof(EntImage) + 64);
+    size_t tbound = 10 * 256 + n * (sizeof(DevImage) + sizeof(K0Image) + 64), max_ent = 0;
     for (size_t i = 0; i < n; i++) {
+        if (it[i].order == SBS_ENTROPY && it[i].stream && it[i].len >= sizeof(EntHeader)) {  // one descriptor per restart interval
+            EntHeader h;
+            memcpy(&h, it[i].stream, sizeof h);
+            max_ent += std::min<size_t>(h.nintervals, (size_t)1 << 24);
+        }
         descs[i] = it[i].desc;
         for (int c = 0; c < 4; c++) descs[i].coefs[c] = nullptr;
         for (int c = 0; c < descs[i].ncomp && c < 4; c++)
             tbound += sizeof(DevComp) + 96 * sizeof(unsigned) + ((size_t)descs[i].comps[c].block_w * descs[i].comps[c].block_h / K1_TILE + 1) * sizeof(DevTile);
         tbound += ((size_t)descs[i].width / 2048 + 1) * sizeof(K2Strip);
     }
+    tbound += max_ent * sizeof(EntImage);
     int rc = grow_device(s.d_tables, tbound);
     if (rc == B200JPG_OK) rc = grow_pinned(s.h_tables, tbound);
     if (rc) return rc;
@@ -218,7 +224,7 @@ int SbsPipeline::enqueue(Slot& s) {
     TableArena arena;
     arena.d = (char*)s.d_tables.p;
     arena.h = (char*)s.h_tables.p;
-    arena.bytes = tbound - n * (sizeof(K0Image) + sizeof(EntImage)) - 3 * 256;
+    arena.bytes = tbound - n * sizeof(K0Image) - max_ent * sizeof(EntImage) - 3 * 256;
     PlanOverrides ov;
     ov.arena = &arena;
     ov.upload_stream = s_in_;
@@ -244,20 +250,22 @@ int SbsPipeline::enqueue(Slot& s) {
             b200jpg_fail(ctx_, B200JPG_ERR_INTERNAL, "output buffer too small");
             continue;
         }
-        if (it[i].order == SBS_ENTROPY) {  // an entropy-coded scan: Huffman decoding happens on the device
-            EntHeader h;
-            if (it[i].len >= sizeof h) memcpy(&h, it[i].stream, sizeof h);
-            if (it[i].len < sizeof h || h.payload_len != it[i].len ||
-                !ent_fill_image(h, descs[i], b->layout[i].coef_off, stream_bytes, total_sub, &h_ent[nent])) {
+        if (it[i].order == SBS_ENTROPY) {  // an entropy-coded scan: Huffman decoding happens on the device, interval by interval
+            unsigned nsub = 0;
+            const unsigned k = ent_fill_images(it[i].stream, it[i].len, descs[i], b->layout[i].coef_off, stream_bytes, total_sub, h_ent + nent,
+                                               max_ent - nent, &nsub);
+            if (k == 0) {
                 s.group.statuses[i] = B200JPG_ERR_INTERNAL;
                 b200jpg_fail(ctx_, B200JPG_ERR_INTERNAL, "malformed entropy payload");
                 continue;
             }
-            max_nsub = std::max(max_nsub, h_ent[nent].nsub);
-            for (int c = 0; c < 4; c++) max_comp_blocks = std::max(max_comp_blocks, h_ent[nent].comp_blocks[c]);
-            total_sub += h_ent[nent].nsub;
-            s.ent_items.push_back(i);
-            nent++;
+            for (unsigned r = 0; r < k; r++) {
+                max_nsub = std::max(max_nsub, h_ent[nent + r].nsub);
+                for (int c = 0; c < 4; c++) max_comp_blocks = std::max(max_comp_blocks, h_ent[nent + r].comp_blocks[c]);
+                s.ent_items.push_back(i);
+            }
+            total_sub += nsub;
+            nent += k;
         } else {
             fill_k0(descs[i], b->layout[i], it[i].order, stream_bytes, &h_k0[nk0]);
             const SbsLayout lay = SbsLayout::make(h_k0[nk0].nb);

@@ -27,9 +27,12 @@ static int g_cta_order = 0;
 struct EmulResult {
     bool eligible = false;
     unsigned status = 0;  // anomaly bits
-    unsigned passes = 0, nsub = 0;
+    unsigned passes = 0, nsub = 0, intervals = 0;
     std::vector<int16_t> coefs;  // all components back to back
 };
+
+struct EmulResult;
+static void emulate_interval(const std::vector<uint8_t>& payload, const EntImage& im, const b200jpg_image_desc& d, int max_passes, EmulResult& r);
 
 static EmulResult emulate(const std::vector<uint8_t>& file, const HostDecoder& probe, const b200jpg_image_desc& d, int max_passes) {
     EmulResult r;
@@ -43,17 +46,25 @@ static EmulResult emulate(const std::vector<uint8_t>& file, const HostDecoder& p
         coef_off[c] = total;
         total += (size_t)d.comps[c].block_w * d.comps[c].block_h * 128;
     }
-    EntImage im;
-    if (!ent_fill_image(h, d, coef_off, 0, 0, &im)) return r;
+    std::vector<EntImage> ims(h.nintervals ? h.nintervals : 1);
+    unsigned nsub_total = 0;
+    if (!ent_fill_images(payload.data(), plen, d, coef_off, 0, 0, ims.data(), ims.size(), &nsub_total)) return r;
     r.eligible = true;
-    r.nsub = im.nsub;
+    r.nsub = nsub_total;
+    r.intervals = (unsigned)ims.size();
     r.coefs.assign(total / 2, 0);
+    for (const EntImage& im : ims) emulate_interval(payload, im, d, max_passes, r);
+    return r;
+}
+
+// one interval (= the whole scan without DRI): what the kernels do for one "image"
+static void emulate_interval(const std::vector<uint8_t>& payload, const EntImage& im, const b200jpg_image_desc& d, int max_passes, EmulResult& r) {
     const EntWordsGlobal words{(const uint32_t*)(payload.data() + im.data_off), im.nwords};
     const uint16_t* tabs = (const uint16_t*)(payload.data() + im.tables_off);
     const unsigned n = im.nsub;
     std::vector<uint64_t> state(n);
     std::vector<uint8_t> chA(n, 1), chB(n, 0);
-    unsigned dummy = 0;
+    unsigned dummy = 0, passes = 0;
     // cold
     for (unsigned i = 0; i < n; i++) {
         EntNullSink sink;
@@ -115,7 +126,7 @@ static EmulResult emulate(const std::vector<uint8_t>& file, const HostDecoder& p
             }
         }
         std::swap(cin, cout);
-        r.passes++;
+        passes++;
         if (!any) break;
     }
     // prefix
@@ -140,7 +151,10 @@ static EmulResult emulate(const std::vector<uint8_t>& file, const HostDecoder& p
         const uint32_t end = last ? im.scan_bits + ENT_TAIL_SLACK_BITS : ent_sub_end(i, n, im.scan_bits);
         unsigned bad = 0;
         const EntState e = ent_decode_range<true>(words, tabs, im.dcslot, im.acslot, im.dec_bpm, st, end, sink, &bad);
-        if (sink.B >= im.total_blocks) completed = true;
+        if (sink.complete()) {
+            completed = true;
+            if (im.tight_end && e.p + 7 < im.scan_bits) bad |= ENT_BAD_TAIL;
+        }
         else if (last) bad |= ENT_INCOMPLETE;
         else if (ent_pack(e) != state[i]) bad |= ENT_BAD_CHAIN;
         r.status |= bad;
@@ -151,14 +165,14 @@ static EmulResult emulate(const std::vector<uint8_t>& file, const HostDecoder& p
         const unsigned hv = (unsigned)im.h[c] * im.v[c];
         uint16_t pred = 0;
         for (unsigned q = 0; q < im.comp_blocks[c]; q++) {
-            const unsigned m = q / hv, rr = q % hv, vy = rr / im.h[c], hx = rr % im.h[c];
+            const unsigned m = im.mcu0 + q / hv, rr = q % hv, vy = rr / im.h[c], hx = rr % im.h[c];
             const unsigned mx = m % im.mcu_w, my = m / im.mcu_w;
             int16_t* blk = r.coefs.data() + ((size_t)im.slab_row[c] + (size_t)(my * im.v[c] + vy) * im.block_w[c] + mx * im.h[c] + hx) * 64;
             pred = (uint16_t)(pred + (uint16_t)blk[0]);
             blk[0] = (int16_t)pred;
         }
     }
-    return r;
+    r.passes = std::max(r.passes, passes);
 }
 
 struct HostResult {
@@ -221,7 +235,7 @@ static int check(const std::vector<uint8_t>& file, const char* name, int max_pas
                k < e.coefs.size() ? e.coefs[k] : -1);
         return 1;
     }
-    if (verbose) printf("%s: device == host, %u subsequences, %u sync passes\n", name, e.nsub, e.passes);
+    if (verbose) printf("%s: device == host, %u subsequences in %u interval(s), %u sync passes\n", name, e.nsub, e.intervals, e.passes);
     return 0;
 }
 

@@ -75,3 +75,39 @@ def test_corrupted_scans_are_flagged_or_identical(emul, tmp_path):
     last = text.strip().splitlines()[-1].split()
     decoded, flagged = int(last[1]), int(last[7])
     assert decoded > 300 and flagged > 100, last  # both outcomes occur
+
+
+def _dri_jpeg(w, h, subsampling, interval, seed=0):
+    """Baseline JPEG with restart markers every `interval` MCUs (PIL's restart_marker_blocks)."""
+    import io
+    import numpy as np
+    from PIL import Image
+    rng = np.random.default_rng(seed)
+    y, x = np.mgrid[0:h, 0:w]
+    img = np.stack([127 + 90 * np.sin(x / 41 + c) + 40 * np.cos(y / 57 + c) for c in range(3)], -1) + rng.normal(0, 6, (h, w, 3))
+    buf = io.BytesIO()
+    Image.fromarray(np.clip(img, 0, 255).astype(np.uint8)).save(buf, "JPEG", quality=90, subsampling=subsampling, restart_marker_blocks=interval)
+    return buf.getvalue()
+
+
+@pytest.mark.parametrize("shape", [(640, 480, 0, 80), (1920, 1080, 2, 120), (200, 200, 2, 7), (333, 217, 1, 21)])
+def test_restart_intervals(emul, tmp_path, shape):
+    """Every restart interval is decoded as a scan of its own (src/decoder.rs:910-931)."""
+    w, h, ss, ri = shape
+    p = tmp_path / "d.jpg"
+    p.write_bytes(_dri_jpeg(w, h, ss, ri))
+    out = run(emul, [str(p)])
+    assert "device == host" in out and "in 1 interval(s)" not in out, out
+
+
+def test_corrupted_restart_interval_scans(emul, tmp_path):
+    """Damage around restart markers: the reference only finds an RSTn that directly follows the interval's last MCU
+    (anything else is an error there), so the device must not accept an interval with whole bytes to spare."""
+    files = []
+    for k, shape in enumerate([(640, 480, 0, 80), (200, 200, 2, 7)]):
+        p = tmp_path / ("d%d.jpg" % k)
+        p.write_bytes(_dri_jpeg(*shape, seed=k))
+        files.append(str(p))
+    text = run(emul, ["--descending", "--corrupt", "300", "3"] + files)
+    last = text.strip().splitlines()[-1].split()
+    assert int(last[1]) > 200 and int(last[7]) > 50, last

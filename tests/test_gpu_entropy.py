@@ -143,3 +143,33 @@ def test_device_resident_outputs(J, oracle_mod, pair):
         assert st == [0] * len(files) and lens == [w.size for w in wants]
         for t, w in zip(d_outs, wants):
             assert np.array_equal(t.cpu().numpy(), w)
+
+
+def test_restart_interval_scans(J, oracle_mod, pair):
+    """DRI files: every restart interval goes to the kernels as a scan of its own; damaged ones behave like the host."""
+    from test_entropy_emul import _dri_jpeg
+    files = [_dri_jpeg(640, 480, 0, 80), _dri_jpeg(1920, 1080, 2, 120), _dri_jpeg(200, 200, 2, 7), _dri_jpeg(333, 217, 1, 21),
+             _dri_jpeg(64, 64, 2, 1)]  # the last one has intervals too small to qualify: host
+    dev = pair[0]
+    before = dev.device_scan_counts
+    outs, st = same(J, pair, files)
+    after = dev.device_scan_counts
+    assert after[0] - before[0] == 4 and after[1] == before[1]
+    assert st == [0] * len(files)
+    for f, o in zip(files, outs):
+        assert np.array_equal(o, oracle_mod.Decoder(f).decode())
+    rng = np.random.default_rng(5)
+    damaged = []
+    for data in files[:3]:
+        sos = data.rfind(b"\xff\xda")
+        for t in range(40):
+            b = bytearray(data)
+            at = int(rng.integers(sos + 14, len(b) - 2))
+            if t % 3 == 0:
+                b[at] ^= 1 << int(rng.integers(0, 8))
+            elif t % 3 == 1:
+                del b[at:min(len(b) - 2, at + 1 + int(rng.integers(0, 48)))]
+            else:
+                b[at:at] = bytes(int(rng.integers(0, 255)) for _ in range(int(rng.integers(1, 5))))
+            damaged.append(bytes(b))
+    same(J, pair, damaged, nthreads=8)
