@@ -11,11 +11,16 @@
 //           state still changes (only threads whose predecessor changed do work).  Subsequence 0 starts from the
 //           true state, so a pass without changes means state[i] = f_i(state[i-1]) for every i: the chain IS the
 //           sequential decode
-//   prefix: exclusive sum of "blocks completed" -> the index of the block every subsequence starts in
-//   write : every thread decodes once more from its predecessor's state and stores the coefficients it meets at
-//           their final place in the dense slab (the layout K1 reads); it re-checks state[i] = f_i(state[i-1]),
-//           so a stream that did not converge (or is malformed in any way) is detected, never mis-decoded
+//   prefix: exclusive sums of "blocks completed" and "AC values met" -> the block every subsequence starts in and
+//           where its values go
+//   write : every thread decodes once more from its predecessor's state and appends what it meets to a compact
+//           per-image stream -- non-zero AC values back to back (contiguous 2-byte stores per thread), one 64-bit
+//           position bitmap, one DC difference and one value offset per block; it re-checks
+//           state[i] = f_i(state[i-1]), so a stream that did not converge (or is malformed in any way) is detected,
+//           never mis-decoded
 //   dc    : DC differences -> DC values, a wrapping int16 prefix sum per component in scan order
+//   expand: kernel K0 (k0_expand.cu, the one that expands the host's sparse block streams) rebuilds the dense slab
+//           K1 reads from bitmaps + values with coalesced 16-byte stores, zeros included
 //
 // Anything the device flags goes back to the host decoder, which reproduces the reference's behaviour for
 // broken streams exactly.  This header is shared by the kernels (ke_entropy.cu), the host code that prepares
@@ -109,9 +114,23 @@ struct alignas(16) EntImage {
     unsigned char h[4], v[4];
     unsigned char mcu_comp[12], mcu_hx[12], mcu_vy[12], dcslot[12], acslot[12];
     unsigned mcu0;    // index of the interval's first MCU in the scan
-    unsigned pad2_[2];
+    unsigned nb_pad;  // blocks of the whole image rounded up to 32: length of the compact stream's per-block arrays
+    unsigned vals_off;              // where the image's value area starts, relative to cs_off (bytes, even)
+    unsigned long long cs_off;      // compact stream of the image inside the device stream buffer: bm | dc | boff
+    unsigned char comp_j0[4];       // index of each component's first block inside an MCU
+    unsigned pad2_[1];
 };
-static_assert(sizeof(EntImage) == 176, "EntImage layout");
+static_assert(sizeof(EntImage) == 192, "EntImage layout");
+
+// The compact stream the write pass produces, per image (all blocks in scan order, index t):
+//   bm  : u64[nb_pad]  bit k (1..63) = the AC coefficient with zig-zag index k is non-zero; bit 0 = values are int16
+//   dc  : i16[nb_pad]  DC difference, after the dc pass the DC value
+//   boff: u32[nb_pad]  byte offset (relative to the start of bm) of the block's first value
+//   values: int16, zig-zag order, at boff -- every restart interval appends to a region of its own (63 values per block
+//           is the worst case), so intervals need no offsets from each other
+// This is sbs.h's stream with per-block instead of per-group offsets (SBS_BLOCK_OFFSETS); K0 expands both.
+ENT_HD size_t ent_cs_header_bytes(size_t nb_pad) { return 14 * nb_pad; }
+ENT_HD size_t ent_cs_values_bytes(size_t nblocks) { return nblocks * 126 + 64; }
 
 // Published per subsequence.  Two states are "equal" for synchronisation purposes when p, k and b agree.
 struct EntState {
@@ -225,48 +244,97 @@ ENT_HD EntState ent_decode_range(const Words& words, const uint16_t* tabs, const
     return r;
 }
 
-// The write pass: coefficients go to their place in the dense slab (blocks of 64 int16 in natural order, per
-// component in raster order -- what Worker::append_row receives, src/decoder.rs:962-983).  DC code words store
-// the DIFFERENCE at position 0; the dc pass turns differences into values.
-struct EntWriteSink {
-    int16_t* coefs;
-    const EntImage* im;
-    const uint8_t* unzz;  // zig-zag index -> natural position
-    uint32_t B;           // blocks of the interval delivered so far (index of the current block inside the interval)
-    uint32_t j, mx, my;
-    int16_t* cur;
-    ENT_HD void locate() {
-        const unsigned c = im->mcu_comp[j];
-        const unsigned bx = mx * im->h[c] + im->mcu_hx[j], by = my * im->v[c] + im->mcu_vy[j];
-        cur = coefs + ((size_t)im->slab_row[c] + (size_t)by * im->block_w[c] + bx) * 64;
-    }
-    ENT_HD void begin(int16_t* slab, const EntImage* image, const uint8_t* unzigzag, uint32_t first_block) {
-        coefs = slab;
-        im = image;
-        unzz = unzigzag;
+// Counts what the write pass will append: AC values (DC differences have their own array).
+struct EntCountSink {
+    uint32_t nvals = 0;
+    ENT_HD void store(unsigned pos, int) { nvals += pos != 0; }
+    ENT_HD bool block_done() { return false; }
+};
+
+ENT_HD void ent_or64(unsigned long long* p, unsigned long long v) {
+#if defined(__CUDA_ARCH__)
+    atomicOr(p, v);
+#else
+    *p |= v;
+#endif
+}
+
+// The write pass.  A block that starts and ends inside one subsequence is written with plain stores; the two (or
+// more) threads that share a block each OR their part of the bitmap into the zero-initialised array.  Values are
+// collected four at a time and leave as one aligned 8-byte store (a lane's 2-byte stores each cost a sector of their
+// own on the way to L2: measured 23 M sectors per 27 images); the up to three values before the first and after the
+// last aligned quad of a subsequence are stored one by one -- the neighbouring subsequences own the rest of those words.
+struct EntCompactSink {
+    unsigned long long* bm;
+    int16_t* dc;
+    uint32_t* boff;
+    int16_t* vals;        // the interval's value region
+    uint32_t vals_rel;    // its byte offset relative to bm (even; the stream itself is 16-byte aligned)
+    uint32_t t;           // scan-order index of the current block inside the image
+    uint32_t B, total;    // blocks of the interval delivered so far / to deliver
+    uint32_t vi, vcap;    // values appended so far / capacity of the region
+    uint32_t quad0;       // vi of the first value that can go into an aligned quad
+    unsigned long long bits, acc;
+    bool own;             // this thread met the block's DC code word
+    ENT_HD void begin(uint8_t* streams, const EntImage* im, uint32_t first_block, uint32_t first_val, bool at_block_start) {
+        uint8_t* cs = streams + im->cs_off;
+        bm = (unsigned long long*)cs;
+        dc = (int16_t*)(cs + 8 * (size_t)im->nb_pad);
+        boff = (uint32_t*)(cs + 10 * (size_t)im->nb_pad);
+        const uint32_t block0 = im->mcu0 * im->bpm;
+        vals_rel = im->vals_off + 126u * block0;
+        vals = (int16_t*)(cs + vals_rel);
         B = first_block;
-        const uint32_t m = im->mcu0 + B / im->bpm;
-        j = B % im->bpm;
-        mx = m % im->mcu_w;
-        my = m / im->mcu_w;
-        cur = slab;
-        if (B < im->total_blocks) locate();
+        total = im->total_blocks;
+        t = block0 + B;
+        vi = first_val;
+        vcap = 63u * total;
+        quad0 = vi + ((4u - ((vals_rel >> 1) + vi)) & 3u);  // (vals_rel / 2 + quad0) % 4 == 0
+        bits = 0;
+        acc = 0;
+        own = at_block_start;
+        if (own && B < total) boff[t] = vals_rel + 2u * vi;
     }
-    ENT_HD bool complete() const { return B >= im->total_blocks; }
-    // only reached with B < total_blocks: begin() is not used past the end, block_done() stops there
-    ENT_HD void store(unsigned pos, int v) { cur[unzz[pos]] = (int16_t)v; }
-    ENT_HD bool block_done() {
-        B++;
-        if (++j == im->bpm) {
-            j = 0;
-            if (++mx == im->mcu_w) {
-                mx = 0;
-                my++;
+    ENT_HD bool complete() const { return B >= total; }
+    // only reached with B < total: begin() is not used past the end, block_done() stops there
+    ENT_HD void store(unsigned pos, int v) {
+        if (pos == 0) {
+            dc[t] = (int16_t)v;
+            return;
+        }
+        bits |= 1ull << pos;
+        if (vi < quad0) {  // head: the word belongs partly to the previous subsequence
+            if (vi < vcap) vals[vi] = (int16_t)v;
+        } else {
+            const unsigned lane = (vi - quad0) & 3u;
+            acc |= (unsigned long long)(uint16_t)v << (16u * lane);
+            if (lane == 3u) {
+                if (vi < vcap) *(unsigned long long*)(vals + vi - 3) = acc;  // little-endian: value j of the quad in bits 16j..16j+15
+                acc = 0;
             }
         }
-        if (B >= im->total_blocks) return true;
-        locate();
+        vi++;
+    }
+    ENT_HD bool block_done() {
+        if (own) bm[t] = bits | 1ull;
+        else if (bits) ent_or64(&bm[t], bits);
+        B++;
+        t++;
+        bits = 0;
+        own = true;
+        if (B >= total) return true;
+        boff[t] = vals_rel + 2u * vi;
         return false;
+    }
+    // after the decode loop: the values of the last, incomplete quad; the block still in progress (it belongs to the next
+    // subsequence as well)
+    ENT_HD void finish() {
+        if (vi > quad0) {
+            const unsigned n = (vi - quad0) & 3u;
+            for (unsigned j = 0; j < n; j++)
+                if (vi - n + j < vcap) vals[vi - n + j] = (int16_t)(acc >> (16u * j));
+        }
+        if (B < total && (own || bits)) ent_or64(&bm[t], bits | (own ? 1ull : 0ull));
     }
 };
 

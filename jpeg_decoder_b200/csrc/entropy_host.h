@@ -160,12 +160,20 @@ inline size_t ent_build_payload(const HostDecoder& hd, const uint8_t* file, size
     return at;
 }
 
+// Bytes of the compact stream (entropy_dev.h) the write pass produces for an image of `nblocks` blocks.
+inline size_t ent_cs_bytes(size_t nblocks) {
+    const size_t nb_pad = (nblocks + 31) / 32 * 32;
+    return (ent_cs_header_bytes(nb_pad) + 15) / 16 * 16 + (ent_cs_values_bytes(nblocks) + 15) / 16 * 16;
+}
+
 // Kernel descriptors of one image -- one per interval -- from its payload and geometry.  coef_off[c] = byte offset of
-// component c's blocks inside the coefficient slab (multiple of 128), sub0 = index of the first subsequence in the
-// group's state arrays.  Returns the number of descriptors written (header.nintervals), 0 when payload and geometry
+// component c's blocks inside the coefficient slab (multiple of 128; only checked: K0 is what writes the slab),
+// cs_off = where the image's compact stream goes inside the device stream buffer (ent_cs_bytes(), 16-byte aligned),
+// sub0 = index of the first subsequence in the group's state arrays.  Returns the number of descriptors written (header.nintervals), 0 when payload and geometry
 // disagree or `cap` is too small; *nsub_total = subsequences over all intervals.
 inline unsigned ent_fill_images(const uint8_t* payload, size_t payload_len, const b200jpg_image_desc& d, const size_t coef_off[4],
-                                unsigned long long payload_off, unsigned sub0, EntImage* out, size_t cap, unsigned* nsub_total) {
+                                unsigned long long payload_off, unsigned long long cs_off, unsigned sub0, EntImage* out, size_t cap,
+                                unsigned* nsub_total) {
     EntHeader h;
     if (payload_len < sizeof h) return 0;
     memcpy(&h, payload, sizeof h);
@@ -204,7 +212,12 @@ inline unsigned ent_fill_images(const uint8_t* payload, size_t payload_len, cons
     }
     if (j != h.bpm || nb != h.total_blocks || nb == 0) return 0;
     base.mcu_w = d.comps[0].block_w / base.h[0];
-    if (base.mcu_w == 0) return 0;
+    if (base.mcu_w == 0 || cs_off % 16 != 0) return 0;
+    base.nb_pad = (nb + 31u) / 32u * 32u;
+    base.vals_off = (unsigned)((ent_cs_header_bytes(base.nb_pad) + 15) / 16 * 16);
+    base.cs_off = cs_off;
+    for (unsigned q = 12; q-- > 0;)
+        if (q < h.bpm) base.comp_j0[base.mcu_comp[q]] = (unsigned char)q;  // descending: the first slot of each component wins
     bool uniform = true;
     for (unsigned q = 0; q < 12; q++) {
         base.dcslot[q] = h.dcslot[q] < h.nslots ? h.dcslot[q] : 0;

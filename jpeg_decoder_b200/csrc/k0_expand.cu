@@ -42,8 +42,9 @@ __global__ void __launch_bounds__(K0_WARPS * 32) k0_expand(const K0Image* __rest
     const unsigned t = g * 32u + lane;
     const unsigned long long bm = ((const unsigned long long*)s)[t];
     const int dcv = ((const short*)(s + 8ull * nb_pad))[t];
-    const unsigned base = ((const unsigned*)(s + 10ull * nb_pad))[g];
-    const uint8_t* vals = s + ((10ull * nb_pad + 4ull * (nb_pad / 32u + 1u) + 15ull) & ~15ull);
+    const bool block_offsets = (im.order & SBS_BLOCK_OFFSETS) != 0;  // device-made stream: one offset per block, relative to s
+    const unsigned base = ((const unsigned*)(s + 10ull * nb_pad))[block_offsets ? t : g];
+    const uint8_t* vals = block_offsets ? s : s + ((10ull * nb_pad + 4ull * (nb_pad / 32u + 1u) + 15ull) & ~15ull);
 
     // byte offset of this lane's values: exclusive scan of the per-block byte counts
     const unsigned bytes = (unsigned)__popcll(bm >> 1) << (unsigned)(bm & 1ull);
@@ -53,7 +54,7 @@ __global__ void __launch_bounds__(K0_WARPS * 32) k0_expand(const K0Image* __rest
         const unsigned o = __shfl_up_sync(0xffffffffu, incl, d);
         if (lane >= (unsigned)d) incl += o;
     }
-    const unsigned off = base + incl - bytes;
+    const unsigned off = block_offsets ? base : base + incl - bytes;
 
     // destination row of this lane's block inside the dense slab
     unsigned row = 0xffffffffu;
@@ -83,11 +84,15 @@ __global__ void __launch_bounds__(K0_WARPS * 32) k0_expand(const K0Image* __rest
             v0 = d;
         } else if ((m >> lane) & 1ull) {
             const unsigned r = (unsigned)__popcll(m & below0);
-            v0 = wide ? (int)(short)((unsigned)vals[o + 2u * r] | ((unsigned)vals[o + 2u * r + 1u] << 8)) : (int)(signed char)vals[o + r];
+            v0 = block_offsets ? (int)*(const short*)(vals + o + 2u * r)  // device-made: always int16, 2-byte aligned
+                 : wide        ? (int)(short)((unsigned)vals[o + 2u * r] | ((unsigned)vals[o + 2u * r + 1u] << 8))
+                               : (int)(signed char)vals[o + r];
         }
         if ((m >> (lane + 32u)) & 1ull) {
             const unsigned r = (unsigned)__popcll(m & below1);
-            v1 = wide ? (int)(short)((unsigned)vals[o + 2u * r] | ((unsigned)vals[o + 2u * r + 1u] << 8)) : (int)(signed char)vals[o + r];
+            v1 = block_offsets ? (int)*(const short*)(vals + o + 2u * r)  // device-made: always int16, 2-byte aligned
+                 : wide        ? (int)(short)((unsigned)vals[o + 2u * r] | ((unsigned)vals[o + 2u * r + 1u] << 8))
+                               : (int)(signed char)vals[o + r];
         }
         tile[warp][b][p0] = (short)v0;
         tile[warp][b][p1] = (short)v1;
@@ -99,6 +104,22 @@ __global__ void __launch_bounds__(K0_WARPS * 32) k0_expand(const K0Image* __rest
         const unsigned r = __shfl_sync(0xffffffffu, row, (int)b);
         if (r != 0xffffffffu) *(int4*)(slab + (size_t)r * 64u + chunk * 8u) = *(const int4*)&tile[warp][b][chunk * 8u];
     }
+}
+
+// zeroes the per-block arrays (bm | dc | boff = 14 bytes per block) of device-made streams before the write pass ORs into them
+__global__ void __launch_bounds__(256) k0_zero_headers(const K0Image* __restrict__ images, uint8_t* __restrict__ streams) {
+    const K0Image& im = images[blockIdx.y];
+    if ((im.order & SBS_BLOCK_OFFSETS) == 0) return;
+    const size_t n16 = (14ull * ((im.nb + 31u) & ~31u) + 15ull) / 16ull;  // nb_pad is a multiple of 32: 14 * nb_pad is a multiple of 16
+    uint4* p = reinterpret_cast<uint4*>(streams + im.stream_off);
+    for (size_t q = (size_t)blockIdx.x * 256u + threadIdx.x; q < n16; q += (size_t)gridDim.x * 256u) p[q] = make_uint4(0u, 0u, 0u, 0u);
+}
+
+cudaError_t launch_k0_zero_headers(const K0Image* d_images, unsigned nimages, unsigned max_blocks, uint8_t* d_streams, cudaStream_t stream) {
+    if (nimages == 0 || max_blocks == 0) return cudaSuccess;
+    const unsigned n16 = (14u * ((max_blocks + 31u) & ~31u) + 15u) / 16u;
+    k0_zero_headers<<<dim3(min((n16 + 255u) / 256u, 64u), nimages), 256, 0, stream>>>(d_images, d_streams);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_k0_expand(const K0Image* d_images, unsigned nimages, unsigned max_blocks, const uint8_t* d_streams, short* d_slab,

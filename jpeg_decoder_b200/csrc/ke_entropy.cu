@@ -1,9 +1,9 @@
 // ke_entropy.cu -- the kernels of device entropy decoding; the algorithm is described in entropy_dev.h.
 //
 //   ent_pass<COLD | WRITE>, ent_sync  one thread per subsequence (ENT_SUB_BITS bits of the scan), 128 per CTA; the image's
-//                                  decoding tables (<= 6.4 KB) live in shared memory, the scan bytes are read through L1
-//                                  (every thread walks its own 128-byte line)
-//   ent_prefix                     per image: exclusive sum of the blocks each subsequence completed
+//                                  decoding tables and its 16 KB of the scan live in shared memory; the write pass
+//                                  appends to the image's compact stream, which K0 (k0_expand.cu) expands
+//   ent_prefix                     per image: exclusive sums of the blocks each subsequence completed and the values it met
 //   ent_dc_sums/_chunks/_apply     DC differences -> DC values (wrapping int16 prefix sum per component), one thread per block
 //
 // grid.y = image, grid.x covers the longest scan of the launch; CTAs past the end of their image exit at once.
@@ -23,10 +23,8 @@ struct EntShared {
     EntImage im;
     EntTables tabs[ENT_MAX_SLOTS];
     uint8_t dcslot[12], acslot[12];
-    uint8_t unzz[64];
 };
 
-__constant__ uint8_t c_unzigzag[64] = ENT_UNZIGZAG_INIT;
 
 // The CTA's share of the scan in shared memory: the 128 subsequences of its threads plus the few words the last code
 // word of the last one may reach into.  Staged once with coalesced 128-bit loads (every thread walking its own
@@ -73,7 +71,6 @@ __device__ __forceinline__ void load_shared(EntShared& sh, const EntImage& im, c
         sh.dcslot[threadIdx.x] = im.dcslot[threadIdx.x];
         sh.acslot[threadIdx.x] = im.acslot[threadIdx.x];
     }
-    if (threadIdx.x < 64) sh.unzz[threadIdx.x] = c_unzigzag[threadIdx.x];
     __syncthreads();
 }
 
@@ -81,6 +78,8 @@ __device__ __forceinline__ void load_shared(EntShared& sh, const EntImage& im, c
 struct EntWork {
     unsigned long long* state;
     unsigned* first_block;
+    unsigned* nvals;      // AC values the subsequence appends to the compact stream
+    unsigned* first_val;  // exclusive prefix of nvals inside the interval
     unsigned char* ch[2];
     unsigned* counters;  // counters[r] != 0: pass r changed some state (counters[0] is set by the cold pass)
     unsigned* status;    // per image: [anomaly bits, completed]
@@ -93,8 +92,7 @@ constexpr unsigned ENT_LOCAL_ITERS = 32;  // synchronisation rounds a CTA runs b
 
 // COLD and WRITE: one decode per thread.
 template <int MODE>
-__global__ void __launch_bounds__(ENT_THREADS) ent_pass(const EntImage* __restrict__ imgs, const uint8_t* __restrict__ streams, EntWork w,
-                                                        short* __restrict__ coefs) {
+__global__ void __launch_bounds__(ENT_THREADS) ent_pass(const EntImage* __restrict__ imgs, uint8_t* streams, EntWork w) {
     const EntImage& im = imgs[blockIdx.y];
     if (blockIdx.x * ENT_THREADS >= im.nsub) return;
     const unsigned i = blockIdx.x * ENT_THREADS + threadIdx.x;
@@ -119,9 +117,10 @@ __global__ void __launch_bounds__(ENT_THREADS) ent_pass(const EntImage* __restri
     st.k = st.b = st.nb = 0;
     unsigned bad = 0;
     if (MODE == ENT_COLD) {
-        EntNullSink sink;
+        EntCountSink sink;
         st_state(&w.state[g], ent_pack(ent_decode_range<false>(words, tabs, sh.dcslot, sh.acslot, im.dec_bpm, st,
                                                                ent_sub_end(i, im.nsub, im.scan_bits), sink, &bad)));
+        w.nvals[g] = sink.nvals;
         w.ch[0][g] = 1;  // the first synchronisation launch looks at everybody
         if (i == 0) w.counters[0] = 1;
     } else {
@@ -129,11 +128,12 @@ __global__ void __launch_bounds__(ENT_THREADS) ent_pass(const EntImage* __restri
             st = ent_unpack(ld_state(&w.state[g - 1]));
             st.nb = 0;
         }
-        EntWriteSink sink;
-        sink.begin(coefs, &sh.im, sh.unzz, w.first_block[g]);
+        EntCompactSink sink;
+        sink.begin(streams, &sh.im, w.first_block[g], w.first_val[g], st.k == 0);
         const bool last = i + 1 == im.nsub;
         const uint32_t end = last ? im.scan_bits + ENT_TAIL_SLACK_BITS : ent_sub_end(i, im.nsub, im.scan_bits);
         const EntState e = ent_decode_range<true>(words, tabs, sh.dcslot, sh.acslot, im.dec_bpm, st, end, sink, &bad);
+        sink.finish();
         if (sink.complete()) {
             w.status[2 * blockIdx.y + 1] = 1;  // every block of the interval has been delivered
             if (im.tight_end && e.p + 7 < im.scan_bits) bad |= ENT_BAD_TAIL;
@@ -148,8 +148,7 @@ __global__ void __launch_bounds__(ENT_THREADS) ent_pass(const EntImage* __restri
 // one launch to the next (read from ch[(pass-1)&1], written to ch[pass&1]).  Inside a launch a CTA keeps iterating on
 // its own 128 subsequences through shared-memory flags until they are quiet; only the hand-over to the next CTA (and
 // whatever is left when ENT_LOCAL_ITERS runs out) waits for the next launch.
-__global__ void __launch_bounds__(ENT_THREADS) ent_sync(const EntImage* __restrict__ imgs, const uint8_t* __restrict__ streams, EntWork w,
-                                                        unsigned pass) {
+__global__ void __launch_bounds__(ENT_THREADS) ent_sync(const EntImage* __restrict__ imgs, const uint8_t* streams, EntWork w, unsigned pass) {
     if (w.counters[pass - 1] == 0) return;  // converged earlier: nothing left to do
     const EntImage& im = imgs[blockIdx.y];
     if (blockIdx.x * ENT_THREADS >= im.nsub) return;
@@ -180,11 +179,12 @@ __global__ void __launch_bounds__(ENT_THREADS) ent_sync(const EntImage* __restri
         if (pending) {
             EntState st = ent_unpack(ld_state(&w.state[g - 1]));
             st.nb = 0;
-            EntNullSink sink;
+            EntCountSink sink;
             unsigned bad = 0;
             const unsigned long long v = ent_pack(ent_decode_range<false>(words, tabs, sh.dcslot, sh.acslot, im.dec_bpm, st, end, sink, &bad));
             changed = ((v ^ mine) & ENT_SYNC_MASK) != 0;
-            if (v != mine) st_state(&w.state[g], v);  // nb may change even when (p, k, b) do not
+            if (v != mine) st_state(&w.state[g], v);  // the counts may change even when (p, k, b) do not
+            w.nvals[g] = sink.nvals;
             mine = v;
         }
         ever |= changed;
@@ -232,23 +232,27 @@ __global__ void __launch_bounds__(SCAN_THREADS) ent_prefix(const EntImage* __res
     const EntImage& im = imgs[blockIdx.x];
     const unsigned n = im.nsub, per = (n + SCAN_THREADS - 1) / SCAN_THREADS;
     const unsigned lo = min(n, threadIdx.x * per), hi = min(n, lo + per);
-    unsigned sum = 0;
-    for (unsigned i = lo; i < hi; i++) sum += ent_unpack(w.state[im.sub0 + i]).nb;
-    unsigned total;
-    unsigned acc = block_exclusive(sum, &total);
+    unsigned blocks = 0, vals = 0;
     for (unsigned i = lo; i < hi; i++) {
-        w.first_block[im.sub0 + i] = acc;
-        acc += ent_unpack(w.state[im.sub0 + i]).nb;
+        blocks += ent_unpack(w.state[im.sub0 + i]).nb;
+        vals += w.nvals[im.sub0 + i];
+    }
+    unsigned total;
+    unsigned acc_b = block_exclusive(blocks, &total), acc_v = block_exclusive(vals, &total);
+    for (unsigned i = lo; i < hi; i++) {
+        w.first_block[im.sub0 + i] = acc_b;
+        w.first_val[im.sub0 + i] = acc_v;
+        acc_b += ent_unpack(w.state[im.sub0 + i]).nb;
+        acc_v += w.nvals[im.sub0 + i];
     }
 }
 
-// coefficient 0 of the q-th block of component c of the interval, in scan order (MCU by MCU, v then h inside an MCU)
-__device__ __forceinline__ short* dc_ptr(short* coefs, const EntImage& im, unsigned c, unsigned q) {
-    const unsigned h = im.h[c], hv = h * im.v[c];
-    const unsigned ml = q / hv, r = q - ml * hv, vy = r / h, hx = r - vy * h;
-    const unsigned m = im.mcu0 + ml;
-    const unsigned my = m / im.mcu_w, mx = m - my * im.mcu_w;
-    return coefs + ((size_t)im.slab_row[c] + (size_t)(my * im.v[c] + vy) * im.block_w[c] + mx * h + hx) * 64;
+// the DC slot (compact stream, scan order) of the q-th block of component c of the interval (MCU by MCU, v then h inside an MCU)
+__device__ __forceinline__ short* dc_ptr(uint8_t* streams, const EntImage& im, unsigned c, unsigned q) {
+    const unsigned hv = (unsigned)im.h[c] * im.v[c];
+    const unsigned ml = q / hv, r = q - ml * hv;
+    short* dc = reinterpret_cast<short*>(streams + im.cs_off + 8ull * im.nb_pad);
+    return dc + (size_t)(im.mcu0 + ml) * im.bpm + im.comp_j0[c] + r;
 }
 
 // src/decoder.rs:1096-1110: dc_predictor = dc_predictor.wrapping_add(diff), per component, along the scan -- a prefix
@@ -257,13 +261,13 @@ __device__ __forceinline__ short* dc_ptr(short* coefs, const EntImage& im, unsig
 //   ent_dc_chunks: exclusive prefix of the chunk sums, one CTA per (component, image)
 //   ent_dc_apply : block-wide inclusive prefix inside the chunk + the chunk's offset, written back
 // grid = (chunks of the largest component of the launch, 4 components, images)
-__global__ void __launch_bounds__(SCAN_THREADS) ent_dc_sums(const EntImage* __restrict__ imgs, const short* __restrict__ coefs,
+__global__ void __launch_bounds__(SCAN_THREADS) ent_dc_sums(const EntImage* __restrict__ imgs, uint8_t* streams,
                                                             unsigned* __restrict__ chunk_sums, unsigned max_chunks) {
     const EntImage& im = imgs[blockIdx.z];
     const unsigned c = blockIdx.y;
     if (c >= im.ncomp || blockIdx.x * SCAN_THREADS >= im.comp_blocks[c]) return;
     const unsigned q = blockIdx.x * SCAN_THREADS + threadIdx.x;
-    const unsigned v = q < im.comp_blocks[c] ? (unsigned)(unsigned short)*dc_ptr(const_cast<short*>(coefs), im, c, q) : 0u;
+    const unsigned v = q < im.comp_blocks[c] ? (unsigned)(unsigned short)*dc_ptr(streams, im, c, q) : 0u;
     unsigned total;
     block_exclusive(v, &total);
     if (threadIdx.x == 0) chunk_sums[((size_t)blockIdx.z * 4 + c) * max_chunks + blockIdx.x] = total;
@@ -286,14 +290,14 @@ __global__ void __launch_bounds__(SCAN_THREADS) ent_dc_chunks(const EntImage* __
     }
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) ent_dc_apply(const EntImage* __restrict__ imgs, short* __restrict__ coefs,
+__global__ void __launch_bounds__(SCAN_THREADS) ent_dc_apply(const EntImage* __restrict__ imgs, uint8_t* streams,
                                                              const unsigned* __restrict__ chunk_sums, unsigned max_chunks) {
     const EntImage& im = imgs[blockIdx.z];
     const unsigned c = blockIdx.y;
     if (c >= im.ncomp || blockIdx.x * SCAN_THREADS >= im.comp_blocks[c]) return;
     const unsigned q = blockIdx.x * SCAN_THREADS + threadIdx.x;
     const bool valid = q < im.comp_blocks[c];
-    short* p = dc_ptr(coefs, im, c, valid ? q : 0u);
+    short* p = dc_ptr(streams, im, c, valid ? q : 0u);
     const unsigned v = valid ? (unsigned)(unsigned short)*p : 0u;
     unsigned total;
     const unsigned ex = block_exclusive(v, &total);
@@ -306,13 +310,12 @@ static unsigned dc_chunks(unsigned max_comp_blocks) { return (max_comp_blocks + 
 
 size_t ent_work_bytes(unsigned total_sub, unsigned nimages, unsigned max_comp_blocks, int max_passes) {
     auto up = [](size_t x) { return (x + 255) / 256 * 256; };
-    return up((size_t)total_sub * 8) + up((size_t)total_sub * 4) + 2 * up(total_sub) + up((size_t)(max_passes + 2) * 4) + up((size_t)nimages * 8) +
+    return up((size_t)total_sub * 8) + 3 * up((size_t)total_sub * 4) + 2 * up(total_sub) + up((size_t)(max_passes + 2) * 4) + up((size_t)nimages * 8) +
            up((size_t)nimages * 4 * dc_chunks(max_comp_blocks) * 4);
 }
 
 cudaError_t launch_entropy(const EntImage* d_images, unsigned nimages, unsigned max_nsub, unsigned total_sub, unsigned max_comp_blocks,
-                           const uint8_t* d_streams, void* d_work, int max_passes, short* d_coefs, unsigned** d_status, cudaStream_t stream,
-                           uint64_t* launches) {
+                           uint8_t* d_streams, void* d_work, int max_passes, unsigned** d_status, cudaStream_t stream, uint64_t* launches) {
     if (nimages == 0 || max_nsub == 0) return cudaSuccess;
     auto up = [](size_t x) { return (x + 255) / 256 * 256; };
     char* p = (char*)d_work;
@@ -320,6 +323,10 @@ cudaError_t launch_entropy(const EntImage* d_images, unsigned nimages, unsigned 
     w.state = (unsigned long long*)p;
     p += up((size_t)total_sub * 8);
     w.first_block = (unsigned*)p;
+    p += up((size_t)total_sub * 4);
+    w.nvals = (unsigned*)p;
+    p += up((size_t)total_sub * 4);
+    w.first_val = (unsigned*)p;
     p += up((size_t)total_sub * 4);
     w.ch[0] = (unsigned char*)p;
     p += up(total_sub);
@@ -346,13 +353,13 @@ cudaError_t launch_entropy(const EntImage* d_images, unsigned nimages, unsigned 
             if (e != cudaSuccess) return e;
         }
         const dim3 grid(sub_grid.x, cnt);
-        ent_pass<ENT_COLD><<<grid, ENT_THREADS, 0, stream>>>(imgs, d_streams, wc, nullptr);
+        ent_pass<ENT_COLD><<<grid, ENT_THREADS, 0, stream>>>(imgs, d_streams, wc);
         for (int r = 1; r <= max_passes; r++) ent_sync<<<grid, ENT_THREADS, 0, stream>>>(imgs, d_streams, wc, (unsigned)r);
         ent_prefix<<<cnt, SCAN_THREADS, 0, stream>>>(imgs, wc);
-        ent_pass<ENT_WRITE><<<grid, ENT_THREADS, 0, stream>>>(imgs, d_streams, wc, d_coefs);
-        ent_dc_sums<<<dim3(nchunks, 4, cnt), SCAN_THREADS, 0, stream>>>(imgs, d_coefs, sums, nchunks);
+        ent_pass<ENT_WRITE><<<grid, ENT_THREADS, 0, stream>>>(imgs, d_streams, wc);
+        ent_dc_sums<<<dim3(nchunks, 4, cnt), SCAN_THREADS, 0, stream>>>(imgs, d_streams, sums, nchunks);
         ent_dc_chunks<<<dim3(4, cnt), SCAN_THREADS, 0, stream>>>(imgs, sums, nchunks);
-        ent_dc_apply<<<dim3(nchunks, 4, cnt), SCAN_THREADS, 0, stream>>>(imgs, d_coefs, sums, nchunks);
+        ent_dc_apply<<<dim3(nchunks, 4, cnt), SCAN_THREADS, 0, stream>>>(imgs, d_streams, sums, nchunks);
         if (launches) *launches += (uint64_t)max_passes + 6;
     }
     return cudaGetLastError();

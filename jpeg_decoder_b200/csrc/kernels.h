@@ -40,10 +40,11 @@ cudaError_t launch_k0_expand(const K0Image* d_images, unsigned nimages, unsigned
 // device entropy decoding (entropy_dev.h, ke_entropy.cu): cold + max_passes sync + prefix + write + dc on `stream`.
 // d_work: ent_work_bytes() bytes; *d_status: per image [anomaly bits, completed] inside d_work, valid after the launch.
 struct EntImage;
+// d_streams holds the payloads and receives the compact streams (EntImage::cs_off) K0 then expands.
 size_t ent_work_bytes(unsigned total_sub, unsigned nimages, unsigned max_comp_blocks, int max_passes);
 cudaError_t launch_entropy(const EntImage* d_images, unsigned nimages, unsigned max_nsub, unsigned total_sub, unsigned max_comp_blocks,
-                           const uint8_t* d_streams, void* d_work, int max_passes, short* d_coefs, unsigned** d_status, cudaStream_t stream,
-                           uint64_t* launches);
+                           uint8_t* d_streams, void* d_work, int max_passes, unsigned** d_status, cudaStream_t stream, uint64_t* launches);
+cudaError_t launch_k0_zero_headers(const K0Image* d_images, unsigned nimages, unsigned max_blocks, uint8_t* d_streams, cudaStream_t stream);
 cudaError_t launch_k1_generic(const K1Params& p, int arith, cudaStream_t stream);
 size_t k1_tma_smem_bytes();
 cudaError_t launch_k1_tma(const CUtensorMap& tmap, const K1QCache& qc, const K1Params& p, int num_sms, cudaStream_t stream);

@@ -33,7 +33,13 @@
 
 namespace b200jpg {
 
-enum : unsigned { SBS_PLANAR = 0, SBS_INTERLEAVED = 1, SBS_NATURAL = 2, SBS_ENTROPY = 4 /* internal: see sbs_pipeline.h */ };
+enum : unsigned {
+    SBS_PLANAR = 0,
+    SBS_INTERLEAVED = 1,
+    SBS_NATURAL = 2,
+    SBS_ENTROPY = 4,        // internal: see sbs_pipeline.h
+    SBS_BLOCK_OFFSETS = 8,  // internal (device-made streams, entropy_dev.h): u32 value offset per block, relative to the stream start
+};
 
 struct SbsLayout {
     size_t nb = 0, nb_pad = 0, off_dc = 0, off_voff = 0, off_vals = 0;

@@ -243,6 +243,11 @@ int SbsPipeline::enqueue(Slot& s) {
     unsigned max_nb = 0, max_nsub = 0, total_sub = 0, max_comp_blocks = 0;
     std::vector<size_t> soff(n, 0);
     s.ent_items.clear();
+    // the compact streams the device writes for entropy images live behind everything that is uploaded
+    size_t cs_at = 0;
+    for (size_t i = 0; i < n; i++)
+        if (!s.group.statuses[i] && it[i].stream) cs_at += it[i].len;
+    cs_at = up(cs_at, 256);
     for (size_t i = 0; i < n; i++) {
         if (s.group.statuses[i]) continue;
         if (!it[i].out || it[i].out_cap < b->layout[i].out_len || !it[i].stream) {
@@ -252,8 +257,8 @@ int SbsPipeline::enqueue(Slot& s) {
         }
         if (it[i].order == SBS_ENTROPY) {  // an entropy-coded scan: Huffman decoding happens on the device, interval by interval
             unsigned nsub = 0;
-            const unsigned k = ent_fill_images(it[i].stream, it[i].len, descs[i], b->layout[i].coef_off, stream_bytes, total_sub, h_ent + nent,
-                                               max_ent - nent, &nsub);
+            const unsigned k = ent_fill_images(it[i].stream, it[i].len, descs[i], b->layout[i].coef_off, stream_bytes, cs_at, total_sub,
+                                               h_ent + nent, max_ent - nent, &nsub);
             if (k == 0) {
                 s.group.statuses[i] = B200JPG_ERR_INTERNAL;
                 b200jpg_fail(ctx_, B200JPG_ERR_INTERNAL, "malformed entropy payload");
@@ -266,6 +271,11 @@ int SbsPipeline::enqueue(Slot& s) {
             }
             total_sub += nsub;
             nent += k;
+            // K0 expands the compact stream like a host-made one (scan order = MCU order; a lone component: raster order)
+            fill_k0(descs[i], b->layout[i], (descs[i].ncomp > 1 ? SBS_INTERLEAVED : SBS_PLANAR) | SBS_BLOCK_OFFSETS, cs_at, &h_k0[nk0]);
+            max_nb = std::max(max_nb, h_k0[nk0].nb);
+            cs_at += ent_cs_bytes(h_k0[nk0].nb);
+            nk0++;
         } else {
             fill_k0(descs[i], b->layout[i], it[i].order, stream_bytes, &h_k0[nk0]);
             const SbsLayout lay = SbsLayout::make(h_k0[nk0].nb);
@@ -281,7 +291,7 @@ int SbsPipeline::enqueue(Slot& s) {
         stream_bytes += it[i].len;
     }
     const int passes = ent_max_passes();
-    rc = grow_device(s.d_streams, stream_bytes + 256);
+    rc = grow_device(s.d_streams, std::max(stream_bytes, cs_at) + 256);
     if (rc == B200JPG_OK) rc = grow_device(s.d_coefs, b->info.coef_bytes + K1_TILE * 128);
     if (rc == B200JPG_OK) rc = grow_device(s.d_planes, b->info.plane_bytes + 256);
     if (rc == B200JPG_OK) rc = grow_device(s.d_out, b->info.out_bytes + 256);
@@ -329,16 +339,16 @@ int SbsPipeline::enqueue(Slot& s) {
     CU_TRY(ctx_, cudaStreamWaitEvent(s_comp_, s.e_h2d, 0));
     unsigned* d_status = nullptr;
     if (nent) {
-        // the write pass stores only non-zero coefficients: the slab starts out zeroed (Worker::start, src/worker/immediate.rs:30-37)
-        CU_TRY(ctx_, cudaMemsetAsync(s.d_coefs.p, 0, b->info.coef_bytes, s_comp_));
+        // Huffman decoding on the device: payloads -> compact streams (bitmaps are OR-ed into: zero them first) ...
+        CU_TRY(ctx_, launch_k0_zero_headers(d_k0, (unsigned)nk0, max_nb, (uint8_t*)s.d_streams.p, s_comp_));
+        CU_TRY(ctx_, launch_entropy(d_ent, (unsigned)nent, max_nsub, total_sub, max_comp_blocks, (uint8_t*)s.d_streams.p, s.d_ent.p, passes, &d_status,
+                                    s_comp_, &ctx_->launches));
+        ctx_->launches++;
     }
-    if (nk0) {
+    if (nk0) {  // ... and K0 expands them together with the streams the host made: the dense slab K1 reads, zeros included
         CU_TRY(ctx_, launch_k0_expand(d_k0, (unsigned)nk0, max_nb, (const uint8_t*)s.d_streams.p, (short*)s.d_coefs.p, s_comp_));
         ctx_->launches++;
     }
-    if (nent)
-        CU_TRY(ctx_, launch_entropy(d_ent, (unsigned)nent, max_nsub, total_sub, max_comp_blocks, (const uint8_t*)s.d_streams.p, s.d_ent.p, passes, (short*)s.d_coefs.p,
-                                    &d_status, s_comp_, &ctx_->launches));
     if (nk0 || nent) {
         rc = batch_launch(b, s.d_coefs.p, s.d_planes.p, s.d_out.p, 3, 0, (unsigned)b->tiles.size(), 0, (unsigned)n, s_comp_);
         if (rc) return rc;

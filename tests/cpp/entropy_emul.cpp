@@ -29,6 +29,7 @@ struct EmulResult {
     unsigned status = 0;  // anomaly bits
     unsigned passes = 0, nsub = 0, intervals = 0;
     std::vector<int16_t> coefs;  // all components back to back
+    std::vector<uint8_t> cs;     // the compact stream of the image (entropy_dev.h)
 };
 
 struct EmulResult;
@@ -48,12 +49,31 @@ static EmulResult emulate(const std::vector<uint8_t>& file, const HostDecoder& p
     }
     std::vector<EntImage> ims(h.nintervals ? h.nintervals : 1);
     unsigned nsub_total = 0;
-    if (!ent_fill_images(payload.data(), plen, d, coef_off, 0, 0, ims.data(), ims.size(), &nsub_total)) return r;
+    if (!ent_fill_images(payload.data(), plen, d, coef_off, 0, 0, 0, ims.data(), ims.size(), &nsub_total)) return r;
     r.eligible = true;
     r.nsub = nsub_total;
     r.intervals = (unsigned)ims.size();
-    r.coefs.assign(total / 2, 0);
+    r.coefs.assign(total / 2, 0x5a5a);  // K0 writes every coefficient, zeros included
+    r.cs.assign(ent_cs_bytes(h.total_blocks), 0xee);
+    memset(r.cs.data(), 0, ent_cs_header_bytes(ims[0].nb_pad));  // k0_zero_headers
     for (const EntImage& im : ims) emulate_interval(payload, im, d, max_passes, r);
+    // K0 (k0_expand.cu) on the compact stream: bitmaps + values -> dense blocks in the slab
+    const EntImage& im0 = ims[0];
+    const unsigned long long* bm = (const unsigned long long*)r.cs.data();
+    const int16_t* dc = (const int16_t*)(r.cs.data() + 8 * (size_t)im0.nb_pad);
+    const uint32_t* boff = (const uint32_t*)(r.cs.data() + 10 * (size_t)im0.nb_pad);
+    for (unsigned t = 0; t < h.total_blocks; t++) {
+        const unsigned m = t / im0.bpm, j = t % im0.bpm, c = im0.mcu_comp[j];
+        const unsigned mx = m % im0.mcu_w, my = m / im0.mcu_w;
+        int16_t* blk = r.coefs.data() + ((size_t)im0.slab_row[c] + (size_t)(my * im0.v[c] + im0.mcu_vy[j]) * im0.block_w[c] + mx * im0.h[c] + im0.mcu_hx[j]) * 64;
+        const int16_t* v = (const int16_t*)(r.cs.data() + boff[t]);
+        unsigned rank = 0;
+        for (unsigned k = 0; k < 64; k++) {
+            if (k == 0) blk[0] = dc[t];
+            else if ((bm[t] >> k) & 1) blk[UNZZ[k]] = v[rank++];
+            else blk[UNZZ[k]] = 0;
+        }
+    }
     return r;
 }
 
@@ -64,12 +84,14 @@ static void emulate_interval(const std::vector<uint8_t>& payload, const EntImage
     const unsigned n = im.nsub;
     std::vector<uint64_t> state(n);
     std::vector<uint8_t> chA(n, 1), chB(n, 0);
+    std::vector<uint32_t> nvals(n, 0);
     unsigned dummy = 0, passes = 0;
     // cold
     for (unsigned i = 0; i < n; i++) {
-        EntNullSink sink;
+        EntCountSink sink;
         EntState st{i * ENT_SUB_BITS, 0, 0, 0};
         state[i] = ent_pack(ent_decode_range<false>(words, tabs, im.dcslot, im.acslot, im.dec_bpm, st, ent_sub_end(i, n, im.scan_bits), sink, &dummy));
+        nvals[i] = sink.nvals;
     }
     // sync, scheduled like ent_sync (ke_entropy.cu): per launch every CTA of 128 subsequences iterates on its own until
     // it is quiet (flags through "shared memory"), states are read and written in place, only the hand-over between
@@ -100,12 +122,13 @@ static void emulate_interval(const std::vector<uint8_t>& payload, const EntImage
                     const unsigned t = cnt - 1 - tt, i = i0 + t;
                     changed[t] = 0;
                     if (!pending[t]) continue;
-                    EntNullSink sink;
+                    EntCountSink sink;
                     const EntState st = ent_unpack(state[i - 1]);
                     const uint64_t v = ent_pack(ent_decode_range<false>(words, tabs, im.dcslot, im.acslot, im.dec_bpm,
                                                                        EntState{st.p, st.k, st.b, 0}, ent_sub_end(i, n, im.scan_bits), sink, &dummy));
                     changed[t] = ((v ^ mine[t]) & ENT_SYNC_MASK) != 0;
                     state[i] = v;
+                    nvals[i] = sink.nvals;
                     mine[t] = v;
                     ever[t] |= changed[t];
                 }
@@ -130,11 +153,13 @@ static void emulate_interval(const std::vector<uint8_t>& payload, const EntImage
         if (!any) break;
     }
     // prefix
-    std::vector<uint32_t> first(n);
-    uint32_t acc = 0;
+    std::vector<uint32_t> first(n), first_val(n);
+    uint32_t acc = 0, accv = 0;
     for (unsigned i = 0; i < n; i++) {
         first[i] = acc;
+        first_val[i] = accv;
         acc += ent_unpack(state[i]).nb;
+        accv += nvals[i];
     }
     // write
     bool completed = false;
@@ -145,12 +170,13 @@ static void emulate_interval(const std::vector<uint8_t>& payload, const EntImage
             st = ent_unpack(state[i - 1]);
             st.nb = 0;
         }
-        EntWriteSink sink;
-        sink.begin(r.coefs.data(), &im, UNZZ, first[i]);
+        EntCompactSink sink;
+        sink.begin(r.cs.data(), &im, first[i], first_val[i], st.k == 0);
         const bool last = i + 1 == n;
         const uint32_t end = last ? im.scan_bits + ENT_TAIL_SLACK_BITS : ent_sub_end(i, n, im.scan_bits);
         unsigned bad = 0;
         const EntState e = ent_decode_range<true>(words, tabs, im.dcslot, im.acslot, im.dec_bpm, st, end, sink, &bad);
+        sink.finish();
         if (sink.complete()) {
             completed = true;
             if (im.tight_end && e.p + 7 < im.scan_bits) bad |= ENT_BAD_TAIL;
@@ -160,16 +186,15 @@ static void emulate_interval(const std::vector<uint8_t>& payload, const EntImage
         r.status |= bad;
     }
     if (!completed) r.status |= ENT_INCOMPLETE;
-    // dc: differences -> values, per component in scan order
+    // dc: differences -> values, per component in scan order, on the compact stream's dc array
+    int16_t* dcarr = (int16_t*)(r.cs.data() + 8 * (size_t)im.nb_pad);
     for (int c = 0; c < d.ncomp; c++) {
         const unsigned hv = (unsigned)im.h[c] * im.v[c];
         uint16_t pred = 0;
         for (unsigned q = 0; q < im.comp_blocks[c]; q++) {
-            const unsigned m = im.mcu0 + q / hv, rr = q % hv, vy = rr / im.h[c], hx = rr % im.h[c];
-            const unsigned mx = m % im.mcu_w, my = m / im.mcu_w;
-            int16_t* blk = r.coefs.data() + ((size_t)im.slab_row[c] + (size_t)(my * im.v[c] + vy) * im.block_w[c] + mx * im.h[c] + hx) * 64;
-            pred = (uint16_t)(pred + (uint16_t)blk[0]);
-            blk[0] = (int16_t)pred;
+            int16_t* p = dcarr + (size_t)(im.mcu0 + q / hv) * im.bpm + im.comp_j0[c] + q % hv;
+            pred = (uint16_t)(pred + (uint16_t)*p);
+            *p = (int16_t)pred;
         }
     }
     r.passes = std::max(r.passes, passes);
