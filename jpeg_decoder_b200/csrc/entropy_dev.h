@@ -174,9 +174,22 @@ static unsigned long long ent_stats_len[32];  // emulator only: code-length hist
 
 // Sinks: what happens to decoded coefficients.
 struct EntNullSink {
+    static constexpr bool kCountOnly = false;
     ENT_HD void store(unsigned, int) {}
     ENT_HD bool block_done() { return false; }
 };
+
+// Counts what the write pass will append: AC values (DC differences have their own array).
+struct EntCountSink {
+    static constexpr bool kCountOnly = true;  // the decoder adds (value bits present && not a DC code word) itself: no branch
+    uint32_t nvals = 0;
+    ENT_HD void store(unsigned, int) {}
+    ENT_HD bool block_done() { return false; }
+};
+
+template <class Sink>
+ENT_HD void sink_count(Sink&, unsigned) {}
+ENT_HD void sink_count(EntCountSink& s, unsigned n) { s.nvals += n; }
 
 // Decodes code words starting at state `st` while they start before bit `end_bit`.  Returns the state after the
 // last one (nb = blocks completed here).  The function is deterministic in (st, end_bit) whatever the bits are:
@@ -210,7 +223,10 @@ ENT_HD EntState ent_decode_range(const Words& words, const uint16_t* tabs, const
             if (CHECK) bad |= ENT_BAD_SYMBOL;
             adv = 1;
         }
-        if (s) {
+        if (Sink::kCountOnly) {
+            // what the write pass will append for this code word (a run leaving the block is flagged there anyway)
+            sink_count(sink, (s != 0u) & (k != 0u));
+        } else if (s) {
             const uint32_t pos = k + adv - 1;
             const uint32_t u = (win << len) >> (32u - s);
             // extend(), src/huffman.rs:98-... / Figure F.12
@@ -244,13 +260,6 @@ ENT_HD EntState ent_decode_range(const Words& words, const uint16_t* tabs, const
     return r;
 }
 
-// Counts what the write pass will append: AC values (DC differences have their own array).
-struct EntCountSink {
-    uint32_t nvals = 0;
-    ENT_HD void store(unsigned pos, int) { nvals += pos != 0; }
-    ENT_HD bool block_done() { return false; }
-};
-
 ENT_HD void ent_or64(unsigned long long* p, unsigned long long v) {
 #if defined(__CUDA_ARCH__)
     atomicOr(p, v);
@@ -265,6 +274,7 @@ ENT_HD void ent_or64(unsigned long long* p, unsigned long long v) {
 // own on the way to L2: measured 23 M sectors per 27 images); the up to three values before the first and after the
 // last aligned quad of a subsequence are stored one by one -- the neighbouring subsequences own the rest of those words.
 struct EntCompactSink {
+    static constexpr bool kCountOnly = false;
     unsigned long long* bm;
     int16_t* dc;
     uint32_t* boff;

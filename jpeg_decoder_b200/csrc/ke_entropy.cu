@@ -35,13 +35,12 @@ constexpr unsigned TILE_EXTRA = 4;
 struct EntWordsTile {
     const uint32_t* tile;  // shared
     uint32_t first;        // word index of tile[0]
-    const uint32_t* w;     // the payload, for the rare read outside the tile (tail slack of the very last subsequence)
-    uint32_t n;
     __device__ __forceinline__ static uint32_t slot(uint32_t j) { return (j & ~31u) + ((j + (j >> 5)) & 31u); }
+    // Words past the tile are only ever asked for by the last subsequence of a scan (its tail slack), where they lie
+    // past the end of the data: zero, like everything the staging loop found beyond nwords.
     __device__ __forceinline__ uint32_t get(uint32_t i) const {
         const uint32_t j = i - first;
-        if (j < TILE_WORDS + TILE_EXTRA) return tile[slot(j)];
-        return i < n ? ent_bswap(__ldg(w + i)) : 0u;
+        return j < TILE_WORDS + TILE_EXTRA ? tile[slot(j)] : 0u;
     }
 };
 __device__ __forceinline__ void stage_tile(uint32_t* tile, const uint32_t* words, uint32_t nwords, uint32_t first) {
@@ -110,7 +109,7 @@ __global__ void __launch_bounds__(ENT_THREADS) ent_pass(const EntImage* __restri
     stage_tile(tile, gwords, im.nwords, blockIdx.x * TILE_WORDS);
     load_shared(sh, im, payload);  // ends with a barrier
     if (!active) return;
-    const EntWordsTile words{tile, blockIdx.x * TILE_WORDS, gwords, im.nwords};
+    const EntWordsTile words{tile, blockIdx.x * TILE_WORDS};
     const uint16_t* tabs = reinterpret_cast<const uint16_t*>(sh.tabs);
     EntState st;
     st.p = i * ENT_SUB_BITS;
@@ -169,7 +168,7 @@ __global__ void __launch_bounds__(ENT_THREADS) ent_sync(const EntImage* __restri
     const uint32_t* gwords = reinterpret_cast<const uint32_t*>(payload + im.data_off);
     stage_tile(tile, gwords, im.nwords, blockIdx.x * TILE_WORDS);
     load_shared(sh, im, payload);  // ends with a barrier
-    const EntWordsTile words{tile, blockIdx.x * TILE_WORDS, gwords, im.nwords};
+    const EntWordsTile words{tile, blockIdx.x * TILE_WORDS};
     const uint16_t* tabs = reinterpret_cast<const uint16_t*>(sh.tabs);
     const uint32_t end = valid ? ent_sub_end(i, im.nsub, im.scan_bits) : 0u;
     unsigned long long mine = valid ? ld_state(&w.state[g]) : 0ull;
