@@ -490,12 +490,14 @@ def main():
         d_pix = torch.empty(Bf * out_per_img, dtype=torch.uint8, device=dev)
         for j in range(Bf):
             jobs[j].out = d_pix.data_ptr() + j * out_per_img
-        ctx.check(J.lib().b200jpg_decode_files(ctx._h, jobs, Bf, nthreads))
-        t0 = time.perf_counter()
-        for _ in range(3):
+        for _ in range(4):   # warm-up: groups are larger in this mode, the engine's device buffers grow (by doubling) to fit them
             ctx.check(J.lib().b200jpg_decode_files(ctx._h, jobs, Bf, nthreads))
         torch.cuda.synchronize()
-        fd_value = Bf * W * H / 1e6 * 3 / (time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            ctx.check(J.lib().b200jpg_decode_files(ctx._h, jobs, Bf, nthreads))
+        torch.cuda.synchronize()
+        fd_value = Bf * W * H / 1e6 * 5 / (time.perf_counter() - t0)
         assert all(jobs[j].status == 0 for j in range(Bf))
         assert bool(np.array_equal(d_pix[:out_per_img].cpu().numpy(), ref0))
         for j in range(Bf):
