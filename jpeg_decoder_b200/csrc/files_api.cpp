@@ -226,10 +226,13 @@ int b200jpg_decode_files(b200jpg_ctx* ctx, b200jpg_file_job* jobs, size_t n, int
     const bool device = want_device_entropy(ctx);
     FileSource src(ctx, jobs, n, nullptr, device);
     int rc = b200jpg::stream_engine_run(ctx, src, nthreads);
-    ctx->device_scans += src.device_scans();
     const std::vector<size_t> retry = src.take_retries();
-    if (!retry.empty()) {  // scans the device flagged (malformed streams, or no convergence): the reference's own loop decides
+    {
+        std::lock_guard<std::mutex> g(ctx->mu);  // calls on one context may come from several threads
+        ctx->device_scans += src.device_scans();
         ctx->device_scan_retries += retry.size();
+    }
+    if (!retry.empty()) {  // scans the device flagged (malformed streams, or no convergence): the reference's own loop decides
         FileSource again(ctx, jobs, n, &retry, false);
         const int rc2 = b200jpg::stream_engine_run(ctx, again, nthreads);
         if (rc == B200JPG_OK) rc = rc2;
