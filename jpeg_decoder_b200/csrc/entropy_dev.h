@@ -14,7 +14,7 @@
 //   prefix: exclusive sums of "blocks completed" and "AC values met" -> the block every subsequence starts in and
 //           where its values go
 //   write : every thread decodes once more from its predecessor's state and appends what it meets to a compact
-//           per-image stream -- non-zero AC values back to back (contiguous 2-byte stores per thread), one 64-bit
+//           per-image stream -- non-zero AC values back to back (aligned 8-byte stores of four values), one 64-bit
 //           position bitmap, one DC difference and one value offset per block; it re-checks
 //           state[i] = f_i(state[i-1]), so a stream that did not converge (or is malformed in any way) is detected,
 //           never mis-decoded
@@ -37,7 +37,6 @@
 namespace b200jpg {
 
 constexpr unsigned ENT_SUB_BITS = 1024;            // one thread's share of the scan
-constexpr unsigned ENT_SUB_BYTES = ENT_SUB_BITS / 8;
 constexpr unsigned ENT_LUT_BITS = 9;               // code words up to this length resolve with one table probe
 constexpr unsigned ENT_SUB_LUT_BITS = 16 - ENT_LUT_BITS;  // longer ones with a second probe, indexed by the remaining bits
 constexpr unsigned ENT_MAX_SUBTABLES = 12;         // ENT_LUT_BITS-bit prefixes that continue into longer code words, per table
@@ -51,7 +50,6 @@ enum : unsigned {
     ENT_BAD_RUN = 2,       // a run that leaves the block (src/decoder.rs:1149-1153 ends the block silently)
     ENT_BAD_CHAIN = 4,     // state[i] != f_i(state[i-1]): the synchronisation passes did not converge
     ENT_INCOMPLETE = 8,    // the scan ended before every block was decoded
-    ENT_BAD_PAYLOAD = 16,  // header / geometry mismatch
     ENT_BAD_TAIL = 32,     // whole bytes left between the last MCU of a restart interval and its RSTn marker
 };
 
@@ -172,13 +170,7 @@ struct EntWordsGlobal {
 static unsigned long long ent_stats_len[32];  // emulator only: code-length histogram
 #endif
 
-// Sinks: what happens to decoded coefficients.
-struct EntNullSink {
-    static constexpr bool kCountOnly = false;
-    ENT_HD void store(unsigned, int) {}
-    ENT_HD bool block_done() { return false; }
-};
-
+// Sinks: what happens to decoded coefficients.  kCountOnly: the decoder only reports how many values it would store.
 // Counts what the write pass will append: AC values (DC differences have their own array).
 struct EntCountSink {
     static constexpr bool kCountOnly = true;  // the decoder adds (value bits present && not a DC code word) itself: no branch
@@ -351,7 +343,7 @@ struct EntCompactSink {
 // where subsequence i of an image ends (the last one ends with the scan)
 ENT_HD uint32_t ent_sub_end(uint32_t i, uint32_t nsub, uint32_t scan_bits) { return i + 1 < nsub ? (i + 1) * ENT_SUB_BITS : scan_bits; }
 
-// zig-zag index -> natural position, src/decoder.rs:27-36
+// zig-zag index -> natural position, src/decoder.rs:27-36 (the CPU emulation's stand-in for K0 uses it)
 #define ENT_UNZIGZAG_INIT                                                                                                      \
     {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6,  7,  14, 21, 28, \
      35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63}

@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(K0_WARPS * 32) k0_expand(const K0Image* __rest
                                                            short* __restrict__ slab) {
     __shared__ __align__(16) short tile[K0_WARPS][32][64];
     const K0Image& im = images[blockIdx.y];
+    if (im.order & SBS_BLOCK_OFFSETS) return;  // device-made streams: k0_expand_blocks
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const unsigned g = blockIdx.x * K0_WARPS + warp;
     const unsigned nb = im.nb;
@@ -106,6 +107,63 @@ __global__ void __launch_bounds__(K0_WARPS * 32) k0_expand(const K0Image* __rest
     }
 }
 
+// K0 for device-made streams (SBS_BLOCK_OFFSETS: every block has its own value offset, values are int16 in zig-zag order).
+// One THREAD per block: it zeroes its 128-byte row of a shared-memory tile, walks the set bits of its bitmap and drops
+// each value at its natural position (~15 values per block instead of 64 slots x rank computations in the warp-per-group
+// kernel above: 5x fewer instructions); the warp then stores its 32 rows cooperatively, four whole 128-byte blocks per
+// instruction.  Rows are swizzled in 16-byte chunks by (thread & 7), so both phases are free of bank conflicts beyond the
+// unavoidable ones of scattered 2-byte stores.
+constexpr int K0B_THREADS = 128;
+__global__ void __launch_bounds__(K0B_THREADS) k0_expand_blocks(const K0Image* __restrict__ images, const uint8_t* __restrict__ streams,
+                                                                short* __restrict__ slab) {
+    __shared__ __align__(16) short tile[K0B_THREADS][64];
+    __shared__ unsigned char unzz[64];
+    const K0Image& im = images[blockIdx.y];
+    if ((im.order & SBS_BLOCK_OFFSETS) == 0) return;
+    const unsigned nb = im.nb;
+    if (blockIdx.x * K0B_THREADS >= nb) return;
+    if (threadIdx.x < 64) unzz[threadIdx.x] = c_unzigzag[threadIdx.x];
+    const unsigned lane = threadIdx.x & 31u, sw = threadIdx.x & 7u;
+    const unsigned t = blockIdx.x * K0B_THREADS + threadIdx.x;
+    const unsigned nb_pad = (nb + 31u) & ~31u;
+    const uint8_t* s = streams + im.stream_off;
+    short* mine = tile[threadIdx.x];
+#pragma unroll
+    for (int c = 0; c < 8; c++) *reinterpret_cast<int4*>(mine + 8 * c) = make_int4(0, 0, 0, 0);
+    __syncthreads();  // unzz
+    unsigned row = 0xffffffffu;
+    if (t < nb) {
+        unsigned long long m = ((const unsigned long long*)s)[t];
+        const short* v = reinterpret_cast<const short*>(s + ((const unsigned*)(s + 10ull * nb_pad))[t]);
+        mine[(0u ^ sw) << 3] = ((const short*)(s + 8ull * nb_pad))[t];  // natural position 0 = chunk 0, element 0
+        m &= ~1ull;
+        while (m) {
+            const unsigned k = (unsigned)__ffsll((long long)m) - 1u;
+            m &= m - 1ull;
+            const unsigned nat = unzz[k];
+            mine[(((nat >> 3) ^ sw) << 3) | (nat & 7u)] = __ldg(v++);
+        }
+        const unsigned mcu = t / im.bpm, j = t - mcu * im.bpm;
+        if ((im.order & SBS_INTERLEAVED) == 0) {
+            const unsigned c = (t >= im.first[1]) + (t >= im.first[2]) + (t >= im.first[3]);
+            row = im.slab_row[c] + (t - im.first[c]);
+        } else {
+            const unsigned c = im.mcu_comp[j];
+            const unsigned my = mcu / im.mcu_w, mx = mcu - my * im.mcu_w;
+            row = im.slab_row[c] + (my * im.v[c] + im.mcu_vy[j]) * im.block_w[c] + mx * im.h[c] + im.mcu_hx[j];
+        }
+    }
+    __syncwarp();
+    const unsigned wbase = threadIdx.x & ~31u;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const unsigned b = (unsigned)i * 4u + (lane >> 3), chunk = lane & 7u;
+        const unsigned r = __shfl_sync(0xffffffffu, row, (int)b);
+        if (r != 0xffffffffu)
+            *reinterpret_cast<int4*>(slab + (size_t)r * 64u + chunk * 8u) = *reinterpret_cast<const int4*>(&tile[wbase + b][(chunk ^ (b & 7u)) << 3]);
+    }
+}
+
 // zeroes the per-block arrays (bm | dc | boff = 14 bytes per block) of device-made streams before the write pass ORs into them
 __global__ void __launch_bounds__(256) k0_zero_headers(const K0Image* __restrict__ images, uint8_t* __restrict__ streams) {
     const K0Image& im = images[blockIdx.y];
@@ -127,7 +185,14 @@ cudaError_t launch_k0_expand(const K0Image* d_images, unsigned nimages, unsigned
     if (nimages == 0 || max_blocks == 0) return cudaSuccess;
     const unsigned groups = (max_blocks + 31u) / 32u;
     dim3 grid((groups + K0_WARPS - 1) / K0_WARPS, nimages);
-    k0_expand<<<grid, K0_WARPS * 32, 0, stream>>>(d_images, d_streams, d_slab);
+    k0_expand<<<grid, K0_WARPS * 32, 0, stream>>>(d_images, d_streams, d_slab);  // host-made streams (skips the others)
+    return cudaGetLastError();
+}
+
+cudaError_t launch_k0_expand_blocks(const K0Image* d_images, unsigned nimages, unsigned max_blocks, const uint8_t* d_streams, short* d_slab,
+                                    cudaStream_t stream) {
+    if (nimages == 0 || max_blocks == 0) return cudaSuccess;
+    k0_expand_blocks<<<dim3((max_blocks + K0B_THREADS - 1) / K0B_THREADS, nimages), K0B_THREADS, 0, stream>>>(d_images, d_streams, d_slab);
     return cudaGetLastError();
 }
 

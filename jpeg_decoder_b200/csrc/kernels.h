@@ -44,6 +44,9 @@ struct EntImage;
 size_t ent_work_bytes(unsigned total_sub, unsigned nimages, unsigned max_comp_blocks, int max_passes);
 cudaError_t launch_entropy(const EntImage* d_images, unsigned nimages, unsigned max_nsub, unsigned total_sub, unsigned max_comp_blocks,
                            uint8_t* d_streams, void* d_work, int max_passes, unsigned** d_status, cudaStream_t stream, uint64_t* launches);
+// device-made streams (SBS_BLOCK_OFFSETS) of the same descriptor list: one thread per block
+cudaError_t launch_k0_expand_blocks(const K0Image* d_images, unsigned nimages, unsigned max_blocks, const uint8_t* d_streams, short* d_slab,
+                                    cudaStream_t stream);
 cudaError_t launch_k0_zero_headers(const K0Image* d_images, unsigned nimages, unsigned max_blocks, uint8_t* d_streams, cudaStream_t stream);
 cudaError_t launch_k1_generic(const K1Params& p, int arith, cudaStream_t stream);
 size_t k1_tma_smem_bytes();

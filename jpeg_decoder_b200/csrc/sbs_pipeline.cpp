@@ -243,6 +243,7 @@ int SbsPipeline::enqueue(Slot& s) {
     unsigned max_nb = 0, max_nsub = 0, total_sub = 0, max_comp_blocks = 0;
     std::vector<size_t> soff(n, 0);
     s.ent_items.clear();
+    s.ent_images = 0;
     // the compact streams the device writes for entropy images live behind everything that is uploaded
     size_t cs_at = 0;
     for (size_t i = 0; i < n; i++)
@@ -276,6 +277,7 @@ int SbsPipeline::enqueue(Slot& s) {
             max_nb = std::max(max_nb, h_k0[nk0].nb);
             cs_at += ent_cs_bytes(h_k0[nk0].nb);
             nk0++;
+            s.ent_images++;
         } else {
             fill_k0(descs[i], b->layout[i], it[i].order, stream_bytes, &h_k0[nk0]);
             const SbsLayout lay = SbsLayout::make(h_k0[nk0].nb);
@@ -345,7 +347,12 @@ int SbsPipeline::enqueue(Slot& s) {
                                     s_comp_, &ctx_->launches));
         ctx_->launches++;
     }
-    if (nk0) {  // ... and K0 expands them together with the streams the host made: the dense slab K1 reads, zeros included
+    // ... and K0 expands them, like the streams the host made: the dense slab K1 reads, zeros included
+    if (nent) {
+        CU_TRY(ctx_, launch_k0_expand_blocks(d_k0, (unsigned)nk0, max_nb, (const uint8_t*)s.d_streams.p, (short*)s.d_coefs.p, s_comp_));
+        ctx_->launches++;
+    }
+    if (nk0 > s.ent_images) {
         CU_TRY(ctx_, launch_k0_expand(d_k0, (unsigned)nk0, max_nb, (const uint8_t*)s.d_streams.p, (short*)s.d_coefs.p, s_comp_));
         ctx_->launches++;
     }

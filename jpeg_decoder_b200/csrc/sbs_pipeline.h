@@ -61,7 +61,8 @@ private:
     };
     struct Slot {
         Buf d_streams, d_coefs, d_planes, d_out, d_tables, h_tables, d_ent, h_status;
-        std::vector<size_t> ent_items;  // group indices of the images whose scan is decoded on the device
+        std::vector<size_t> ent_items;  // group index of the image of every device-decoded restart interval
+        size_t ent_images = 0;          // images of the group whose scan is decoded on the device
         cudaEvent_t e_h2d = nullptr, e_comp = nullptr, e_done = nullptr;
         bool busy = false, h2d_reported = false;
         b200jpg_batch* batch = nullptr;
