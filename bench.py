@@ -485,6 +485,17 @@ def main():
         f_out[:] = 0
         ctx_h = J.Context(device=local_rank, arith=arith, k1_kernel=kmap[args.k1], k2_kernel=kmap[args.k2], entropy=J.ENTROPY_HOST)
         fh_value, _ = time_files(ctx_h)
+
+        def decode_latency_ms(c, reps=20):   # Decoder::new + decode() of one 1080p file, pixels in pageable host memory
+            J.Decoder(jpegs[0], c).decode()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                px = J.Decoder(jpegs[0], c).decode()
+            dt = (time.perf_counter() - t0) / reps
+            assert bool(np.array_equal(px, ref0))
+            return 1e3 * dt
+        single = {"device_entropy_ms": decode_latency_ms(ctx), "host_entropy_ms": decode_latency_ms(ctx_h),
+                  "api": "b200jpg_decoder_new + b200jpg_decoder_decode (Decoder::decode) on one %dx%d file, latency per call" % (W, H)}
         ctx_h.close()
         # the same call with the pixel buffers in DEVICE memory (an on-GPU consumer, e.g. a training input pipeline): no D2H
         d_pix = torch.empty(Bf * out_per_img, dtype=torch.uint8, device=dev)
@@ -508,6 +519,7 @@ def main():
                      "calls": f_reps, "scans_decoded_on_device": int(scans[0]), "scans_handed_back_to_host": int(scans[1]),
                      "device_outputs": {"value": fd_value, "unit": "MP/s",
                                         "api": "same call, b200jpg_file_job.out in device memory: JPEG bytes over PCIe, pixels stay in HBM"},
+                     "single_image": single,
                      "host_entropy": {"value": fh_value, "unit": "MP/s",
                                       "api": "same call with B200JPG_ENTROPY_HOST: Huffman on the host threads -> sparse block streams -> K0/K1/K2"},
                      "api": "b200jpg_decode_files (JPEG bytes -> pinned host pixels; host threads parse markers and copy the scan, "

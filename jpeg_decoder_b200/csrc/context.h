@@ -4,6 +4,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <stdlib.h>
+#include <string.h>
+
 #include <mutex>
 #include <string>
 
@@ -44,3 +47,13 @@ struct b200jpg_ctx {
     void (*files_engine_free)(void*) = nullptr;
 };
 
+
+// Where Huffman decoding of qualifying scans happens (B200JPG_ENTROPY_*); the environment variable exists for tests and
+// benchmarks that want to compare both routes with one binary.
+inline bool b200jpg_device_entropy_enabled(const b200jpg_ctx* ctx) {
+    if (const char* e = getenv("B200JPG_ENTROPY")) {
+        if (!strcmp(e, "host")) return false;
+        if (!strcmp(e, "device")) return true;
+    }
+    return ctx && ctx->entropy != B200JPG_ENTROPY_HOST;
+}

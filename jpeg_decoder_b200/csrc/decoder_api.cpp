@@ -7,37 +7,43 @@
 #include <string>
 #include <vector>
 
+#include <memory>
+
 #include "../../include/b200jpg.h"
+#include "context.h"
 #include "host_decoder.h"
 
 using b200jpg::HostDecoder;
 
 struct b200jpg_decoder {
     b200jpg_ctx* ctx;
+    const uint8_t* data;
+    size_t len;
     HostDecoder host;
+    std::unique_ptr<HostDecoder> again;  // a second, complete host decode when the device route hands the image back
     std::vector<uint8_t> pixels;
     std::vector<uint8_t> icc;
     std::string err;
-    b200jpg_decoder(b200jpg_ctx* c, const uint8_t* data, size_t len) : ctx(c), host(data, len) {}
+    b200jpg_decoder(b200jpg_ctx* c, const uint8_t* d, size_t n) : ctx(c), data(d), len(n), host(d, n) {}
 };
 
 // Fills `desc` with what decode_planes hands to compute_image (src/decoder.rs:617-696).
-static int fill_desc(b200jpg_decoder* d, b200jpg_image_desc* desc) {
-    const auto& f = d->host.frame();
+static int fill_desc(b200jpg_decoder* d, const HostDecoder& host, b200jpg_image_desc* desc) {
+    const auto& f = host.frame();
     memset(desc, 0, sizeof *desc);
     desc->width = f.output_w;
     desc->height = f.output_h;
     desc->ncomp = (uint8_t)f.comps.size();
-    desc->color_transform = (uint8_t)d->host.determine_color_transform();
+    desc->color_transform = (uint8_t)host.determine_color_transform();
     for (size_t i = 0; i < f.comps.size() && i < 4; i++) {
         // "not all components have data", src/decoder.rs:1306-1308
-        if (!d->host.component_has_data((int)i)) {
+        if (!host.component_has_data((int)i)) {
             d->err = "invalid JPEG format: not all components have data";
             return B200JPG_ERR_FORMAT;
         }
         desc->comps[i] = f.comps[i];
-        desc->qt[i] = d->host.component_qtable((int)i);
-        desc->coefs[i] = d->host.coefficients((int)i);
+        desc->qt[i] = host.component_qtable((int)i);
+        desc->coefs[i] = host.coefficients((int)i);
     }
     return B200JPG_OK;
 }
@@ -77,14 +83,23 @@ int b200jpg_decoder_scale(b200jpg_decoder* d, uint16_t req_w, uint16_t req_h, ui
     if (rc) d->err = d->host.error();
     return rc;
 }
+// the host decoder to run a complete entropy decode on: d->host, unless decode() already stopped it at the scan to send
+// the scan to the GPU (then a fresh one)
+static HostDecoder& full_host(b200jpg_decoder* d) {
+    if (!d->host.device_scan().eligible) return d->host;
+    d->again.reset(new HostDecoder(d->data, d->len));
+    return *d->again;
+}
+
 int b200jpg_decoder_entropy_decode(b200jpg_decoder* d, b200jpg_image_desc* desc) {
     if (!d || !desc) return B200JPG_ERR_INTERNAL;
-    int rc = d->host.entropy_decode();
+    HostDecoder& host = full_host(d);
+    int rc = host.entropy_decode();
     if (rc) {
-        d->err = d->host.error();
+        d->err = host.error();
         return rc;
     }
-    return fill_desc(d, desc);
+    return fill_desc(d, host, desc);
 }
 int b200jpg_decoder_total_blocks(b200jpg_decoder* d, size_t* nblocks) {
     if (!d || !nblocks) return B200JPG_ERR_INTERNAL;
@@ -108,29 +123,33 @@ int b200jpg_decoder_entropy_decode_sbs(b200jpg_decoder* d, uint8_t* buf, size_t 
         d->err = "internal: sparse block stream buffer is smaller than b200jpg_sbs_worst_bytes()";
         return B200JPG_ERR_INTERNAL;
     }
-    d->host.set_sbs_sink(buf);
-    rc = d->host.entropy_decode();
+    HostDecoder& host = full_host(d);
+    if (&host != &d->host) {
+        rc = host.read_info();
+        if (rc) {
+            d->err = host.error();
+            return rc;
+        }
+    }
+    host.set_sbs_sink(buf);
+    rc = host.entropy_decode();
     if (rc) {
-        d->err = d->host.error();
+        d->err = host.error();
         return rc;
     }
-    rc = fill_desc(d, desc);
+    rc = fill_desc(d, host, desc);
     if (rc) return rc;
     for (int i = 0; i < 4; i++) desc->coefs[i] = nullptr;  // the coefficients are in the stream
     stream->data = buf;
-    stream->len = d->host.sbs_length();
-    stream->order = (int)d->host.sbs_order();
+    stream->len = host.sbs_length();
+    stream->order = (int)host.sbs_order();
     return B200JPG_OK;
 }
-int b200jpg_decoder_decode(b200jpg_decoder* d, const uint8_t** pixels, size_t* len) {
-    if (!d || !pixels || !len) return B200JPG_ERR_INTERNAL;
+// Worker half of decode(): the dense coefficients of `host` through the GPU batch path.
+static int run_worker_path(b200jpg_decoder* d, const HostDecoder& host, const uint8_t** pixels, size_t* len) {
     b200jpg_image_desc desc;
-    int rc = b200jpg_decoder_entropy_decode(d, &desc);
+    int rc = fill_desc(d, host, &desc);
     if (rc) return rc;
-    if (!d->ctx) {  // no CPU fallback for the worker path
-        d->err = "internal: decoder was created without a device context; the worker path only exists on the GPU";
-        return B200JPG_ERR_INTERNAL;
-    }
     d->pixels.assign((size_t)desc.width * desc.height * desc.ncomp, 0);
     uint8_t* out = d->pixels.data();
     size_t cap = d->pixels.size();
@@ -144,6 +163,55 @@ int b200jpg_decoder_decode(b200jpg_decoder* d, const uint8_t** pixels, size_t* l
     *pixels = d->pixels.data();
     *len = d->pixels.size();
     return B200JPG_OK;
+}
+
+// Decoder::decode, src/decoder.rs:292-295.  A complete baseline scan (entropy_dev.h) does not wait for the host's
+// sequential Huffman loop -- 6.6 ms for a 1080p image: the host parses the markers up to the scan (metadata, tables),
+// the scan itself goes through the whole-file engine and is Huffman-decoded on the GPU (< 1 ms).  Everything else, and
+// anything the device hands back, takes the host loop, whose pixels and errors are the reference's.
+int b200jpg_decoder_decode(b200jpg_decoder* d, const uint8_t** pixels, size_t* len) {
+    if (!d || !pixels || !len) return B200JPG_ERR_INTERNAL;
+    if (!d->ctx) {  // no CPU fallback for the worker path
+        const int rc0 = d->host.entropy_decode();
+        if (rc0) {
+            d->err = d->host.error();
+            return rc0;
+        }
+        d->err = "internal: decoder was created without a device context; the worker path only exists on the GPU";
+        return B200JPG_ERR_INTERNAL;
+    }
+    const bool device_route = b200jpg_device_entropy_enabled(d->ctx) && d->host.default_config();
+    d->host.probe_device_scan(device_route);
+    int rc = d->host.device_scan().eligible ? (int)b200jpg::B200JPG_INTERNAL_DEVICE_SCAN : d->host.entropy_decode();
+    if (rc == b200jpg::B200JPG_INTERNAL_DEVICE_SCAN) {
+        const auto& f = d->host.frame();
+        d->pixels.assign((size_t)f.output_w * f.output_h * f.comps.size(), 0);
+        b200jpg_file_job job;
+        memset(&job, 0, sizeof job);
+        job.data = d->data;
+        job.len = d->len;
+        job.out = d->pixels.data();
+        job.out_cap = d->pixels.size();
+        rc = b200jpg_decode_files(d->ctx, &job, 1, 1);
+        if (rc == B200JPG_OK && job.status == B200JPG_OK && job.out_len == d->pixels.size()) {
+            *pixels = d->pixels.data();
+            *len = d->pixels.size();
+            return B200JPG_OK;
+        }
+        // an error, or a partial image: the complete host decode words it (and decides, should the two ever differ)
+        d->again.reset(new HostDecoder(d->data, d->len));
+        rc = d->again->entropy_decode();
+        if (rc) {
+            d->err = d->again->error();
+            return rc;
+        }
+        return run_worker_path(d, *d->again, pixels, len);
+    }
+    if (rc) {
+        d->err = d->host.error();
+        return rc;
+    }
+    return run_worker_path(d, d->host, pixels, len);
 }
 const char* b200jpg_decoder_error(const b200jpg_decoder* d) { return d ? d->err.c_str() : "no decoder"; }
 int b200jpg_decoder_icc_profile(b200jpg_decoder* d, const uint8_t** data, size_t* len) {

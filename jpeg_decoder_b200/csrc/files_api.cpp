@@ -197,14 +197,6 @@ private:
     std::atomic<size_t> device_scans_{0};
 };
 
-bool want_device_entropy(const b200jpg_ctx* ctx) {
-    if (const char* e = getenv("B200JPG_ENTROPY")) {
-        if (!strcmp(e, "host")) return false;
-        if (!strcmp(e, "device")) return true;
-    }
-    return ctx->entropy != B200JPG_ENTROPY_HOST;
-}
-
 }  // namespace
 
 extern "C" {
@@ -223,7 +215,7 @@ int b200jpg_read_info_files(b200jpg_file_job* jobs, size_t n, int nthreads) {
 
 int b200jpg_decode_files(b200jpg_ctx* ctx, b200jpg_file_job* jobs, size_t n, int nthreads) {
     if (!ctx || (!jobs && n)) return B200JPG_ERR_INTERNAL;
-    const bool device = want_device_entropy(ctx);
+    const bool device = b200jpg_device_entropy_enabled(ctx);
     FileSource src(ctx, jobs, n, nullptr, device);
     int rc = b200jpg::stream_engine_run(ctx, src, nthreads);
     const std::vector<size_t> retry = src.take_retries();

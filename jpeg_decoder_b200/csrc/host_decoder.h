@@ -85,6 +85,14 @@ public:
     // what decode_scan records for the worker when a component is finished by the (only) scan
     void capture_final_qtables();
 
+    // nothing was set that the whole-file batch path does not know about (colour transform override, size limit, scaling)
+    bool default_config() const {
+        if (has_ct_ || buffer_limit_ != (size_t)-1) return false;
+        for (const auto& c : frame_.comps)
+            if (c.dct_scale != 8) return false;
+        return true;
+    }
+
     bool has_frame() const { return has_frame_; }
     const FrameInfo& frame() const { return frame_; }
     int determine_color_transform() const;  // src/decoder.rs:698-764
