@@ -185,7 +185,7 @@ int b200jpg_decoder_decode(b200jpg_decoder* d, const uint8_t** pixels, size_t* l
     int rc = d->host.device_scan().eligible ? (int)b200jpg::B200JPG_INTERNAL_DEVICE_SCAN : d->host.entropy_decode();
     if (rc == b200jpg::B200JPG_INTERNAL_DEVICE_SCAN) {
         const auto& f = d->host.frame();
-        d->pixels.assign((size_t)f.output_w * f.output_h * f.comps.size(), 0);
+        d->pixels.resize((size_t)f.output_w * f.output_h * f.comps.size());  // every byte is written by the download
         b200jpg_file_job job;
         memset(&job, 0, sizeof job);
         job.data = d->data;
