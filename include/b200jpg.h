@@ -251,7 +251,9 @@ B200JPG_API int b200jpg_decoder_read_info(b200jpg_decoder *d);                  
 B200JPG_API int b200jpg_decoder_info(const b200jpg_decoder *d, b200jpg_image_info *info);
 B200JPG_API int b200jpg_decoder_scale(b200jpg_decoder *d, uint16_t req_w, uint16_t req_h, uint16_t *w,
                                       uint16_t *h); /* :278 */
-/* Decoder::decode(), :293 -- pixels are owned by the decoder until free / next decode */
+/* Decoder::decode(), :293 -- pixels are owned by the decoder until free / next decode.  Complete baseline scans are
+ * Huffman-decoded on the GPU (see B200JPG_ENTROPY_*) unless a colour transform, a size limit or a scale was set;
+ * everything else, and anything the device hands back, takes the host loop -- same pixels, same errors. */
 B200JPG_API int b200jpg_decoder_decode(b200jpg_decoder *d, const uint8_t **pixels, size_t *len);
 B200JPG_API const char *b200jpg_decoder_error(const b200jpg_decoder *d);
 /* icc_profile :211, exif_data :199, xmp_data :206 -- return 1 if present */
