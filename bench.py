@@ -292,6 +292,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
+            os.environ["NCCL_DEBUG"] = "WARN"   # stdout carries ONE line, the JSON: no "NCCL version ..." banner
         dist.init_process_group("nccl", device_id=dev)
 
     cfg = workload.CONFIGS[args.config]
@@ -453,6 +455,42 @@ def main():
 
     # ---- whole files: JPEG bytes -> pixels (host Huffman on the NUMA-local cores + GPU worker path) ----
     files_e2e = None
+    if world > 1:
+        # every rank decodes its own shard of files on its own GPU; the host cores the ranks share are split between them
+        ok, f_dt, f_reps, Bf = 1, 0.0, 3, 256
+        try:
+            nthreads = max(2, len(os.sched_getaffinity(0)) // world)
+            jpegs = [workload.synth_jpeg(W, H, cfg["seed"] + k, cfg["subsampling"]) for k in range(min(U, 4))]
+            f_out = torch.empty(Bf * out_per_img, dtype=torch.uint8, pin_memory=True).numpy()
+            fbufs = [np.frombuffer(j, dtype=np.uint8) for j in jpegs]
+            jobs = (J.FileJob * Bf)()
+            for j in range(Bf):
+                jobs[j].data, jobs[j].len = fbufs[j % len(jpegs)].ctypes.data, fbufs[j % len(jpegs)].size
+                jobs[j].out, jobs[j].out_cap = f_out[j * out_per_img:].ctypes.data, out_per_img
+            ctx.check(J.lib().b200jpg_decode_files(ctx._h, jobs, Bf, nthreads))   # warm-up
+        except Exception as e:   # a rank that fails still takes part in the collectives below
+            ok = 0
+            print("rank %d: files section failed: %r" % (rank, e), file=sys.stderr)
+        dist.barrier()
+        t0 = time.perf_counter()
+        try:
+            if ok:
+                for _ in range(f_reps):
+                    ctx.check(J.lib().b200jpg_decode_files(ctx._h, jobs, Bf, nthreads))
+                ok = int(all(jobs[j].status == 0 for j in range(Bf)))
+        except Exception as e:
+            ok = 0
+            print("rank %d: files section failed: %r" % (rank, e), file=sys.stderr)
+        f_dt = time.perf_counter() - t0
+        t = torch.tensor([f_dt, -float(ok)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)   # slowest rank; -ok: any failure wins
+        if rank == 0:
+            if t[1].item() == -1.0:
+                files_e2e = {"value": world * Bf * W * H / 1e6 * f_reps / float(t[0].item()), "unit": "MP/s", "images": world * Bf,
+                             "host_threads_per_rank": nthreads,
+                             "api": "b200jpg_decode_files on every rank's shard (JPEG bytes -> pinned host pixels, Huffman decoding on the GPUs)"}
+            else:
+                files_e2e = {"error": "a rank failed, see stderr"}
     if rank == 0 and world == 1:
         # host threads = the CPUs of the GPU's NUMA node (this process is bound to them): measured faster than using
         # both sockets (profiles/r01_files_trace.txt)
