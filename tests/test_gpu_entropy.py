@@ -173,3 +173,43 @@ def test_restart_interval_scans(J, oracle_mod, pair):
                 b[at:at] = bytes(int(rng.integers(0, 255)) for _ in range(int(rng.integers(1, 5))))
             damaged.append(bytes(b))
     same(J, pair, damaged, nthreads=8)
+
+
+def test_concurrent_calls(J, oracle_mod):
+    """b200jpg_decode_files from several host threads at once -- on one shared context (calls serialise on the context's
+    engine) and on contexts of their own (two engines share the GPU), there with Decoder.decode() in between (a context
+    with its own stream per host thread is the documented way to call the rest of the ABI concurrently)."""
+    import threading
+    from jpeg_decoder_b200 import workload
+    files = [workload.synth_jpeg(640, 360, seed=300 + k, subsampling=2) for k in range(6)]
+    files.append(workload.synth_jpeg(320, 200, seed=310, subsampling=0, progressive=True))
+    wants = [oracle_mod.Decoder(f).decode() for f in files]
+    shared = J.Context(device=0)
+    own = [J.Context(device=0) for _ in range(2)]
+    errors = []
+
+    def worker(ctx, reps, seed, single):
+        try:
+            rng = np.random.default_rng(seed)
+            for _ in range(reps):
+                order = rng.permutation(len(files))
+                outs, st, _ = J.decode_files(ctx, [files[i] for i in order], nthreads=2)
+                for i, o, s_ in zip(order, outs, st):
+                    if s_ != 0 or not np.array_equal(o, wants[i]):
+                        errors.append((seed, int(i), s_))
+                i = int(rng.integers(0, len(files)))
+                if single and not np.array_equal(J.Decoder(files[i], ctx).decode(), wants[i]):
+                    errors.append((seed, i, "decode"))
+        except Exception as e:  # noqa: BLE001
+            errors.append((seed, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(shared, 6, 1, False)), threading.Thread(target=worker, args=(shared, 6, 2, False)),
+               threading.Thread(target=worker, args=(own[0], 6, 3, True)), threading.Thread(target=worker, args=(own[1], 6, 4, True))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    assert not any(t.is_alive() for t in threads), "deadlock"
+    assert not errors, errors[:5]
+    for c in own + [shared]:
+        c.close()
