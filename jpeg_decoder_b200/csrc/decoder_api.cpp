@@ -8,6 +8,7 @@
 #include <vector>
 
 #include <memory>
+#include <mutex>
 
 #include "../../include/b200jpg.h"
 #include "context.h"
@@ -15,16 +16,80 @@
 
 using b200jpg::HostDecoder;
 
+// Pixel buffers of decoders: page-locked (the download runs at link speed instead of through the driver's staging
+// buffer) and recycled through a small process-wide pool -- cudaHostAlloc costs about a millisecond, a 1080p decode two.
+namespace {
+struct PinnedPool {
+    struct Buf {
+        uint8_t* p;
+        size_t cap;
+    };
+    std::mutex mu;
+    std::vector<Buf> free_list;
+    static constexpr size_t kMaxBuffers = 8, kMaxBytes = (size_t)512 << 20;
+    uint8_t* get(size_t need, size_t* cap) {
+        {
+            std::lock_guard<std::mutex> g(mu);
+            size_t best = free_list.size();
+            for (size_t i = 0; i < free_list.size(); i++)
+                if (free_list[i].cap >= need && (best == free_list.size() || free_list[i].cap < free_list[best].cap)) best = i;
+            if (best != free_list.size()) {
+                const Buf b = free_list[best];
+                free_list.erase(free_list.begin() + (long)best);
+                *cap = b.cap;
+                return b.p;
+            }
+        }
+        size_t want = (size_t)1 << 16;
+        while (want < need) want <<= 1;
+        if (want - need > need / 2) want = (need + 65535) / 65536 * 65536;  // large images: not the next power of two
+        void* p = nullptr;
+        if (cudaHostAlloc(&p, want, cudaHostAllocPortable) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        *cap = want;
+        return (uint8_t*)p;
+    }
+    void put(uint8_t* p, size_t cap) {
+        if (!p) return;
+        {
+            std::lock_guard<std::mutex> g(mu);
+            size_t total = cap;
+            for (const Buf& b : free_list) total += b.cap;
+            if (free_list.size() < kMaxBuffers && total <= kMaxBytes) {
+                free_list.push_back(Buf{p, cap});
+                return;
+            }
+        }
+        cudaFreeHost(p);
+    }
+};
+PinnedPool g_pixel_pool;
+}  // namespace
+
 struct b200jpg_decoder {
     b200jpg_ctx* ctx;
     const uint8_t* data;
     size_t len;
     HostDecoder host;
     std::unique_ptr<HostDecoder> again;  // a second, complete host decode when the device route hands the image back
-    std::vector<uint8_t> pixels;
+    uint8_t* pixels = nullptr;  // page-locked, from g_pixel_pool
+    size_t pixels_cap = 0, pixels_len = 0;
     std::vector<uint8_t> icc;
     std::string err;
     b200jpg_decoder(b200jpg_ctx* c, const uint8_t* d, size_t n) : ctx(c), data(d), len(n), host(d, n) {}
+    ~b200jpg_decoder() { g_pixel_pool.put(pixels, pixels_cap); }
+    // a buffer of at least n bytes (contents undefined); false when page-locked memory cannot be had
+    bool reserve_pixels(size_t n) {
+        if (pixels_cap < n || !pixels) {
+            g_pixel_pool.put(pixels, pixels_cap);
+            pixels = g_pixel_pool.get(n ? n : 1, &pixels_cap);
+            if (!pixels) pixels_cap = 0;
+        }
+        pixels_len = pixels ? n : 0;
+        return pixels != nullptr;
+    }
 };
 
 // Fills `desc` with what decode_planes hands to compute_image (src/decoder.rs:617-696).
@@ -150,9 +215,12 @@ static int run_worker_path(b200jpg_decoder* d, const HostDecoder& host, const ui
     b200jpg_image_desc desc;
     int rc = fill_desc(d, host, &desc);
     if (rc) return rc;
-    d->pixels.assign((size_t)desc.width * desc.height * desc.ncomp, 0);
-    uint8_t* out = d->pixels.data();
-    size_t cap = d->pixels.size();
+    if (!d->reserve_pixels((size_t)desc.width * desc.height * desc.ncomp)) {
+        d->err = "internal: no page-locked memory for the pixels";
+        return B200JPG_ERR_INTERNAL;
+    }
+    uint8_t* out = d->pixels;
+    size_t cap = d->pixels_len;
     int status = B200JPG_OK;
     rc = b200jpg_decode_batch(d->ctx, &desc, 1, &out, &cap, &status);
     if (rc == B200JPG_OK) rc = status;
@@ -160,8 +228,8 @@ static int run_worker_path(b200jpg_decoder* d, const HostDecoder& host, const ui
         d->err = b200jpg_last_error(d->ctx);
         return rc;
     }
-    *pixels = d->pixels.data();
-    *len = d->pixels.size();
+    *pixels = d->pixels;
+    *len = d->pixels_len;
     return B200JPG_OK;
 }
 
@@ -185,17 +253,20 @@ int b200jpg_decoder_decode(b200jpg_decoder* d, const uint8_t** pixels, size_t* l
     int rc = d->host.device_scan().eligible ? (int)b200jpg::B200JPG_INTERNAL_DEVICE_SCAN : d->host.entropy_decode();
     if (rc == b200jpg::B200JPG_INTERNAL_DEVICE_SCAN) {
         const auto& f = d->host.frame();
-        d->pixels.resize((size_t)f.output_w * f.output_h * f.comps.size());  // every byte is written by the download
+        if (!d->reserve_pixels((size_t)f.output_w * f.output_h * f.comps.size())) {
+            d->err = "internal: no page-locked memory for the pixels";
+            return B200JPG_ERR_INTERNAL;
+        }
         b200jpg_file_job job;
         memset(&job, 0, sizeof job);
         job.data = d->data;
         job.len = d->len;
-        job.out = d->pixels.data();
-        job.out_cap = d->pixels.size();
+        job.out = d->pixels;
+        job.out_cap = d->pixels_len;
         rc = b200jpg_decode_files(d->ctx, &job, 1, 1);
-        if (rc == B200JPG_OK && job.status == B200JPG_OK && job.out_len == d->pixels.size()) {
-            *pixels = d->pixels.data();
-            *len = d->pixels.size();
+        if (rc == B200JPG_OK && job.status == B200JPG_OK && job.out_len == d->pixels_len) {
+            *pixels = d->pixels;
+            *len = d->pixels_len;
             return B200JPG_OK;
         }
         // an error, or a partial image: the complete host decode words it (and decides, should the two ever differ)
