@@ -270,11 +270,35 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE line, the JSON: everything else that writes to file descriptor 1 from here on -- NCCL's
+    "NCCL version ..." banner, library chatter -- goes to stderr; emit() writes the result to the real stdout."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_RESULT_FD, data)
 
 
 def main():
     args = parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
         return
@@ -601,7 +625,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
-        print(json.dumps(line))
+        emit(line)
     e_batch.close()
     batch.close()
     ctx.close()
