@@ -111,3 +111,37 @@ def test_corrupted_restart_interval_scans(emul, tmp_path):
     text = run(emul, ["--descending", "--corrupt", "300", "3"] + files)
     last = text.strip().splitlines()[-1].split()
     assert int(last[1]) > 200 and int(last[7]) > 50, last
+
+
+def test_eligibility_edges(emul, tmp_path):
+    """What decides host vs device before any kernel runs (csrc/entropy_host.h): anything but stuffed bytes and the
+    expected RSTn up to an EOI keeps the scan on the host; harmless oddities (bytes after EOI, spare bytes after the last
+    MCU) do not.  Wherever the device route is taken the emulator also checks it against the host decoder."""
+    from jpeg_decoder_b200 import workload
+    base = workload.synth_jpeg(160, 120, seed=21, subsampling=2)
+    assert base.endswith(b"\xff\xd9")
+    sos = base.rfind(b"\xff\xda")
+    mid = sos + 14 + (len(base) - sos - 16) // 2
+    while base[mid - 1] == 0xFF or base[mid] == 0xFF:   # do not cut a stuffed pair
+        mid += 1
+    dri = _dri_jpeg(200, 200, 2, 7)
+    rst = dri.find(b"\xff\xd1")
+    cases = {
+        "plain": (base, "device == host"),
+        "bytes_after_eoi": (base + b"\x00\x01\x02garbage", "device == host"),
+        "spare_bytes_before_eoi": (base[:-2] + b"\x00\x00\x00" + base[-2:], "device == host"),
+        "rst_without_dri": (base[:mid] + b"\xff\xd0" + base[mid:], "host path"),
+        "fill_bytes_before_eoi": (base[:-2] + b"\xff\xff\xd9", "host path"),
+        "no_eoi": (base[:-2], "host path"),
+        "other_marker_in_scan": (base[:mid] + b"\xff\xe0\x00\x02" + base[mid:], "host path"),
+        "second_scan_follows": (base[:-2] + base[sos:], "host path"),
+        "dri_plain": (dri, "device == host"),
+        "dri_wrong_rst_number": (dri[:rst] + b"\xff\xd3" + dri[rst + 2:], "host path"),
+        "dri_missing_rst": (dri[:rst] + dri[rst + 2:], "host path"),
+    }
+    for name, (data, want) in cases.items():
+        p = tmp_path / (name + ".jpg")
+        p.write_bytes(data)
+        out = run(emul, [str(p)])
+        line = out.strip().splitlines()[0]
+        assert want in line, (name, line)
