@@ -79,6 +79,11 @@ enum { B200JPG_COMPACT_AUTO = 0, B200JPG_COMPACT_OFF = 1, B200JPG_COMPACT_ON = 2
  * device flags as irregular in any way, is decoded by the host loop, so results and errors never differ. */
 enum { B200JPG_ENTROPY_AUTO = 0, B200JPG_ENTROPY_HOST = 1, B200JPG_ENTROPY_DEVICE = 2 };
 
+/* Dense coefficients -> pixels in one kernel (KF, csrc/kf_fused.cu: the planes are staged in shared memory and never
+ * written to HBM) for 3-component YCbCr 4:2:0 / 4:4:4 images at full IDCT size in scalar arithmetic, whenever both
+ * stages are run in one call; OFF always runs K1 then K2 through the plane slab.  Same bytes either way. */
+enum { B200JPG_FUSE_AUTO = 0, B200JPG_FUSE_OFF = 1 };
+
 /* kernel selection, for tests and profiling (0 = pick the fastest applicable kernel) */
 enum { B200JPG_KERNEL_AUTO = 0, B200JPG_KERNEL_GENERIC = 1, B200JPG_KERNEL_FAST = 2 };
 
@@ -102,7 +107,7 @@ typedef struct {
     int host_compact; /* b200jpg_batch_run_host: B200JPG_COMPACT_* (0 = decide per batch)   */
     int host_threads; /* host threads of the host-fed paths; 0 = one per CPU of the process */
     int entropy;      /* b200jpg_decode_files: B200JPG_ENTROPY_* (0 = device where it applies)    */
-    int reserved[1];
+    int fuse;         /* B200JPG_FUSE_*: one fused kernel (planes never leave the SM) where it applies, or K1 + K2 */
 } b200jpg_options;
 
 typedef struct b200jpg_ctx b200jpg_ctx;
@@ -192,6 +197,8 @@ typedef struct {
     size_t n_pixels;    /* sum of width*height                   */
     size_t k1_algorithmic_bytes; /* 128 B read + dct_scale^2 B written per block */
     size_t k2_algorithmic_bytes; /* plane bytes read once + pixel bytes written  */
+    size_t kf_algorithmic_bytes; /* fused kernel: 128 B read per block + pixel bytes written (planes stay on chip) */
+    size_t n_fused;              /* images the fused kernel takes when both stages run in one call */
 } b200jpg_batch_info;
 
 /* Validates every image (same errors as the reference: NonIntegerSubsamplingRatio

@@ -16,7 +16,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._native import (ARITH_SCALAR, ARITH_SSSE3, ENTROPY_AUTO, ENTROPY_DEVICE, ENTROPY_HOST, COMPACT_AUTO, COMPACT_OFF, COMPACT_ON, CP_DCT_PROGRESSIVE, CP_DCT_SEQUENTIAL, CP_LOSSLESS, CT_CMYK,
+from ._native import (ARITH_SCALAR, ARITH_SSSE3, FUSE_AUTO, FUSE_OFF, ENTROPY_AUTO, ENTROPY_DEVICE, ENTROPY_HOST, COMPACT_AUTO, COMPACT_OFF, COMPACT_ON, CP_DCT_PROGRESSIVE, CP_DCT_SEQUENTIAL, CP_LOSSLESS, CT_CMYK,
                       CT_GRAYSCALE, CT_JCS_BG_RGB, CT_JCS_BG_YCC, CT_NONE, CT_RGB, CT_UNKNOWN, CT_YCBCR, CT_YCCK,
                       ERR_FORMAT, ERR_INTERNAL, ERR_IO, ERR_UNSUPPORTED, KERNEL_AUTO, KERNEL_FAST, KERNEL_GENERIC, OK,
                       PF_CMYK32, PF_L8, PF_L16, PF_RGB24, SBS_INTERLEAVED, SBS_NATURAL, SBS_PLANAR, BatchInfo, Component, FileJob, ImageDesc,
@@ -81,13 +81,14 @@ class Context:
     """b200jpg_ctx: one per device/stream."""
 
     def __init__(self, device=0, arith=ARITH_SCALAR, k1_kernel=KERNEL_AUTO, k2_kernel=KERNEL_AUTO, stream=None,
-                 host_compact=COMPACT_AUTO, host_threads=0, entropy=0):
+                 host_compact=COMPACT_AUTO, host_threads=0, entropy=0, fuse=0):
         opt = Options()
         lib().b200jpg_default_options(C.byref(opt))
         opt.device, opt.arith, opt.k1_kernel, opt.k2_kernel = device, arith, k1_kernel, k2_kernel
         opt.stream = stream
         opt.host_compact, opt.host_threads = host_compact, host_threads
         opt.entropy = entropy  # ENTROPY_AUTO / ENTROPY_HOST / ENTROPY_DEVICE
+        opt.fuse = fuse        # FUSE_AUTO / FUSE_OFF
         h = C.c_void_p()
         rc = lib().b200jpg_create(C.byref(opt), C.byref(h))
         if rc:

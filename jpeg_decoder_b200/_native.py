@@ -24,7 +24,7 @@ class Component(C.Structure):
 
 class Options(C.Structure):
     _fields_ = [("device", C.c_int), ("arith", C.c_int), ("k1_kernel", C.c_int), ("k2_kernel", C.c_int),
-                ("stream", C.c_void_p), ("host_compact", C.c_int), ("host_threads", C.c_int), ("entropy", C.c_int), ("reserved", C.c_int * 1)]
+                ("stream", C.c_void_p), ("host_compact", C.c_int), ("host_threads", C.c_int), ("entropy", C.c_int), ("fuse", C.c_int)]
 
 
 class ImageDesc(C.Structure):
@@ -35,7 +35,7 @@ class ImageDesc(C.Structure):
 class BatchInfo(C.Structure):
     _fields_ = [("coef_bytes", C.c_size_t), ("plane_bytes", C.c_size_t), ("out_bytes", C.c_size_t),
                 ("n_blocks", C.c_size_t), ("n_pixels", C.c_size_t), ("k1_algorithmic_bytes", C.c_size_t),
-                ("k2_algorithmic_bytes", C.c_size_t)]
+                ("k2_algorithmic_bytes", C.c_size_t), ("kf_algorithmic_bytes", C.c_size_t), ("n_fused", C.c_size_t)]
 
 
 class ImageInfo(C.Structure):
@@ -56,6 +56,7 @@ class SbsStream(C.Structure):
 SBS_PLANAR, SBS_INTERLEAVED, SBS_NATURAL = 0, 1, 2
 COMPACT_AUTO, COMPACT_OFF, COMPACT_ON = 0, 1, 2
 ENTROPY_AUTO, ENTROPY_HOST, ENTROPY_DEVICE = 0, 1, 2
+FUSE_AUTO, FUSE_OFF = 0, 1
 
 # every symbol include/b200jpg.h declares (tests/test_abi.py checks the two lists agree)
 EXPORTS = {

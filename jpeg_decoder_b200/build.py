@@ -6,9 +6,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libb200jpg.so")
-SOURCES = ["k0_expand.cu", "ke_entropy.cu", "k1_idct.cu", "k2_color.cu", "pipeline.cu", "sbs_pipeline.cpp", "sbs_api.cpp", "stream_engine.cpp", "host_decoder.cpp",
+SOURCES = ["k0_expand.cu", "ke_entropy.cu", "k1_idct.cu", "k2_color.cu", "kf_fused.cu", "pipeline.cu", "sbs_pipeline.cpp", "sbs_api.cpp", "stream_engine.cpp", "host_decoder.cpp",
            "decoder_api.cpp", "files_api.cpp"]
-HEADERS = ["device_types.h", "kernels.h", "host_decoder.h", "context.h", "sbs.h", "sbs_pipeline.h", "batch_internal.h", "ptx.cuh", "ring_book.h", "stream_engine.h", "entropy_dev.h", "entropy_host.h", os.path.join("..", "..", "include", "b200jpg.h")]
+HEADERS = ["device_types.h", "kernels.h", "host_decoder.h", "context.h", "sbs.h", "sbs_pipeline.h", "batch_internal.h", "ptx.cuh", "idct_core.cuh", "color_core.cuh", "ring_book.h", "stream_engine.h", "entropy_dev.h", "entropy_host.h", os.path.join("..", "..", "include", "b200jpg.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-fvisibility=hidden,-O3,-pthread", "-shared"]
 

@@ -46,6 +46,14 @@ struct b200jpg_batch {
     std::vector<unsigned> strip_first;   // per image: index of its first strip (n + 1 entries)
     unsigned strip_items = 0;
     K2Strip* d_strips = nullptr;
+    // fused kernel KF (kf_fused.cu): per mode the column work list of the images it can take, in image order
+    std::vector<FColumn> fcols[KF_NMODES];
+    std::vector<unsigned> fcol_first[KF_NMODES];  // per image: index of its first column (n + 1 entries)
+    std::vector<signed char> fmode;               // per image: KF_MODE_* or -1 (needs K1 + K2)
+    unsigned fitems[KF_NMODES] = {0, 0};
+    unsigned f_ystride[KF_NMODES] = {0, 0}, f_cstride[KF_NMODES] = {0, 0};
+    FColumn* d_fcols[KF_NMODES] = {nullptr, nullptr};
+    CUtensorMap tmap32;  // same slab, 32-row box
     // device copies of the tables
     DevComp* d_comps = nullptr;
     DevTile* d_tiles = nullptr;

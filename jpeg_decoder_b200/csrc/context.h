@@ -23,6 +23,7 @@ struct b200jpg_ctx {
     int host_compact = B200JPG_COMPACT_AUTO;
     int host_threads = 0;
     int entropy = B200JPG_ENTROPY_AUTO;
+    int fuse = B200JPG_FUSE_AUTO;
     cudaStream_t stream = nullptr;   // main stream (caller's or ours)
     cudaStream_t stream2 = nullptr;  // second stream of the host pipeline
     bool own_stream = false;

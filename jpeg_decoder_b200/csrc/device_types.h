@@ -67,4 +67,36 @@ struct __align__(16) K2Strip {
     unsigned npairs;      // height / 2 + 1
 };
 
+// ---- fused kernel KF (kf_fused.cu): dense coefficients -> pixels, planes staged in shared memory only ----------
+// Work list: one FColumn per (image, column strip of <= 1920 pixels); an item = one MCU row of a column.  Per MCU row a
+// column's blocks form up to four contiguous runs of slab rows (luma block rows, Cb, Cr), each fetched as 32-block boxes.
+enum : unsigned { KF_MODE_444 = 0, KF_MODE_420 = 1, KF_NMODES = 2 };
+
+struct __align__(16) FRun {
+    unsigned slab_row0;  // slab row (128 B units) of the run's first block in MCU row 0 of the image
+    unsigned step;       // slab rows from one MCU row to the next (v * block_w of the component)
+    unsigned len;        // blocks of the run per MCU row (halo blocks included)
+    unsigned wrap;       // blocks per block row inside the run (== len unless two luma block rows were merged)
+    unsigned comp;       // component 0..2
+    unsigned dst_x;      // byte offset inside a staged plane row where block column 0 of the run lands
+    unsigned dst_row;    // staged row of the run's first block row (0 or 8)
+    unsigned box0;       // index of the run's first 32-block box within the item
+};
+
+struct __align__(16) FColumn {
+    unsigned image;       // index into DevImage[]
+    unsigned comp0;       // index of the image's first DevComp (three consecutive entries)
+    unsigned first_item;  // index of the column's first MCU row in the flattened item sequence of its mode
+    unsigned nrows;       // MCU rows
+    unsigned x0;          // first output pixel of the strip (multiple of the MCU width)
+    unsigned wpx;         // output pixels of the strip
+    unsigned cx_base;     // 4:2:0: global index of the chroma sample staged at byte 16 of a chroma row
+    unsigned nruns;
+    unsigned nboxes;      // boxes per item
+    unsigned ngroups;     // 16-pixel groups per output row of the strip
+    unsigned gmagic;      // ceil(2^32 / ngroups): task / ngroups == __umulhi(task, gmagic) for every task index used
+    unsigned pad;
+    FRun run[4];
+};
+
 }  // namespace b200jpg

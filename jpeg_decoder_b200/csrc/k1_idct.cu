@@ -21,121 +21,12 @@
 #include "device_types.h"
 #include "kernels.h"
 #include "ptx.cuh"
+#include "idct_core.cuh"
 
 #define K1_DEFAULT_MODE 5
 
 namespace b200jpg {
 
-// ---------------------------------------------------------------------------------------------
-// Scalar arithmetic, src/idct.rs.  Everything is Wrapping<i32>: unsigned ops wrap, `>>` on int is
-// an arithmetic shift.
-// ---------------------------------------------------------------------------------------------
-// stbi_f2f(x) = (x * 4096 + 0.5) as i32 in f32, src/idct.rs:572-574; values checked in
-// tests/test_oracle_kat.py against the oracle, which evaluates the f32 expression.
-#define F2F_0_5411961 2217u
-#define F2F_N1_847759065 ((unsigned)-7567)
-#define F2F_0_765366865 3135u
-#define F2F_1_175875602 4816u
-#define F2F_0_298631336 1223u
-#define F2F_2_053119869 8410u
-#define F2F_3_072711026 12586u
-#define F2F_1_501321110 6149u
-#define F2F_N0_899976223 ((unsigned)-3685)
-#define F2F_N2_562915447 ((unsigned)-10497)
-#define F2F_N1_961570560 ((unsigned)-8034)
-#define F2F_N0_390180644 ((unsigned)-1597)
-
-__device__ __forceinline__ int sar(unsigned x, int n) { return (int)x >> n; }
-
-// d = { sat_u8(a) << 8 | sat_u8(b) } | (c << 16)   (one I2IP instruction)
-__device__ __forceinline__ unsigned pack_sat_u8(int a, int b, unsigned c) {
-    unsigned d;
-    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
-// bytes (b0,b1,b2,b3) = clamp(v0..v3)
-__device__ __forceinline__ unsigned pack4_sat_u8(int v0, int v1, int v2, int v3) {
-    return pack_sat_u8(v1, v0, pack_sat_u8(v3, v2, 0u));
-}
-
-// One 1-D pass of the stb_image butterfly, src/idct.rs:378-447.  `s0` already carries any bias the
-// caller folded in; xs is added to the even part (x_scale).
-#define IDCT_1D(s0, s1, s2, s3, s4, s5, s6, s7, xs, x0, x1, x2, x3, t0, t1, t2, t3) \
-    {                                                                                \
-        unsigned p1_ = ((s2) + (s6)) * F2F_0_5411961;                                \
-        unsigned e2_ = p1_ + (s6) * F2F_N1_847759065;                                \
-        unsigned e3_ = p1_ + (s2) * F2F_0_765366865;                                 \
-        unsigned e0_ = (((s0) + (s4)) << 12) + (xs);                                 \
-        unsigned e1_ = (((s0) - (s4)) << 12) + (xs);                                 \
-        x0 = e0_ + e3_;                                                              \
-        x3 = e0_ - e3_;                                                              \
-        x1 = e1_ + e2_;                                                              \
-        x2 = e1_ - e2_;                                                              \
-        unsigned q3_ = (s7) + (s3), q4_ = (s5) + (s1), q1_ = (s7) + (s1), q2_ = (s5) + (s3); \
-        unsigned p5_ = (q3_ + q4_) * F2F_1_175875602;                                \
-        q1_ = p5_ + q1_ * F2F_N0_899976223;                                          \
-        q2_ = p5_ + q2_ * F2F_N2_562915447;                                          \
-        q3_ = q3_ * F2F_N1_961570560;                                                \
-        q4_ = q4_ * F2F_N0_390180644;                                                \
-        t3 = (s1) * F2F_1_501321110 + (q1_ + q4_);                                   \
-        t2 = (s3) * F2F_3_072711026 + (q2_ + q3_);                                   \
-        t1 = (s5) * F2F_2_053119869 + (q2_ + q4_);                                   \
-        t0 = (s7) * F2F_0_298631336 + (q1_ + q3_);                                   \
-    }
-
-// add / subtract issued on the FMA pipe: IMAD with a multiplier (+1 / -1) that only the host knows,
-// read from the kernel-parameter constant bank so ptxas cannot fold it back into an IADD3
-#define fma_add(a, b) ((a) * p.one + (b))
-#define fma_sub(a, b) ((b) * p.minus_one + (a))
-// output butterfly x +- t in one of two styles: 0 = plain add (ptxas picks IADD3, ALU pipe, half rate),
-// 1 = IMAD with the opaque +-1 multiplier (FMA pipe, full rate)
-#define K1_BFLY_ADD(STYLE, x, t) ((STYLE) == 1 ? fma_add((t), (x)) : ((x) + (t)))
-#define K1_BFLY_SUB(STYLE, x, t) ((STYLE) == 1 ? fma_sub((x), (t)) : ((x) - (t)))
-
-__device__ __forceinline__ unsigned sext_lo(unsigned w) { return (unsigned)(int)(short)(w & 0xffffu); }
-__device__ __forceinline__ unsigned sext_hi(unsigned w) { return (unsigned)((int)w >> 16); }
-
-// Full-precision reference form of one 8x8 block (zero-AC shortcuts included, src/idct.rs:279-295,
-// 344-353).  Used by the generic kernel and as the exact slow path of the fast kernel.
-__device__ void idct8x8_scalar_exact(const short* __restrict__ c, const unsigned* __restrict__ q, uint8_t* dst,
-                                     unsigned stride) {
-    unsigned temp[64];
-#pragma unroll 1
-    for (int i = 0; i < 8; i++) {
-        bool acz = (c[i + 8] | c[i + 16] | c[i + 24] | c[i + 32] | c[i + 40] | c[i + 48] | c[i + 56]) == 0;
-        if (acz) {
-            unsigned dc = ((unsigned)(int)c[i] * q[i]) << 2;
-#pragma unroll
-            for (int k = 0; k < 8; k++) temp[i + 8 * k] = dc;
-        } else {
-            unsigned s[8];
-#pragma unroll
-            for (int k = 0; k < 8; k++) s[k] = (unsigned)(int)c[i + 8 * k] * q[i + 8 * k];
-            unsigned x0, x1, x2, x3, t0, t1, t2, t3;
-            IDCT_1D(s[0], s[1], s[2], s[3], s[4], s[5], s[6], s[7], 512u, x0, x1, x2, x3, t0, t1, t2, t3);
-            temp[i] = (unsigned)sar(x0 + t3, 10);
-            temp[i + 56] = (unsigned)sar(x0 - t3, 10);
-            temp[i + 8] = (unsigned)sar(x1 + t2, 10);
-            temp[i + 48] = (unsigned)sar(x1 - t2, 10);
-            temp[i + 16] = (unsigned)sar(x2 + t1, 10);
-            temp[i + 40] = (unsigned)sar(x2 - t1, 10);
-            temp[i + 24] = (unsigned)sar(x3 + t0, 10);
-            temp[i + 32] = (unsigned)sar(x3 - t0, 10);
-        }
-    }
-    const unsigned XS = 65536u + (128u << 17);
-#pragma unroll 1
-    for (int r = 0; r < 8; r++) {
-        const unsigned* s = temp + 8 * r;
-        // the row shortcut (src/idct.rs:344-353) is algebraically identical to the general form
-        unsigned x0, x1, x2, x3, t0, t1, t2, t3;
-        IDCT_1D(s[0], s[1], s[2], s[3], s[4], s[5], s[6], s[7], XS, x0, x1, x2, x3, t0, t1, t2, t3);
-        uint2 o;
-        o.x = pack4_sat_u8(sar(x0 + t3, 17), sar(x1 + t2, 17), sar(x2 + t1, 17), sar(x3 + t0, 17));
-        o.y = pack4_sat_u8(sar(x3 - t0, 17), sar(x2 - t1, 17), sar(x1 - t2, 17), sar(x0 - t3, 17));
-        *reinterpret_cast<uint2*>(dst + (size_t)r * stride) = o;
-    }
-}
 
 // src/idct.rs:456-517
 __device__ void idct4x4_scalar(const short* __restrict__ c, const unsigned* __restrict__ q, uint8_t* dst, unsigned stride) {
@@ -305,36 +196,6 @@ constexpr int K1_STAGE_BYTES = K1_TILE * 128;
 // ---------------------------------------------------------------------------------------------
 constexpr int K1_STAGES = 3;
 
-__device__ __forceinline__ unsigned dp2a_lo_su(unsigned a, unsigned b, unsigned c) {
-    unsigned d;
-    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
-__device__ __forceinline__ unsigned dp2a_hi_su(unsigned a, unsigned b, unsigned c) {
-    unsigned d;
-    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
-
-#define K1_DEQ8_ROW(k, B0, B1, B2, B3)                          \
-    {                                                           \
-        const unsigned bias_ = (k == 0) ? 0x80000u : 0u;        \
-        s[k][0] = dp2a_lo_su(raw[k].x, (B0), bias_);            \
-        s[k][1] = dp2a_hi_su(raw[k].x, (B0), bias_);            \
-        s[k][2] = dp2a_lo_su(raw[k].y, (B1), bias_);            \
-        s[k][3] = dp2a_hi_su(raw[k].y, (B1), bias_);            \
-        s[k][4] = dp2a_lo_su(raw[k].z, (B2), bias_);            \
-        s[k][5] = dp2a_hi_su(raw[k].z, (B2), bias_);            \
-        s[k][6] = dp2a_lo_su(raw[k].w, (B3), bias_);            \
-        s[k][7] = dp2a_hi_su(raw[k].w, (B3), bias_);            \
-    }
-
-template <int SLOT>
-__device__ __forceinline__ void dequant_q8_const(const uint4 (&raw)[8], unsigned (&s)[8][8], const K1QCache& qc) {
-#pragma unroll
-    for (int k = 0; k < 8; k++)
-        K1_DEQ8_ROW(k, qc.b[SLOT][4 * k + 0], qc.b[SLOT][4 * k + 1], qc.b[SLOT][4 * k + 2], qc.b[SLOT][4 * k + 3]);
-}
 
 // MODE = column-pass style + 4 * row-pass style of the output butterflies (K1_BFLY_ADD): 0 plain, 1 IMAD.
 // Measured (sweep_r01*.jsonl): ALU-pipe instructions issue at half rate on sm_100, IMAD at full rate, and the
@@ -414,39 +275,18 @@ k1_idct8_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ K
         uint8_t* dst = p.planes + comp.plane_off + (size_t)by * 8u * comp.stride + (size_t)bx * 8u;
 
         unsigned s[8][8];
-        const unsigned qslot = comp.qflags >> 8;
-        if (comp.qflags & 1u) {  // 8-bit table: IDP.2A dequantisation
-            if (qslot == 0) dequant_q8_const<0>(raw, s, qc);
-            else if (qslot == 1) dequant_q8_const<1>(raw, s, qc);
-            else if (qslot == 2) dequant_q8_const<2>(raw, s, qc);
-            else if (qslot == 3) dequant_q8_const<3>(raw, s, qc);
-            else {
-#pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    const uint4 b = __ldg(qp4 + k);
-                    K1_DEQ8_ROW(k, b.x, b.y, b.z, b.w);
-                }
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const uint4 qa = __ldg(q4 + 2 * k), qb = __ldg(q4 + 2 * k + 1);
-                const unsigned bias = (k == 0) ? 0x80000u : 0u;
-                s[k][0] = sext_lo(raw[k].x) * qa.x + bias;
-                s[k][1] = sext_hi(raw[k].x) * qa.y + bias;
-                s[k][2] = sext_lo(raw[k].y) * qa.z + bias;
-                s[k][3] = sext_hi(raw[k].y) * qa.w + bias;
-                s[k][4] = sext_lo(raw[k].z) * qb.x + bias;
-                s[k][5] = sext_hi(raw[k].z) * qb.y + bias;
-                s[k][6] = sext_lo(raw[k].w) * qb.z + bias;
-                s[k][7] = sext_hi(raw[k].w) * qb.w + bias;
-            }
-        }
-        const unsigned oor = (s[0][0] | s[0][1] | s[0][2] | s[0][3] | s[0][4] | s[0][5] | s[0][6] | s[0][7]) >> 20;
+        const unsigned oor = dequant_block(raw, s, comp.qflags, qc, q4, qp4);
         if (oor != 0) {
             idct8x8_scalar_exact(p.coefs + ((size_t)tile.slab_row + tid) * 64, reinterpret_cast<const unsigned*>(q4), dst, comp.stride);
             continue;
         }
+        if constexpr ((MODE & 8) != 0) {
+            // direct form (idct_core.cuh): fewest instructions, IMAD and ALU work in balance
+            uint2 rows[8];
+            idct8x8_direct(s, rows);
+#pragma unroll
+            for (int r = 0; r < 8; r++) *reinterpret_cast<uint2*>(dst + (size_t)r * comp.stride) = rows[r];
+        } else {
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             unsigned x0, x1, x2, x3, t0, t1, t2, t3;
@@ -476,6 +316,7 @@ k1_idct8_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ K
                                sar(K1_BFLY_SUB(RS, x0, t3), 17));
             *reinterpret_cast<uint2*>(dst + (size_t)r * comp.stride) = o;
         }
+        }
     }
 }
 
@@ -504,7 +345,7 @@ cudaError_t launch_k1_tma(const CUtensorMap& tmap, const K1QCache& qc, const K1P
     if (p.ntiles == 0) return cudaSuccess;
     static bool attr_set = false;
     if (!attr_set) {
-        const void* fns[2] = {(const void*)k1_idct8_tma<0>, (const void*)k1_idct8_tma<5>};
+        const void* fns[3] = {(const void*)k1_idct8_tma<0>, (const void*)k1_idct8_tma<5>, (const void*)k1_idct8_tma<8>};
         for (const void* f : fns) {
             cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_tma_smem_bytes());
             if (e != cudaSuccess) return e;
@@ -516,6 +357,7 @@ cudaError_t launch_k1_tma(const CUtensorMap& tmap, const K1QCache& qc, const K1P
     switch (k1_mode() & 15) {
 #define K1_CASE(M) case M: k1_idct8_tma<M><<<grid, K1_TILE, k1_tma_smem_bytes(), stream>>>(tmap, qc, p); break;
         K1_CASE(0)
+        K1_CASE(8)
         default: k1_idct8_tma<5><<<grid, K1_TILE, k1_tma_smem_bytes(), stream>>>(tmap, qc, p); break;
     }
     return cudaGetLastError();

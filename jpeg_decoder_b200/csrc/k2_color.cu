@@ -25,23 +25,10 @@
 #include "device_types.h"
 #include "kernels.h"
 #include "ptx.cuh"
+#include "color_core.cuh"
 
 namespace b200jpg {
 
-__device__ __forceinline__ unsigned pack_sat_u8(int a, int b, unsigned c) {
-    unsigned d;
-    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
-
-// src/decoder.rs:1486-1508.  stbi_f2f(x) = (x * 2^20 + 0.5) as i32 evaluated in f32:
-// 1.40200 -> 1470104, 0.34414 -> 360857, 0.71414 -> 748830, 1.77200 -> 1858077
-// (checked against the oracle's f32 evaluation in tests/test_oracle_kat.py).
-#define C_R_CR 1470104
-#define C_G_CB 360857
-#define C_G_CR 748830
-#define C_B_CB 1858077
-#define YCC_HALF (1 << 19)
 
 // (r, g, b) before clamping, already shifted down: no intermediate can overflow i32.
 __device__ __forceinline__ void ycbcr_scalar(int y, int cb, int cr, int& r, int& g, int& b) {
@@ -49,21 +36,6 @@ __device__ __forceinline__ void ycbcr_scalar(int y, int cb, int cr, int& r, int&
     const int yr = y * (1 << 20) + (YCC_HALF - 128 * C_R_CR);
     const int yg = y * (1 << 20) + (YCC_HALF + 128 * C_G_CB + 128 * C_G_CR);
     const int yb = y * (1 << 20) + (YCC_HALF - 128 * C_B_CB);
-    r = (yr + C_R_CR * cr) >> 20;
-    g = (yg - C_G_CB * cb - C_G_CR * cr) >> 20;
-    b = (yb + C_B_CB * cb) >> 20;
-}
-
-// same value with y supplied as y << 16
-// `sixteen` is (16, 16, 16) -- three separate words so the products are not merged -- passed through the kernel parameters so that ptxas keeps y16 * 16 + K as one IMAD (FMA
-// pipe, full rate) instead of a shift and three adds on the half-rate ALU pipe (K2Params::sixteen)
-struct YccRegs {  // opaque register copies of (16, 16, 16) and of the three additive constants
-    int3 mul, add;
-};
-__device__ __forceinline__ void ycbcr_scalar_y16(int y16, int cb, int cr, int& r, int& g, int& b, const YccRegs& k) {
-    const int yr = y16 * k.mul.x + k.add.x;
-    const int yg = y16 * k.mul.y + k.add.y;
-    const int yb = y16 * k.mul.z + k.add.z;
     r = (yr + C_R_CR * cr) >> 20;
     g = (yg - C_G_CB * cb - C_G_CR * cr) >> 20;
     b = (yb + C_B_CB * cb) >> 20;
@@ -168,111 +140,6 @@ __global__ void __launch_bounds__(256) k2_generic(K2Params p, unsigned first, un
 // (width % 16 != 0) fall back to 32-bit or byte stores inside store_words, the last group of a row is ragged.
 // grid.x = ceil(G/128) * P, G = width/16, P = height/2 + 1; grid.y = image
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned prmt(unsigned a, unsigned b, unsigned sel) {
-    unsigned d;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
-    return d;
-}
-
-struct Chroma16 {  // upsampled chroma for 16 pixels of the two rows of the pair
-    int odd[16];   // output row 2p-1 (near = chroma row p-1)
-    int even[16];  // output row 2p   (near = chroma row p)
-};
-
-// a*: chroma row A = max(p-1,0); b*: chroma row B = min(p, in_h-1).  lo/hi = samples i0..i0+3 / i0+4..i0+7,
-// L / R = clamped halo samples i0-1 / i0+8.
-__device__ __forceinline__ void h2v2_16(unsigned a_lo, unsigned a_hi, unsigned aL, unsigned aR, unsigned b_lo,
-                                        unsigned b_hi, unsigned bL, unsigned bR, Chroma16& o) {
-    // shifted words: s0 = (L, 0, 1, 2), s1 = (3, 4, 5, 6), s2 = (7, R, -, -)
-    const unsigned as0 = prmt(aL, a_lo, 0x6540), as1 = prmt(a_lo, a_hi, 0x6543), as2 = prmt(a_hi, aR, 0x0043);
-    const unsigned bs0 = prmt(bL, b_lo, 0x6540), bs1 = prmt(b_lo, b_hi, 0x6543), bs2 = prmt(b_hi, bR, 0x0043);
-    // P[j] = (a[i-1], a[i], b[i-1], b[i]) for i = i0 + j
-    unsigned P[9];
-    P[0] = prmt(as0, bs0, 0x5410);
-    P[1] = prmt(a_lo, b_lo, 0x5410);
-    P[2] = prmt(as0, bs0, 0x7632);
-    P[3] = prmt(a_lo, b_lo, 0x7632);
-    P[4] = prmt(as1, bs1, 0x5410);
-    P[5] = prmt(a_hi, b_hi, 0x5410);
-    P[6] = prmt(as1, bs1, 0x7632);
-    P[7] = prmt(a_hi, b_hi, 0x7632);
-    P[8] = prmt(as2, bs2, 0x5410);
-    // weights on (a[i-1], a[i], b[i-1], b[i]); t = 3 near + far
-    const unsigned W_A_EVEN = 0x03010903u;  // near = A: out[2i]   = 3 t[i] + t[i-1]
-    const unsigned W_A_ODD = 0x01030309u;   // near = A: out[2i-1] = 3 t[i-1] + t[i]
-    const unsigned W_B_EVEN = 0x09030301u;  // near = B: out[2i]
-    const unsigned W_B_ODD = 0x03090103u;   // near = B: out[2i-1]
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-        o.odd[2 * j] = (int)(__dp4a(P[j], W_A_EVEN, 8u) >> 4);
-        o.odd[2 * j + 1] = (int)(__dp4a(P[j + 1], W_A_ODD, 8u) >> 4);
-        o.even[2 * j] = (int)(__dp4a(P[j], W_B_EVEN, 8u) >> 4);
-        o.even[2 * j + 1] = (int)(__dp4a(P[j + 1], W_B_ODD, 8u) >> 4);
-    }
-}
-
-// 16 pixels: y bytes in yv (4 words), chroma ints -> 48 output bytes at `dst` (16-byte aligned)
-// the three multipliers as opaque register values (so the additive constants can be IMAD immediates)
-__device__ __forceinline__ int3 opaque_regs(int3 v) {
-    int3 r;
-    asm volatile("mov.u32 %0, %1;" : "=r"(r.x) : "r"(v.x));
-    asm volatile("mov.u32 %0, %1;" : "=r"(r.y) : "r"(v.y));
-    asm volatile("mov.u32 %0, %1;" : "=r"(r.z) : "r"(v.z));
-    return r;
-}
-
-__device__ __forceinline__ YccRegs make_ycc_regs(int3 sixteen, bool opaque) {
-    YccRegs k;
-    k.mul = sixteen;
-    k.add = make_int3(YCC_HALF - 128 * C_R_CR, YCC_HALF + 128 * C_G_CB + 128 * C_G_CR, YCC_HALF - 128 * C_B_CB);
-    if (opaque) {
-        k.mul = opaque_regs(k.mul);
-        k.add = opaque_regs(k.add);
-    }
-    return k;
-}
-
-// Stores the first `nbytes` (<= 4*NW) bytes of ow[] at dst: 128-bit stores when dst is 16-byte aligned (always
-// the case when width % 16 == 0), 32-bit stores when 4-byte aligned, byte stores otherwise / for a ragged tail.
-template <int NW>
-__device__ __forceinline__ void store_words(uint8_t* dst, const unsigned (&ow)[NW], unsigned nbytes) {
-    const unsigned a = (unsigned)(uintptr_t)dst;
-    if (nbytes == 4u * NW && (a & 15u) == 0) {
-#pragma unroll
-        for (int k = 0; k < NW / 4; k++)
-            reinterpret_cast<uint4*>(dst)[k] = make_uint4(ow[4 * k], ow[4 * k + 1], ow[4 * k + 2], ow[4 * k + 3]);
-    } else if (nbytes == 4u * NW && (a & 3u) == 0) {
-#pragma unroll
-        for (int k = 0; k < NW; k++) reinterpret_cast<unsigned*>(dst)[k] = ow[k];
-    } else {
-#pragma unroll
-        for (int k = 0; k < 4 * NW; k++)
-            if ((unsigned)k < nbytes) dst[k] = (uint8_t)(ow[k >> 2] >> (8 * (k & 3)));
-    }
-}
-
-// npx = number of valid pixels of this 16-pixel group (16 except for the last group of a ragged row)
-__device__ __forceinline__ void ycbcr_store16(const uint4 yv, const int* cb, const int* cr, uint8_t* dst, const YccRegs& sixteen,
-                                              unsigned npx) {
-    const unsigned yw[4] = {yv.x, yv.y, yv.z, yv.w};
-    unsigned ow[12];
-#pragma unroll
-    for (int w = 0; w < 4; w++) {
-        int r[4], g[4], b[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            // one PRMT puts luma byte k at bits 16..23 (y << 16); the << 4 folds into the IMADs below
-            const int y16 = (int)prmt(yw[w], 0u, 0x4044u | ((unsigned)k << 8));
-            ycbcr_scalar_y16(y16, cb[4 * w + k], cr[4 * w + k], r[k], g[k], b[k], sixteen);
-        }
-        // bytes: R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3
-        ow[3 * w + 0] = pack_sat_u8(g[0], r[0], pack_sat_u8(r[1], b[0], 0u));
-        ow[3 * w + 1] = pack_sat_u8(b[1], g[1], pack_sat_u8(g[2], r[2], 0u));
-        ow[3 * w + 2] = pack_sat_u8(r[3], b[2], pack_sat_u8(b[3], g[3], 0u));
-    }
-    store_words<12>(dst, ow, 3u * npx);
-}
-
 // ---------------------------------------------------------------------------------------------
 // The kernel: a thread walks K2_RP consecutive row pairs of its 16-pixel column group (K2_RP = 1 is the
 // default: measured fastest because it keeps 8 CTAs = 32 warps per SM; 4 reuses chroma rows in registers
@@ -284,22 +151,6 @@ int g_k2_mode = -1;
 struct ChromaRow {  // one chroma row segment: samples i0..i0+7 plus the clamped halo samples
     unsigned lo, hi, L, R;
 };
-
-// selector that keeps bytes 0..m-1 of a word and replicates byte m-1 into the rest (m = 1..4)
-__device__ __forceinline__ unsigned keep_sel(unsigned m) {
-    return (0x3210u & ((1u << (4u * m)) - 1u)) | ((((m - 1u) * 0x1111u) << (4u * m)) & 0xffffu);
-}
-
-// bytes nvalid..7 of the 8-byte window := byte nvalid-1 (nvalid = 1..7): two PRMTs with computed selectors
-__device__ __forceinline__ uint2 replicate_last_sample(uint2 v, unsigned nvalid) {
-    if (nvalid <= 4u) {
-        v.x = prmt(v.x, 0u, keep_sel(nvalid));
-        v.y = prmt(v.x, 0u, (nvalid - 1u) * 0x1111u);
-    } else {
-        v.y = prmt(v.y, 0u, keep_sel(nvalid - 4u));
-    }
-    return v;
-}
 
 // in_w = samples in the row: in the last group of a ragged row the bytes at i >= in_w (block padding) are replaced by
 // the last valid sample, which is exactly the reference's edge rule (out[2 in_w - 1] uses t[in_w-1] alone)
@@ -560,12 +411,14 @@ __global__ void __launch_bounds__(128) k2_ycbcr444(K2Params p, unsigned first, u
     const uint4 yv = load_row16(p.planes + img.c[0].plane_off + (size_t)y * img.c[0].stride, g, img.c[0].stride);
     const uint4 bv = load_row16(p.planes + img.c[1].plane_off + (size_t)y * img.c[1].stride, g, img.c[1].stride);
     const uint4 rv = load_row16(p.planes + img.c[2].plane_off + (size_t)y * img.c[2].stride, g, img.c[2].stride);
-    const unsigned bw[4] = {bv.x, bv.y, bv.z, bv.w}, rw[4] = {rv.x, rv.y, rv.z, rv.w};
+    // byte ^ 0x80 read as a signed byte is byte - 128: one LOP3 per word, the sign extension rides in the PRMT
+    const unsigned bw[4] = {bv.x ^ 0x80808080u, bv.y ^ 0x80808080u, bv.z ^ 0x80808080u, bv.w ^ 0x80808080u};
+    const unsigned rw[4] = {rv.x ^ 0x80808080u, rv.y ^ 0x80808080u, rv.z ^ 0x80808080u, rv.w ^ 0x80808080u};
     int cb[16], cr[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-        cb[k] = (int)prmt(bw[k >> 2], 0u, 0x4440u | (unsigned)(k & 3));
-        cr[k] = (int)prmt(rw[k >> 2], 0u, 0x4440u | (unsigned)(k & 3));
+        cb[k] = (int)prmt(bw[k >> 2], 0u, 0x8880u + 0x1111u * (unsigned)(k & 3));
+        cr[k] = (int)prmt(rw[k >> 2], 0u, 0x8880u + 0x1111u * (unsigned)(k & 3));
     }
     ycbcr_store16(yv, cb, cr, p.out + img.out_off + ((size_t)y * W + g * 16u) * 3u, make_ycc_regs(p.sixteen, true), min(16u, W - g * 16u));
 }

@@ -68,6 +68,23 @@ int k2_mode();
 constexpr unsigned K2_FLAG_LDG_TAKES_420T = 1u;  // K2Params::flags: the load/store 4:2:0 kernel also takes the bulk-copy path's images
 cudaError_t launch_k2_gray(const K2Params& p, unsigned first, unsigned count, unsigned max_w, unsigned max_h, cudaStream_t stream);
 
+// KF: fused dequant + IDCT + upsample + colour (kf_fused.cu); tmap32 = the coefficient slab as [rows][64 x u16] with a
+// 32-row box and 128B swizzle.  `mode` = KF_MODE_*; cols[0..ncols) are the columns of that mode inside the launch range.
+struct KFParams {
+    const FColumn* cols;
+    const DevComp* comps;
+    const unsigned* qtabs;
+    const unsigned* qpack;
+    const short* coefs;
+    const DevImage* images;
+    uint8_t* out;
+    unsigned ncols, item_base, total_items;
+    unsigned ystride, cstride;  // bytes per staged luma / chroma row (batch-wide maxima, multiples of 16)
+    int sixteen;
+};
+size_t kf_smem_bytes(unsigned mode, unsigned ystride, unsigned cstride);
+cudaError_t launch_kf(unsigned mode, const CUtensorMap& tmap32, const K1QCache& qc, const KFParams& p, int num_sms, cudaStream_t stream);
+
 extern int g_k1_mode, g_k2_mode;  // profiling knobs, see b200jpg_debug_set_kernel_modes
 
 }  // namespace b200jpg

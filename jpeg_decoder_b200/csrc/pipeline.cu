@@ -60,6 +60,7 @@ int b200jpg_create(const b200jpg_options* opt, b200jpg_ctx** out) {
     ctx->host_compact = o.host_compact;
     ctx->host_threads = o.host_threads;
     ctx->entropy = o.entropy;
+    ctx->fuse = o.fuse;
     if (cudaSetDevice(o.device) != cudaSuccess) { delete ctx; return B200JPG_ERR_INTERNAL; }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, o.device) != cudaSuccess) { delete ctx; return B200JPG_ERR_INTERNAL; }
@@ -314,6 +315,91 @@ static int plan_image(const b200jpg_ctx* ctx, const b200jpg_image_desc& d, DevIm
     return B200JPG_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused kernel KF: can this image take it, and if so its column strips (device_types.h: FColumn / FRun).
+// Eligible: 3-component YCbCr in scalar arithmetic at full IDCT size whose K2 path is the 4:2:0 or the 4:4:4 one,
+// with the standard block grids (luma 2x2 blocks per MCU over 1x1 chroma, or 1x1 throughout).
+// ---------------------------------------------------------------------------------------------
+static bool fuse_enabled(const b200jpg_ctx* ctx) {
+    if (const char* e = getenv("B200JPG_FUSE")) return atoi(e) != 0;  // profiling: 0 forces K1 + K2
+    return ctx->fuse != B200JPG_FUSE_OFF;
+}
+
+static int fused_mode_of(const b200jpg_ctx* ctx, const b200jpg_image_desc& d, const DevImage& img) {
+    if (ctx->arith != B200JPG_ARITH_SCALAR || ctx->k1_kernel == B200JPG_KERNEL_GENERIC || ctx->k2_kernel == B200JPG_KERNEL_GENERIC) return -1;
+    if (d.ncomp != 3 || img.cc != CC_YCBCR || img.ssse3_pixels != 0) return -1;
+    for (int k = 0; k < 3; k++)
+        if (d.comps[k].dct_scale != 8) return -1;
+    const b200jpg_component *y = &d.comps[0], *cb = &d.comps[1], *cr = &d.comps[2];
+    if (cb->block_w != cr->block_w || cb->block_h != cr->block_h || cb->size_w != cr->size_w || cb->size_h != cr->size_h) return -1;
+    if (img.path == K2_PATH_444) {
+        if (y->h != 1 || y->v != 1 || cb->h != 1 || cb->v != 1 || cr->h != 1 || cr->v != 1) return -1;
+        if (y->block_w != cb->block_w || y->block_h != cb->block_h) return -1;
+        if ((unsigned)y->block_w * 8u < d.width || (unsigned)y->block_h != (d.height + 7u) / 8u) return -1;
+        return KF_MODE_444;
+    }
+    if (img.path == K2_PATH_420 || img.path == K2_PATH_420R || img.path == K2_PATH_420T) {
+        if (y->h != 2 || y->v != 2 || cb->h != 1 || cb->v != 1 || cr->h != 1 || cr->v != 1) return -1;
+        if (y->block_w != 2 * cb->block_w || y->block_h != 2 * cb->block_h) return -1;
+        if ((unsigned)cb->block_w * 16u < d.width || (unsigned)cb->block_h != (d.height + 15u) / 16u) return -1;
+        if (cb->size_w != (d.width + 1u) / 2u || cb->size_h != (d.height + 1u) / 2u) return -1;
+        return KF_MODE_420;
+    }
+    return -1;
+}
+
+static void plan_fused_columns(b200jpg_batch* b, unsigned image, int mode, const b200jpg_image_desc& d, const ImageLayout& L, unsigned comp0) {
+    const unsigned mcu_px = mode == KF_MODE_420 ? 16u : 8u;
+    const unsigned mcu_w = d.comps[1].block_w, nrows = d.comps[1].block_h;
+    const unsigned ms_max = 1920u / mcu_px;
+    // only the MCUs that hold visible pixels (block grids may be wider than the image)
+    const unsigned mcu_vis = (d.width + mcu_px - 1u) / mcu_px;
+    const unsigned nstrips = (mcu_vis + ms_max - 1u) / ms_max;
+    const unsigned ms_each = (mcu_vis + nstrips - 1u) / nstrips;
+    const unsigned slab[3] = {(unsigned)(L.coef_off[0] / 128), (unsigned)(L.coef_off[1] / 128), (unsigned)(L.coef_off[2] / 128)};
+    for (unsigned m0 = 0; m0 < mcu_vis; m0 += ms_each) {
+        const unsigned ms = std::min(ms_each, mcu_vis - m0);
+        FColumn c;
+        memset(&c, 0, sizeof c);
+        c.image = image;
+        c.comp0 = comp0;
+        c.first_item = b->fitems[mode];
+        c.nrows = nrows;
+        c.x0 = m0 * mcu_px;
+        c.wpx = std::min(ms * mcu_px, (unsigned)d.width - c.x0);
+        c.ngroups = (c.wpx + 15u) / 16u;
+        c.gmagic = c.ngroups > 1 ? (unsigned)((0x100000000ull + c.ngroups - 1u) / c.ngroups) : 0u;
+        unsigned nr = 0, box = 0;
+        auto add_run = [&](unsigned comp, unsigned row0, unsigned step, unsigned len, unsigned wrap, unsigned dst_x, unsigned dst_row) {
+            FRun& r = c.run[nr++];
+            r.slab_row0 = row0; r.step = step; r.len = len; r.wrap = wrap; r.comp = comp; r.dst_x = dst_x; r.dst_row = dst_row; r.box0 = box;
+            box += (len + 31u) / 32u;
+        };
+        if (mode == KF_MODE_420) {
+            const unsigned ybw = d.comps[0].block_w, cbw = mcu_w;
+            if (m0 == 0 && ms == (unsigned)cbw) {  // the strip spans whole block rows: the two luma block rows are contiguous
+                add_run(0, slab[0], 2u * ybw, 2u * ybw, ybw, 0, 0);
+            } else {
+                add_run(0, slab[0] + 2u * m0, 2u * ybw, 2u * ms, 2u * ms, 0, 0);
+                add_run(0, slab[0] + ybw + 2u * m0, 2u * ybw, 2u * ms, 2u * ms, 0, 8);
+            }
+            const unsigned hl = m0 > 0 ? 1u : 0u, hr = m0 + ms < cbw ? 1u : 0u;  // horizontal halo of the triangle filter
+            c.cx_base = 8u * (m0 - hl);
+            add_run(1, slab[1] + m0 - hl, cbw, ms + hl + hr, ms + hl + hr, 16, 0);
+            add_run(2, slab[2] + m0 - hl, cbw, ms + hl + hr, ms + hl + hr, 16, 0);
+            b->f_ystride[mode] = std::max(b->f_ystride[mode], (16u * ms + 15u) & ~15u);
+            b->f_cstride[mode] = std::max(b->f_cstride[mode], ((16u + 8u * (ms + hl + hr) + 15u) & ~15u) + 16u);
+        } else {
+            for (unsigned k = 0; k < 3; k++) add_run(k, slab[k] + m0, d.comps[k].block_w, ms, ms, 0, 0);
+            b->f_ystride[mode] = std::max(b->f_ystride[mode], (8u * ms + 15u) & ~15u);
+        }
+        c.nruns = nr;
+        c.nboxes = box;
+        b->fcols[mode].push_back(c);
+        b->fitems[mode] += nrows;
+    }
+}
+
 void batch_release_device(b200jpg_batch* b) {
     if (!b) return;
     if (!b->tables_borrowed) {
@@ -323,6 +409,7 @@ void batch_release_device(b200jpg_batch* b) {
         cudaFree(b->d_qtabs);
         cudaFree(b->d_qpack);
         cudaFree(b->d_strips);
+        for (auto& f : b->d_fcols) cudaFree(f);
     }
     if (b->slabs_borrowed) {
         std::lock_guard<std::mutex> lock(b->ctx->mu);
@@ -333,7 +420,7 @@ void batch_release_device(b200jpg_batch* b) {
         cudaFree(b->d_planes);
         cudaFree(b->d_out);
     }
-    b->d_comps = nullptr; b->d_tiles = nullptr; b->d_images = nullptr; b->d_qtabs = nullptr; b->d_qpack = nullptr; b->d_strips = nullptr;
+    b->d_comps = nullptr; b->d_tiles = nullptr; b->d_images = nullptr; b->d_qtabs = nullptr; b->d_qpack = nullptr; b->d_strips = nullptr; b->d_fcols[0] = b->d_fcols[1] = nullptr;
     b->d_coefs = nullptr; b->d_planes = nullptr; b->d_out = nullptr;
 }
 
@@ -348,6 +435,7 @@ int batch_create_impl(b200jpg_ctx* ctx, const b200jpg_image_desc* imgs, size_t n
     b->layout.resize(n);
     b->images.resize(n);
     b->planes_absolute = ov.plane_addr != nullptr;
+    b->fmode.assign(n, -1);
     std::map<std::string, unsigned> qt_index;
     size_t coef_off = 0, plane_off = 0, out_off = 0;
     int first_error = B200JPG_OK;
@@ -356,6 +444,7 @@ int batch_create_impl(b200jpg_ctx* ctx, const b200jpg_image_desc* imgs, size_t n
         const b200jpg_image_desc& d = imgs[i];
         ImageLayout& L = b->layout[i];
         b->strip_first.push_back((unsigned)b->strips.size());
+        for (unsigned m = 0; m < KF_NMODES; m++) b->fcol_first[m].push_back((unsigned)b->fcols[m].size());
         std::string err;
         int rc = plan_image(ctx, d, &b->images[i], &err);
         for (int k = 0; rc == B200JPG_OK && k < d.ncomp; k++)
@@ -374,6 +463,7 @@ int batch_create_impl(b200jpg_ctx* ctx, const b200jpg_image_desc* imgs, size_t n
         }
         DevImage& img = b->images[i];
         L.tile_first = (unsigned)b->tiles.size();
+        const unsigned comp0 = (unsigned)b->comps.size();
         for (int k = 0; k < d.ncomp; k++) {
             const b200jpg_component& c = d.comps[k];
             const size_t nblocks = (size_t)c.block_w * c.block_h;
@@ -448,6 +538,16 @@ int batch_create_impl(b200jpg_ctx* ctx, const b200jpg_image_desc* imgs, size_t n
                 b->strip_items += npairs;
             }
         }
+        {
+            const int fm = fused_mode_of(ctx, d, img);
+            b->fmode[i] = (signed char)fm;
+            if (fm >= 0) {
+                plan_fused_columns(b, (unsigned)i, fm, d, L, comp0);
+                b->info.n_fused++;
+                for (int k = 0; k < d.ncomp; k++) b->info.kf_algorithmic_bytes += (size_t)d.comps[k].block_w * d.comps[k].block_h * 128;
+                b->info.kf_algorithmic_bytes += L.out_len;
+            }
+        }
         if (img.path < K2_NPATHS) {
             b->path_used[img.path] = true;
             b->path_max_w[img.path] = std::max(b->path_max_w[img.path], img.width);
@@ -488,10 +588,13 @@ int batch_create_impl(b200jpg_ctx* ctx, const b200jpg_image_desc* imgs, size_t n
     if (e == cudaSuccess) e = upload((void**)&b->d_qtabs, b->qtabs.data(), b->qtabs.size() * sizeof(unsigned));
     if (e == cudaSuccess) e = upload((void**)&b->d_qpack, b->qpack.data(), b->qpack.size() * sizeof(unsigned));
     if (e == cudaSuccess) e = upload((void**)&b->d_strips, b->strips.data(), b->strips.size() * sizeof(K2Strip));
+    for (unsigned m = 0; m < KF_NMODES; m++)
+        if (e == cudaSuccess) e = upload((void**)&b->d_fcols[m], b->fcols[m].data(), b->fcols[m].size() * sizeof(FColumn));
     if (e == cudaSuccess && ov.arena && arena_used)
         e = cudaMemcpyAsync(ov.arena->d, ov.arena->h, arena_used, cudaMemcpyHostToDevice, up_stream);
     b->table_bytes = arena_used;
     b->strip_first.push_back((unsigned)b->strips.size());
+    for (unsigned m = 0; m < KF_NMODES; m++) b->fcol_first[m].push_back((unsigned)b->fcols[m].size());
     memset(&b->qcache, 0, sizeof b->qcache);
     for (size_t t = 0; t < 4 && t < b->qt_is8.size(); t++)
         memcpy(b->qcache.b[t], b->qpack.data() + 32 * t, 32 * sizeof(unsigned));
@@ -521,6 +624,15 @@ static int ensure_tensor_map(b200jpg_batch* b, const void* d_coefs) {
         snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
         return fail(ctx, B200JPG_ERR_INTERNAL, buf);
     }
+    cuuint32_t box32[2] = {64, 32};
+    r = ctx->encode(&b->tmap32, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(d_coefs), gdim, gstride, box32, estride,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char buf[96];
+        snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled (32-row box) failed with CUresult %d", (int)r);
+        return fail(ctx, B200JPG_ERR_INTERNAL, buf);
+    }
     b->tmap_base = d_coefs;
     return B200JPG_OK;
 }
@@ -529,6 +641,37 @@ static int ensure_tensor_map(b200jpg_batch* b, const void* d_coefs) {
 int batch_launch(b200jpg_batch* b, const void* d_coefs, void* d_planes, void* d_out, int stages, unsigned tile_first,
                         unsigned tile_count, unsigned img_first, unsigned img_count, cudaStream_t stream) {
     b200jpg_ctx* ctx = b->ctx;
+    // both stages in one call and every image of the range eligible: the fused kernel, planes never leave the SM
+    if (stages == 3 && img_count && fuse_enabled(ctx) && ((uintptr_t)d_coefs % 16 == 0) && d_out) {
+        bool all = true;
+        for (unsigned i = img_first; i < img_first + img_count && all; i++) all = b->layout[i].status != B200JPG_OK || b->fmode[i] >= 0;
+        if (all) {
+            for (unsigned m = 0; m < KF_NMODES; m++) {
+                const unsigned c0 = b->fcol_first[m][img_first], c1 = b->fcol_first[m][img_first + img_count];
+                if (c1 == c0) continue;
+                int rc = ensure_tensor_map(b, d_coefs);
+                if (rc) return rc;
+                KFParams p;
+                p.cols = b->d_fcols[m] + c0;
+                p.comps = b->d_comps;
+                p.qtabs = b->d_qtabs;
+                p.qpack = b->d_qpack;
+                p.coefs = (const short*)d_coefs;
+                p.images = b->d_images;
+                p.out = (uint8_t*)d_out;
+                p.ncols = c1 - c0;
+                p.item_base = b->fcols[m][c0].first_item;
+                p.total_items = (c1 < b->fcols[m].size() ? b->fcols[m][c1].first_item : b->fitems[m]) - p.item_base;
+                p.ystride = b->f_ystride[m];
+                p.cstride = b->f_cstride[m];
+                p.sixteen = 16;
+                cudaError_t e = launch_kf(m, b->tmap32, b->qcache, p, ctx->num_sms, stream);
+                if (e != cudaSuccess) return cuda_fail(ctx, e, "KF launch");
+                ctx->launches++;
+            }
+            return B200JPG_OK;
+        }
+    }
     if ((stages & 1) && tile_count) {
         K1Params p;
         p.tiles = b->d_tiles + tile_first;

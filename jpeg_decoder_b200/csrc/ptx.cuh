@@ -49,6 +49,12 @@ __device__ __forceinline__ void bulk_load_1d(unsigned dst, const void* src, unsi
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
+// d = { sat_u8(a) << 8 | sat_u8(b) } | (c << 16)   (one I2IP instruction)
+__device__ __forceinline__ unsigned pack_sat_u8(int a, int b, unsigned c) {
+    unsigned d;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
 __device__ __forceinline__ uint4 lds128(unsigned addr) {
     uint4 v;
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
