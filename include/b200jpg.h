@@ -81,8 +81,11 @@ enum { B200JPG_ENTROPY_AUTO = 0, B200JPG_ENTROPY_HOST = 1, B200JPG_ENTROPY_DEVIC
 
 /* Dense coefficients -> pixels in one kernel (KF, csrc/kf_fused.cu: the planes are staged in shared memory and never
  * written to HBM) for 3-component YCbCr 4:2:0 / 4:4:4 images at full IDCT size in scalar arithmetic, whenever both
- * stages are run in one call; OFF always runs K1 then K2 through the plane slab.  Same bytes either way. */
-enum { B200JPG_FUSE_AUTO = 0, B200JPG_FUSE_OFF = 1 };
+ * stages are run in one call.  Same bytes either way; which route is faster was measured on B200:
+ * AUTO fuses 4:4:4 (where K2 alone is HBM-bound) and runs K1 then K2 for 4:2:0 (both routes issue the same number of
+ * instructions and are bound by integer issue, the fused one pays for its CTA-wide barriers); ON fuses everything
+ * eligible; OFF never fuses. */
+enum { B200JPG_FUSE_AUTO = 0, B200JPG_FUSE_OFF = 1, B200JPG_FUSE_ON = 2 };
 
 /* kernel selection, for tests and profiling (0 = pick the fastest applicable kernel) */
 enum { B200JPG_KERNEL_AUTO = 0, B200JPG_KERNEL_GENERIC = 1, B200JPG_KERNEL_FAST = 2 };
@@ -121,6 +124,9 @@ B200JPG_API const char *b200jpg_version(void);
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */
 B200JPG_API uint64_t b200jpg_launch_count(const b200jpg_ctx *ctx);
 B200JPG_API int b200jpg_synchronize(b200jpg_ctx *ctx);
+/* changes b200jpg_options.fuse of a live context (B200JPG_FUSE_*): lets one plan be run both ways, e.g. to time the
+ * two-kernel route next to the fused kernel on the same buffers */
+B200JPG_API void b200jpg_set_fuse(b200jpg_ctx *ctx, int fuse);
 /* b200jpg_decode_files since creation: scans whose Huffman decoding ran on the device, and how many of those the
  * device flagged and handed back to the host loop (see B200JPG_ENTROPY_*) */
 B200JPG_API void b200jpg_device_scan_counts(const b200jpg_ctx *ctx, uint64_t *decoded, uint64_t *retried);

@@ -16,7 +16,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._native import (ARITH_SCALAR, ARITH_SSSE3, FUSE_AUTO, FUSE_OFF, ENTROPY_AUTO, ENTROPY_DEVICE, ENTROPY_HOST, COMPACT_AUTO, COMPACT_OFF, COMPACT_ON, CP_DCT_PROGRESSIVE, CP_DCT_SEQUENTIAL, CP_LOSSLESS, CT_CMYK,
+from ._native import (ARITH_SCALAR, ARITH_SSSE3, FUSE_AUTO, FUSE_OFF, FUSE_ON, ENTROPY_AUTO, ENTROPY_DEVICE, ENTROPY_HOST, COMPACT_AUTO, COMPACT_OFF, COMPACT_ON, CP_DCT_PROGRESSIVE, CP_DCT_SEQUENTIAL, CP_LOSSLESS, CT_CMYK,
                       CT_GRAYSCALE, CT_JCS_BG_RGB, CT_JCS_BG_YCC, CT_NONE, CT_RGB, CT_UNKNOWN, CT_YCBCR, CT_YCCK,
                       ERR_FORMAT, ERR_INTERNAL, ERR_IO, ERR_UNSUPPORTED, KERNEL_AUTO, KERNEL_FAST, KERNEL_GENERIC, OK,
                       PF_CMYK32, PF_L8, PF_L16, PF_RGB24, SBS_INTERLEAVED, SBS_NATURAL, SBS_PLANAR, BatchInfo, Component, FileJob, ImageDesc,
@@ -88,13 +88,14 @@ class Context:
         opt.stream = stream
         opt.host_compact, opt.host_threads = host_compact, host_threads
         opt.entropy = entropy  # ENTROPY_AUTO / ENTROPY_HOST / ENTROPY_DEVICE
-        opt.fuse = fuse        # FUSE_AUTO / FUSE_OFF
+        opt.fuse = fuse        # FUSE_AUTO / FUSE_OFF / FUSE_ON
         h = C.c_void_p()
         rc = lib().b200jpg_create(C.byref(opt), C.byref(h))
         if rc:
             raise B200JpgError(rc, "b200jpg_create failed: no usable sm_100 CUDA device (there is no CPU fallback)")
         self._h = h
         self.arith = arith
+        self.fuse = fuse
 
     def close(self):
         if getattr(self, "_h", None):
@@ -109,6 +110,10 @@ class Context:
 
     def synchronize(self):
         self.check(lib().b200jpg_synchronize(self._h))
+
+    def set_fuse(self, fuse):
+        """FUSE_AUTO: the fused kernel where it is the faster route (4:4:4); FUSE_ON: wherever it applies; FUSE_OFF: never."""
+        lib().b200jpg_set_fuse(self._h, fuse)
 
     @property
     def launch_count(self):

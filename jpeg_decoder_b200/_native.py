@@ -56,7 +56,7 @@ class SbsStream(C.Structure):
 SBS_PLANAR, SBS_INTERLEAVED, SBS_NATURAL = 0, 1, 2
 COMPACT_AUTO, COMPACT_OFF, COMPACT_ON = 0, 1, 2
 ENTROPY_AUTO, ENTROPY_HOST, ENTROPY_DEVICE = 0, 1, 2
-FUSE_AUTO, FUSE_OFF = 0, 1
+FUSE_AUTO, FUSE_OFF, FUSE_ON = 0, 1, 2
 
 # every symbol include/b200jpg.h declares (tests/test_abi.py checks the two lists agree)
 EXPORTS = {
@@ -68,6 +68,7 @@ EXPORTS = {
     "b200jpg_launch_count": (C.c_uint64, [C.c_void_p]),
     "b200jpg_device_scan_counts": (None, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "b200jpg_synchronize": (C.c_int, [C.c_void_p]),
+    "b200jpg_set_fuse": (None, [C.c_void_p, C.c_int]),
     "b200jpg_update_component_sizes": (C.c_int, [C.c_uint16, C.c_uint16, C.POINTER(Component), C.c_int,
                                                  C.POINTER(C.c_uint16), C.POINTER(C.c_uint16)]),
     "b200jpg_choose_idct_size": (C.c_int, [C.c_uint16] * 4),

@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
 #include <string>
 
@@ -28,10 +29,11 @@ struct b200jpg_ctx {
     cudaStream_t stream2 = nullptr;  // second stream of the host pipeline
     bool own_stream = false;
     int num_sms = 148;
-    uint64_t launches = 0;
+    std::atomic<uint64_t> launches{0};  // bumped from the stream-engine threads as well as from API calls
     uint64_t device_scans = 0, device_scan_retries = 0;  // b200jpg_decode_files: scans Huffman-decoded on the GPU / sent back to the host
     PFN_tensorMapEncodeTiled encode = nullptr;
-    std::string err;
+    std::string err;  // guarded by err_mu (b200jpg_fail is called from paths that do not hold mu)
+    std::mutex err_mu;
     // grow-only caches so that repeated batches / file chunks do not pay cudaMalloc / cudaHostAlloc each time
     struct Buf {
         void* p = nullptr;

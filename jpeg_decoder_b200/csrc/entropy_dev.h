@@ -216,8 +216,10 @@ ENT_HD EntState ent_decode_range(const Words& words, const uint16_t* tabs, const
             adv = 1;
         }
         if (Sink::kCountOnly) {
-            // what the write pass will append for this code word (a run leaving the block is flagged there anyway)
-            sink_count(sink, (s != 0u) & (k != 0u));
+            // what the write pass will append for this code word: an AC value that lands inside the block (a run leaving
+            // the block stores nothing and is flagged there; counting it would let value offsets run past the 63 values
+            // per block the stream's value region is sized for)
+            sink_count(sink, (s != 0u) & (k != 0u) & (k + adv <= 64u));
         } else if (s) {
             const uint32_t pos = k + adv - 1;
             const uint32_t u = (win << len) >> (32u - s);

@@ -105,9 +105,11 @@ bool HuffTable::build(const uint8_t bits[16], const uint8_t* vals, int nvals, bo
     uint8_t huffsize[272];
     uint16_t huffcode[272];
     int n = 0;
+    for (int i = 0; i < 16; i++) n += bits[i];
+    if (n == 0 || n > 256 || n != nvals) return false;  // before anything is written: 16 counts of 255 would overrun huffsize
+    n = 0;
     for (int i = 0; i < 16; i++)
         for (int k = 0; k < bits[i]; k++) huffsize[n++] = (uint8_t)(i + 1);
-    if (n == 0 || n > 256 || n != nvals) return false;
     uint8_t code_size = huffsize[0];
     uint32_t code = 0;
     for (int i = 0; i < n; i++) {

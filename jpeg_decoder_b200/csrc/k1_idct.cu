@@ -23,7 +23,7 @@
 #include "ptx.cuh"
 #include "idct_core.cuh"
 
-#define K1_DEFAULT_MODE 5
+#define K1_DEFAULT_MODE 8
 
 namespace b200jpg {
 
@@ -357,8 +357,8 @@ cudaError_t launch_k1_tma(const CUtensorMap& tmap, const K1QCache& qc, const K1P
     switch (k1_mode() & 15) {
 #define K1_CASE(M) case M: k1_idct8_tma<M><<<grid, K1_TILE, k1_tma_smem_bytes(), stream>>>(tmap, qc, p); break;
         K1_CASE(0)
-        K1_CASE(8)
-        default: k1_idct8_tma<5><<<grid, K1_TILE, k1_tma_smem_bytes(), stream>>>(tmap, qc, p); break;
+        K1_CASE(5)
+        default: k1_idct8_tma<8><<<grid, K1_TILE, k1_tma_smem_bytes(), stream>>>(tmap, qc, p); break;
     }
     return cudaGetLastError();
 }

@@ -138,7 +138,10 @@ __global__ void __launch_bounds__(ENT_THREADS) ent_pass(const EntImage* __restri
             if (im.tight_end && e.p + 7 < im.scan_bits) bad |= ENT_BAD_TAIL;
         }
         else if (last) bad |= ENT_INCOMPLETE;
-        else if (ent_pack(e) != ld_state(&w.state[g])) bad |= ENT_BAD_CHAIN;
+        // the chain check covers what the prefix sums were built from: the end state AND the number of values -- a
+        // successor that re-synchronises inside its subsequence ends in the same state with a different count, which
+        // would shift every later value offset of the interval (possible when the sync passes ran out of budget)
+        else if (ent_pack(e) != ld_state(&w.state[g]) || sink.vi - w.first_val[g] != w.nvals[g]) bad |= ENT_BAD_CHAIN;
         if (bad) atomicOr(&w.status[2 * blockIdx.y], bad);
     }
 }

@@ -82,7 +82,9 @@ struct KFParams {
     unsigned ystride, cstride;  // bytes per staged luma / chroma row (batch-wide maxima, multiples of 16)
     int sixteen;
 };
-size_t kf_smem_bytes(unsigned mode, unsigned ystride, unsigned cstride);
+size_t kf_smem_bytes(unsigned mode, unsigned ystride, unsigned cstride, unsigned warps);
+unsigned kf_warps();     // warps per CTA of the fused kernel (4 or 8)
+unsigned kf_strip_px();  // widest column strip the planner may cut (pixels, multiple of 16)
 cudaError_t launch_kf(unsigned mode, const CUtensorMap& tmap32, const K1QCache& qc, const KFParams& p, int num_sms, cudaStream_t stream);
 
 extern int g_k1_mode, g_k2_mode;  // profiling knobs, see b200jpg_debug_set_kernel_modes

@@ -37,14 +37,13 @@
 
 namespace b200jpg {
 
-constexpr unsigned KF_WARPS = 8;
-constexpr unsigned KF_THREADS = KF_WARPS * 32;
+constexpr unsigned KF_DEFAULT_WARPS = 4;
 constexpr unsigned KF_BOX = 32;                // blocks per TMA box = one warp's lanes
 constexpr unsigned KF_SLOT_BYTES = KF_BOX * 128;
 // staged plane rows: 4:2:0 = 16 luma + 2 carry, 8 chroma + 2 carry per component; 4:4:4 = 8 rows per component
 constexpr unsigned KF_YROWS_420 = 18, KF_CROWS_420 = 10, KF_ROWS_444 = 8;
 
-size_t kf_smem_bytes(unsigned mode, unsigned ystride, unsigned cstride) {
+size_t kf_smem_bytes(unsigned mode, unsigned ystride, unsigned cstride, unsigned KF_WARPS) {
     const size_t planes = mode == KF_MODE_420 ? (size_t)KF_YROWS_420 * ystride + 2u * KF_CROWS_420 * cstride : (size_t)3u * KF_ROWS_444 * ystride;
     return 1024 + (size_t)KF_WARPS * KF_SLOT_BYTES + planes;
 }
@@ -80,9 +79,11 @@ __device__ __forceinline__ void kf_wait(unsigned bar, unsigned parity) {
         if (++spins > (1u << 24)) __trap();
 }
 
-template <unsigned MODE>
-__global__ void __launch_bounds__(KF_THREADS, 2)
+// KF_WARPS warps per CTA, 16 / KF_WARPS CTAs per SM (the register file holds 16 warps at 128 registers)
+template <unsigned MODE, unsigned KF_WARPS>
+__global__ void __launch_bounds__(KF_WARPS * 32, 16 / KF_WARPS)
 kf_fused(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ K1QCache qc, KFParams p) {
+    constexpr unsigned KF_THREADS = KF_WARPS * 32;
     extern __shared__ __align__(1024) uint8_t kf_smem[];
     __shared__ __align__(8) unsigned long long full_bar[KF_WARPS];
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -278,21 +279,45 @@ kf_fused(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ K1QCa
 }
 
 // ---------------------------------------------------------------------------------------------
+// profiling knobs (defaults measured on B200, profiles/r02_kf_sweep.md): warps per CTA and strip width
+static unsigned kf_env(const char* name, unsigned dflt) {
+    const char* e = getenv(name);
+    return e ? (unsigned)atoi(e) : dflt;
+}
+unsigned kf_warps() {
+    static unsigned w = 0;
+    if (!w) w = kf_env("B200JPG_KF_WARPS", KF_DEFAULT_WARPS) == 4 ? 4 : 8;
+    return w;
+}
+unsigned kf_strip_px() {
+    static unsigned px = 0;
+    if (!px) {
+        px = kf_env("B200JPG_KF_STRIP", kf_warps() == 4 ? 960 : 1920);
+        px = px < 128 ? 128 : (px > 1920 ? 1920 : px) / 16 * 16;
+    }
+    return px;
+}
+
+template <unsigned MODE, unsigned W>
+static cudaError_t launch_kf_t(const CUtensorMap& tmap32, const K1QCache& qc, const KFParams& p, int num_sms, cudaStream_t stream) {
+    const size_t smem_bytes = kf_smem_bytes(MODE, p.ystride, p.cstride, W);
+    static size_t attr_set = 0;
+    if (attr_set < smem_bytes) {
+        cudaError_t e = cudaFuncSetAttribute(kf_fused<MODE, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        if (e != cudaSuccess) return e;
+        attr_set = smem_bytes;
+    }
+    unsigned grid = (unsigned)num_sms * (16u / W);
+    if (grid > p.total_items) grid = p.total_items;
+    kf_fused<MODE, W><<<grid, W * 32, smem_bytes, stream>>>(tmap32, qc, p);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_kf(unsigned mode, const CUtensorMap& tmap32, const K1QCache& qc, const KFParams& p, int num_sms, cudaStream_t stream) {
     if (p.ncols == 0 || p.total_items == 0) return cudaSuccess;
-    const size_t smem_bytes = kf_smem_bytes(mode, p.ystride, p.cstride);
-    static size_t attr_set[KF_NMODES] = {0, 0};
-    if (attr_set[mode] < smem_bytes) {
-        const void* fn = mode == KF_MODE_420 ? (const void*)kf_fused<KF_MODE_420> : (const void*)kf_fused<KF_MODE_444>;
-        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-        if (e != cudaSuccess) return e;
-        attr_set[mode] = smem_bytes;
-    }
-    unsigned grid = (unsigned)num_sms * 2u;
-    if (grid > p.total_items) grid = p.total_items;
-    if (mode == KF_MODE_420) kf_fused<KF_MODE_420><<<grid, KF_THREADS, smem_bytes, stream>>>(tmap32, qc, p);
-    else kf_fused<KF_MODE_444><<<grid, KF_THREADS, smem_bytes, stream>>>(tmap32, qc, p);
-    return cudaGetLastError();
+    const bool w4 = kf_warps() == 4;
+    if (mode == KF_MODE_420) return w4 ? launch_kf_t<KF_MODE_420, 4>(tmap32, qc, p, num_sms, stream) : launch_kf_t<KF_MODE_420, 8>(tmap32, qc, p, num_sms, stream);
+    return w4 ? launch_kf_t<KF_MODE_444, 4>(tmap32, qc, p, num_sms, stream) : launch_kf_t<KF_MODE_444, 8>(tmap32, qc, p, num_sms, stream);
 }
 
 }  // namespace b200jpg

@@ -25,7 +25,10 @@
 // context
 // ---------------------------------------------------------------------------------------------
 int b200jpg_fail(b200jpg_ctx* ctx, int code, const std::string& msg) {
-    if (ctx) ctx->err = msg;
+    if (ctx) {
+        std::lock_guard<std::mutex> lock(ctx->err_mu);
+        ctx->err = msg;
+    }
     return code;
 }
 int b200jpg_cuda_fail(b200jpg_ctx* ctx, cudaError_t e, const char* what) {
@@ -95,11 +98,21 @@ void b200jpg_destroy(b200jpg_ctx* ctx) {
     for (auto& sc : ctx->scratch) cudaFree(sc.p);
     delete ctx;
 }
-const char* b200jpg_last_error(const b200jpg_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
-uint64_t b200jpg_launch_count(const b200jpg_ctx* ctx) { return ctx ? ctx->launches : 0; }
+const char* b200jpg_last_error(const b200jpg_ctx* ctx) {
+    if (!ctx) return "no context";
+    // a per-thread copy: the pointer stays valid while other threads keep failing into ctx->err
+    static thread_local std::string copy;
+    std::lock_guard<std::mutex> lock(const_cast<b200jpg_ctx*>(ctx)->err_mu);
+    copy = ctx->err;
+    return copy.c_str();
+}
+uint64_t b200jpg_launch_count(const b200jpg_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
 void b200jpg_device_scan_counts(const b200jpg_ctx* ctx, uint64_t* decoded, uint64_t* retried) {
     if (decoded) *decoded = ctx ? ctx->device_scans : 0;
     if (retried) *retried = ctx ? ctx->device_scan_retries : 0;
+}
+void b200jpg_set_fuse(b200jpg_ctx* ctx, int fuse) {
+    if (ctx) ctx->fuse = fuse;
 }
 int b200jpg_synchronize(b200jpg_ctx* ctx) {
     if (!ctx) return B200JPG_ERR_INTERNAL;
@@ -320,9 +333,13 @@ static int plan_image(const b200jpg_ctx* ctx, const b200jpg_image_desc& d, DevIm
 // Eligible: 3-component YCbCr in scalar arithmetic at full IDCT size whose K2 path is the 4:2:0 or the 4:4:4 one,
 // with the standard block grids (luma 2x2 blocks per MCU over 1x1 chroma, or 1x1 throughout).
 // ---------------------------------------------------------------------------------------------
-static bool fuse_enabled(const b200jpg_ctx* ctx) {
-    if (const char* e = getenv("B200JPG_FUSE")) return atoi(e) != 0;  // profiling: 0 forces K1 + K2
-    return ctx->fuse != B200JPG_FUSE_OFF;
+// which sampling modes the fused kernel takes: bit m set = KF_MODE_m
+static unsigned fuse_modes(const b200jpg_ctx* ctx) {
+    int f = ctx->fuse;
+    if (const char* e = getenv("B200JPG_FUSE")) f = atoi(e) == 0 ? B200JPG_FUSE_OFF : (atoi(e) == 2 ? B200JPG_FUSE_AUTO : B200JPG_FUSE_ON);  // profiling
+    if (f == B200JPG_FUSE_OFF) return 0u;
+    if (f == B200JPG_FUSE_ON) return (1u << KF_MODE_444) | (1u << KF_MODE_420);
+    return 1u << KF_MODE_444;
 }
 
 static int fused_mode_of(const b200jpg_ctx* ctx, const b200jpg_image_desc& d, const DevImage& img) {
@@ -351,7 +368,7 @@ static int fused_mode_of(const b200jpg_ctx* ctx, const b200jpg_image_desc& d, co
 static void plan_fused_columns(b200jpg_batch* b, unsigned image, int mode, const b200jpg_image_desc& d, const ImageLayout& L, unsigned comp0) {
     const unsigned mcu_px = mode == KF_MODE_420 ? 16u : 8u;
     const unsigned mcu_w = d.comps[1].block_w, nrows = d.comps[1].block_h;
-    const unsigned ms_max = 1920u / mcu_px;
+    const unsigned ms_max = kf_strip_px() / mcu_px;
     // only the MCUs that hold visible pixels (block grids may be wider than the image)
     const unsigned mcu_vis = (d.width + mcu_px - 1u) / mcu_px;
     const unsigned nstrips = (mcu_vis + ms_max - 1u) / ms_max;
@@ -561,7 +578,7 @@ int batch_create_impl(b200jpg_ctx* ctx, const b200jpg_image_desc* imgs, size_t n
     b->info.coef_bytes = align_up(coef_off, 1024);
     b->info.plane_bytes = ov.plane_addr ? 0 : align_up(plane_off, 256);
     b->info.out_bytes = align_up(out_off, 256);
-    if (first_error) ctx->err = first_msg;
+    if (first_error) b200jpg_fail(ctx, first_error, first_msg);
 
     cudaStream_t up_stream = ov.upload_stream ? ov.upload_stream : ctx->stream;
     size_t arena_used = 0;
@@ -642,9 +659,11 @@ int batch_launch(b200jpg_batch* b, const void* d_coefs, void* d_planes, void* d_
                         unsigned tile_count, unsigned img_first, unsigned img_count, cudaStream_t stream) {
     b200jpg_ctx* ctx = b->ctx;
     // both stages in one call and every image of the range eligible: the fused kernel, planes never leave the SM
-    if (stages == 3 && img_count && fuse_enabled(ctx) && ((uintptr_t)d_coefs % 16 == 0) && d_out) {
+    const unsigned fmodes = fuse_modes(ctx);
+    if (stages == 3 && img_count && fmodes && ((uintptr_t)d_coefs % 16 == 0) && d_out) {
         bool all = true;
-        for (unsigned i = img_first; i < img_first + img_count && all; i++) all = b->layout[i].status != B200JPG_OK || b->fmode[i] >= 0;
+        for (unsigned i = img_first; i < img_first + img_count && all; i++)
+            all = b->layout[i].status != B200JPG_OK || (b->fmode[i] >= 0 && ((fmodes >> b->fmode[i]) & 1u));
         if (all) {
             for (unsigned m = 0; m < KF_NMODES; m++) {
                 const unsigned c0 = b->fcol_first[m][img_first], c1 = b->fcol_first[m][img_first + img_count];

@@ -79,6 +79,27 @@ int b200jpg_sbs_from_dense(const b200jpg_image_desc* img, uint8_t* buf, size_t c
     return B200JPG_OK;
 }
 
+}  // extern "C"
+
+// K0 places block j of MCU (mx, my) of an interleaved stream at row (my*v+vy)*block_w + mx*h+hx of its component: that
+// lands inside the component's slab only when every block grid is exactly mcu_w*h x mcu_h*v (parser.rs:306-307) and an MCU
+// has at most 12 blocks (the descriptor's table size).
+static bool interleaved_geometry_ok(const b200jpg_image_desc& d) {
+    if (d.ncomp < 1 || d.ncomp > 4) return true;  // rejected by the planner with its own message
+    unsigned bpm = 0, mcu_w = 0, mcu_h = 0;
+    for (int c = 0; c < d.ncomp; c++) {
+        const b200jpg_component& k = d.comps[c];
+        if (k.h == 0 || k.v == 0 || k.block_w % k.h != 0 || k.block_h % k.v != 0) return false;
+        const unsigned mw = k.block_w / k.h, mh = k.block_h / k.v;
+        if (c == 0) { mcu_w = mw; mcu_h = mh; }
+        else if (mw != mcu_w || mh != mcu_h) return false;
+        bpm += (unsigned)k.h * k.v;
+    }
+    return bpm <= 12 && mcu_w > 0 && mcu_h > 0;
+}
+
+extern "C" {
+
 int b200jpg_decode_batch_sbs(b200jpg_ctx* ctx, const b200jpg_image_desc* imgs, const b200jpg_sbs_stream* streams, size_t n,
                              uint8_t* const* outs, const size_t* out_caps, int* statuses) {
     if (!ctx || (n && (!imgs || !streams || !outs || !out_caps))) return B200JPG_ERR_INTERNAL;
@@ -98,6 +119,10 @@ int b200jpg_decode_batch_sbs(b200jpg_ctx* ctx, const b200jpg_image_desc* imgs, c
         for (size_t i = i0; i < n && i < i0 + group_max; i++) {
             if (streams[i].order < 0 || streams[i].order > (int)(SBS_INTERLEAVED | SBS_NATURAL)) {
                 local[i] = B200JPG_ERR_INTERNAL;
+                continue;
+            }
+            if ((streams[i].order & SBS_INTERLEAVED) && !interleaved_geometry_ok(imgs[i])) {
+                local[i] = b200jpg_fail(ctx, B200JPG_ERR_INTERNAL, "interleaved stream: block grids are not mcu_w*h x mcu_h*v, or more than 12 blocks per MCU");
                 continue;
             }
             if (imgs[i].ncomp >= 1 && imgs[i].ncomp <= 4 && !sbs_valid(streams[i].data, streams[i].len, desc_blocks(imgs[i]))) {

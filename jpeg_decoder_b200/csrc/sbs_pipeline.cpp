@@ -343,9 +343,10 @@ int SbsPipeline::enqueue(Slot& s) {
     if (nent) {
         // Huffman decoding on the device: payloads -> compact streams (bitmaps are OR-ed into: zero them first) ...
         CU_TRY(ctx_, launch_k0_zero_headers(d_k0, (unsigned)nk0, max_nb, (uint8_t*)s.d_streams.p, s_comp_));
+        uint64_t ent_launches = 0;
         CU_TRY(ctx_, launch_entropy(d_ent, (unsigned)nent, max_nsub, total_sub, max_comp_blocks, (uint8_t*)s.d_streams.p, s.d_ent.p, passes, &d_status,
-                                    s_comp_, &ctx_->launches));
-        ctx_->launches++;
+                                    s_comp_, &ent_launches));
+        ctx_->launches += ent_launches + 1;
     }
     // ... and K0 expands them, like the streams the host made: the dense slab K1 reads, zeros included
     if (nent) {

@@ -139,8 +139,7 @@ int stream_engine_run(b200jpg_ctx* ctx, JobSource& src, int nthreads) {
         eng->pipe.reset(new SbsPipeline(ctx, 4));
         if (!eng->pipe->ok()) {
             eng->pipe.reset();
-            ctx->err = "internal: could not create the device pipeline (streams / events)";
-            return B200JPG_ERR_INTERNAL;
+            return b200jpg_fail(ctx, B200JPG_ERR_INTERNAL, "internal: could not create the device pipeline (streams / events)");
         }
     }
     while (eng->rings.size() < (size_t)nthreads) eng->rings.emplace_back(new Ring());

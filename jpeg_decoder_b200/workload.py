@@ -6,17 +6,22 @@ the input format of the hot path -- and replicated to the batch size.  The devic
 int16, so kernel bytes are content-independent.
 """
 import io
+import os
 
 import numpy as np
 
-from . import Decoder
+GOLDEN_BENCHES = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "benches")
 
 CONFIGS = {
-    # name: (width, height, PIL subsampling, seed base, default batch per GPU)
+    # BASELINE.json configs[1..3] (configs[0], tower.jpg on the CPU, is the reference arm's own case; configs[4] is
+    # cfg2 at 8 x 1024 images, i.e. `bench.py --gpus 8`)
     "cfg2": dict(width=1920, height=1080, subsampling=2, seed=1234, batch=1024,
                  desc="1024 synthetic 1920x1080 baseline 4:2:0 JPEGs (q90)"),
     "cfg3": dict(width=3840, height=2160, subsampling=0, seed=5000, batch=1024,
                  desc="1024 synthetic 3840x2160 baseline 4:4:4 JPEGs (q90)"),
+    "cfg4": dict(width=512, height=512, file="tower_progressive.jpg", batch=512,
+                 desc="benches/tower_progressive.jpg x512 (progressive, 10 scans, 4:4:4; the host accumulates the scans "
+                      "and feeds the finished coefficients)"),
     "tiny": dict(width=256, height=144, subsampling=2, seed=77, batch=8, desc="smoke-sized 4:2:0"),
 }
 
@@ -45,10 +50,20 @@ def synth_jpeg(width, height, seed, subsampling=2, quality=90, progressive=False
     return buf.getvalue()
 
 
+def config_jpeg(cfg_name, k=0):
+    """The k-th distinct JPEG of a config: the reference's bench file (same bytes for every k) or a synthetic one."""
+    cfg = CONFIGS[cfg_name]
+    if "file" in cfg:
+        with open(os.path.join(GOLDEN_BENCHES, cfg["file"]), "rb") as f:
+            return f.read()
+    return synth_jpeg(cfg["width"], cfg["height"], cfg["seed"] + k, cfg["subsampling"])
+
+
 class UniqueImage:
     """One entropy-decoded image: geometry + dense coefficients (numpy, host)."""
 
     def __init__(self, jpeg_bytes):
+        from . import Decoder
         dec = Decoder(jpeg_bytes)
         desc = dec.entropy_decode()
         self.width, self.height, self.ncomp = desc.width, desc.height, desc.ncomp
@@ -58,6 +73,7 @@ class UniqueImage:
         self.coefs = [dec.coefficients(desc, i) for i in range(desc.ncomp)]
         self.qts = [dec.qtable(desc, i) for i in range(desc.ncomp)]
         self.jpeg_bytes = len(jpeg_bytes)
+        self.jpeg = jpeg_bytes
         dec.close()
 
     @property
@@ -66,9 +82,9 @@ class UniqueImage:
 
 
 def build_unique(cfg_name, n_unique, first_index=0):
-    cfg = CONFIGS[cfg_name]
-    return [UniqueImage(synth_jpeg(cfg["width"], cfg["height"], cfg["seed"] + first_index + k, cfg["subsampling"]))
-            for k in range(n_unique)]
+    if "file" in CONFIGS[cfg_name]:
+        n_unique = 1
+    return [UniqueImage(config_jpeg(cfg_name, first_index + k)) for k in range(n_unique)]
 
 
 def shard_range(n_items, rank, world_size):

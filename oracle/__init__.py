@@ -14,7 +14,7 @@ import numpy as np
 _DIR = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_DIR, "liboracle.so")
 
-ARITH_SCALAR, ARITH_SSSE3 = 0, 1
+ARITH_SCALAR, ARITH_SSSE3, ARITH_SSSE3_NATIVE = 0, 1, 2
 CT_NONE, CT_UNKNOWN, CT_GRAYSCALE, CT_RGB, CT_YCBCR, CT_CMYK, CT_YCCK, CT_JCS_BG_YCC, CT_JCS_BG_RGB = range(9)
 OK, ERR_FORMAT, ERR_UNSUPPORTED, ERR_IO, ERR_INTERNAL = range(5)
 
@@ -75,6 +75,12 @@ def lib():
                                     C.c_uint16, C.c_uint16, C.c_int, C.c_void_p, C.c_size_t]
     L.orc_hotpath_batch.argtypes = [C.c_int, C.c_int, C.c_size_t, C.POINTER(Component), C.c_int, C.POINTER(C.c_void_p),
                                     C.POINTER(C.c_void_p), C.c_uint16, C.c_uint16, C.c_int, C.POINTER(C.c_void_p), C.c_size_t]
+    L.orc_hotpath_image_mt.argtypes = [C.c_int, C.c_int, C.POINTER(Component), C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                       C.c_uint16, C.c_uint16, C.c_int, C.c_void_p, C.c_size_t]
+    L.orc_decoder_set_threads.argtypes = [C.c_void_p, C.c_int]
+    L.orc_decoder_set_threads.restype = None
+    L.orc_decoder_set_taps.argtypes = [C.c_void_p, C.c_int]
+    L.orc_decoder_set_taps.restype = None
     L.orc_decoder_new.restype = C.c_void_p
     L.orc_decoder_new.argtypes = [C.c_void_p, C.c_size_t, C.c_int]
     L.orc_decoder_free.argtypes = [C.c_void_p]
@@ -210,7 +216,7 @@ def compute_image(components, planes, out_w, out_h, color_transform, arith=ARITH
     return out[:ol.value]
 
 
-def hotpath_image(components, qts, coefs, out_w, out_h, color_transform, arith=ARITH_SCALAR):
+def hotpath_image(components, qts, coefs, out_w, out_h, color_transform, arith=ARITH_SCALAR, nthreads=1):
     n = len(components)
     qs = [np.ascontiguousarray(q, dtype=np.uint16).reshape(64) for q in qts]
     cs = [np.ascontiguousarray(c, dtype=np.int16).reshape(-1) for c in coefs]
@@ -218,7 +224,7 @@ def hotpath_image(components, qts, coefs, out_w, out_h, color_transform, arith=A
     cp = (C.c_void_p * 4)(*([c.ctypes.data for c in cs] + [None] * (4 - n)))
     cap = int(out_w) * int(out_h) * n
     out = np.zeros(cap, dtype=np.uint8)
-    rc = lib().orc_hotpath_image(arith, components, n, qp, cp, out_w, out_h, color_transform, _ptr(out), cap)
+    rc = lib().orc_hotpath_image_mt(arith, nthreads, components, n, qp, cp, out_w, out_h, color_transform, _ptr(out), cap)
     if rc:
         raise OracleError(rc, lib().orc_last_error().decode())
     return out if n > 1 else out[:components[0].size_w * components[0].size_h]
@@ -256,6 +262,13 @@ class Decoder:
 
     def set_color_transform(self, ct):
         lib().orc_decoder_set_color_transform(self._d, ct)
+
+    def set_threads(self, n):
+        """compute_image rows over n threads (the rayon build's colour stage); default 1"""
+        lib().orc_decoder_set_threads(self._d, n)
+
+    def set_taps(self, on):
+        lib().orc_decoder_set_taps(self._d, int(bool(on)))
 
     def set_max_decoding_buffer_size(self, n):
         lib().orc_decoder_set_max_decoding_buffer_size(self._d, n)

@@ -27,7 +27,11 @@ extern "C" {
 /* Arithmetic variants of the reference hot path. */
 enum {
     ORC_ARITH_SCALAR = 0, /* src/idct.rs:260-370 + src/decoder.rs:1486-1508 (feature platform_independent) */
-    ORC_ARITH_SSSE3 = 1   /* src/arch/ssse3.rs (x86 default build) */
+    ORC_ARITH_SSSE3 = 1,  /* src/arch/ssse3.rs (x86 default build), portable lane-by-lane emulation */
+    ORC_ARITH_SSSE3_NATIVE = 2 /* the same arithmetic through <tmmintrin.h>, i.e. the instructions an x86-64 build
+                                  of the reference executes (src/arch/mod.rs:13-57 selects them at run time);
+                                  identical bytes to ORC_ARITH_SSSE3 (tests/test_oracle_kat.py); the timed CPU
+                                  baseline.  Falls back to the emulation when built without -mssse3. */
 };
 
 /* src/decoder.rs:79-98, same order as the Rust enum */
@@ -96,6 +100,16 @@ const char *orc_last_error(void);
 int orc_hotpath_image(int arith, const orc_component *comps, int ncomp, const uint16_t *const qts[4],
                       const int16_t *const coefs[4], uint16_t out_w, uint16_t out_h, int color_transform,
                       uint8_t *out, size_t cap);
+/* Single-image latency shape of the reference's rayon build: IDCT inline on the calling thread
+ * (src/worker/rayon.rs:121-132), then the output rows split over nthreads threads (one rayon task per
+ * row, src/worker/rayon.rs:204-216). */
+int orc_hotpath_image_mt(int arith, int nthreads, const orc_component *comps, int ncomp,
+                         const uint16_t *const qts[4], const int16_t *const coefs[4], uint16_t out_w,
+                         uint16_t out_h, int color_transform, uint8_t *out, size_t cap);
+/* compute_image with the rows split over nthreads threads (compute_image_parallel, src/worker/rayon.rs:193-219) */
+int orc_compute_image_mt(int arith, int nthreads, const orc_component *comps, int ncomp,
+                         const uint8_t *const *planes, const size_t *plane_len, uint16_t out_w, uint16_t out_h,
+                         int color_transform, uint8_t *out, size_t cap, size_t *out_len);
 /* n images with identical geometry spread over nthreads pthreads (one image per thread at a
  * time: what an outer par_iter over Decoder::decode gives the reference). */
 int orc_hotpath_batch(int arith, int nthreads, size_t n, const orc_component *comps, int ncomp,
@@ -115,6 +129,10 @@ orc_decoder *orc_decoder_new(const uint8_t *data, size_t len, int arith);
 void orc_decoder_free(orc_decoder *d);
 void orc_decoder_set_color_transform(orc_decoder *d, int ct);
 void orc_decoder_set_max_decoding_buffer_size(orc_decoder *d, size_t max);
+/* threads compute_image may use (default 1; > 1 = the rayon build's row-parallel colour stage) */
+void orc_decoder_set_threads(orc_decoder *d, int nthreads);
+/* test taps (coefficient / plane copies kept for orc_decoder_coefficients / _plane): on by default, off when timing */
+void orc_decoder_set_taps(orc_decoder *d, int on);
 int orc_decoder_read_info(orc_decoder *d);
 int orc_decoder_info(const orc_decoder *d, orc_image_info *info); /* 1 if available */
 int orc_decoder_scale(orc_decoder *d, uint16_t req_w, uint16_t req_h, uint16_t *w, uint16_t *h);

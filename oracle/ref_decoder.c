@@ -128,6 +128,8 @@ struct orc_decoder {
     const uint8_t *data;
     size_t len, pos;
     int arith;
+    int nthreads; /* compute_image: rows split over this many threads (rayon build), default 1 */
+    int no_taps;  /* skip the test taps (copies of the planes) */
 
     int has_frame;
     frame_info frame;
@@ -798,6 +800,7 @@ static int decode_block_sa(orc_decoder *d, int16_t *coefficients, const huff_tab
 
 /* ---- test tap ------------------------------------------------------------------------------ */
 static void tap_append(orc_decoder *d, int frame_comp, const int16_t *row, size_t n) {
+    if (d->no_taps) return;
     size_t need = d->tap_len[frame_comp] + n;
     if (need > d->tap_cap[frame_comp]) {
         size_t cap = d->tap_cap[frame_comp] ? d->tap_cap[frame_comp] * 2 : 4096;
@@ -1048,13 +1051,13 @@ static int decode_planes(orc_decoder *d, orc_worker *worker) {
         free(d->tap_plane[i]);
         d->tap_plane[i] = NULL;
         d->tap_plane_len[i] = d->plane_len[i];
-        if (d->planes[i]) {
+        if (d->planes[i] && !d->no_taps) {
             d->tap_plane[i] = (uint8_t *)malloc(d->plane_len[i] ? d->plane_len[i] : 1);
             memcpy(d->tap_plane[i], d->planes[i], d->plane_len[i]);
         }
     }
-    int rc = orc_compute_image(d->arith, frame->comps, frame->ncomp, (const uint8_t *const *)d->planes, d->plane_len,
-                               frame->output_w, frame->output_h, d->final_ct, d->pixels, need, &d->pixels_len);
+    int rc = orc_compute_image_mt(d->arith, d->nthreads, frame->comps, frame->ncomp, (const uint8_t *const *)d->planes,
+                                  d->plane_len, frame->output_w, frame->output_h, d->final_ct, d->pixels, need, &d->pixels_len);
     if (rc) FAIL(d, rc, "%s", orc_last_error());
     return ORC_OK;
 }
@@ -1257,6 +1260,8 @@ void orc_decoder_set_color_transform(orc_decoder *d, int ct) {
     d->color_transform = ct;
 }
 void orc_decoder_set_max_decoding_buffer_size(orc_decoder *d, size_t max) { d->buffer_limit = max; }
+void orc_decoder_set_threads(orc_decoder *d, int nthreads) { d->nthreads = nthreads; }
+void orc_decoder_set_taps(orc_decoder *d, int on) { d->no_taps = !on; }
 int orc_decoder_read_info(orc_decoder *d) { return decode_internal(d, 1); }
 /* src/decoder.rs:171-194 */
 int orc_decoder_info(const orc_decoder *d, orc_image_info *info) {

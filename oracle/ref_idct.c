@@ -337,7 +337,9 @@ void orc_idct_block(int arith, int scale, const int16_t c[64], const uint16_t q[
                     uint8_t *out) {
     switch (scale) {
     case 8:
-        if (arith == ORC_ARITH_SSSE3)
+        if (arith == ORC_ARITH_SSSE3_NATIVE && orc_idct8x8_ssse3_intrin(c, q, stride, out))
+            break;
+        if (arith == ORC_ARITH_SSSE3 || arith == ORC_ARITH_SSSE3_NATIVE)
             idct8x8_ssse3_emul(c, q, stride, out);
         else
             idct8x8_scalar(c, q, stride, out);

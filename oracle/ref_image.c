@@ -357,7 +357,10 @@ static int color_convert(int arith, int cc, int ncomp, uint8_t *const lb[4], siz
         return ORC_OK;
     case CC_YCBCR: { /* src/decoder.rs:1406-1437 */
         size_t done = 0;
-        if (arith == ORC_ARITH_SSSE3) done = ycbcr_line_ssse3_emul(lb[0], lb[1], lb[2], out, w);
+        if (arith == ORC_ARITH_SSSE3_NATIVE && orc_ycbcr_line_ssse3_intrin(lb[0], lb[1], lb[2], out, w, &done)) {
+        } else if (arith == ORC_ARITH_SSSE3 || arith == ORC_ARITH_SSSE3_NATIVE) {
+            done = ycbcr_line_ssse3_emul(lb[0], lb[1], lb[2], out, w);
+        }
         for (size_t i = done; i < n; i++) ycbcr_to_rgb(lb[0][i], lb[1][i], lb[2][i], out + 3 * i);
         return ORC_OK;
     }
@@ -461,14 +464,63 @@ int orc_compute_image(int arith, const orc_component *comps, int ncomp, const ui
     return rc;
 }
 
+/* compute_image_parallel, src/worker/rayon.rs:193-219: the reference spawns one rayon task per output row; here
+ * the rows are dealt to nthreads pthreads in interleaved order (same work, same per-row scratch). */
+typedef struct {
+    const assembler *a;
+    const uint8_t *const *planes;
+    size_t out_w, out_h, line, first, step;
+    uint8_t *out;
+    int rc;
+} rows_job;
+
+static void *rows_main(void *p) {
+    rows_job *j = (rows_job *)p;
+    uint8_t *scratch = (uint8_t *)malloc(j->a->up.line_buffer_size * (size_t)j->a->ncomp + 64);
+    for (size_t row = j->first; row < j->out_h && !j->rc; row += j->step)
+        j->rc = assemble_row(j->a, j->planes, row, j->out_w, scratch, j->out + row * j->line);
+    free(scratch);
+    return NULL;
+}
+
+int orc_compute_image_mt(int arith, int nthreads, const orc_component *comps, int ncomp,
+                         const uint8_t *const *planes, const size_t *plane_len, uint16_t out_w, uint16_t out_h,
+                         int color_transform, uint8_t *out, size_t cap, size_t *out_len) {
+    if (nthreads <= 1 || ncomp <= 1)
+        return orc_compute_image(arith, comps, ncomp, planes, plane_len, out_w, out_h, color_transform, out, cap, out_len);
+    for (int i = 0; i < ncomp; i++)
+        if (!planes[i] || plane_len[i] == 0) return fail(ORC_ERR_FORMAT, "not all components have data");
+    assembler a;
+    int rc = assembler_init(&a, arith, comps, ncomp, out_w, out_h, color_transform);
+    if (rc) return rc;
+    size_t line = (size_t)out_w * ncomp;
+    if (cap < line * out_h) return fail(ORC_ERR_INTERNAL, "output buffer too small");
+    if (nthreads > (int)out_h) nthreads = out_h;
+    rows_job *jobs = (rows_job *)calloc((size_t)nthreads, sizeof *jobs);
+    pthread_t *th = (pthread_t *)calloc((size_t)nthreads, sizeof *th);
+    for (int t = 0; t < nthreads; t++) {
+        rows_job j = {&a, planes, out_w, out_h, line, (size_t)t, (size_t)nthreads, out, 0};
+        jobs[t] = j;
+        pthread_create(&th[t], NULL, rows_main, &jobs[t]);
+    }
+    for (int t = 0; t < nthreads; t++) {
+        pthread_join(th[t], NULL);
+        if (jobs[t].rc) rc = jobs[t].rc;
+    }
+    free(jobs);
+    free(th);
+    if (out_len) *out_len = line * out_h;
+    return rc;
+}
+
 /* ---------------------------------------------------------------------------------------------
  * Whole hot path for one image from dense coefficients: what decode_scan + decode_planes push
  * through the worker boundary for a baseline interleaved image (src/decoder.rs:848-861, 1058,
  * 1068-1078, 689-694).
  * ------------------------------------------------------------------------------------------ */
-int orc_hotpath_image(int arith, const orc_component *comps, int ncomp, const uint16_t *const qts[4],
-                      const int16_t *const coefs[4], uint16_t out_w, uint16_t out_h, int color_transform,
-                      uint8_t *out, size_t cap) {
+int orc_hotpath_image_mt(int arith, int nthreads, const orc_component *comps, int ncomp,
+                         const uint16_t *const qts[4], const int16_t *const coefs[4], uint16_t out_w,
+                         uint16_t out_h, int color_transform, uint8_t *out, size_t cap) {
     orc_worker *w = orc_worker_new(arith);
     uint8_t *planes[4] = {0, 0, 0, 0};
     size_t lens[4] = {0, 0, 0, 0};
@@ -481,11 +533,17 @@ int orc_hotpath_image(int arith, const orc_component *comps, int ncomp, const ui
     }
     for (int i = 0; i < ncomp && !rc; i++) rc = orc_worker_get_result(w, i, &planes[i], &lens[i]);
     if (!rc)
-        rc = orc_compute_image(arith, comps, ncomp, (const uint8_t *const *)planes, lens, out_w, out_h,
-                               color_transform, out, cap, NULL);
+        rc = orc_compute_image_mt(arith, nthreads, comps, ncomp, (const uint8_t *const *)planes, lens, out_w, out_h,
+                                  color_transform, out, cap, NULL);
     for (int i = 0; i < 4; i++) free(planes[i]);
     orc_worker_free(w);
     return rc;
+}
+
+int orc_hotpath_image(int arith, const orc_component *comps, int ncomp, const uint16_t *const qts[4],
+                      const int16_t *const coefs[4], uint16_t out_w, uint16_t out_h, int color_transform,
+                      uint8_t *out, size_t cap) {
+    return orc_hotpath_image_mt(arith, 1, comps, ncomp, qts, coefs, out_w, out_h, color_transform, out, cap);
 }
 
 typedef struct {

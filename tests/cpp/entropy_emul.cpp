@@ -182,7 +182,7 @@ static void emulate_interval(const std::vector<uint8_t>& payload, const EntImage
             if (im.tight_end && e.p + 7 < im.scan_bits) bad |= ENT_BAD_TAIL;
         }
         else if (last) bad |= ENT_INCOMPLETE;
-        else if (ent_pack(e) != state[i]) bad |= ENT_BAD_CHAIN;
+        else if (ent_pack(e) != state[i] || sink.vi - first_val[i] != nvals[i]) bad |= ENT_BAD_CHAIN;
         r.status |= bad;
     }
     if (!completed) r.status |= ENT_INCOMPLETE;

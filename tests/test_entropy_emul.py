@@ -145,3 +145,24 @@ def test_eligibility_edges(emul, tmp_path):
         out = run(emul, [str(p)])
         line = out.strip().splitlines()[0]
         assert want in line, (name, line)
+
+
+@pytest.mark.parametrize("passes", [0, 1, 2])
+def test_exhausted_sync_budget_is_flagged_not_misdecoded(emul, tmp_path, passes):
+    """When the synchronisation passes run out of budget with a change still pending, a successor's state and value
+    count date from its predecessor's OLD state.  The write pass re-decodes from the new one: it usually ends in the same
+    state (codes self-synchronise) with a DIFFERENT value count -- which would shift every later value offset.  The
+    chain check therefore compares the count as well (ke_entropy.cu); the emulator mirrors it.  Property: with any
+    budget, accepted => identical to the host decoder (the emulator's own check), and at least the big scan is not
+    accepted with a budget this small."""
+    from jpeg_decoder_b200 import workload
+    files = []
+    for k, (w, h, ss) in enumerate([(1920, 1080, 2), (640, 480, 0), (333, 217, 1)]):
+        p = tmp_path / ("b%d.jpg" % k)
+        p.write_bytes(workload.synth_jpeg(w, h, seed=40 + k, subsampling=ss))
+        files.append(str(p))
+    for order in ([], ["--descending"]):
+        text = run(emul, order + ["--passes", str(passes)] + files)   # rc 0 = nothing accepted that differs from the host
+        first = [l for l in text.splitlines() if l.split(":")[0].endswith("b0.jpg")][0]
+        if passes == 0:
+            assert "flagged" in first, first

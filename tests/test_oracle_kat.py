@@ -97,8 +97,8 @@ def test_kernel_constants_match_f32_evaluation():
     stbi_f2f(x) = (x * 4096 + 0.5) as i32 (src/idct.rs:572-574) and (x * 2^20 + 0.5) as i32 (src/decoder.rs:1502-1504)."""
     import os
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    k1 = open(os.path.join(root, "jpeg_decoder_b200", "csrc", "k1_idct.cu")).read()
-    k2 = open(os.path.join(root, "jpeg_decoder_b200", "csrc", "k2_color.cu")).read()
+    k1 = open(os.path.join(root, "jpeg_decoder_b200", "csrc", "idct_core.cuh")).read()   # shared by K1 and the fused kernel
+    k2 = open(os.path.join(root, "jpeg_decoder_b200", "csrc", "color_core.cuh")).read()  # shared by K2 and the fused kernel
 
     def f2f(x, bits):
         return int(np.float32(x) * np.float32(2 ** bits) + np.float32(0.5))
@@ -115,3 +115,44 @@ def test_kernel_constants_match_f32_evaluation():
     for name, v in want2.items():
         m = re.search(r"#define %s (-?\d+)" % name, k2)
         assert m and int(m.group(1)) == v, (name, v)
+
+
+def test_direct_form_pass_is_the_butterfly_mod_2_32():
+    """idct_core.cuh evaluates the 1-D pass of src/idct.rs:378-447 in "direct form" (IDCT_1D_DIRECT: the odd half as a
+    4x4 constant matrix seeded with the even half).  Everything between two shifts is Wrapping<i32>, so the regrouping
+    must be an identity over Z/2^32: checked here on the CPU with exact integers, extremes included."""
+    M = 1 << 32
+    A, B, Cc, D = 2217, -7567, 3135, 4816
+    E1, E2, E3, E4 = -3685, -10497, -8034, -1597
+    G1, G3, G5, G7 = 6149, 12586, 8410, 1223
+
+    def butterfly(s, xs):   # the reference's order of operations
+        s0, s1, s2, s3, s4, s5, s6, s7 = s
+        p1 = (s2 + s6) * A
+        e2, e3 = p1 + s6 * B, p1 + s2 * Cc
+        e0, e1 = ((s0 + s4) << 12) + xs, ((s0 - s4) << 12) + xs
+        x0, x3, x1, x2 = e0 + e3, e0 - e3, e1 + e2, e1 - e2
+        q3, q4, q1, q2 = s7 + s3, s5 + s1, s7 + s1, s5 + s3
+        p5 = (q3 + q4) * D
+        q1, q2, q3, q4 = p5 + q1 * E1, p5 + q2 * E2, q3 * E3, q4 * E4
+        t3, t2, t1, t0 = s1 * G1 + q1 + q4, s3 * G3 + q2 + q3, s5 * G5 + q2 + q4, s7 * G7 + q1 + q3
+        return [v % M for v in (x0 + t3, x1 + t2, x2 + t1, x3 + t0, x3 - t0, x2 - t1, x1 - t2, x0 - t3)]
+
+    def direct(s, xs):      # IDCT_1D_DIRECT, every intermediate reduced mod 2^32 like the GPU's registers
+        s0, s1, s2, s3, s4, s5, s6, s7 = s
+        e3 = (s2 * ((A + Cc) % M) + s6 * (A % M)) % M
+        e2 = (s2 * (A % M) + s6 * ((A + B) % M)) % M
+        e0, e1 = ((((s0 + s4) % M) << 12) + xs) % M, ((((s0 - s4) % M) << 12) + xs) % M
+        x0, x3, x1, x2 = (e0 + e3) % M, (e0 - e3) % M, (e1 + e2) % M, (e1 - e2) % M
+        o0 = (x0 + s1 * ((G1 + D + E1 + E4) % M) + s3 * (D % M) + s5 * ((D + E4) % M) + s7 * ((D + E1) % M)) % M
+        o1 = (x1 + s1 * (D % M) + s3 * ((G3 + D + E2 + E3) % M) + s5 * ((D + E2) % M) + s7 * ((D + E3) % M)) % M
+        o2 = (x2 + s1 * ((D + E4) % M) + s3 * ((D + E2) % M) + s5 * ((G5 + D + E2 + E4) % M) + s7 * (D % M)) % M
+        o3 = (x3 + s1 * ((D + E1) % M) + s3 * ((D + E3) % M) + s5 * (D % M) + s7 * ((G7 + D + E1 + E3) % M)) % M
+        return [o0, o1, o2, o3, (2 * x3 - o3) % M, (2 * x2 - o2) % M, (2 * x1 - o1) % M, (2 * x0 - o0) % M]
+
+    rng = np.random.default_rng(42)
+    cases = [list(map(int, rng.integers(0, M, 8))) for _ in range(3000)]
+    cases += [[int(v) % M for v in rng.choice([0, 1, -1, 2 ** 31 - 1, -2 ** 31, 32767 * 65535, -32768 * 65535], 8)] for _ in range(500)]
+    for s in cases:
+        for xs in (512 % M, (512 + 2 ** 31) % M, (65536 + (128 << 17)) % M):
+            assert butterfly(s, xs) == direct(s, xs)
