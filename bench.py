@@ -299,7 +299,7 @@ def cpu_files_throughput(jpegs, width, height, nthreads, target_seconds, arith):
         t0 = time.perf_counter()
         assert all(r == 0 for r in ex.map(one, range(nthreads)))
         pilot = time.perf_counter() - t0
-        n = nthreads * max(1, min(64, int(target_seconds / max(pilot, 1e-3))))
+        n = nthreads * max(1, min(512, int(target_seconds / max(pilot, 1e-3))))
         t0 = time.perf_counter()
         assert all(r == 0 for r in ex.map(one, range(n)))
         dt = time.perf_counter() - t0
@@ -705,7 +705,7 @@ def main():
 
     # ---- e2e: whole files, JPEG bytes in host memory -> RGB in pinned host memory (b200jpg_decode_files) ----
     nthreads = max(1, my_cpus)
-    Bf = 256 if world > 1 else min(2048, max(256, 16 * nthreads))
+    Bf = 256 if world > 1 else 512
     jpegs = [u.jpeg for u in unique[:4]]
     jpeg_bytes = int(np.mean([len(j) for j in jpegs]))
     f_out = torch.empty(Bf * out_per_img, dtype=torch.uint8, pin_memory=True)

@@ -80,6 +80,25 @@ __device__ __forceinline__ void h2v2_16(unsigned a_lo, unsigned a_hi, unsigned a
     }
 }
 
+// H2V1 (4:2:2, src/upsampler.rs:134-163) for 16 output pixels: out[2i] = (3 a[i] + a[i-1] + 2) >> 2,
+// out[2i+1] = (3 a[i] + a[i+1] + 2) >> 2 with clamped ends -- the horizontal half of the triangle filter above, one
+// IDP.4A per sample on byte pairs (a[i-1], a[i]); results CENTRED (minus 128), like h2v2_16.
+// lo / hi = samples i0..i0+3 / i0+4..i0+7, L / R = the clamped halo samples i0-1 / i0+8.
+__device__ __forceinline__ void h2v1_16(unsigned lo, unsigned hi, unsigned L, unsigned R, int (&o)[16]) {
+    // pair j = (a[i0+j-1], a[i0+j]) sits in word w[j] at bytes pos[j], pos[j]+1: only the pairs that straddle a word
+    // need a PRMT, the others are read in place by moving the weights to their byte lanes
+    const unsigned s0 = prmt(L, lo, 0x0040), s1 = prmt(lo, hi, 0x0043), s2 = prmt(hi, R, 0x0043);
+    const unsigned w[9] = {s0, lo, lo, lo, s1, hi, hi, hi, s2};
+    constexpr unsigned pos[9] = {0, 0, 1, 2, 0, 0, 1, 2, 0};
+    constexpr unsigned W_EVEN = 0x0301u, W_ODD = 0x0103u;  // out[2i] = a[i-1] + 3 a[i]; out[2i-1] = 3 a[i-1] + a[i]
+    constexpr unsigned BIAS = 2u - 128u * 4u;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        o[2 * j] = (int)__dp4a(w[j], W_EVEN << (8u * pos[j]), BIAS) >> 2;
+        o[2 * j + 1] = (int)__dp4a(w[j + 1], W_ODD << (8u * pos[j + 1]), BIAS) >> 2;
+    }
+}
+
 __device__ __forceinline__ YccRegs make_ycc_regs(int3 sixteen, bool opaque) {
     YccRegs k;
     k.mul = sixteen.x;

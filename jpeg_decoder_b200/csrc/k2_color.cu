@@ -424,6 +424,98 @@ __global__ void __launch_bounds__(128) k2_ycbcr444(K2Params p, unsigned first, u
 }
 
 // ---------------------------------------------------------------------------------------------
+// 4:2:2 YCbCr (H2V1 chroma, src/upsampler.rs:134-163; the layout of MJPEG / camera files): thread = 16 pixels of one row,
+// 8 chroma samples + the two clamped halo samples per component.  grid.x = ceil(G/128) * height, grid.y = image
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k2_ycbcr422(K2Params p, unsigned first, unsigned gchunks) {
+    const DevImage& img = p.images[first + blockIdx.y];
+    if (img.path != K2_PATH_422) return;
+    const unsigned y = blockIdx.x / gchunks;
+    const unsigned g = (blockIdx.x % gchunks) * 128u + threadIdx.x;
+    const unsigned W = img.width;
+    if (y >= img.height || g * 16u >= W) return;
+    const uint4 yv = load_row16(p.planes + img.c[0].plane_off + (size_t)y * img.c[0].stride, g, img.c[0].stride);
+    const unsigned in_w = img.c[1].in_w, i0 = g * 8u;
+    const unsigned iL = i0 > 0 ? i0 - 1u : 0u, iR = min(i0 + 8u, in_w - 1u);
+    int cb[16], cr[16];
+#pragma unroll
+    for (int c = 1; c <= 2; c++) {
+        const uint8_t* row = p.planes + img.c[c].plane_off + (size_t)y * img.c[c].stride;
+        uint2 v = __ldg(reinterpret_cast<const uint2*>(row + i0));
+        if (i0 + 8u > in_w) v = replicate_last_sample(v, in_w - i0);  // block padding := last valid sample (the edge rule)
+        h2v1_16(v.x, v.y, __ldg(row + iL), __ldg(row + iR), c == 1 ? cb : cr);
+    }
+    ycbcr_store16(yv, cb, cr, p.out + img.out_off + ((size_t)y * W + g * 16u) * 3u, make_ycc_regs(p.sixteen, true), min(16u, W - g * 16u));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Every component at full resolution and nothing to compute but bytes: RGB (src/decoder.rs:1391-1404), CMYK (1458-1474),
+// YCCK (1439-1456), ColorTransform::None (1476-1484).  Thread = 16 pixels of one row: 16-byte loads per component,
+// interleave with PRMT, 16-byte stores.  grid.x = ceil(G/128) * height, grid.y = image
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k2_bytes(K2Params p, unsigned first, unsigned gchunks) {
+    const DevImage& img = p.images[first + blockIdx.y];
+    if (img.path != K2_PATH_BYTES) return;
+    const unsigned y = blockIdx.x / gchunks;
+    const unsigned g = (blockIdx.x % gchunks) * 128u + threadIdx.x;
+    const unsigned W = img.width, n = img.ncomp;
+    if (y >= img.height || g * 16u >= W) return;
+    const unsigned npx = min(16u, W - g * 16u);
+    unsigned v[4][4];
+#pragma unroll
+    for (unsigned k = 0; k < 4; k++) {
+        uint4 t = make_uint4(0u, 0u, 0u, 0u);
+        if (k < n) t = load_row16(p.planes + img.c[k].plane_off + (size_t)y * img.c[k].stride, g, img.c[k].stride);
+        v[k][0] = t.x; v[k][1] = t.y; v[k][2] = t.z; v[k][3] = t.w;
+    }
+    uint8_t* const row = p.out + img.out_off + (size_t)y * W * n;
+    if (img.cc == CC_NOCONVERT) {  // the components side by side inside every row
+        for (unsigned k = 0; k < n; k++) store_words<4>(row + (size_t)k * W + g * 16u, v[k], npx);
+        return;
+    }
+    if (img.cc == CC_RGB) {
+        unsigned ow[12];
+#pragma unroll
+        for (int w = 0; w < 4; w++) {  // R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3
+            const unsigned r = v[0][w], gg = v[1][w], b = v[2][w];
+            ow[3 * w + 0] = prmt(prmt(r, gg, 0x0140), b, 0x2410);
+            ow[3 * w + 1] = prmt(prmt(r, gg, 0x0625), b, 0x2150);
+            ow[3 * w + 2] = prmt(prmt(r, gg, 0x0073), b, 0x7106);
+        }
+        store_words<12>(row + (size_t)g * 48u, ow, 3u * npx);
+        return;
+    }
+    unsigned ow[16];
+    if (img.cc == CC_CMYK) {  // 255 - x on every byte, then C M Y K per pixel
+#pragma unroll
+        for (int w = 0; w < 4; w++) {
+            const unsigned c = ~v[0][w], m = ~v[1][w], yy = ~v[2][w], k = ~v[3][w];
+            const unsigned cm01 = prmt(c, m, 0x5140), cm23 = prmt(c, m, 0x7362), yk01 = prmt(yy, k, 0x5140), yk23 = prmt(yy, k, 0x7362);
+            ow[4 * w + 0] = prmt(cm01, yk01, 0x5410);
+            ow[4 * w + 1] = prmt(cm01, yk01, 0x7632);
+            ow[4 * w + 2] = prmt(cm23, yk23, 0x5410);
+            ow[4 * w + 3] = prmt(cm23, yk23, 0x7632);
+        }
+    } else {  // CC_YCCK: YCbCr -> RGB (always the scalar formula, src/decoder.rs:1447), K inverted
+        const YccRegs ycc = make_ycc_regs(p.sixteen, true);
+#pragma unroll
+        for (int w = 0; w < 4; w++) {
+            const unsigned bw = v[1][w] ^ 0x80808080u, rw = v[2][w] ^ 0x80808080u, kw = ~v[3][w];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int y16 = (int)prmt(v[0][w], 0u, 0x4044u | ((unsigned)q << 8));
+                const int cbm = (int)prmt(bw, 0u, 0x8880u + 0x1111u * (unsigned)q), crm = (int)prmt(rw, 0u, 0x8880u + 0x1111u * (unsigned)q);
+                const int kk = (int)prmt(kw, 0u, 0x4440u | (unsigned)q);
+                int r, gg, b;
+                ycbcr_scalar_y16(y16, cbm, crm, r, gg, b, ycc);
+                ow[4 * w + q] = pack_sat_u8(gg, r, pack_sat_u8(kk, b, 0u));
+            }
+        }
+    }
+    store_words<16>(row + (size_t)g * 64u, ow, 4u * npx);
+}
+
+// ---------------------------------------------------------------------------------------------
 // 1-component images: compact the plane from stride block_w*dct_scale to `width` (src/decoder.rs:1310-1332).
 // Thread = 16 bytes of one row.  grid = (ceil(ceil(W/16)/128), height, images)
 // ---------------------------------------------------------------------------------------------
@@ -486,6 +578,16 @@ cudaError_t launch_k2_444(const K2Params& p, unsigned first, unsigned count, uns
     const unsigned gchunks = ((max_w + 15u) / 16u + 127u) / 128u;
     dim3 grid(gchunks * max_h, count);
     k2_ycbcr444<<<grid, 128, 0, stream>>>(p, first, gchunks);
+    return cudaGetLastError();
+}
+// kernels whose grid is (ceil(G/128) * max_h, images): path selects k2_ycbcr444 / k2_ycbcr422 / k2_bytes
+cudaError_t launch_k2_rows16(unsigned path, const K2Params& p, unsigned first, unsigned count, unsigned max_w, unsigned max_h, cudaStream_t stream) {
+    if (count == 0 || max_w == 0 || max_h == 0) return cudaSuccess;
+    const unsigned gchunks = ((max_w + 15u) / 16u + 127u) / 128u;
+    dim3 grid(gchunks * max_h, count);
+    if (path == K2_PATH_422) k2_ycbcr422<<<grid, 128, 0, stream>>>(p, first, gchunks);
+    else if (path == K2_PATH_BYTES) k2_bytes<<<grid, 128, 0, stream>>>(p, first, gchunks);
+    else k2_ycbcr444<<<grid, 128, 0, stream>>>(p, first, gchunks);
     return cudaGetLastError();
 }
 cudaError_t launch_k2_gray(const K2Params& p, unsigned first, unsigned count, unsigned max_w, unsigned max_h, cudaStream_t stream) {

@@ -62,6 +62,8 @@ cudaError_t launch_k2_420(const K2Params& p, unsigned first, unsigned count, uns
 cudaError_t launch_k2_444(const K2Params& p, unsigned first, unsigned count, unsigned max_w, unsigned max_h,
                           cudaStream_t stream);
 
+cudaError_t launch_k2_rows16(unsigned path, const K2Params& p, unsigned first, unsigned count, unsigned max_w, unsigned max_h,
+                             cudaStream_t stream);
 cudaError_t launch_k2_420_tma(const K2Params& p, const K2Strip* strips, unsigned nstrips, unsigned item_base, unsigned total_items,
                               int num_sms, cudaStream_t stream);
 int k2_mode();

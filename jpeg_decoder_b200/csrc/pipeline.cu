@@ -324,6 +324,16 @@ static int plan_image(const b200jpg_ctx* ctx, const b200jpg_image_desc& d, DevIm
         else if (u[0].kind == UP_H1V1 && u[1].kind == UP_H1V1 && u[2].kind == UP_H1V1 && u[0].stride % 8 == 0 &&
                  u[1].stride % 8 == 0 && u[2].stride % 8 == 0)
             img->path = K2_PATH_444;
+        else if (u[0].kind == UP_H1V1 && u[1].kind == UP_H2V1 && u[2].kind == UP_H2V1 && u[0].stride % 8 == 0 &&
+                 u[1].stride % 8 == 0 && u[2].stride % 8 == 0 && u[1].in_w == u[2].in_w && u[1].in_w == (d.width + 1u) / 2u &&
+                 groups * 16u <= ((u[0].stride + 15u) & ~15u) && groups * 8u <= u[1].stride && groups * 8u <= u[2].stride)
+            img->path = K2_PATH_422;
+    }
+    // every component at full resolution, bytes only: RGB / CMYK / YCCK / None
+    if (ctx->k2_kernel != B200JPG_KERNEL_GENERIC && (img->cc == CC_RGB || img->cc == CC_CMYK || img->cc == CC_YCCK || img->cc == CC_NOCONVERT)) {
+        bool ok = true;
+        for (int i = 0; i < n; i++) ok = ok && img->c[i].kind == UP_H1V1 && img->c[i].stride % 8 == 0 && img->c[i].stride >= d.width;
+        if (ok) img->path = K2_PATH_BYTES;
     }
     return B200JPG_OK;
 }
@@ -751,7 +761,7 @@ int batch_launch(b200jpg_batch* b, const void* d_coefs, void* d_planes, void* d_
                 else if (path == K2_PATH_GENERIC) e = launch_k2_generic(p, first, count, max_w, max_h, stream);
                 else if (path == K2_PATH_420 || path == K2_PATH_420R)
                     e = launch_k2_420(p, first, count, max_w, max_h, path == K2_PATH_420R, stream);
-                else e = launch_k2_444(p, first, count, max_w, max_h, stream);
+                else e = launch_k2_rows16((unsigned)path, p, first, count, max_w, max_h, stream);
                 if (e != cudaSuccess) return cuda_fail(ctx, e, "K2 launch");
                 ctx->launches++;
             }

@@ -81,6 +81,7 @@ private:
     std::vector<Slot> slots_;
     size_t next_ = 0, oldest_ = 0;  // tickets: slot = ticket % nslots
     bool last_device_outs_ = false;
+    bool async_alloc_ = false;  // slot buffers come from the stream-ordered allocator (cudaMallocAsync on s_in_)
     const void* last_coefs_ = nullptr;
     int error_ = B200JPG_OK;
 };
