@@ -222,6 +222,19 @@ B200JPG_API int b200jpg_batch_image_layout(const b200jpg_batch *b, size_t i, siz
  * context's stream (no synchronisation).  stages: bit0 = K1, bit1 = K2. */
 B200JPG_API int b200jpg_batch_run_device(b200jpg_batch *b, const void *d_coefs, void *d_planes, void *d_out,
                                          int stages);
+/* On-device output formats for GPU-side consumers: converts the interleaved RGB8 pixel slab a
+ * device-resident run produced (d_out of b200jpg_batch_run_device, image i at its out_off) into the layout a training
+ * or inference input pipeline wants, image by image at the same relative offsets (out_off for the 8-bit layout,
+ * 4 * out_off bytes for the float layouts).  Float samples are value * scale[c] + bias[c] (NULL = 1 and 0): exact for
+ * scale 1 / bias 0, otherwise one fp32 FMA per sample.  Only 3-component images; others are skipped (status ERR_FORMAT
+ * in statuses[i] when given).  Enqueued on the context's stream, no synchronisation. */
+enum {
+    B200JPG_FMT_RGB8_PLANAR = 1,  /* CHW uint8: three W*H planes per image  */
+    B200JPG_FMT_RGB_F32_NHWC = 2, /* HWC float32 (interleaved)              */
+    B200JPG_FMT_RGB_F32_NCHW = 3  /* CHW float32: three W*H planes per image */
+};
+B200JPG_API int b200jpg_batch_format_device(b200jpg_batch *b, const void *d_out, int format, void *d_dst, const float scale[3],
+                                            const float bias[3], int *statuses);
 /* Host-to-host run: the coefficients named in the descs -> pixels in outs[i] (out_caps[i] bytes).  Either the
  * dense buffers are uploaded as they are (H2D, K1, K2, D2H, chunked and double-buffered over two streams through
  * internal device slabs), or -- b200jpg_options.host_compact -- host threads first compact them into sparse block

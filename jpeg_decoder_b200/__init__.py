@@ -16,7 +16,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._native import (ARITH_SCALAR, ARITH_SSSE3, FUSE_AUTO, FUSE_OFF, FUSE_ON, ENTROPY_AUTO, ENTROPY_DEVICE, ENTROPY_HOST, COMPACT_AUTO, COMPACT_OFF, COMPACT_ON, CP_DCT_PROGRESSIVE, CP_DCT_SEQUENTIAL, CP_LOSSLESS, CT_CMYK,
+from ._native import (ARITH_SCALAR, ARITH_SSSE3, FUSE_AUTO, FUSE_OFF, FUSE_ON, FMT_RGB8_PLANAR, FMT_RGB_F32_NHWC, FMT_RGB_F32_NCHW, ENTROPY_AUTO, ENTROPY_DEVICE, ENTROPY_HOST, COMPACT_AUTO, COMPACT_OFF, COMPACT_ON, CP_DCT_PROGRESSIVE, CP_DCT_SEQUENTIAL, CP_LOSSLESS, CT_CMYK,
                       CT_GRAYSCALE, CT_JCS_BG_RGB, CT_JCS_BG_YCC, CT_NONE, CT_RGB, CT_UNKNOWN, CT_YCBCR, CT_YCCK,
                       ERR_FORMAT, ERR_INTERNAL, ERR_IO, ERR_UNSUPPORTED, KERNEL_AUTO, KERNEL_FAST, KERNEL_GENERIC, OK,
                       PF_CMYK32, PF_L8, PF_L16, PF_RGB24, SBS_INTERLEAVED, SBS_NATURAL, SBS_PLANAR, BatchInfo, Component, FileJob, ImageDesc,
@@ -212,6 +212,14 @@ class Batch:
     def run_device(self, d_coefs, d_planes, d_out, stages=3):
         """Enqueue K1 (bit 0) and/or K2 (bit 1) on the context's stream; raw device addresses."""
         self.ctx.check(lib().b200jpg_batch_run_device(self._h, d_coefs, d_planes, d_out, stages))
+
+    def format_device(self, d_out, fmt, d_dst, scale=None, bias=None):
+        """b200jpg_batch_format_device: interleaved RGB8 slab -> planar u8 / float NHWC / float NCHW (device pointers)."""
+        sc = (C.c_float * 3)(*scale) if scale is not None else None
+        bi = (C.c_float * 3)(*bias) if bias is not None else None
+        st = (C.c_int * self.n)()
+        self.ctx.check(lib().b200jpg_batch_format_device(self._h, d_out, fmt, d_dst, sc, bi, st))
+        return list(st)
 
     def run_host(self, outs):
         """Host coefficients (from the descs) -> host pixels in `outs` (list of uint8 arrays or raw addresses)."""

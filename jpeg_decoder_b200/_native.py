@@ -57,6 +57,7 @@ SBS_PLANAR, SBS_INTERLEAVED, SBS_NATURAL = 0, 1, 2
 COMPACT_AUTO, COMPACT_OFF, COMPACT_ON = 0, 1, 2
 ENTROPY_AUTO, ENTROPY_HOST, ENTROPY_DEVICE = 0, 1, 2
 FUSE_AUTO, FUSE_OFF, FUSE_ON = 0, 1, 2
+FMT_RGB8_PLANAR, FMT_RGB_F32_NHWC, FMT_RGB_F32_NCHW = 1, 2, 3
 
 # every symbol include/b200jpg.h declares (tests/test_abi.py checks the two lists agree)
 EXPORTS = {
@@ -89,6 +90,7 @@ EXPORTS = {
     "b200jpg_batch_image_layout": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t),
                                              C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "b200jpg_batch_run_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "b200jpg_batch_format_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "b200jpg_batch_run_host": (C.c_int, [C.c_void_p, C.POINTER(ImageDesc), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
                                          C.POINTER(C.c_int)]),
     "b200jpg_decode_batch": (C.c_int, [C.c_void_p, C.POINTER(ImageDesc), C.c_size_t, C.POINTER(C.c_void_p),

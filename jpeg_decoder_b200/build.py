@@ -28,12 +28,17 @@ def up_to_date():
     return all(os.path.getmtime(d) <= t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and up_to_date():
+def build(force=False, verbose=False, out=None, defines=()):
+    """out / defines: an experiment build beside the product library (scripts/, profiling only), e.g.
+    build(out="libb200jpg_sub512.so", defines=["B200JPG_ENT_SUB_BITS=512"]); selected at run time with B200JPG_SO."""
+    if out is None and os.environ.get("B200JPG_SO"):   # a prebuilt experiment library (never built implicitly)
+        return os.path.join(HERE, os.environ["B200JPG_SO"])
+    target = os.path.join(HERE, out) if out else SO
+    if out is None and not force and up_to_date():
         return SO
-    cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [nvcc()] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", target] + [os.path.join(CSRC, s) for s in SOURCES]
     subprocess.check_call(cmd)
-    return SO
+    return target
 
 
 if __name__ == "__main__":

@@ -125,10 +125,28 @@ __device__ __forceinline__ void store_words(uint8_t* dst, const unsigned (&ow)[N
     }
 }
 
+// The SSSE3 colour path (src/arch/ssse3.rs:208-244) from a luma byte and CENTRED chroma.  Its saturating adds can never
+// saturate for 8-bit inputs -- |cb6|, |cr6| <= 8192, so |cr_140200| <= 11486, |cb_177200| <= 14517,
+// |cb_034414 + cr_071414| <= 8671 and 32 <= y6 <= 16352: every sum stays inside int16 -- so plain adds are exact
+// (checked exhaustively over all 2^24 inputs in tests/test_oracle_kat.py).  mulhrs(a, c) == (a * c + 2^14) >> 15.
+__device__ __forceinline__ void ycbcr_ssse3_centred(int y, int cbm, int crm, int& r, int& g, int& b) {
+    const int y6 = y * 64 + 32, cb6 = cbm * 64, cr6 = crm * 64;
+    const int cr_140200 = ((cr6 * 13173 + 16384) >> 15) + cr6;
+    const int cb_034414 = (cb6 * 11276 + 16384) >> 15;
+    const int cr_071414 = (cr6 * 23401 + 16384) >> 15;
+    const int cb_177200 = ((cb6 * 25297 + 16384) >> 15) + cb6;
+    r = (y6 + cr_140200) >> 6;
+    g = (y6 - (cb_034414 + cr_071414)) >> 6;
+    b = (y6 + cb_177200) >> 6;
+}
+
 // 16 pixels: luma bytes in yv (4 words), CENTRED chroma (cb - 128, cr - 128) -> 48 output bytes at dst.
 // npx = number of valid pixels of this 16-pixel group (16 except for the last group of a ragged row)
+// SSSE3 = the x86 build's arithmetic: the first nss pixels of the group (0, 8 or 16: the SIMD loop covers
+// (W / 8 - 1) * 8 pixels of a row, src/arch/ssse3.rs:206) take the SSSE3 formula, the rest the scalar one.
+template <bool SSSE3 = false>
 __device__ __forceinline__ void ycbcr_store16(const uint4 yv, const int* cb, const int* cr, uint8_t* dst, const YccRegs& sixteen,
-                                              unsigned npx) {
+                                              unsigned npx, unsigned nss = 0) {
     const unsigned yw[4] = {yv.x, yv.y, yv.z, yv.w};
     unsigned ow[12];
 #pragma unroll
@@ -136,6 +154,10 @@ __device__ __forceinline__ void ycbcr_store16(const uint4 yv, const int* cb, con
         int r[4], g[4], b[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
+            if (SSSE3 && 4u * (unsigned)w < nss) {
+                ycbcr_ssse3_centred((int)prmt(yw[w], 0u, 0x4440u | (unsigned)k), cb[4 * w + k], cr[4 * w + k], r[k], g[k], b[k]);
+                continue;
+            }
             // one PRMT puts luma byte k at bits 16..23 (y << 16); the << 4 folds into the IMADs below
             const int y16 = (int)prmt(yw[w], 0u, 0x4044u | ((unsigned)k << 8));
             ycbcr_scalar_y16(y16, cb[4 * w + k], cr[4 * w + k], r[k], g[k], b[k], sixteen);

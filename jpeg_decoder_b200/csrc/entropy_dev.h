@@ -36,7 +36,10 @@
 
 namespace b200jpg {
 
-constexpr unsigned ENT_SUB_BITS = 1024;            // one thread's share of the scan
+#ifndef B200JPG_ENT_SUB_BITS
+#define B200JPG_ENT_SUB_BITS 1024
+#endif
+constexpr unsigned ENT_SUB_BITS = B200JPG_ENT_SUB_BITS;  // one thread's share of the scan (a build-time knob: profiles/r02_entropy_subbits.md)
 constexpr unsigned ENT_LUT_BITS = 9;               // code words up to this length resolve with one table probe
 constexpr unsigned ENT_SUB_LUT_BITS = 16 - ENT_LUT_BITS;  // longer ones with a second probe, indexed by the remaining bits
 constexpr unsigned ENT_MAX_SUBTABLES = 12;         // ENT_LUT_BITS-bit prefixes that continue into longer code words, per table

@@ -257,4 +257,143 @@ __device__ __forceinline__ void idct8x8_direct(unsigned (&s)[8][8], uint2 (&rows
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Scaled IDCT (Decoder::scale, src/idct.rs:456-565) on a block held as eight 16-byte rows: only the low-frequency
+// corner is read, everything stays in registers.  coefficient (r, c) = half (c & 1) of word c / 2 of raw[r].
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned raw_coef(const uint4& row, int c) {
+    const unsigned w = c < 2 ? row.x : (c < 4 ? row.y : (c < 6 ? row.z : row.w));
+    return (c & 1) ? sext_hi(w) : sext_lo(w);
+}
+// src/idct.rs:456-517; q = the table as u32[64]
+__device__ __forceinline__ void idct4x4_regs(const uint4 (&raw)[8], const unsigned* __restrict__ q, uint8_t* dst, unsigned stride) {
+    unsigned temp[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const unsigned s0 = raw_coef(raw[0], i) * __ldg(q + i), s1 = raw_coef(raw[1], i) * __ldg(q + i + 8);
+        const unsigned s2 = raw_coef(raw[2], i) * __ldg(q + i + 16), s3 = raw_coef(raw[3], i) * __ldg(q + i + 24);
+        const unsigned x0 = (s0 + s2) << 2, x2 = (s0 - s2) << 2;
+        const unsigned p1 = (s1 + s3) * F2F_0_5411961;
+        const unsigned t0 = (unsigned)sar(p1 + s3 * F2F_N1_847759065 + 512u, 10);
+        const unsigned t2 = (unsigned)sar(p1 + s1 * F2F_0_765366865 + 512u, 10);
+        temp[0][i] = x0 + t2;
+        temp[3][i] = x0 - t2;
+        temp[1][i] = x2 + t0;
+        temp[2][i] = x2 - t0;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const unsigned s0 = temp[i][0], s1 = temp[i][1], s2 = temp[i][2], s3 = temp[i][3];
+        const unsigned x0 = ((s0 + s2) << 12) + (1u << 16) + (128u << 17);
+        const unsigned x2 = ((s0 - s2) << 12) + (1u << 16) + (128u << 17);
+        const unsigned p1 = (s1 + s3) * F2F_0_5411961;
+        const unsigned t0 = p1 + s3 * F2F_N1_847759065;
+        const unsigned t2 = p1 + s1 * F2F_0_765366865;
+        *reinterpret_cast<unsigned*>(dst + (size_t)i * stride) = pack4_sat_u8(sar(x0 + t2, 17), sar(x2 + t0, 17), sar(x2 - t0, 17), sar(x0 - t2, 17));
+    }
+}
+// src/idct.rs:519-553
+__device__ __forceinline__ void idct2x2_regs(const uint4 (&raw)[8], const unsigned* __restrict__ q, uint8_t* dst, unsigned stride) {
+    const unsigned s00 = raw_coef(raw[0], 0) * __ldg(q), s10 = raw_coef(raw[1], 0) * __ldg(q + 8);
+    const unsigned s01 = raw_coef(raw[0], 1) * __ldg(q + 1), s11 = raw_coef(raw[1], 1) * __ldg(q + 9);
+    const unsigned x0 = s00 + s10 + 4u + (128u << 3), x2 = s00 - s10 + 4u + (128u << 3);
+    const unsigned x1 = s01 + s11, x3 = s01 - s11;
+    *reinterpret_cast<unsigned short*>(dst) = (unsigned short)pack4_sat_u8(sar(x0 + x1, 3), sar(x0 - x1, 3), 0, 0);
+    *reinterpret_cast<unsigned short*>(dst + stride) = (unsigned short)pack4_sat_u8(sar(x2 + x3, 3), sar(x2 - x3, 3), 0, 0);
+}
+// src/idct.rs:555-565 (Wrapping<i32> division truncates toward zero)
+__device__ __forceinline__ void idct1x1_regs(const uint4 (&raw)[8], const unsigned* __restrict__ q, uint8_t* dst) {
+    const int s0 = (int)(raw_coef(raw[0], 0) * __ldg(q) + 1024u) / 8;
+    dst[0] = (uint8_t)min(max(s0, 0), 255);
+}
+
+// ---------------------------------------------------------------------------------------------
+// SSSE3 arithmetic in registers (src/arch/ssse3.rs:8-84, 124-192): int16 lanes carried in int32 registers.
+//   adds / subs  saturate: VIADDMNMX + VIMNMX
+//   mulhrs(a, c) = (((a * c) >> 14) + 1) >> 1 == (a * c + 2^14) >> 15 (floor identities); every multiplier is a
+//                  constant with |c| < 2^15, so the result always fits int16 and needs no truncation: IMAD + SHF
+// ---------------------------------------------------------------------------------------------
+// (spelled in PTX: left to itself the compiler recognises a saturating i16 add, narrows the whole data flow to 16-bit
+// types and emulates them with compare / select / PRMT sequences -- 3x the instructions)
+__device__ __forceinline__ int s3_adds(int a, int b) {
+    int r;
+    asm("{\n.reg .s32 t;\nadd.s32 t, %1, %2;\nmax.s32 t, t, -32768;\nmin.s32 %0, t, 32767;\n}" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+__device__ __forceinline__ int s3_subs(int a, int b) {
+    int r;
+    asm("{\n.reg .s32 t;\nsub.s32 t, %1, %2;\nmax.s32 t, t, -32768;\nmin.s32 %0, t, 32767;\n}" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+__device__ __forceinline__ int s3_mulhrs(int a, int c) { return (a * c + 16384) >> 15; }
+
+// idct8, src/arch/ssse3.rs:8-84, on one lane (eight registers, in place)
+__device__ __forceinline__ void s3_idct8(int& d0, int& d1, int& d2, int& d3, int& d4, int& d5, int& d6, int& d7) {
+    int p2 = d2, p3 = d6;
+    int p1 = s3_mulhrs(s3_adds(p2, p3), 17734);
+    int t2 = s3_subs(s3_subs(p1, p3), s3_mulhrs(p3, 27779));
+    int t3 = s3_adds(p1, s3_mulhrs(p2, 25079));
+    p2 = d0;
+    p3 = d4;
+    int t0 = s3_adds(p2, p3), t1 = s3_subs(p2, p3);
+    const int x0 = s3_adds(t0, t3), x3 = s3_subs(t0, t3), x1 = s3_adds(t1, t2), x2 = s3_subs(t1, t2);
+    t0 = d7;
+    t1 = d5;
+    t2 = d3;
+    t3 = d1;
+    p3 = s3_adds(t0, t2);
+    int p4 = s3_adds(t1, t3);
+    p1 = s3_adds(t0, t3);
+    p2 = s3_adds(t1, t2);
+    int p5 = s3_adds(p3, p4);
+    p5 = s3_adds(p5, s3_mulhrs(p5, 5763));
+    t0 = s3_mulhrs(t0, 9786);
+    t1 = s3_adds(s3_adds(t1, t1), s3_mulhrs(t1, 1741));
+    t2 = s3_adds(s3_adds(t2, s3_adds(t2, t2)), s3_mulhrs(t2, 2383));
+    t3 = s3_adds(t3, s3_mulhrs(t3, 16427));
+    p1 = s3_subs(p5, s3_mulhrs(p1, 29490));
+    p2 = s3_subs(s3_subs(s3_subs(p5, p2), p2), s3_mulhrs(p2, 18446));
+    p3 = s3_subs(s3_mulhrs(p3, -31509), p3);
+    p4 = s3_mulhrs(p4, -12785);
+    t3 = s3_adds(s3_adds(p1, p4), t3);
+    t2 = s3_adds(s3_adds(p2, p3), t2);
+    t1 = s3_adds(s3_adds(p2, p4), t1);
+    t0 = s3_adds(s3_adds(p1, p3), t0);
+    d0 = s3_adds(x0, t3);
+    d7 = s3_subs(x0, t3);
+    d1 = s3_adds(x1, t2);
+    d6 = s3_subs(x1, t2);
+    d2 = s3_adds(x2, t1);
+    d5 = s3_subs(x2, t1);
+    d3 = s3_adds(x3, t0);
+    d4 = s3_subs(x3, t0);
+}
+
+// dequantize_and_idct_block_8x8, src/arch/ssse3.rs:124-192, whole block in registers.  q4 = the table as u32[64].
+// _mm_mullo_epi16 and _mm_slli_epi16(.., 3) both wrap at 16 bits: (c * q * 8) mod 2^16, read as int16.
+__device__ __forceinline__ void idct8x8_ssse3_regs(const uint4 (&raw)[8], const uint4* __restrict__ q4, uint2 (&rows)[8]) {
+    int d[8][8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const uint4 qa = __ldg(q4 + 2 * k), qb = __ldg(q4 + 2 * k + 1);
+        const unsigned w[4] = {raw[k].x, raw[k].y, raw[k].z, raw[k].w};
+        const unsigned q[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            // only the low 16 bits of the product matter, so the low half needs no extraction
+            d[k][2 * j] = (int)(short)(unsigned short)(w[j] * (q[2 * j] << 3));
+            d[k][2 * j + 1] = (int)(short)(unsigned short)((w[j] >> 16) * (q[2 * j + 1] << 3));
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) s3_idct8(d[0][k], d[1][k], d[2][k], d[3][k], d[4][k], d[5][k], d[6][k], d[7][k]);  // down the columns (ssse3.rs:162)
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        s3_idct8(d[r][0], d[r][1], d[r][2], d[r][3], d[r][4], d[r][5], d[r][6], d[r][7]);  // transpose-idct8-transpose = along the rows
+        // adds(.., OFFSET + ROUNDING_BIAS) >> 6, packus (ssse3.rs:173-185)
+        rows[r].x = pack4_sat_u8(s3_adds(d[r][0], 8224) >> 6, s3_adds(d[r][1], 8224) >> 6, s3_adds(d[r][2], 8224) >> 6, s3_adds(d[r][3], 8224) >> 6);
+        rows[r].y = pack4_sat_u8(s3_adds(d[r][4], 8224) >> 6, s3_adds(d[r][5], 8224) >> 6, s3_adds(d[r][6], 8224) >> 6, s3_adds(d[r][7], 8224) >> 6);
+    }
+}
+
 }  // namespace b200jpg

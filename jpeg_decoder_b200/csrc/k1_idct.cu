@@ -201,7 +201,10 @@ constexpr int K1_STAGES = 3;
 // Measured (sweep_r01*.jsonl): ALU-pipe instructions issue at half rate on sm_100, IMAD at full rate, and the
 // kernel is bound by the ALU pipe in style 0 and by issue slots in style 1; 5 (= both IMAD) is the fastest.  All variants are bit-identical; they only move work
 // between the ALU and FMA pipes (the kernel is integer-issue bound, not HBM bound).
-template <int MODE>
+// ARITH: 0 = scalar (src/idct.rs), 1 = SSSE3 int16 lanes (src/arch/ssse3.rs) for the 8x8 blocks.
+// SCALED: components may have dct_scale 4 / 2 / 1 (Decoder::scale); those blocks take the reduced transforms, which
+// exist in scalar arithmetic only (src/idct.rs:247-253).  A separate instantiation: the hot one stays lean.
+template <int MODE, int ARITH = 0, bool SCALED = false>
 __global__ void __launch_bounds__(K1_TILE, 4)
 k1_idct8_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ K1QCache qc, K1Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -272,8 +275,23 @@ k1_idct8_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ K
             by += bx / comp.block_w;
             bx %= comp.block_w;
         }
-        uint8_t* dst = p.planes + comp.plane_off + (size_t)by * 8u * comp.stride + (size_t)bx * 8u;
+        const unsigned sc = SCALED ? comp.dct_scale : 8u;
+        uint8_t* dst = p.planes + comp.plane_off + (size_t)by * sc * comp.stride + (size_t)bx * sc;
+        if (SCALED && sc != 8u) {  // warp-uniform: a tile belongs to one component
+            const unsigned* q = reinterpret_cast<const unsigned*>(q4);
+            if (sc == 4u) idct4x4_regs(raw, q, dst, comp.stride);
+            else if (sc == 2u) idct2x2_regs(raw, q, dst, comp.stride);
+            else idct1x1_regs(raw, q, dst);
+            continue;
+        }
 
+        if constexpr (ARITH == 1) {
+            uint2 rows[8];
+            idct8x8_ssse3_regs(raw, q4, rows);
+#pragma unroll
+            for (int r = 0; r < 8; r++) *reinterpret_cast<uint2*>(dst + (size_t)r * comp.stride) = rows[r];
+            continue;
+        }
         unsigned s[8][8];
         const unsigned oor = dequant_block(raw, s, comp.qflags, qc, q4, qp4);
         if (oor != 0) {
@@ -341,8 +359,25 @@ static int k1_mode() {
 
 size_t k1_tma_smem_bytes() { return (size_t)K1_STAGES * K1_STAGE_BYTES + 1024; }
 
-cudaError_t launch_k1_tma(const CUtensorMap& tmap, const K1QCache& qc, const K1Params& p, int num_sms, cudaStream_t stream) {
+cudaError_t launch_k1_tma(const CUtensorMap& tmap, const K1QCache& qc, const K1Params& p, int arith, bool scaled, int num_sms, cudaStream_t stream) {
     if (p.ntiles == 0) return cudaSuccess;
+    if (arith == 1 || scaled) {  // the less travelled variants: SSSE3 arithmetic and / or scaled components
+        static bool attr_set3 = false;
+        if (!attr_set3) {
+            const void* fns[3] = {(const void*)k1_idct8_tma<8, 1, false>, (const void*)k1_idct8_tma<8, 1, true>, (const void*)k1_idct8_tma<8, 0, true>};
+            for (const void* f : fns) {
+                cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_tma_smem_bytes());
+                if (e != cudaSuccess) return e;
+            }
+            attr_set3 = true;
+        }
+        unsigned grid3 = (unsigned)num_sms * 4u;
+        if (grid3 > p.ntiles) grid3 = p.ntiles;
+        if (arith == 1 && scaled) k1_idct8_tma<8, 1, true><<<grid3, K1_TILE, k1_tma_smem_bytes(), stream>>>(tmap, qc, p);
+        else if (arith == 1) k1_idct8_tma<8, 1, false><<<grid3, K1_TILE, k1_tma_smem_bytes(), stream>>>(tmap, qc, p);
+        else k1_idct8_tma<8, 0, true><<<grid3, K1_TILE, k1_tma_smem_bytes(), stream>>>(tmap, qc, p);
+        return cudaGetLastError();
+    }
     static bool attr_set = false;
     if (!attr_set) {
         const void* fns[3] = {(const void*)k1_idct8_tma<0>, (const void*)k1_idct8_tma<5>, (const void*)k1_idct8_tma<8>};

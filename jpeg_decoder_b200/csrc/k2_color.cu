@@ -168,7 +168,7 @@ __device__ __forceinline__ ChromaRow load_chroma_row(const uint8_t* row, unsigne
 
 // RAGGED: images whose chroma width is not a multiple of 8 (the last 8-sample window of a row then needs the
 // edge sample replicated); a separate instantiation so that the common case keeps 64 registers / 8 CTAs per SM.
-template <unsigned K2_RP, int MINB, bool RAGGED>
+template <unsigned K2_RP, int MINB, bool RAGGED, bool SSSE3 = false>
 __global__ void __launch_bounds__(128, MINB) k2_ycbcr420(K2Params p, unsigned first) {
     const DevImage& img = p.images[first + blockIdx.z];
     if (RAGGED ? img.path != K2_PATH_420R : (img.path != K2_PATH_420 && !(img.path == K2_PATH_420T && (p.flags & K2_FLAG_LDG_TAKES_420T)))) return;
@@ -188,6 +188,7 @@ __global__ void __launch_bounds__(128, MINB) k2_ycbcr420(K2Params p, unsigned fi
     const unsigned iL = i0 > 0 ? i0 - 1 : 0, iR = min(i0 + 8u, in_w - 1);
     const YccRegs sixteen = make_ycc_regs(p.sixteen, true);
     const unsigned npx = min(16u, W - g * 16u);
+    const unsigned nss = SSSE3 ? min(16u, max(img.ssse3_pixels, g * 16u) - g * 16u) : 0u;
 
     // chroma row A of the first pair
     const unsigned rA0 = p0 > 0 ? p0 - 1 : 0;
@@ -204,8 +205,8 @@ __global__ void __launch_bounds__(128, MINB) k2_ycbcr420(K2Params p, unsigned fi
         Chroma16 cb, cr;
         h2v2_16(ba.lo, ba.hi, ba.L, ba.R, bb.lo, bb.hi, bb.L, bb.R, cb);
         h2v2_16(ra.lo, ra.hi, ra.L, ra.R, rb.lo, rb.hi, rb.L, rb.R, cr);
-        if (pr > 0) ycbcr_store16(yv_odd, cb.odd, cr.odd, out + (size_t)y_odd * W * 3u, sixteen, npx);      // output row 2p-1
-        if (2 * pr < H) ycbcr_store16(yv_even, cb.even, cr.even, out + (size_t)y_even * W * 3u, sixteen, npx);  // output row 2p
+        if (pr > 0) ycbcr_store16<SSSE3>(yv_odd, cb.odd, cr.odd, out + (size_t)y_odd * W * 3u, sixteen, npx, nss);      // output row 2p-1
+        if (2 * pr < H) ycbcr_store16<SSSE3>(yv_even, cb.even, cr.even, out + (size_t)y_even * W * 3u, sixteen, npx, nss);  // output row 2p
         ba = bb;
         ra = rb;
     }
@@ -401,6 +402,7 @@ __device__ __forceinline__ uint4 load_row16(const uint8_t* row, unsigned g, unsi
     return make_uint4(lo.x, lo.y, hi.x, hi.y);
 }
 
+template <bool SSSE3>
 __global__ void __launch_bounds__(128) k2_ycbcr444(K2Params p, unsigned first, unsigned gchunks) {
     const DevImage& img = p.images[first + blockIdx.y];
     if (img.path != K2_PATH_444) return;
@@ -420,13 +422,15 @@ __global__ void __launch_bounds__(128) k2_ycbcr444(K2Params p, unsigned first, u
         cb[k] = (int)prmt(bw[k >> 2], 0u, 0x8880u + 0x1111u * (unsigned)(k & 3));
         cr[k] = (int)prmt(rw[k >> 2], 0u, 0x8880u + 0x1111u * (unsigned)(k & 3));
     }
-    ycbcr_store16(yv, cb, cr, p.out + img.out_off + ((size_t)y * W + g * 16u) * 3u, make_ycc_regs(p.sixteen, true), min(16u, W - g * 16u));
+    ycbcr_store16<SSSE3>(yv, cb, cr, p.out + img.out_off + ((size_t)y * W + g * 16u) * 3u, make_ycc_regs(p.sixteen, true), min(16u, W - g * 16u),
+                         SSSE3 ? min(16u, max(img.ssse3_pixels, g * 16u) - g * 16u) : 0u);
 }
 
 // ---------------------------------------------------------------------------------------------
 // 4:2:2 YCbCr (H2V1 chroma, src/upsampler.rs:134-163; the layout of MJPEG / camera files): thread = 16 pixels of one row,
 // 8 chroma samples + the two clamped halo samples per component.  grid.x = ceil(G/128) * height, grid.y = image
 // ---------------------------------------------------------------------------------------------
+template <bool SSSE3>
 __global__ void __launch_bounds__(128) k2_ycbcr422(K2Params p, unsigned first, unsigned gchunks) {
     const DevImage& img = p.images[first + blockIdx.y];
     if (img.path != K2_PATH_422) return;
@@ -445,7 +449,8 @@ __global__ void __launch_bounds__(128) k2_ycbcr422(K2Params p, unsigned first, u
         if (i0 + 8u > in_w) v = replicate_last_sample(v, in_w - i0);  // block padding := last valid sample (the edge rule)
         h2v1_16(v.x, v.y, __ldg(row + iL), __ldg(row + iR), c == 1 ? cb : cr);
     }
-    ycbcr_store16(yv, cb, cr, p.out + img.out_off + ((size_t)y * W + g * 16u) * 3u, make_ycc_regs(p.sixteen, true), min(16u, W - g * 16u));
+    ycbcr_store16<SSSE3>(yv, cb, cr, p.out + img.out_off + ((size_t)y * W + g * 16u) * 3u, make_ycc_regs(p.sixteen, true), min(16u, W - g * 16u),
+                         SSSE3 ? min(16u, max(img.ssse3_pixels, g * 16u) - g * 16u) : 0u);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -552,6 +557,11 @@ cudaError_t launch_k2_420(const K2Params& p, unsigned first, unsigned count, uns
     const unsigned npairs = max_h / 2u + 1u;
     const unsigned rp = k2_mode() == 4 ? 4u : 1u;
     dim3 grid(((max_w + 15u) / 16u + 127u) / 128u, (npairs + rp - 1u) / rp, count);
+    if (p.flags & K2_FLAG_SSSE3) {  // the x86 build's colour arithmetic on the first (W / 8 - 1) * 8 pixels of every row
+        if (ragged) k2_ycbcr420<1, 6, true, true><<<dim3(grid.x, npairs, count), 128, 0, stream>>>(p, first);
+        else k2_ycbcr420<1, 6, false, true><<<dim3(grid.x, npairs, count), 128, 0, stream>>>(p, first);
+        return cudaGetLastError();
+    }
     if (ragged) k2_ycbcr420<1, 7, true><<<dim3(grid.x, npairs, count), 128, 0, stream>>>(p, first);
     else if (rp == 4) k2_ycbcr420<4, 5, false><<<grid, 128, 0, stream>>>(p, first);
     else k2_ycbcr420<1, 8, false><<<grid, 128, 0, stream>>>(p, first);
@@ -572,22 +582,82 @@ cudaError_t launch_k2_420_tma(const K2Params& p, const K2Strip* strips, unsigned
     k2_ycbcr420_tma<<<grid, K2T_THREADS, smem_bytes, stream>>>(p, strips, nstrips, item_base, total_items);
     return cudaGetLastError();
 }
-cudaError_t launch_k2_444(const K2Params& p, unsigned first, unsigned count, unsigned max_w, unsigned max_h,
-                          cudaStream_t stream) {
+// ---------------------------------------------------------------------------------------------
+// K3: interleaved RGB8 -> the layout of an on-GPU consumer (b200jpg_batch_format_device).  Thread = 16 pixels of one
+// row: three 16-byte loads, then 3 x 16-byte stores (planar u8) or 12 / 3 x 4 float4 stores.  HBM-bound by design.
+// ---------------------------------------------------------------------------------------------
+struct K3Params {
+    const DevImage* images;
+    const uint8_t* src;
+    uint8_t* dst;
+    float scale[3], bias[3];
+    int format;
+};
+__global__ void __launch_bounds__(128) k3_format(K3Params p, unsigned first, unsigned gchunks) {
+    const DevImage& img = p.images[first + blockIdx.y];
+    if (img.ncomp != 3 || img.width == 0) return;
+    const unsigned y = blockIdx.x / gchunks;
+    const unsigned g = (blockIdx.x % gchunks) * 128u + threadIdx.x;
+    const unsigned W = img.width, H = img.height;
+    if (y >= H || g * 16u >= W) return;
+    const unsigned npx = min(16u, W - g * 16u);
+    const uint8_t* src = p.src + img.out_off + ((size_t)y * W + g * 16u) * 3u;
+    unsigned char px[48];
+    if (npx == 16u && ((uintptr_t)src & 15u) == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) reinterpret_cast<uint4*>(px)[k] = __ldg(reinterpret_cast<const uint4*>(src) + k);
+    } else {
+        for (unsigned k = 0; k < 48u; k++) px[k] = k < 3u * npx ? src[k] : 0;
+    }
+    const size_t plane = (size_t)W * H;
+    if (p.format == 1) {  // CHW uint8
+        uint8_t* base = p.dst + img.out_off + (size_t)y * W + g * 16u;
+        for (int c = 0; c < 3; c++) {
+            unsigned ow[4];
+#pragma unroll
+            for (int w = 0; w < 4; w++)
+                ow[w] = px[12 * w + c] | ((unsigned)px[12 * w + 3 + c] << 8) | ((unsigned)px[12 * w + 6 + c] << 16) | ((unsigned)px[12 * w + 9 + c] << 24);
+            store_words<4>(base + (size_t)c * plane, ow, npx);
+        }
+        return;
+    }
+    float* fdst = reinterpret_cast<float*>(p.dst + 4u * img.out_off);
+    if (p.format == 2) {  // HWC float32
+        float* o = fdst + ((size_t)y * W + g * 16u) * 3u;
+        for (unsigned k = 0; k < 3u * npx; k++) o[k] = fmaf((float)px[k], p.scale[k % 3u], p.bias[k % 3u]);
+    } else {              // CHW float32
+        for (int c = 0; c < 3; c++) {
+            float* o = fdst + (size_t)c * plane + (size_t)y * W + g * 16u;
+            for (unsigned k = 0; k < npx; k++) o[k] = fmaf((float)px[3 * k + c], p.scale[c], p.bias[c]);
+        }
+    }
+}
+cudaError_t launch_k3_format(const DevImage* images, unsigned first, unsigned count, unsigned max_w, unsigned max_h, const void* src, void* dst,
+                             int format, const float scale[3], const float bias[3], cudaStream_t stream) {
     if (count == 0 || max_w == 0 || max_h == 0) return cudaSuccess;
+    K3Params p;
+    p.images = images;
+    p.src = (const uint8_t*)src;
+    p.dst = (uint8_t*)dst;
+    for (int c = 0; c < 3; c++) {
+        p.scale[c] = scale ? scale[c] : 1.0f;
+        p.bias[c] = bias ? bias[c] : 0.0f;
+    }
+    p.format = format;
     const unsigned gchunks = ((max_w + 15u) / 16u + 127u) / 128u;
-    dim3 grid(gchunks * max_h, count);
-    k2_ycbcr444<<<grid, 128, 0, stream>>>(p, first, gchunks);
+    k3_format<<<dim3(gchunks * max_h, count), 128, 0, stream>>>(p, first, gchunks);
     return cudaGetLastError();
 }
+
 // kernels whose grid is (ceil(G/128) * max_h, images): path selects k2_ycbcr444 / k2_ycbcr422 / k2_bytes
 cudaError_t launch_k2_rows16(unsigned path, const K2Params& p, unsigned first, unsigned count, unsigned max_w, unsigned max_h, cudaStream_t stream) {
     if (count == 0 || max_w == 0 || max_h == 0) return cudaSuccess;
     const unsigned gchunks = ((max_w + 15u) / 16u + 127u) / 128u;
     dim3 grid(gchunks * max_h, count);
-    if (path == K2_PATH_422) k2_ycbcr422<<<grid, 128, 0, stream>>>(p, first, gchunks);
+    const bool s3 = (p.flags & K2_FLAG_SSSE3) != 0;
+    if (path == K2_PATH_422) s3 ? k2_ycbcr422<true><<<grid, 128, 0, stream>>>(p, first, gchunks) : k2_ycbcr422<false><<<grid, 128, 0, stream>>>(p, first, gchunks);
     else if (path == K2_PATH_BYTES) k2_bytes<<<grid, 128, 0, stream>>>(p, first, gchunks);
-    else k2_ycbcr444<<<grid, 128, 0, stream>>>(p, first, gchunks);
+    else s3 ? k2_ycbcr444<true><<<grid, 128, 0, stream>>>(p, first, gchunks) : k2_ycbcr444<false><<<grid, 128, 0, stream>>>(p, first, gchunks);
     return cudaGetLastError();
 }
 cudaError_t launch_k2_gray(const K2Params& p, unsigned first, unsigned count, unsigned max_w, unsigned max_h, cudaStream_t stream) {

@@ -50,7 +50,7 @@ cudaError_t launch_k0_expand_blocks(const K0Image* d_images, unsigned nimages, u
 cudaError_t launch_k0_zero_headers(const K0Image* d_images, unsigned nimages, unsigned max_blocks, uint8_t* d_streams, cudaStream_t stream);
 cudaError_t launch_k1_generic(const K1Params& p, int arith, cudaStream_t stream);
 size_t k1_tma_smem_bytes();
-cudaError_t launch_k1_tma(const CUtensorMap& tmap, const K1QCache& qc, const K1Params& p, int num_sms, cudaStream_t stream);
+cudaError_t launch_k1_tma(const CUtensorMap& tmap, const K1QCache& qc, const K1Params& p, int arith, bool scaled, int num_sms, cudaStream_t stream);
 
 // K2: max_w/max_h = largest output size in [first, first+count); the grid covers that and images
 // smaller than it exit early.  `path` selects the kernel; images whose DevImage::path differs are
@@ -59,14 +59,15 @@ cudaError_t launch_k2_generic(const K2Params& p, unsigned first, unsigned count,
                               cudaStream_t stream);
 cudaError_t launch_k2_420(const K2Params& p, unsigned first, unsigned count, unsigned max_w, unsigned max_h, bool ragged,
                           cudaStream_t stream);
-cudaError_t launch_k2_444(const K2Params& p, unsigned first, unsigned count, unsigned max_w, unsigned max_h,
-                          cudaStream_t stream);
 
 cudaError_t launch_k2_rows16(unsigned path, const K2Params& p, unsigned first, unsigned count, unsigned max_w, unsigned max_h,
                              cudaStream_t stream);
+cudaError_t launch_k3_format(const DevImage* images, unsigned first, unsigned count, unsigned max_w, unsigned max_h, const void* src, void* dst,
+                             int format, const float scale[3], const float bias[3], cudaStream_t stream);
 cudaError_t launch_k2_420_tma(const K2Params& p, const K2Strip* strips, unsigned nstrips, unsigned item_base, unsigned total_items,
                               int num_sms, cudaStream_t stream);
 int k2_mode();
+constexpr unsigned K2_FLAG_SSSE3 = 2u;           // K2Params::flags: SSSE3 colour arithmetic on DevImage::ssse3_pixels pixels per row
 constexpr unsigned K2_FLAG_LDG_TAKES_420T = 1u;  // K2Params::flags: the load/store 4:2:0 kernel also takes the bulk-copy path's images
 cudaError_t launch_k2_gray(const K2Params& p, unsigned first, unsigned count, unsigned max_w, unsigned max_h, cudaStream_t stream);
 

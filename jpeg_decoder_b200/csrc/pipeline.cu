@@ -313,7 +313,7 @@ static int plan_image(const b200jpg_ctx* ctx, const b200jpg_image_desc& d, DevIm
     // kernel choice
     img->path = K2_PATH_GENERIC;
     if (ctx->k2_kernel != B200JPG_KERNEL_GENERIC && img->cc == CC_GRAY && img->c[0].stride % 8 == 0) img->path = K2_PATH_GRAY;
-    if (ctx->k2_kernel != B200JPG_KERNEL_GENERIC && img->cc == CC_YCBCR && img->ssse3_pixels == 0) {
+    if (ctx->k2_kernel != B200JPG_KERNEL_GENERIC && img->cc == CC_YCBCR) {
         const DevUpComp* u = img->c;
         const unsigned groups = (d.width + 15u) / 16u;
         if (u[0].kind == UP_H1V1 && u[1].kind == UP_H2V2 && u[2].kind == UP_H2V2 && u[0].stride % 16 == 0 &&
@@ -712,14 +712,14 @@ int batch_launch(b200jpg_batch* b, const void* d_coefs, void* d_planes, void* d_
         p.ntiles = tile_count;
         p.one = 1u;
         p.minus_one = 0xffffffffu;
-        const bool tma_ok = ctx->arith == B200JPG_ARITH_SCALAR && b->all_scale8 && b->k1_tma_aligned &&
+        const bool tma_ok = b->k1_tma_aligned &&
                             ((uintptr_t)d_coefs % 16 == 0) && ((uintptr_t)d_planes % 8 == 0);
         if (ctx->k1_kernel == B200JPG_KERNEL_FAST && !tma_ok)
-            return fail(ctx, B200JPG_ERR_INTERNAL, "k1_kernel=FAST requested but the batch is not eligible (needs scalar arithmetic, dct_scale 8)");
+            return fail(ctx, B200JPG_ERR_INTERNAL, "k1_kernel=FAST requested but the batch is not eligible (plane offsets must be 8-byte aligned)");
         if (tma_ok && ctx->k1_kernel != B200JPG_KERNEL_GENERIC) {
             int rc = ensure_tensor_map(b, d_coefs);
             if (rc) return rc;
-            CU_TRY(ctx, launch_k1_tma(b->tmap, b->qcache, p, ctx->num_sms, stream));
+            CU_TRY(ctx, launch_k1_tma(b->tmap, b->qcache, p, ctx->arith == B200JPG_ARITH_SSSE3 ? 1 : 0, !b->all_scale8, ctx->num_sms, stream));
         } else {
             CU_TRY(ctx, launch_k1_generic(p, ctx->arith, stream));
         }
@@ -732,8 +732,9 @@ int batch_launch(b200jpg_batch* b, const void* d_coefs, void* d_planes, void* d_
         p.out = (uint8_t*)d_out;
         p.nimages = (unsigned)b->n;
         p.sixteen = make_int3(16, 16, 16);
-        const bool bulk = k2_mode() == 0 && ((uintptr_t)d_planes % 16 == 0);
-        p.flags = bulk ? 0u : K2_FLAG_LDG_TAKES_420T;
+        // (the bulk-copy fed 4:2:0 kernel exists in scalar arithmetic only; SSSE3 mode takes the load/store one)
+        const bool bulk = k2_mode() == 0 && ((uintptr_t)d_planes % 16 == 0) && ctx->arith != B200JPG_ARITH_SSSE3;
+        p.flags = (bulk ? 0u : K2_FLAG_LDG_TAKES_420T) | (ctx->arith == B200JPG_ARITH_SSSE3 ? K2_FLAG_SSSE3 : 0u);
         if (bulk && b->path_used[K2_PATH_420T]) {
             const unsigned s0 = b->strip_first[img_first], s1 = b->strip_first[img_first + img_count];
             if (s1 > s0) {
@@ -810,6 +811,29 @@ int b200jpg_batch_run_device(b200jpg_batch* b, const void* d_coefs, void* d_plan
     b200jpg_ctx* ctx = b->ctx;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     return batch_launch(b, d_coefs, d_planes, d_out, stages, 0, (unsigned)b->tiles.size(), 0, (unsigned)b->n, ctx->stream);
+}
+
+int b200jpg_batch_format_device(b200jpg_batch* b, const void* d_out, int format, void* d_dst, const float scale[3], const float bias[3],
+                                int* statuses) {
+    if (!b || !d_out || !d_dst) return B200JPG_ERR_INTERNAL;
+    b200jpg_ctx* ctx = b->ctx;
+    if (format < B200JPG_FMT_RGB8_PLANAR || format > B200JPG_FMT_RGB_F32_NCHW) return fail(ctx, B200JPG_ERR_INTERNAL, "unknown output format");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    unsigned max_w = 0, max_h = 0;
+    for (size_t i = 0; i < b->n; i++) {
+        const bool ok = b->layout[i].status == B200JPG_OK && b->images[i].ncomp == 3;
+        if (statuses) statuses[i] = ok ? B200JPG_OK : (b->layout[i].status ? b->layout[i].status : B200JPG_ERR_FORMAT);
+        if (ok) {
+            max_w = std::max(max_w, b->images[i].width);
+            max_h = std::max(max_h, b->images[i].height);
+        }
+    }
+    for (size_t first = 0; first < b->n; first += 65535u) {
+        const unsigned count = (unsigned)std::min<size_t>(65535u, b->n - first);
+        CU_TRY(ctx, launch_k3_format(b->d_images, (unsigned)first, count, max_w, max_h, d_out, d_dst, format, scale, bias, ctx->stream));
+        ctx->launches++;
+    }
+    return B200JPG_OK;
 }
 
 // Host -> host: chunked, double-buffered over two streams (H2D | K1 | K2 | D2H overlap across chunks).

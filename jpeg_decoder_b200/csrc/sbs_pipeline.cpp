@@ -74,7 +74,9 @@ int SbsPipeline::grow_device(Buf& b, size_t need) {
     if (need <= b.cap) return B200JPG_OK;
     // doubling, so that a buffer regrows a handful of times in its life.  The slot is idle (its previous group has
     // retired), and every stream that touches the buffer afterwards first waits for work enqueued on s_in_.
-    const size_t want = up(std::max(need + need / 4, 2 * b.cap), 1 << 20);
+    // (group sizes depend on timing -- how many images were ready when the submitter came round -- so a new maximum can
+    // turn up many calls into a run: twice the need, so that the buffers settle after two or three regrowths)
+    const size_t want = up(std::max(2 * need, 2 * b.cap), 1 << 20);
     if (async_alloc_) {
         if (b.p) CU_TRY(ctx_, cudaFreeAsync(b.p, s_in_));
         b.p = nullptr;

@@ -156,3 +156,45 @@ def test_direct_form_pass_is_the_butterfly_mod_2_32():
     for s in cases:
         for xs in (512 % M, (512 + 2 ** 31) % M, (65536 + (128 << 17)) % M):
             assert butterfly(s, xs) == direct(s, xs)
+
+
+def test_ssse3_colour_path_never_saturates_for_8bit_inputs(oracle_mod):
+    """color_core.cuh evaluates the SSSE3 colour path (src/arch/ssse3.rs:208-244) with plain adds: for 8-bit inputs no
+    saturating add of that path can saturate.  Exhaustive over all 2^24 (y, cb, cr): the saturating form (the oracle's
+    emulation, restated with numpy) and the plain form give the same bytes, and both equal the C oracle on a sample."""
+    y = np.arange(256, dtype=np.int32)[:, None, None]
+    cb = np.arange(256, dtype=np.int32)[None, :, None]
+    cr = np.arange(256, dtype=np.int32)[None, None, :]
+
+    def sat(v):
+        return np.clip(v, -32768, 32767)
+
+    def mulhrs(a, c):
+        return (((a * c) >> 14) + 1) >> 1
+
+    y6 = sat((y << 6) + 32)
+    cb6, cr6 = sat((cb << 6) - 8192), sat((cr << 6) - 8192)
+    r_s = sat(y6 + sat(mulhrs(cr6, 13173) + cr6)) >> 6
+    g_s = sat(y6 - sat(mulhrs(cb6, 11276) + mulhrs(cr6, 23401))) >> 6
+    b_s = sat(y6 + sat(mulhrs(cb6, 25297) + cb6)) >> 6
+    cbm, crm = (cb - 128) * 64, (cr - 128) * 64
+    yy = y * 64 + 32
+    r_p = (yy + ((crm * 13173 + 16384) >> 15) + crm) >> 6
+    g_p = (yy - (((cbm * 11276 + 16384) >> 15) + ((crm * 23401 + 16384) >> 15))) >> 6
+    b_p = (yy + ((cbm * 25297 + 16384) >> 15) + cbm) >> 6
+    assert np.array_equal(np.broadcast_to(r_s, (256, 256, 256)), np.broadcast_to(r_p, (256, 256, 256)))
+    assert np.array_equal(g_s, g_p)
+    assert np.array_equal(np.broadcast_to(b_s, (256, 256, 256)), np.broadcast_to(b_p, (256, 256, 256)))
+    # and the numpy restatement is the oracle's: one row of 40 pixels through the real intrinsics
+    import ctypes as C
+    rng = np.random.default_rng(9)
+    n = 40
+    yy8, cb8, cr8 = (rng.integers(0, 256, n).astype(np.uint8) for _ in range(3))
+    out = np.zeros(3 * n, np.uint8)
+    done = C.c_size_t()
+    if oracle_mod.lib().orc_ycbcr_line_ssse3_intrin(yy8.ctypes.data, cb8.ctypes.data, cr8.ctypes.data, out.ctypes.data, n, C.byref(done)):
+        k = done.value
+        assert k == 32
+        want = np.stack([np.clip(r_s[yy8[:k], 0, cr8[:k]], 0, 255), np.clip(g_s[yy8[:k], cb8[:k], cr8[:k]], 0, 255),
+                         np.clip(b_s[yy8[:k], cb8[:k], 0], 0, 255)], -1).astype(np.uint8)
+        assert np.array_equal(out[:3 * k].reshape(k, 3), want)
