@@ -850,6 +850,34 @@ def main():
                 except Exception as e:   # an extra config must not take the headline down with it
                     configs[name] = {"error": repr(e)}
                     torch.cuda.empty_cache()
+        if args.config == "cfg2" and not args.no_extra_configs:
+            # the kernels behind everything else compute_image accepts, at 1080p x 256: one number each next to the headline
+            variants = {}
+            vsteps = 3
+            for name, v in workload.VARIANTS.items():
+                try:
+                    uq = [workload.UniqueImage(workload.variant_jpeg(name, k), v.get("scale")) for k in range(2)]
+                    mv = measure_config(J, torch, ctx, dev, stream, uq, 0, 256, vsteps, peak)
+                    w_out, h_out = uq[0].width, uq[0].height
+                    variants[name] = {"workload": v["desc"] + " x256", "value": 256 * w_out * h_out / 1e6 * vsteps / (mv["ms"] / 1e3), "unit": "MP/s (output pixels)",
+                                      "parity": mv["parity"],
+                                      "kernels": {k: {"ms": x["ms"], "frac": x["frac"]} for k, x in mv["kernels"].items()}}
+                    mv["wl"].close()
+                except Exception as e:
+                    variants[name] = {"error": repr(e)}
+                torch.cuda.empty_cache()
+            try:   # the x86 build's arithmetic (int16 lanes) on the headline workload
+                ctx3 = J.Context(device=local_rank, arith=J.ARITH_SSSE3, stream=stream.cuda_stream)
+                m3 = measure_config(J, torch, ctx3, dev, stream, unique, 0, 256, vsteps, peak)
+                variants["ssse3_arithmetic"] = {"workload": cfg["desc"] + " x256, arith = ssse3 (bit-exact vs the oracle's src/arch/ssse3.rs restatement)",
+                                                "value": 256 * W * H / 1e6 * vsteps / (m3["ms"] / 1e3), "unit": "MP/s", "parity": m3["parity"],
+                                                "kernels": {k: {"ms": x["ms"], "frac": x["frac"]} for k, x in m3["kernels"].items()}}
+                m3["wl"].close()
+                ctx3.close()
+            except Exception as e:
+                variants["ssse3_arithmetic"] = {"error": repr(e)}
+            torch.cuda.empty_cache()
+            configs["variants"] = variants
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             oimgs = [OracleImage(u.jpeg) for u in unique[:4]]

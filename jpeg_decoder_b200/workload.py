@@ -50,6 +50,33 @@ def synth_jpeg(width, height, seed, subsampling=2, quality=90, progressive=False
     return buf.getvalue()
 
 
+# Variants of the hot path that BASELINE.json does not name but compute_image accepts:
+# each is measured by bench.py at 1080p so that the kernels behind them have a number next to the headline.
+VARIANTS = {
+    "ycbcr422": dict(width=1920, height=1080, mode="RGB", subsampling=1, seed=7100, desc="1920x1080 baseline 4:2:2 (H2V1 chroma)"),
+    "gray": dict(width=1920, height=1080, mode="L", subsampling=None, seed=7200, desc="1920x1080 baseline greyscale"),
+    "cmyk": dict(width=1920, height=1080, mode="CMYK", subsampling=None, seed=7300, desc="1920x1080 baseline CMYK (4 components, Adobe APP14)"),
+    "scaled_half": dict(width=1920, height=1080, mode="RGB", subsampling=2, seed=7400, scale=(960, 540),
+                        desc="1920x1080 4:2:0 decoded at 1/2 size (Decoder::scale -> 4x4 IDCT)"),
+}
+
+
+def variant_jpeg(name, k=0):
+    from PIL import Image
+    v = VARIANTS[name]
+    px = synth_pixels(v["width"], v["height"], v["seed"] + k)
+    if v["mode"] == "L":
+        im = Image.fromarray(px[..., 0])
+    elif v["mode"] == "CMYK":
+        im = Image.fromarray(np.concatenate([px, 255 - px[..., :1]], axis=-1), "CMYK")
+    else:
+        im = Image.fromarray(px)
+    buf = io.BytesIO()
+    kw = {} if v["subsampling"] is None else {"subsampling": v["subsampling"]}
+    im.save(buf, "JPEG", quality=90, **kw)
+    return buf.getvalue()
+
+
 def config_jpeg(cfg_name, k=0):
     """The k-th distinct JPEG of a config: the reference's bench file (same bytes for every k) or a synthetic one."""
     cfg = CONFIGS[cfg_name]
@@ -62,9 +89,12 @@ def config_jpeg(cfg_name, k=0):
 class UniqueImage:
     """One entropy-decoded image: geometry + dense coefficients (numpy, host)."""
 
-    def __init__(self, jpeg_bytes):
+    def __init__(self, jpeg_bytes, scale=None):
         from . import Decoder
         dec = Decoder(jpeg_bytes)
+        if scale is not None:   # Decoder::scale before decoding: the components come back with dct_scale 4 / 2 / 1
+            dec.read_info()
+            dec.scale(*scale)
         desc = dec.entropy_decode()
         self.width, self.height, self.ncomp = desc.width, desc.height, desc.ncomp
         self.color_transform = desc.color_transform

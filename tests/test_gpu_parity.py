@@ -235,6 +235,16 @@ def test_k2_colour_transforms(J, oracle_mod, ctxs, variant):
                 assert np.array_equal(got, want), (w, h, ncomp, sampling, ct)
 
 
+@pytest.mark.parametrize("variant", [("scalar", "auto"), ("scalar", "generic"), ("ssse3", "auto")])
+@pytest.mark.parametrize("name", ["h2v2", "h2v1", "h1v2"])
+def test_k2_hand_derived_upsampling_vectors(J, ctxs, variant, name):
+    """The kernels against bytes worked out by hand from src/upsampler.rs (tests/hand_vectors.py): no oracle involved."""
+    from hand_vectors import planes_for
+    comps, planes, w, h, want = planes_for(J.make_components, name, np.random.default_rng(1))
+    got = J.compute_image(ctxs[variant], comps, planes, w, h, J.CT_RGB).reshape(h, w, 3)
+    assert np.array_equal(got[..., 1], want), (name, got[..., 1])
+
+
 def test_k2_error_mapping(J, oracle_mod, ctxs):
     """choose_color_convert_func / choose_upsampler errors (src/decoder.rs:1344-1386, src/upsampler.rs:93-98)."""
     ctx = ctxs[("scalar", "auto")]
@@ -263,9 +273,7 @@ def test_k2_error_mapping(J, oracle_mod, ctxs):
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("variant", VARIANTS)
 def test_whole_files_bit_exact_and_golden(J, oracle_mod, ctxs, variant):
-    ctx = ctxs[variant]
-    if variant[1] == "fast":
-        pytest.skip("K1 FAST is pinned per batch (scaled / odd files need the generic kernel); covered by the batch tests")
+    ctx = ctxs[variant]   # "fast" pins the TMA-fed K1, which takes every scale and both arithmetic variants since round 2
     oa = oarith(oracle_mod, variant[0])
     n = 0
     for p in reftest_files() + bench_files():

@@ -172,3 +172,24 @@ def test_read_info_files(oracle_mod, J):
         assert st == 0, p
         assert (info.width, info.height, info.pixel_format, info.coding_process) == (oi.width, oi.height, oi.pixel_format, oi.coding_process)
         assert out_len == info.width * info.height * {0: 1, 1: 1, 2: 3, 3: 4}[info.pixel_format]
+
+
+def test_oracle_output_is_frozen(oracle_mod):
+    """tests/golden/oracle_hashes.json (scripts/make_oracle_hashes.py) holds the sha256 of the oracle's pixels for every
+    fixture in both arithmetic variants, taken when the oracle was validated against the reference's goldens: the exact
+    pin that the +-3 PNG comparison cannot give.  ORC_ARITH_SSSE3_NATIVE (the timed CPU baseline) must hash the same as
+    the emulation."""
+    import hashlib
+    import json
+    pins = json.load(open(os.path.join(GOLDEN, "oracle_hashes.json")))
+    assert len(pins) >= 40
+    for rel, entry in pins.items():
+        data = open(os.path.join(GOLDEN, rel), "rb").read()
+        for name, a in (("scalar", oracle_mod.ARITH_SCALAR), ("ssse3", oracle_mod.ARITH_SSSE3), ("ssse3", oracle_mod.ARITH_SSSE3_NATIVE)):
+            want = entry[name]
+            try:
+                px = oracle_mod.Decoder(data, a).decode()
+                got = {"sha256": hashlib.sha256(px.tobytes()).hexdigest(), "bytes": int(px.size)}
+            except oracle_mod.OracleError as e:
+                got = {"error": int(e.code)}
+            assert got == want, (rel, name)

@@ -4,6 +4,7 @@ tests: src/idct.rs:580-657 (three IDCT KATs), src/parser.rs:312-329 (geometry), 
 import re
 
 import numpy as np
+import pytest
 
 COEFS = [-14, -39, 58, -2, 3, 3, 0, 1, 11, 27, 4, -3, 3, 0, 1, 0, -6, -13, -9, -1, -2, -1, 0, 0, -4, 0, -1, -2, 0, 0, 0, 0,
          3, 0, 0, 0, 0, 0, 0, 0, -3, -2, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0]
@@ -198,3 +199,13 @@ def test_ssse3_colour_path_never_saturates_for_8bit_inputs(oracle_mod):
         want = np.stack([np.clip(r_s[yy8[:k], 0, cr8[:k]], 0, 255), np.clip(g_s[yy8[:k], cb8[:k], cr8[:k]], 0, 255),
                          np.clip(b_s[yy8[:k], cb8[:k], 0], 0, 255)], -1).astype(np.uint8)
         assert np.array_equal(out[:3 * k].reshape(k, 3), want)
+
+
+@pytest.mark.parametrize("name", ["h2v2", "h2v1", "h1v2"])
+def test_hand_derived_upsampling_vectors(oracle_mod, name):
+    """The oracle against bytes worked out by hand from src/upsampler.rs (tests/hand_vectors.py)."""
+    from hand_vectors import planes_for
+    comps, planes, w, h, want = planes_for(oracle_mod.make_components, name, np.random.default_rng(1))
+    for arith in (oracle_mod.ARITH_SCALAR, oracle_mod.ARITH_SSSE3):
+        got = oracle_mod.compute_image(comps, planes, w, h, oracle_mod.CT_RGB, arith=arith).reshape(h, w, 3)
+        assert np.array_equal(got[..., 1], want), (name, got[..., 1])
