@@ -560,8 +560,11 @@ def measure_config(J, torch, ctx, dev, stream, unique, lo, B, steps, peak, sampl
 def roofline_of(m, peak, peak_src, cfgname, B):
     traffic = None
     try:
+        # DRAM bytes per image of the dominant kernel from the committed `ncu --set full` capture (scripts/ncu_traffic.py),
+        # scaled to this launch's batch: per launch, like `achieved`
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = tr.get("%s:%d" % (cfgname, B), {}).get(m["dominant"])
+        per_image = tr.get(cfgname, {}).get(m["dominant"])
+        traffic = per_image * B if per_image is not None else None
     except Exception:
         pass
     return {"bound": "hbm", "kernel": m["dominant"], "achieved": m["dom_gbs"], "peak": peak, "unit": "GB/s", "frac": m["dom_gbs"] / peak,

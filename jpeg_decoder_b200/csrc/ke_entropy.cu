@@ -166,40 +166,58 @@ __global__ void __launch_bounds__(ENT_THREADS) ent_sync(const EntImage* __restri
     }
     __shared__ EntShared sh;
     __shared__ uint32_t tile[TILE_WORDS + 32];
-    __shared__ unsigned char s_changed[ENT_THREADS];
+    // per subsequence of this CTA (index = threadIdx of its owner): last published state, flags; and the compacted work list
+    __shared__ unsigned long long s_mine[ENT_THREADS];
+    __shared__ unsigned char s_pend[ENT_THREADS], s_chg[ENT_THREADS], s_ever[ENT_THREADS], s_list[ENT_THREADS];
+    __shared__ unsigned s_n;
     const uint8_t* payload = streams + im.payload_off;
     const uint32_t* gwords = reinterpret_cast<const uint32_t*>(payload + im.data_off);
     stage_tile(tile, gwords, im.nwords, blockIdx.x * TILE_WORDS);
+    const unsigned t = threadIdx.x;
+    s_mine[t] = valid ? ld_state(&w.state[g]) : 0ull;
+    s_pend[t] = pending ? 1 : 0;
+    s_chg[t] = 0;
+    s_ever[t] = 0;
     load_shared(sh, im, payload);  // ends with a barrier
     const EntWordsTile words{tile, blockIdx.x * TILE_WORDS};
     const uint16_t* tabs = reinterpret_cast<const uint16_t*>(sh.tabs);
-    const uint32_t end = valid ? ent_sub_end(i, im.nsub, im.scan_bits) : 0u;
-    unsigned long long mine = valid ? ld_state(&w.state[g]) : 0ull;
-    bool ever = false, changed = false;
+    bool quiet = false;
+    // Every round the pending subsequences are gathered onto the first threads of the CTA: after the first round only a
+    // few of the 128 are pending (measured: 9.5 of 32 lanes active per instruction), and a re-decode costs the same
+    // issue slots whether 3 or 32 lanes of its warp take part.
     for (unsigned iter = 0; iter < ENT_LOCAL_ITERS; iter++) {
-        changed = false;
-        if (pending) {
-            EntState st = ent_unpack(ld_state(&w.state[g - 1]));
+        if (t == 0) s_n = 0;
+        __syncthreads();
+        if (s_pend[t]) s_list[atomicAdd(&s_n, 1u)] = (unsigned char)t;
+        s_chg[t] = 0;
+        __syncthreads();
+        if (t < s_n) {
+            const unsigned j = s_list[t];  // the subsequence this thread re-decodes (any order: rounds are order-free)
+            const unsigned ij = blockIdx.x * ENT_THREADS + j, gj = im.sub0 + ij;
+            EntState st = ent_unpack(ld_state(&w.state[gj - 1]));
             st.nb = 0;
             EntCountSink sink;
             unsigned bad = 0;
-            const unsigned long long v = ent_pack(ent_decode_range<false>(words, tabs, sh.dcslot, sh.acslot, im.dec_bpm, st, end, sink, &bad));
-            changed = ((v ^ mine) & ENT_SYNC_MASK) != 0;
-            if (v != mine) st_state(&w.state[g], v);  // the counts may change even when (p, k, b) do not
-            w.nvals[g] = sink.nvals;
-            mine = v;
+            const unsigned long long v = ent_pack(ent_decode_range<false>(words, tabs, sh.dcslot, sh.acslot, im.dec_bpm, st,
+                                                                         ent_sub_end(ij, im.nsub, im.scan_bits), sink, &bad));
+            const unsigned long long mine = s_mine[j];
+            const bool changed = ((v ^ mine) & ENT_SYNC_MASK) != 0;
+            if (v != mine) st_state(&w.state[gj], v);  // the counts may change even when (p, k, b) do not
+            w.nvals[gj] = sink.nvals;
+            s_mine[j] = v;
+            s_chg[j] = changed ? 1 : 0;
+            if (changed) s_ever[j] = 1;
         }
-        ever |= changed;
-        s_changed[threadIdx.x] = changed ? 1 : 0;
         __syncthreads();  // flags and states of this round are visible to the CTA
-        pending = valid && threadIdx.x > 0 && s_changed[threadIdx.x - 1] != 0;  // (threads past the image's end own no state)
-        if (!__syncthreads_or(pending)) {
-            changed = false;  // everything inside the CTA has been consumed
+        const bool next = valid && t > 0 && s_chg[t - 1] != 0;  // (threads past the image's end own no state)
+        s_pend[t] = next ? 1 : 0;
+        if (!__syncthreads_or(next)) {
+            quiet = true;  // everything inside the CTA has been consumed
             break;
         }
     }
     // for the next launch: the successor of my last thread lives in another CTA; changes of the final round are unconsumed
-    const bool flag = valid && (changed || (threadIdx.x == ENT_THREADS - 1 && ever));
+    const bool flag = valid && ((!quiet && s_chg[t] != 0) || (t == ENT_THREADS - 1 && s_ever[t] != 0));
     if (valid) ch_out[g] = flag ? 1 : 0;
     if (flag) w.counters[pass] = 1;
 }
