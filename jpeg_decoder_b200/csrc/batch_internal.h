@@ -68,6 +68,7 @@ struct b200jpg_batch {
     void* d_planes = nullptr;
     void* d_out = nullptr;
     bool planes_absolute = false;  // plane_off holds absolute device addresses (worker path)
+    bool outs_absolute = false;    // out_off holds absolute device addresses (whole-file engine, pixels staying on the device)
     bool slabs_borrowed = false;   // d_coefs/d_planes/d_out belong to the context's scratch cache
     bool tables_borrowed = false;  // the d_* tables live in a caller's TableArena
     size_t table_bytes = 0;        // bytes of that arena in use
@@ -90,6 +91,7 @@ struct TableArena {
 
 struct PlanOverrides {
     const unsigned long long (*plane_addr)[4] = nullptr;  // per image absolute device addresses of the planes
+    const unsigned long long* out_addr = nullptr;         // per image absolute device address of the pixels (no pixel slab)
     const TableArena* arena = nullptr;                    // nullptr: cudaMalloc each table
     cudaStream_t upload_stream = nullptr;                 // nullptr: the context's main stream
 };

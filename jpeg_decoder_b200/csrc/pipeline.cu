@@ -462,6 +462,7 @@ int batch_create_impl(b200jpg_ctx* ctx, const b200jpg_image_desc* imgs, size_t n
     b->layout.resize(n);
     b->images.resize(n);
     b->planes_absolute = ov.plane_addr != nullptr;
+    b->outs_absolute = ov.out_addr != nullptr;
     b->fmode.assign(n, -1);
     std::map<std::string, unsigned> qt_index;
     size_t coef_off = 0, plane_off = 0, out_off = 0;
@@ -548,10 +549,10 @@ int batch_create_impl(b200jpg_ctx* ctx, const b200jpg_image_desc* imgs, size_t n
         }
         L.tile_count = (unsigned)b->tiles.size() - L.tile_first;
         out_off = align_up(out_off, 256);
-        L.out_off = out_off;
+        L.out_off = ov.out_addr ? (size_t)ov.out_addr[i] : out_off;   // absolute: the kernels write the caller's buffer directly
         L.out_len = (size_t)d.width * d.height * d.ncomp;
-        img.out_off = out_off;
-        out_off += L.out_len;
+        img.out_off = L.out_off;
+        if (!ov.out_addr) out_off += L.out_len;
         b->info.n_pixels += (size_t)d.width * d.height;
         b->info.k2_algorithmic_bytes += L.out_len;
         // bulk-copy fed 4:2:0 kernel: every row it copies must start on a 16-byte boundary (cp.async.bulk)
@@ -670,7 +671,7 @@ int batch_launch(b200jpg_batch* b, const void* d_coefs, void* d_planes, void* d_
     b200jpg_ctx* ctx = b->ctx;
     // both stages in one call and every image of the range eligible: the fused kernel, planes never leave the SM
     const unsigned fmodes = fuse_modes(ctx);
-    if (stages == 3 && img_count && fmodes && ((uintptr_t)d_coefs % 16 == 0) && d_out) {
+    if (stages == 3 && img_count && fmodes && ((uintptr_t)d_coefs % 16 == 0) && (d_out || b->outs_absolute)) {
         bool all = true;
         for (unsigned i = img_first; i < img_first + img_count && all; i++)
             all = b->layout[i].status != B200JPG_OK || (b->fmode[i] >= 0 && ((fmodes >> b->fmode[i]) & 1u));

@@ -236,8 +236,19 @@ int SbsPipeline::enqueue(Slot& s) {
         for (int c = 0; c < descs[i].ncomp && c < 4; c++)
             tbound += sizeof(DevComp) + 96 * sizeof(unsigned) + ((size_t)descs[i].comps[c].block_w * descs[i].comps[c].block_h / K1_TILE + 1) * sizeof(DevTile);
         tbound += ((size_t)descs[i].width / 2048 + 1) * sizeof(K2Strip);
+        tbound += ((size_t)descs[i].width / 960 + 2) * sizeof(FColumn);
     }
-    tbound += max_ent * sizeof(EntImage);
+    tbound += max_ent * sizeof(EntImage) + 1024;
+    // Pixel buffers in device memory (every image of the group): the kernels write them directly -- no pixel slab, no
+    // device-to-device copy afterwards (unified addressing tells host from device pointers).
+    bool device_outs = n > 0;
+    std::vector<unsigned long long> out_addr(n, 0ull);
+    for (size_t i = 0; i < n && device_outs; i++) {
+        cudaPointerAttributes pa;
+        if (!it[i].out || cudaPointerGetAttributes(&pa, it[i].out) != cudaSuccess || pa.type != cudaMemoryTypeDevice) device_outs = false;
+        out_addr[i] = (unsigned long long)(uintptr_t)it[i].out;
+    }
+    cudaGetLastError();
     int rc = grow_device(s.d_tables, tbound);
     if (rc == B200JPG_OK) rc = grow_pinned(s.h_tables, tbound);
     if (rc) return rc;
@@ -249,6 +260,7 @@ int SbsPipeline::enqueue(Slot& s) {
     PlanOverrides ov;
     ov.arena = &arena;
     ov.upload_stream = s_in_;
+    if (device_outs) ov.out_addr = out_addr.data();
     rc = batch_create_impl(ctx_, descs.data(), n, s.group.statuses.data(), ov, &s.batch);
     if (rc) return rc;
     b200jpg_batch* b = s.batch;
@@ -348,12 +360,6 @@ int SbsPipeline::enqueue(Slot& s) {
     // Pixels that leave over PCIe: one compute stream, first in first out, so that the oldest group finishes (and starts
     // downloading) as early as possible.  Pixels that stay in device memory: nothing downstream is waiting, and two
     // alternating streams let the next group's kernels fill the SMs during the latency-bound synchronisation rounds.
-    bool device_outs = true;
-    for (size_t i = 0; i < n && device_outs; i++) {
-        cudaPointerAttributes pa;
-        if (!it[i].out || cudaPointerGetAttributes(&pa, it[i].out) != cudaSuccess || pa.type != cudaMemoryTypeDevice) device_outs = false;
-    }
-    cudaGetLastError();
     cudaStream_t s_comp_ = s_comp2_[device_outs ? (next_ & 1) : 0];
     if (device_outs != last_device_outs_) {  // switching modes: do not let the two streams' groups race each other's events
         for (auto& sc : s_comp2_) CU_TRY(ctx_, cudaStreamSynchronize(sc));
@@ -379,14 +385,14 @@ int SbsPipeline::enqueue(Slot& s) {
         ctx_->launches++;
     }
     if (nk0 || nent) {
-        rc = batch_launch(b, s.d_coefs.p, s.d_planes.p, s.d_out.p, 3, 0, (unsigned)b->tiles.size(), 0, (unsigned)n, s_comp_);
+        rc = batch_launch(b, s.d_coefs.p, s.d_planes.p, device_outs ? nullptr : s.d_out.p, 3, 0, (unsigned)b->tiles.size(), 0, (unsigned)n, s_comp_);
         if (rc) return rc;
     }
     CU_TRY(ctx_, cudaEventRecord(s.e_comp, s_comp_));
     // copy-out (cudaMemcpyDefault: the callers' pixel buffers may be host OR device memory -- unified addressing tells)
     CU_TRY(ctx_, cudaStreamWaitEvent(s_out_, s.e_comp, 0));
     if (nent) CU_TRY(ctx_, cudaMemcpyAsync(s.h_status.p, d_status, nent * 8, cudaMemcpyDeviceToHost, s_out_));
-    {
+    if (!device_outs) {
         char* out_dst = nullptr;
         size_t out_src = 0, out_bytes = 0;
         for (size_t i = 0; i < n; i++) {
@@ -402,8 +408,8 @@ int SbsPipeline::enqueue(Slot& s) {
             }
         }
         if (out_bytes) CU_TRY(ctx_, cudaMemcpyAsync(out_dst, (char*)s.d_out.p + out_src, out_bytes, cudaMemcpyDefault, s_out_));
-        CU_TRY(ctx_, cudaEventRecord(s.e_done, s_out_));
     }
+    CU_TRY(ctx_, cudaEventRecord(s.e_done, s_out_));
     return B200JPG_OK;
 }
 

@@ -235,6 +235,13 @@ int stream_engine_run(b200jpg_ctx* ctx, JobSource& src, int nthreads) {
     // larger when they stay on the device (per-group latencies amortise over more images)
     const bool dev_out = src.outputs_on_device();
     const size_t max_items = dev_out ? 96 : 32, max_bytes = (size_t)(dev_out ? 640 : 160) << 20;
+    // A short bounded wait lets a few more images join a very small group.  Waiting for LARGE groups when the pixels stay
+    // on the device (to amortise the latency-bound synchronisation rounds of the entropy kernels) was measured and loses:
+    // 54.6 GP/s with min 1, 50.4 / 47.8 / 45.7 with min 24 / 48 / 96 images (profiles/r02_files_group_size.jsonl) --
+    // small groups alternating over two compute streams overlap better than large ones amortise.  B200JPG_GROUP_MIN: knob.
+    static const size_t min_items_env = getenv("B200JPG_GROUP_MIN") ? (size_t)atoi(getenv("B200JPG_GROUP_MIN")) : 0;
+    const size_t min_items = min_items_env ? min_items_env : 4;
+    const int fill_us = min_items_env > 4 ? 1500 : 150;
     size_t ngroups = 0, nitems = 0;
     double idle_ms = 0, submit_ms = 0;
     int result = B200JPG_OK;
@@ -245,8 +252,13 @@ int stream_engine_run(b200jpg_ctx* ctx, JobSource& src, int nthreads) {
             std::unique_lock<std::mutex> lk(mu);
             const double w0 = now_ms();
             if (queue.empty() && workers_active > 0) items_cv.wait_for(lk, std::chrono::microseconds(200));
-            // a short second wait lets a few more images join a very small group (fewer, larger launches)
-            if (!queue.empty() && queue.size() < 4 && workers_active > 0) items_cv.wait_for(lk, std::chrono::microseconds(150));
+            // a bounded second wait lets more images join a small group (fewer, larger launches)
+            if (!queue.empty() && queue.size() < min_items && workers_active > 0) {
+                const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(fill_us);
+                while (queue.size() < min_items && workers_active > 0 && (ngroups > 0 || !dev_out) &&
+                       items_cv.wait_until(lk, deadline) != std::cv_status::timeout) {
+                }
+            }
             idle_ms += now_ms() - w0;
             size_t bytes = 0;
             while (!queue.empty() && group.size() < max_items && bytes < max_bytes) {

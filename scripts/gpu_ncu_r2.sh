@@ -14,3 +14,6 @@ echo "== launch list"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extra-configs > $OUT/ncu_bench.log 2>&1
 grep -E "k1_|k2_|kf_|k0_|ent_" $OUT/launches.csv | awk -F'","' '{print $5}' | sed 's/(.*//' | sort | uniq -c | sort -rn | head -20
 ls -la $OUT
+echo "== group size A/B (device outputs)"
+for g in 1 24 48 96; do B200JPG_GROUP_MIN=$g timeout 300 python scripts/files_bench.py --dev-out --reps 10 --tag "groupmin-$g" 2>/dev/null | tee -a $OUT/group_ab.jsonl | cut -c1-330; done
+B200JPG_GROUP_MIN=48 timeout 300 python scripts/files_bench.py --reps 6 --tag "hostout" 2>/dev/null | tee -a $OUT/group_ab.jsonl | cut -c1-330
