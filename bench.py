@@ -849,6 +849,13 @@ def main():
                                           "api": "b200jpg_decode_files x512: progressive scans are entropy-decoded and accumulated on the host threads "
                                                  "(src/decoder.rs:400-412, 1035-1048), the finished coefficients go to the GPU as sparse streams"}
                         del f4
+                    if not args.no_cpu_baseline:   # the CPU arm on the same config (bounded samples), for a like-for-like ratio
+                        oi = [OracleImage(u.jpeg) for u in uq[:2]]
+                        ncores = os.cpu_count() or 1
+                        cv, cs = cpu_hotpath_throughput(oi, ncores, 2.5, args.cpu_arith)
+                        cf, cfs = cpu_files_throughput([u.jpeg for u in uq[:2]], c2["width"], c2["height"], ncores, 2.5, args.cpu_arith)
+                        entry["cpu_baseline"] = {"value": cv, "unit": "MP/s", "cores": ncores, "kind": "port", "arith": args.cpu_arith, "sample": cs,
+                                                 "files": {"value": cf, "unit": "MP/s", "sample": cfs}}
                     configs[name] = entry
                 except Exception as e:   # an extra config must not take the headline down with it
                     configs[name] = {"error": repr(e)}
