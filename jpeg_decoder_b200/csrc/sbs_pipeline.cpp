@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 
 #include "entropy_host.h"
 
@@ -21,6 +22,7 @@ static int ent_max_passes() {
 }
 
 static inline size_t up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static inline double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 SbsPipeline::SbsPipeline(b200jpg_ctx* ctx, int nslots) : ctx_(ctx) {
     if (cudaSetDevice(ctx->device) != cudaSuccess) return;
@@ -70,13 +72,15 @@ SbsPipeline::~SbsPipeline() {
     if (s_out_) cudaStreamDestroy(s_out_);
 }
 
-int SbsPipeline::grow_device(Buf& b, size_t need) {
+int SbsPipeline::grow_device(Buf& b, size_t need, size_t hint) {
     if (need <= b.cap) return B200JPG_OK;
+    const double t0 = now_ms();
+    struct Tally { SbsPipeline* p; double t0; ~Tally() { p->grow_ms += now_ms() - t0; p->grows++; } } tally{this, t0};
     // doubling, so that a buffer regrows a handful of times in its life.  The slot is idle (its previous group has
     // retired), and every stream that touches the buffer afterwards first waits for work enqueued on s_in_.
     // (group sizes depend on timing -- how many images were ready when the submitter came round -- so a new maximum can
     // turn up many calls into a run: twice the need, so that the buffers settle after two or three regrowths)
-    const size_t want = up(std::max(2 * need, 2 * b.cap), 1 << 20);
+    const size_t want = up(need <= hint ? hint : std::max(2 * need, 2 * b.cap), 1 << 20);   // within the reservation: once and for all
     if (async_alloc_) {
         if (b.p) CU_TRY(ctx_, cudaFreeAsync(b.p, s_in_));
         b.p = nullptr;
@@ -91,12 +95,14 @@ int SbsPipeline::grow_device(Buf& b, size_t need) {
     b.cap = want;
     return B200JPG_OK;
 }
-int SbsPipeline::grow_pinned(Buf& b, size_t need) {
+int SbsPipeline::grow_pinned(Buf& b, size_t need, size_t hint) {
     if (need <= b.cap) return B200JPG_OK;
+    const double t0 = now_ms();
+    struct Tally { SbsPipeline* p; double t0; ~Tally() { p->grow_ms += now_ms() - t0; p->grows++; } } tally{this, t0};
     if (b.p) cudaFreeHost(b.p);
     b.p = nullptr;
     b.cap = 0;
-    const size_t want = up(need + need / 4, 1 << 16);
+    const size_t want = up(need <= hint ? hint : need + need / 4, 1 << 16);
     CU_TRY(ctx_, cudaHostAlloc(&b.p, want, cudaHostAllocDefault));
     b.cap = want;
     return B200JPG_OK;
@@ -192,12 +198,16 @@ int SbsPipeline::submit(std::vector<SbsItem>&& items) {
     if (items.empty()) return B200JPG_OK;
     CU_TRY(ctx_, cudaSetDevice(ctx_->device));
     if (next_ - oldest_ >= slots_.size()) {  // the slot we are about to reuse is still in flight
+        const double t_w = now_ms();
+        struct Tally { SbsPipeline* p; double t0; ~Tally() { p->retire_wait_ms += now_ms() - t0; } } tally{this, t_w};
         retire(slots_[oldest_ % slots_.size()], true);
         oldest_++;
     }
     Slot& s = slots_[next_ % slots_.size()];
     s.group.items = std::move(items);
+    const double t_enq = now_ms();
     const int rc = enqueue(s);
+    enqueue_ms += now_ms() - t_enq;
     if (rc != B200JPG_OK) {  // leave the slot reusable: nothing of this group may still be running
         cudaStreamSynchronize(s_in_);
         for (auto& sc : s_comp2_) cudaStreamSynchronize(sc);
@@ -249,8 +259,8 @@ int SbsPipeline::enqueue(Slot& s) {
         out_addr[i] = (unsigned long long)(uintptr_t)it[i].out;
     }
     cudaGetLastError();
-    int rc = grow_device(s.d_tables, tbound);
-    if (rc == B200JPG_OK) rc = grow_pinned(s.h_tables, tbound);
+    int rc = grow_device(s.d_tables, tbound, reserve_ ? (size_t)8 << 20 : 0);
+    if (rc == B200JPG_OK) rc = grow_pinned(s.h_tables, tbound, reserve_ ? (size_t)8 << 20 : 0);
     if (rc) return rc;
 
     TableArena arena;
@@ -326,12 +336,15 @@ int SbsPipeline::enqueue(Slot& s) {
         stream_bytes += it[i].len;
     }
     const int passes = ent_max_passes();
-    rc = grow_device(s.d_streams, std::max(stream_bytes, cs_at) + 256);
-    if (rc == B200JPG_OK) rc = grow_device(s.d_coefs, b->info.coef_bytes + K1_TILE * 128);
-    if (rc == B200JPG_OK) rc = grow_device(s.d_planes, b->info.plane_bytes + 256);
-    if (rc == B200JPG_OK) rc = grow_device(s.d_out, b->info.out_bytes + 256);
-    if (rc == B200JPG_OK && nent) rc = grow_device(s.d_ent, ent_work_bytes(total_sub, (unsigned)nent, max_comp_blocks, passes));
-    if (rc == B200JPG_OK && nent) rc = grow_pinned(s.h_status, nent * 8);
+    // reservation: one more image than the cap may join a group; planes are half the coefficient bytes, pixels at most as
+    // many, the compact streams of device-decoded scans 140 B per block against 128 B dense, plus the uploaded payloads
+    const size_t R = reserve_ ? reserve_ + reserve_ / 8 : 0;
+    rc = grow_device(s.d_streams, std::max(stream_bytes, cs_at) + 256, R + R / 4 + (R ? (size_t)32 << 20 : 0));
+    if (rc == B200JPG_OK) rc = grow_device(s.d_coefs, b->info.coef_bytes + K1_TILE * 128, R);
+    if (rc == B200JPG_OK) rc = grow_device(s.d_planes, b->info.plane_bytes + 256, R / 2);
+    if (rc == B200JPG_OK) rc = grow_device(s.d_out, b->info.out_bytes + 256, device_outs ? 0 : R);
+    if (rc == B200JPG_OK && nent) rc = grow_device(s.d_ent, ent_work_bytes(total_sub, (unsigned)nent, max_comp_blocks, passes), R / 16);
+    if (rc == B200JPG_OK && nent) rc = grow_pinned(s.h_status, nent * 8, reserve_ ? (size_t)1 << 20 : 0);
     if (rc) return rc;
 
     // copy-in

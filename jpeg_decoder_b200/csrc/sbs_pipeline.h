@@ -54,6 +54,16 @@ public:
     // optional: keep dense slab copies for debugging (tests): after drain(), the last group's coefficient slab
     const void* last_coef_slab() const { return last_coefs_; }
 
+    // The caller's bound on the dense coefficient bytes of one group (the stream engine's group cap): slot buffers are sized
+    // for it the first time they are needed, so that nothing regrows in steady state.  A regrowth of a few hundred MB costs
+    // 15-50 ms even from the stream-ordered allocator (measured: profiles/r02_files_regrowth_trace.txt); group sizes depend on
+    // timing, so without the reservation a new maximum -- and a stall -- can turn up many calls into a run.
+    void reserve_for_group_bytes(size_t coef_bytes) { reserve_ = coef_bytes; }
+
+    // trace counters (B200JPG_TRACE): time and count of buffer regrowths, time inside enqueue, time waiting for a slot
+    double grow_ms = 0, enqueue_ms = 0, retire_wait_ms = 0;
+    unsigned grows = 0;
+
 private:
     struct Buf {
         void* p = nullptr;
@@ -68,8 +78,8 @@ private:
         b200jpg_batch* batch = nullptr;
         Group group;
     };
-    int grow_device(Buf& b, size_t need);
-    int grow_pinned(Buf& b, size_t need);
+    int grow_device(Buf& b, size_t need, size_t hint = 0);
+    int grow_pinned(Buf& b, size_t need, size_t hint = 0);
     void retire(Slot& s, bool wait);
     int enqueue(Slot& s);
 
@@ -81,6 +91,7 @@ private:
     std::vector<Slot> slots_;
     size_t next_ = 0, oldest_ = 0;  // tickets: slot = ticket % nslots
     bool last_device_outs_ = false;
+    size_t reserve_ = 0;
     bool async_alloc_ = false;  // slot buffers come from the stream-ordered allocator (cudaMallocAsync on s_in_)
     const void* last_coefs_ = nullptr;
     int error_ = B200JPG_OK;

@@ -216,6 +216,9 @@ int stream_engine_run(b200jpg_ctx* ctx, JobSource& src, int nthreads) {
     };
 
     SbsPipeline& pipe = *eng->pipe;
+    pipe.reserve_for_group_bytes((size_t)(src.outputs_on_device() ? 640 : 160) << 20);
+    pipe.grow_ms = pipe.enqueue_ms = pipe.retire_wait_ms = 0;
+    pipe.grows = 0;
     auto release = [&](const std::vector<SbsItem>& items) {
         for (const SbsItem& it : items) eng->rings[(size_t)it.thread]->book.release(it.ring_end);
         {
@@ -300,9 +303,11 @@ int stream_engine_run(b200jpg_ctx* ctx, JobSource& src, int nthreads) {
     if (trace)
         fprintf(stderr,
                 "[b200jpg] %s: %zu images, %d host threads, %.1f ms; %zu groups (%.1f images each); submitter idle %.1f ms, "
-                "busy %.1f ms; host threads: %.2f ms/image, waiting for ring space %.1f ms in total\n",
+                "busy %.1f ms (enqueue %.1f, of it %u buffer regrowths %.1f; waiting for a free slot %.1f); host threads: %.2f ms/image, "
+                "waiting for ring space %.1f ms in total\n",
                 src.name(), n, nthreads, now_ms() - t_start, ngroups, ngroups ? (double)nitems / ngroups : 0.0, idle_ms, submit_ms,
-                nitems ? produce_us.load() / 1e3 / nitems : 0.0, ring_wait_us.load() / 1e3);
+                pipe.enqueue_ms, pipe.grows, pipe.grow_ms, pipe.retire_wait_ms, nitems ? produce_us.load() / 1e3 / nitems : 0.0,
+                ring_wait_us.load() / 1e3);
     return result;
 }
 
