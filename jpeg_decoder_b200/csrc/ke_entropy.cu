@@ -17,7 +17,10 @@ namespace b200jpg {
 namespace {
 
 constexpr int ENT_COLD = 0, ENT_WRITE = 2;
-constexpr unsigned ENT_THREADS = 128;
+#ifndef B200JPG_ENT_THREADS
+#define B200JPG_ENT_THREADS 128
+#endif
+constexpr unsigned ENT_THREADS = B200JPG_ENT_THREADS;  // subsequences per CTA (build-time knob, with ENT_SUB_BITS)
 
 struct EntShared {
     EntImage im;

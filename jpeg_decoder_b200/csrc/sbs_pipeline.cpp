@@ -40,12 +40,20 @@ SbsPipeline::SbsPipeline(b200jpg_ctx* ctx, int nslots) : ctx_(ctx) {
         async_alloc_ = true;
     }
     cudaGetLastError();
+    if (const char* e = getenv("B200JPG_COMP_STREAMS")) ncomp_streams_ = (unsigned)std::min(4, std::max(1, atoi(e)));
+    if (const char* e = getenv("B200JPG_SLOTS")) nslots = std::min(8, std::max(2, atoi(e)));
     slots_.resize((size_t)std::max(2, nslots));
+    timeline_ = getenv("B200JPG_TIMELINE") != nullptr;
+    const unsigned ev_flags = timeline_ ? cudaEventDefault : cudaEventDisableTiming;
     for (auto& s : slots_) {
-        if (cudaEventCreateWithFlags(&s.e_h2d, cudaEventDisableTiming) != cudaSuccess) return;
-        if (cudaEventCreateWithFlags(&s.e_comp, cudaEventDisableTiming) != cudaSuccess) return;
-        if (cudaEventCreateWithFlags(&s.e_done, cudaEventDisableTiming) != cudaSuccess) return;
+        if (cudaEventCreateWithFlags(&s.e_h2d, ev_flags) != cudaSuccess) return;
+        if (cudaEventCreateWithFlags(&s.e_comp, ev_flags) != cudaSuccess) return;
+        if (cudaEventCreateWithFlags(&s.e_done, ev_flags) != cudaSuccess) return;
+        if (timeline_)
+            for (auto& e : s.e_t0)
+                if (cudaEventCreate(&e) != cudaSuccess) return;
     }
+    if (timeline_ && cudaEventCreate(&e_base_) != cudaSuccess) return;
     ok_ = true;
 }
 
@@ -62,10 +70,14 @@ SbsPipeline::~SbsPipeline() {
         cudaFree(s.d_ent.p);
         if (s.h_tables.p) cudaFreeHost(s.h_tables.p);
         if (s.h_status.p) cudaFreeHost(s.h_status.p);
+        if (s.h_stage.p) cudaFreeHost(s.h_stage.p);
         if (s.e_h2d) cudaEventDestroy(s.e_h2d);
         if (s.e_comp) cudaEventDestroy(s.e_comp);
         if (s.e_done) cudaEventDestroy(s.e_done);
+        for (auto& e : s.e_t0)
+            if (e) cudaEventDestroy(e);
     }
+    if (e_base_) cudaEventDestroy(e_base_);
     if (s_in_) cudaStreamDestroy(s_in_);
     for (auto& sc : s_comp2_)
         if (sc) cudaStreamDestroy(sc);
@@ -135,6 +147,14 @@ void SbsPipeline::retire(Slot& s, bool wait) {
                         s.group.items[i].desc.width, s.group.items[i].desc.height, st[0], st[1]);
         }
     }
+    if (timeline_) {
+        float t[6] = {0, 0, 0, 0, 0, 0};
+        cudaEvent_t ev[6] = {s.e_t0[0], s.e_h2d, s.e_t0[1], s.e_comp, s.e_t0[2], s.e_done};
+        for (int k = 0; k < 6; k++) cudaEventElapsedTime(&t[k], e_base_, ev[k]);
+        cudaGetLastError();
+        fprintf(stderr, "[b200jpg] timeline: group of %3zu enqueued %7.2f | upload %7.2f-%7.2f | kernels %7.2f-%7.2f | download %7.2f-%7.2f | retired %7.2f\n",
+                s.group.items.size(), s.t_enq - t_base_, t[0], t[1], t[2], t[3], t[4], t[5], now_ms() - t_base_);
+    }
     if (on_done) on_done(s.group);
     if (s.batch) {
         batch_release_device(s.batch);
@@ -191,6 +211,14 @@ static void fill_k0(const b200jpg_image_desc& d, const ImageLayout& L, unsigned 
     k->bpm = j ? j : 1;
     k->mcu_w = d.comps[0].h ? d.comps[0].block_w / d.comps[0].h : 1;
     if (k->mcu_w == 0) k->mcu_w = 1;
+}
+
+void SbsPipeline::timeline_begin() {
+    if (!timeline_ || !ok_) return;
+    cudaSetDevice(ctx_->device);
+    cudaEventRecord(e_base_, s_in_);
+    cudaEventSynchronize(e_base_);
+    t_base_ = now_ms();
 }
 
 int SbsPipeline::submit(std::vector<SbsItem>&& items) {
@@ -348,7 +376,25 @@ int SbsPipeline::enqueue(Slot& s) {
     if (rc) return rc;
 
     // copy-in
-    {
+    s.t_enq = now_ms();
+    if (timeline_) CU_TRY(ctx_, cudaEventRecord(s.e_t0[0], s_in_));
+    // Pixels that leave over PCIe: the group's streams go up as ONE copy from a page-locked staging buffer the submitter
+    // fills.  While the download stream saturates the link every upload operation crawls (17 MB in 2.4 ms) and slows the
+    // download; ~27 of them per group cost the download 8 % more than one (scripts/pcie_probe3.py; 15.2 -> 16.0 GP/s,
+    // profiles/r02_files_gather_ab.jsonl).  The gather is a host memcpy of 0.3 B per pixel on the submitter thread, which
+    // otherwise waits for the download anyway; with pixels staying on the device it would be the bottleneck (measured:
+    // 65 -> 23 GP/s), so there the streams are uploaded from where the host threads wrote them.  B200JPG_GATHER=0/1 forces.
+    static const int gather_env = getenv("B200JPG_GATHER") ? atoi(getenv("B200JPG_GATHER")) : -1;
+    const bool gather = gather_env >= 0 ? gather_env != 0 : !device_outs;
+    if (gather && stream_bytes) {
+        rc = grow_pinned(s.h_stage, stream_bytes, reserve_ ? (size_t)48 << 20 : 0);
+        if (rc) return rc;
+        for (size_t i = 0; i < n; i++)
+            if (!s.group.statuses[i]) memcpy((char*)s.h_stage.p + soff[i], it[i].stream, it[i].len);
+        CU_TRY(ctx_, cudaMemcpyAsync(s.d_streams.p, s.h_stage.p, stream_bytes, cudaMemcpyHostToDevice, s_in_));
+        h2d_copies++;
+    }
+    if (!gather) {
         const char* run_src = nullptr;
         size_t run_dst = 0, run_bytes = 0;
         for (size_t i = 0; i < n; i++) {
@@ -362,23 +408,27 @@ int SbsPipeline::enqueue(Slot& s) {
                 run_src = src;
                 run_dst = dst;
                 run_bytes = it[i].len;
+                h2d_copies++;
             }
         }
         if (run_bytes) CU_TRY(ctx_, cudaMemcpyAsync((char*)s.d_streams.p + run_dst, run_src, run_bytes, cudaMemcpyHostToDevice, s_in_));
-        if (nk0) CU_TRY(ctx_, cudaMemcpyAsync((void*)d_k0, h_k0, nk0 * sizeof(K0Image), cudaMemcpyHostToDevice, s_in_));
-        if (nent) CU_TRY(ctx_, cudaMemcpyAsync((void*)d_ent, h_ent, nent * sizeof(EntImage), cudaMemcpyHostToDevice, s_in_));
-        CU_TRY(ctx_, cudaEventRecord(s.e_h2d, s_in_));
     }
+    // the K0 and entropy descriptors lie behind each other in the table arena: one copy
+    if (nk0 || nent)
+        CU_TRY(ctx_, cudaMemcpyAsync((void*)d_k0, h_k0, (nent ? ent_at + nent * sizeof(EntImage) : k0_at + nk0 * sizeof(K0Image)) - k0_at,
+                                     cudaMemcpyHostToDevice, s_in_));
+    CU_TRY(ctx_, cudaEventRecord(s.e_h2d, s_in_));
     // compute
     // Pixels that leave over PCIe: one compute stream, first in first out, so that the oldest group finishes (and starts
-    // downloading) as early as possible.  Pixels that stay in device memory: nothing downstream is waiting, and two
-    // alternating streams let the next group's kernels fill the SMs during the latency-bound synchronisation rounds.
-    cudaStream_t s_comp_ = s_comp2_[device_outs ? (next_ & 1) : 0];
+    // downloading) as early as possible.  Pixels that stay in device memory: nothing downstream is waiting, and rotating
+    // over four streams lets the following groups' kernels fill the SMs during the latency-bound synchronisation rounds.
+    cudaStream_t s_comp_ = s_comp2_[device_outs ? next_ % ncomp_streams_ : 0];
     if (device_outs != last_device_outs_) {  // switching modes: do not let the two streams' groups race each other's events
         for (auto& sc : s_comp2_) CU_TRY(ctx_, cudaStreamSynchronize(sc));
         last_device_outs_ = device_outs;
     }
     CU_TRY(ctx_, cudaStreamWaitEvent(s_comp_, s.e_h2d, 0));
+    if (timeline_) CU_TRY(ctx_, cudaEventRecord(s.e_t0[1], s_comp_));
     unsigned* d_status = nullptr;
     if (nent) {
         // Huffman decoding on the device: payloads -> compact streams (bitmaps are OR-ed into: zero them first) ...
@@ -404,6 +454,7 @@ int SbsPipeline::enqueue(Slot& s) {
     CU_TRY(ctx_, cudaEventRecord(s.e_comp, s_comp_));
     // copy-out (cudaMemcpyDefault: the callers' pixel buffers may be host OR device memory -- unified addressing tells)
     CU_TRY(ctx_, cudaStreamWaitEvent(s_out_, s.e_comp, 0));
+    if (timeline_) CU_TRY(ctx_, cudaEventRecord(s.e_t0[2], s_out_));
     if (nent) CU_TRY(ctx_, cudaMemcpyAsync(s.h_status.p, d_status, nent * 8, cudaMemcpyDeviceToHost, s_out_));
     if (!device_outs) {
         char* out_dst = nullptr;
@@ -418,6 +469,7 @@ int SbsPipeline::enqueue(Slot& s) {
                 out_dst = (char*)it[i].out;
                 out_src = L.out_off;
                 out_bytes = L.out_len;
+                d2h_copies++;
             }
         }
         if (out_bytes) CU_TRY(ctx_, cudaMemcpyAsync(out_dst, (char*)s.d_out.p + out_src, out_bytes, cudaMemcpyDefault, s_out_));

@@ -62,7 +62,10 @@ public:
 
     // trace counters (B200JPG_TRACE): time and count of buffer regrowths, time inside enqueue, time waiting for a slot
     double grow_ms = 0, enqueue_ms = 0, retire_wait_ms = 0;
-    unsigned grows = 0;
+    // B200JPG_TIMELINE=1: one stderr line per group with the device times of its upload, kernels and download (ms since the
+    // call began) -- the poor man's timeline where no system profiler is installed
+    void timeline_begin();
+    unsigned grows = 0, h2d_copies = 0, d2h_copies = 0;  // copies = cudaMemcpyAsync calls for streams / pixels
 
 private:
     struct Buf {
@@ -70,10 +73,12 @@ private:
         size_t cap = 0;
     };
     struct Slot {
-        Buf d_streams, d_coefs, d_planes, d_out, d_tables, h_tables, d_ent, h_status;
+        Buf d_streams, d_coefs, d_planes, d_out, d_tables, h_tables, d_ent, h_status, h_stage;
         std::vector<size_t> ent_items;  // group index of the image of every device-decoded restart interval
         size_t ent_images = 0;          // images of the group whose scan is decoded on the device
         cudaEvent_t e_h2d = nullptr, e_comp = nullptr, e_done = nullptr;
+        cudaEvent_t e_t0[3] = {nullptr, nullptr, nullptr};  // B200JPG_TIMELINE: when the upload / the kernels / the download of the group began
+        double t_enq = 0;  // host clock when the group was handed to the streams
         bool busy = false, h2d_reported = false;
         b200jpg_batch* batch = nullptr;
         Group group;
@@ -85,13 +90,17 @@ private:
 
     b200jpg_ctx* ctx_;
     bool ok_ = false;
-    // two compute streams, alternating by group: the synchronisation rounds of device entropy decoding are latency-bound
+    // up to four compute streams, taken in turn by the groups: the synchronisation rounds of device entropy decoding are latency-bound
     // (a few lanes busy per round), so the next group's throughput-bound kernels fill the machine meanwhile
-    cudaStream_t s_in_ = nullptr, s_comp2_[2] = {nullptr, nullptr}, s_out_ = nullptr;
+    cudaStream_t s_in_ = nullptr, s_comp2_[4] = {nullptr, nullptr, nullptr, nullptr}, s_out_ = nullptr;
+    unsigned ncomp_streams_ = 4;  // compute streams device-output groups rotate over (B200JPG_COMP_STREAMS, 1..4; measured 53.5 / 59.8 / 64.3 / 65.7 GP/s: profiles/r02_files_streams_ab.jsonl)
     std::vector<Slot> slots_;
     size_t next_ = 0, oldest_ = 0;  // tickets: slot = ticket % nslots
     bool last_device_outs_ = false;
     size_t reserve_ = 0;
+    bool timeline_ = false;
+    cudaEvent_t e_base_ = nullptr;
+    double t_base_ = 0;
     bool async_alloc_ = false;  // slot buffers come from the stream-ordered allocator (cudaMallocAsync on s_in_)
     const void* last_coefs_ = nullptr;
     int error_ = B200JPG_OK;

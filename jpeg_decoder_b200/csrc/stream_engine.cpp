@@ -136,7 +136,7 @@ int stream_engine_run(b200jpg_ctx* ctx, JobSource& src, int nthreads) {
     std::lock_guard<std::mutex> call_lock(eng->call_mu);
     if (cudaSetDevice(ctx->device) != cudaSuccess) return B200JPG_ERR_INTERNAL;
     if (!eng->pipe) {
-        eng->pipe.reset(new SbsPipeline(ctx, 4));
+        eng->pipe.reset(new SbsPipeline(ctx, 8));
         if (!eng->pipe->ok()) {
             eng->pipe.reset();
             return b200jpg_fail(ctx, B200JPG_ERR_INTERNAL, "internal: could not create the device pipeline (streams / events)");
@@ -218,7 +218,8 @@ int stream_engine_run(b200jpg_ctx* ctx, JobSource& src, int nthreads) {
     SbsPipeline& pipe = *eng->pipe;
     pipe.reserve_for_group_bytes((size_t)(src.outputs_on_device() ? 640 : 160) << 20);
     pipe.grow_ms = pipe.enqueue_ms = pipe.retire_wait_ms = 0;
-    pipe.grows = 0;
+    pipe.grows = pipe.h2d_copies = pipe.d2h_copies = 0;
+    pipe.timeline_begin();
     auto release = [&](const std::vector<SbsItem>& items) {
         for (const SbsItem& it : items) eng->rings[(size_t)it.thread]->book.release(it.ring_end);
         {
@@ -241,7 +242,7 @@ int stream_engine_run(b200jpg_ctx* ctx, JobSource& src, int nthreads) {
     // A short bounded wait lets a few more images join a very small group.  Waiting for LARGE groups when the pixels stay
     // on the device (to amortise the latency-bound synchronisation rounds of the entropy kernels) was measured and loses:
     // 54.6 GP/s with min 1, 50.4 / 47.8 / 45.7 with min 24 / 48 / 96 images (profiles/r02_files_group_size.jsonl) --
-    // small groups alternating over two compute streams overlap better than large ones amortise.  B200JPG_GROUP_MIN: knob.
+    // small groups taking turns on several compute streams overlap better than large ones amortise.  B200JPG_GROUP_MIN: knob.
     static const size_t min_items_env = getenv("B200JPG_GROUP_MIN") ? (size_t)atoi(getenv("B200JPG_GROUP_MIN")) : 0;
     const size_t min_items = min_items_env ? min_items_env : 4;
     const int fill_us = min_items_env > 4 ? 1500 : 150;
@@ -279,6 +280,9 @@ int stream_engine_run(b200jpg_ctx* ctx, JobSource& src, int nthreads) {
             if (!group.empty()) {
                 ngroups++;
                 nitems += group.size();
+                // neighbouring jobs next to each other: callers usually lay their pixel buffers out that way, and pixels that are
+                // contiguous on both sides leave the device as one copy
+                std::sort(group.begin(), group.end(), [](const SbsItem& a, const SbsItem& b) { return a.job < b.job; });
                 std::vector<SbsItem> copy = group;
                 const int rc = pipe.submit(std::move(group));
                 if (rc != B200JPG_OK) {  // device-level failure: these images fail, their ring space is released
@@ -302,10 +306,10 @@ int stream_engine_run(b200jpg_ctx* ctx, JobSource& src, int nthreads) {
     if (result == B200JPG_OK && host_error.load() != B200JPG_OK) result = host_error.load();
     if (trace)
         fprintf(stderr,
-                "[b200jpg] %s: %zu images, %d host threads, %.1f ms; %zu groups (%.1f images each); submitter idle %.1f ms, "
+                "[b200jpg] %s: %zu images, %d host threads, %.1f ms; %zu groups (%.1f images each; %u upload and %u download copies); submitter idle %.1f ms, "
                 "busy %.1f ms (enqueue %.1f, of it %u buffer regrowths %.1f; waiting for a free slot %.1f); host threads: %.2f ms/image, "
                 "waiting for ring space %.1f ms in total\n",
-                src.name(), n, nthreads, now_ms() - t_start, ngroups, ngroups ? (double)nitems / ngroups : 0.0, idle_ms, submit_ms,
+                src.name(), n, nthreads, now_ms() - t_start, ngroups, ngroups ? (double)nitems / ngroups : 0.0, pipe.h2d_copies, pipe.d2h_copies, idle_ms, submit_ms,
                 pipe.enqueue_ms, pipe.grows, pipe.grow_ms, pipe.retire_wait_ms, nitems ? produce_us.load() / 1e3 / nitems : 0.0,
                 ring_wait_us.load() / 1e3);
     return result;
