@@ -56,10 +56,17 @@ enum : unsigned {
     ENT_BAD_TAIL = 32,     // whole bytes left between the last MCU of a restart interval and its RSTn marker
 };
 
-// One table entry: bits 0..4 code length, bits 5..8 number of value bits that follow the code, bits 9..15 how far
-// the zig-zag index advances (run + 1; 64 = end of block; 0 = anomaly).  Length 31 marks a first-level entry whose
-// prefix continues into longer code words: bits 5..15 then hold the index of the second-level table.
-ENT_HD uint32_t ent_entry(unsigned len, unsigned s, unsigned adv) { return len | (s << 5) | (adv << 9); }
+// One table entry: bits 0..4 how many bits the code word and its value bits take together (<= 16 + 11), bits 5..8 the
+// number of value bits, bits 9..15 how far the zig-zag index advances (run + 1; 64 = end of block).  The decode loop
+// of the counting passes then needs one mask for the bit position and one shift for the index, nothing else.
+// Anomalies (no code word matches, DC category > 11, EOBn in a sequential scan: adv = 0 here) are stored as "value bits =
+// 15, advance 1, the code length alone": only the write pass looks for the 15 -- it alone decodes the true code words.
+// Total 31 marks a first-level entry whose prefix continues into longer code words: bits 5..15 then hold the index of
+// the second-level table.
+constexpr uint32_t ENT_S_ANOMALY = 15;
+ENT_HD uint32_t ent_entry(unsigned len, unsigned s, unsigned adv) {
+    return adv ? (len + s) | (s << 5) | (adv << 9) : len | (ENT_S_ANOMALY << 5) | (1u << 9);
+}
 constexpr uint32_t ENT_LINK = 31;
 
 // Decoding tables of one Huffman table ("slot"): two levels, so that every code word resolves with at most two
@@ -209,32 +216,34 @@ ENT_HD EntState ent_decode_range(const Words& words, const uint16_t* tabs, const
         uint32_t e = tabs[off + (win >> (32u - ENT_LUT_BITS))];
         if ((e & 31u) == ENT_LINK)
             e = tabs[off + (1u << ENT_LUT_BITS) + ((e >> 5) << ENT_SUB_LUT_BITS) + ((win >> 16) & ((1u << ENT_SUB_LUT_BITS) - 1u))];
-        const uint32_t len = e & 31u, s = (e >> 5) & 15u;
-        uint32_t adv = e >> 9;
+        const uint32_t tot = e & 31u, adv = e >> 9;
+        uint32_t s = (e >> 5) & 15u;
 #if defined(ENT_STATS)
-        ent_stats_len[len]++;
+        ent_stats_len[tot - (s == ENT_S_ANOMALY ? 0u : s)]++;
 #endif
-        if (adv == 0) {
-            if (CHECK) bad |= ENT_BAD_SYMBOL;
-            adv = 1;
-        }
         if (Sink::kCountOnly) {
             // what the write pass will append for this code word: an AC value that lands inside the block (a run leaving
             // the block stores nothing and is flagged there; counting it would let value offsets run past the 63 values
             // per block the stream's value region is sized for)
             sink_count(sink, (s != 0u) & (k != 0u) & (k + adv <= 64u));
-        } else if (s) {
-            const uint32_t pos = k + adv - 1;
-            const uint32_t u = (win << len) >> (32u - s);
-            // extend(), src/huffman.rs:98-... / Figure F.12
-            const int v = u < (1u << (s - 1)) ? (int)u - (int)(1u << s) + 1 : (int)u;
-            if (pos <= 63u) sink.store(pos, v);
-            else if (CHECK) bad |= ENT_BAD_RUN;
+        } else {
+            if (s == ENT_S_ANOMALY) {
+                if (CHECK) bad |= ENT_BAD_SYMBOL;
+                s = 0;
+            }
+            if (s) {
+                const uint32_t pos = k + adv - 1;
+                const uint32_t u = (win << (tot - s)) >> (32u - s);
+                // extend(), src/huffman.rs:98-... / Figure F.12
+                const int v = u < (1u << (s - 1)) ? (int)u - (int)(1u << s) + 1 : (int)u;
+                if (pos <= 63u) sink.store(pos, v);
+                else if (CHECK) bad |= ENT_BAD_RUN;
+            }
         }
-        p += len + s;
+        p += tot;
         k += adv;
         const uint32_t nwi = p >> 5;
-        if (nwi != wi) {  // len + s <= 31: at most one word further
+        if (nwi != wi) {  // tot <= 27: at most one word further
             hi = lo;
             lo = words.get(nwi + 1);
             wi = nwi;

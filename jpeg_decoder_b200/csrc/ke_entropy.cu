@@ -29,25 +29,29 @@ struct EntShared {
 };
 
 
-// The CTA's share of the scan in shared memory: the 128 subsequences of its threads plus the few words the last code
-// word of the last one may reach into.  Staged once with coalesced 128-bit loads (every thread walking its own
-// 128-byte line through L1 thrashes it: measured 5 % hit rate), byte-swapped on the way in, and rotated by the row
-// number so that lanes sitting at the same offset of their own subsequence hit different banks.
-constexpr unsigned TILE_WORDS = ENT_THREADS * (ENT_SUB_BITS / 32);  // 4096
-constexpr unsigned TILE_EXTRA = 4;
-struct EntWordsTile {
-    const uint32_t* tile;  // shared
-    uint32_t first;        // word index of tile[0]
-    __device__ __forceinline__ static uint32_t slot(uint32_t j) { return (j & ~31u) + ((j + (j >> 5)) & 31u); }
-    // Words past the tile are only ever asked for by the last subsequence of a scan (its tail slack), where they lie
-    // past the end of the data: zero, like everything the staging loop found beyond nwords.
-    __device__ __forceinline__ uint32_t get(uint32_t i) const {
-        const uint32_t j = i - first;
-        return j < TILE_WORDS + TILE_EXTRA ? tile[slot(j)] : 0u;
-    }
+// The CTA's share of the scan in shared memory, TRANSPOSED: tile[n * ENT_THREADS + t] = word n of the CTA's subsequence t,
+// n = 0 .. SUB_WORDS + 1 (the last code word of a subsequence may reach two words into the next one: every column
+// carries copies of them).  A thread walks down its own column, so whatever offsets the lanes of a warp are at, they
+// hit 32 different banks, the next word is one row further and nothing has to be bounds-checked (the only reads
+// past a column are the tail slack of a scan's last subsequence in the write pass, where everything beyond is zero:
+// clamped to the column's last word, which is zero there too).  Staged once with coalesced 128-bit loads (every thread
+// walking its own 128-byte line through L1 thrashes it: measured 5 % hit rate), byte-swapped on the way in.
+constexpr unsigned SUB_WORDS = ENT_SUB_BITS / 32;
+constexpr unsigned COL_WORDS = SUB_WORDS + 2;
+constexpr unsigned TILE_WORDS = ENT_THREADS * SUB_WORDS;  // words of the scan a CTA owns
+struct EntWordsColumn {
+    const uint32_t* col;  // shared: word 0 of the subsequence
+    uint32_t first;       // its index in the scan
+    __device__ __forceinline__ uint32_t get(uint32_t i) const { return col[min(i - first, COL_WORDS - 1u) * ENT_THREADS]; }
 };
+__device__ __forceinline__ void stage_put(uint32_t* tile, uint32_t w, uint32_t v) {  // w: index inside the CTA's share (+ 2)
+    const uint32_t t = w / SUB_WORDS, n = w % SUB_WORDS;
+    v = ent_bswap(v);
+    if (t < ENT_THREADS) tile[n * ENT_THREADS + t] = v;
+    if (n < 2u && t > 0u) tile[(SUB_WORDS + n) * ENT_THREADS + t - 1u] = v;
+}
 __device__ __forceinline__ void stage_tile(uint32_t* tile, const uint32_t* words, uint32_t nwords, uint32_t first) {
-    for (unsigned q = threadIdx.x; q < (TILE_WORDS + TILE_EXTRA) / 4; q += ENT_THREADS) {
+    for (unsigned q = threadIdx.x; q < TILE_WORDS / 4 + 1; q += ENT_THREADS) {  // + 1: the two words behind the share
         const uint32_t i = first + 4 * q;
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
         if (i + 3 < nwords) v = __ldg(reinterpret_cast<const uint4*>(words + i));  // payloads are 16-byte aligned and padded
@@ -56,10 +60,10 @@ __device__ __forceinline__ void stage_tile(uint32_t* tile, const uint32_t* words
             v.y = i + 1 < nwords ? __ldg(words + i + 1) : 0u;
             v.z = i + 2 < nwords ? __ldg(words + i + 2) : 0u;
         }
-        tile[EntWordsTile::slot(4 * q)] = ent_bswap(v.x);
-        tile[EntWordsTile::slot(4 * q + 1)] = ent_bswap(v.y);
-        tile[EntWordsTile::slot(4 * q + 2)] = ent_bswap(v.z);
-        tile[EntWordsTile::slot(4 * q + 3)] = ent_bswap(v.w);
+        stage_put(tile, 4 * q, v.x);
+        stage_put(tile, 4 * q + 1, v.y);
+        stage_put(tile, 4 * q + 2, v.z);
+        stage_put(tile, 4 * q + 3, v.w);
     }
 }
 
@@ -106,13 +110,13 @@ __global__ void __launch_bounds__(ENT_THREADS) ent_pass(const EntImage* __restri
         if (!__syncthreads_or(active)) return;
     }
     __shared__ EntShared sh;
-    __shared__ uint32_t tile[TILE_WORDS + 32];
+    __shared__ uint32_t tile[COL_WORDS * ENT_THREADS];
     const uint8_t* payload = streams + im.payload_off;
     const uint32_t* gwords = reinterpret_cast<const uint32_t*>(payload + im.data_off);
     stage_tile(tile, gwords, im.nwords, blockIdx.x * TILE_WORDS);
     load_shared(sh, im, payload);  // ends with a barrier
     if (!active) return;
-    const EntWordsTile words{tile, blockIdx.x * TILE_WORDS};
+    const EntWordsColumn words{tile + threadIdx.x, i * SUB_WORDS};
     const uint16_t* tabs = reinterpret_cast<const uint16_t*>(sh.tabs);
     EntState st;
     st.p = i * ENT_SUB_BITS;
@@ -152,7 +156,29 @@ __global__ void __launch_bounds__(ENT_THREADS) ent_pass(const EntImage* __restri
 // SYNC launch number `pass` (1, 2, ...).  ch[] flags carry "my state changed and my successor has not seen it yet" from
 // one launch to the next (read from ch[(pass-1)&1], written to ch[pass&1]).  Inside a launch a CTA keeps iterating on
 // its own 128 subsequences through shared-memory flags until they are quiet; only the hand-over to the next CTA (and
-// whatever is left when ENT_LOCAL_ITERS runs out) waits for the next launch.
+// whatever is left when ENT_LOCAL_ITERS runs out) waits for the next launch.  Launch 1 re-decodes every subsequence;
+// after that a quarter of them is pending, then 5 %, 1 %, ... for four to six rounds of one subsequence walk each
+// (tests/cpp/entropy_emul.cpp with ENT_EMUL_ROUNDS=1).
+// Measured and not kept (profiles/r02_entropy_sync_variants.md): the rounds in a kernel of their own that stages nothing
+// (2 KB of shared memory per waiting CTA instead of 35, scan and tables through L1) -- 8 % slower under load, the L1 is
+// not the rounds' alone; a warp per pending subsequence probing 32 bit positions at once -- no faster per code word than
+// the lone lane, and three times the instructions.
+template <class Words>
+__device__ __forceinline__ void sync_redecode(const EntImage& im, const EntWork& w, const Words& words, const uint16_t* tabs, const uint8_t* dcslot,
+                                              const uint8_t* acslot, unsigned ij, unsigned long long mine, unsigned long long* v_out, bool* changed) {
+    const unsigned gj = im.sub0 + ij;
+    EntState st = ent_unpack(ld_state(&w.state[gj - 1]));
+    st.nb = 0;
+    EntCountSink sink;
+    unsigned bad = 0;
+    const unsigned long long v =
+        ent_pack(ent_decode_range<false>(words, tabs, dcslot, acslot, im.dec_bpm, st, ent_sub_end(ij, im.nsub, im.scan_bits), sink, &bad));
+    *changed = ((v ^ mine) & ENT_SYNC_MASK) != 0;
+    if (v != mine) st_state(&w.state[gj], v);  // the counts may change even when (p, k, b) do not
+    w.nvals[gj] = sink.nvals;
+    *v_out = v;
+}
+
 __global__ void __launch_bounds__(ENT_THREADS) ent_sync(const EntImage* __restrict__ imgs, const uint8_t* streams, EntWork w, unsigned pass) {
     if (w.counters[pass - 1] == 0) return;  // converged earlier: nothing left to do
     const EntImage& im = imgs[blockIdx.y];
@@ -167,26 +193,24 @@ __global__ void __launch_bounds__(ENT_THREADS) ent_sync(const EntImage* __restri
         if (valid) ch_out[g] = 0;
         return;
     }
-    __shared__ EntShared sh;
-    __shared__ uint32_t tile[TILE_WORDS + 32];
     // per subsequence of this CTA (index = threadIdx of its owner): last published state, flags; and the compacted work list
     __shared__ unsigned long long s_mine[ENT_THREADS];
     __shared__ unsigned char s_pend[ENT_THREADS], s_chg[ENT_THREADS], s_ever[ENT_THREADS], s_list[ENT_THREADS];
     __shared__ unsigned s_n;
     const uint8_t* payload = streams + im.payload_off;
     const uint32_t* gwords = reinterpret_cast<const uint32_t*>(payload + im.data_off);
-    stage_tile(tile, gwords, im.nwords, blockIdx.x * TILE_WORDS);
+    __shared__ EntShared sh;
+    __shared__ uint32_t tile[COL_WORDS * ENT_THREADS];
     const unsigned t = threadIdx.x;
     s_mine[t] = valid ? ld_state(&w.state[g]) : 0ull;
     s_pend[t] = pending ? 1 : 0;
     s_chg[t] = 0;
     s_ever[t] = 0;
+    stage_tile(tile, gwords, im.nwords, blockIdx.x * TILE_WORDS);
     load_shared(sh, im, payload);  // ends with a barrier
-    const EntWordsTile words{tile, blockIdx.x * TILE_WORDS};
     const uint16_t* tabs = reinterpret_cast<const uint16_t*>(sh.tabs);
     bool quiet = false;
-    // Every round the pending subsequences are gathered onto the first threads of the CTA: after the first round only a
-    // few of the 128 are pending (measured: 9.5 of 32 lanes active per instruction), and a re-decode costs the same
+    // Every round the pending subsequences are gathered onto the first threads of the CTA: a re-decode costs the same
     // issue slots whether 3 or 32 lanes of its warp take part.
     for (unsigned iter = 0; iter < ENT_LOCAL_ITERS; iter++) {
         if (t == 0) s_n = 0;
@@ -196,17 +220,10 @@ __global__ void __launch_bounds__(ENT_THREADS) ent_sync(const EntImage* __restri
         __syncthreads();
         if (t < s_n) {
             const unsigned j = s_list[t];  // the subsequence this thread re-decodes (any order: rounds are order-free)
-            const unsigned ij = blockIdx.x * ENT_THREADS + j, gj = im.sub0 + ij;
-            EntState st = ent_unpack(ld_state(&w.state[gj - 1]));
-            st.nb = 0;
-            EntCountSink sink;
-            unsigned bad = 0;
-            const unsigned long long v = ent_pack(ent_decode_range<false>(words, tabs, sh.dcslot, sh.acslot, im.dec_bpm, st,
-                                                                         ent_sub_end(ij, im.nsub, im.scan_bits), sink, &bad));
-            const unsigned long long mine = s_mine[j];
-            const bool changed = ((v ^ mine) & ENT_SYNC_MASK) != 0;
-            if (v != mine) st_state(&w.state[gj], v);  // the counts may change even when (p, k, b) do not
-            w.nvals[gj] = sink.nvals;
+            unsigned long long v;
+            bool changed;
+            const unsigned ij = blockIdx.x * ENT_THREADS + j;
+            sync_redecode(im, w, EntWordsColumn{tile + j, ij * SUB_WORDS}, tabs, sh.dcslot, sh.acslot, ij, s_mine[j], &v, &changed);
             s_mine[j] = v;
             s_chg[j] = changed ? 1 : 0;
             if (changed) s_ever[j] = 1;
@@ -377,7 +394,7 @@ cudaError_t launch_entropy(const EntImage* d_images, unsigned nimages, unsigned 
         }
         const dim3 grid(sub_grid.x, cnt);
         ent_pass<ENT_COLD><<<grid, ENT_THREADS, 0, stream>>>(imgs, d_streams, wc);
-        for (int r = 1; r <= max_passes; r++) ent_sync<<<grid, ENT_THREADS, 0, stream>>>(imgs, d_streams, wc, (unsigned)r);
+for (int r = 1; r <= max_passes; r++) ent_sync<<<grid, ENT_THREADS, 0, stream>>>(imgs, d_streams, wc, (unsigned)r);
         ent_prefix<<<cnt, SCAN_THREADS, 0, stream>>>(imgs, wc);
         ent_pass<ENT_WRITE><<<grid, ENT_THREADS, 0, stream>>>(imgs, d_streams, wc);
         ent_dc_sums<<<dim3(nchunks, 4, cnt), SCAN_THREADS, 0, stream>>>(imgs, d_streams, sums, nchunks);

@@ -77,6 +77,12 @@ static EmulResult emulate(const std::vector<uint8_t>& file, const HostDecoder& p
     return r;
 }
 
+// ENT_EMUL_ROUNDS=1: per synchronisation launch and CTA-local round, how many CTAs were still iterating and how many
+// subsequences they re-decoded (what the latency of ent_sync is made of)
+struct RoundStat { unsigned ctas = 0, pending = 0, warps = 0; };
+static bool g_round_stats = getenv("ENT_EMUL_ROUNDS") != nullptr;
+static std::vector<std::vector<RoundStat>> g_rounds(64);
+
 // one interval (= the whole scan without DRI): what the kernels do for one "image"
 static void emulate_interval(const std::vector<uint8_t>& payload, const EntImage& im, const b200jpg_image_desc& d, int max_passes, EmulResult& r) {
     const EntWordsGlobal words{(const uint32_t*)(payload.data() + im.data_off), im.nwords};
@@ -116,6 +122,15 @@ static void emulate_interval(const std::vector<uint8_t>& payload, const EntImage
             }
             std::vector<uint64_t> mine(state.begin() + i0, state.begin() + i0 + cnt);
             for (unsigned iter = 0; iter < LOCAL; iter++) {
+                if (g_round_stats) {
+                    unsigned np = 0;
+                    for (unsigned t = 0; t < cnt; t++) np += pending[t];
+                    auto& st = g_rounds[(size_t)pass];
+                    if (st.size() <= iter) st.resize(iter + 1);
+                    st[iter].ctas++;
+                    st[iter].pending += np;
+                    st[iter].warps += (np + 31) / 32;
+                }
                 // threads of a CTA run concurrently: evaluate in descending order so that a thread mostly sees its
                 // predecessor's OLD state (the adversarial interleaving)
                 for (unsigned tt = 0; tt < cnt; tt++) {
@@ -317,6 +332,11 @@ int main(int argc, char** argv) {
             }
         }
     }
+    if (g_round_stats)
+        for (size_t pass = 0; pass < g_rounds.size(); pass++)
+            for (size_t it = 0; it < g_rounds[pass].size(); it++)
+                printf("launch %zu round %zu: %u CTAs, %u subsequences re-decoded (%.1f per CTA), %u warps after gathering\n", pass + 1, it + 1,
+                       g_rounds[pass][it].ctas, g_rounds[pass][it].pending, (double)g_rounds[pass][it].pending / g_rounds[pass][it].ctas, g_rounds[pass][it].warps);
 #if defined(ENT_STATS)
     {
         unsigned long long tot = 0, acc = 0;
