@@ -275,10 +275,13 @@ ENT_HD void ent_or64(unsigned long long* p, unsigned long long v) {
 }
 
 // The write pass.  A block that starts and ends inside one subsequence is written with plain stores; the two (or
-// more) threads that share a block each OR their part of the bitmap into the zero-initialised array.  Values are
-// collected four at a time and leave as one aligned 8-byte store (a lane's 2-byte stores each cost a sector of their
-// own on the way to L2: measured 23 M sectors per 27 images); the up to three values before the first and after the
-// last aligned quad of a subsequence are stored one by one -- the neighbouring subsequences own the rest of those words.
+// more) threads that share a block each OR their part of the bitmap into the zero-initialised array.  Values leave
+// four at a time as one aligned 8-byte store (a lane's 2-byte stores each cost a sector of their own on the way to
+// L2: measured 23 M sectors per 27 images).  They are shifted into a 64-bit window from the top -- two instructions
+// per value, no variable shift -- so that after four values the oldest sits in the low 16 bits (little-endian order);
+// a quad is due whenever the value's address is the last of an aligned 8 bytes.  The up to three values before the
+// first and after the last aligned quad of a subsequence are stored one by one: the neighbouring subsequences own
+// the rest of those words.
 struct EntCompactSink {
     static constexpr bool kCountOnly = false;
     unsigned long long* bm;
@@ -289,8 +292,10 @@ struct EntCompactSink {
     uint32_t t;           // scan-order index of the current block inside the image
     uint32_t B, total;    // blocks of the interval delivered so far / to deliver
     uint32_t vi, vcap;    // values appended so far / capacity of the region
-    uint32_t quad0;       // vi of the first value that can go into an aligned quad
-    unsigned long long bits, acc;
+    uint32_t vfirst;      // vi of this subsequence's first value
+    uint32_t phase;       // ((vals_rel / 2 + vi) & 3) == 3  <=>  value vi ends an aligned quad; phase = (vals_rel / 2) & 3
+    uint32_t acc_lo, acc_hi;  // the last four values, the newest in the top 16 bits
+    unsigned long long bits;
     bool own;             // this thread met the block's DC code word
     ENT_HD void begin(uint8_t* streams, const EntImage* im, uint32_t first_block, uint32_t first_val, bool at_block_start) {
         uint8_t* cs = streams + im->cs_off;
@@ -303,15 +308,17 @@ struct EntCompactSink {
         B = first_block;
         total = im->total_blocks;
         t = block0 + B;
-        vi = first_val;
+        vi = vfirst = first_val;
         vcap = 63u * total;
-        quad0 = vi + ((4u - ((vals_rel >> 1) + vi)) & 3u);  // (vals_rel / 2 + quad0) % 4 == 0
+        phase = (vals_rel >> 1) & 3u;
         bits = 0;
-        acc = 0;
+        acc_lo = acc_hi = 0;
         own = at_block_start;
         if (own && B < total) boff[t] = vals_rel + 2u * vi;
     }
     ENT_HD bool complete() const { return B >= total; }
+    // value number `slot` (0 = oldest) of the window
+    ENT_HD int16_t window(unsigned slot) const { return (int16_t)(slot < 2u ? acc_lo >> (16u * slot) : acc_hi >> (16u * (slot - 2u))); }
     // only reached with B < total: begin() is not used past the end, block_done() stops there
     ENT_HD void store(unsigned pos, int v) {
         if (pos == 0) {
@@ -319,14 +326,18 @@ struct EntCompactSink {
             return;
         }
         bits |= 1ull << pos;
-        if (vi < quad0) {  // head: the word belongs partly to the previous subsequence
-            if (vi < vcap) vals[vi] = (int16_t)v;
-        } else {
-            const unsigned lane = (vi - quad0) & 3u;
-            acc |= (unsigned long long)(uint16_t)v << (16u * lane);
-            if (lane == 3u) {
-                if (vi < vcap) *(unsigned long long*)(vals + vi - 3) = acc;  // little-endian: value j of the quad in bits 16j..16j+15
-                acc = 0;
+        acc_lo = (acc_lo >> 16) | (acc_hi << 16);
+        acc_hi = (acc_hi >> 16) | ((uint32_t)(uint16_t)v << 16);
+        if (((vi + phase) & 3u) == 3u) {  // value vi closes an aligned quad
+            if (vi >= vfirst + 3u) {
+                if (vi < vcap) *(unsigned long long*)(vals + vi - 3) = (unsigned long long)acc_lo | ((unsigned long long)acc_hi << 32);
+            } else {  // head: the quad began in the previous subsequence; mine are its last vi - vfirst + 1 values
+                const unsigned n = vi - vfirst + 1u;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+                for (unsigned j = 0; j < n; j++)
+                    if (vfirst + j < vcap) vals[vfirst + j] = window(4u - n + j);
             }
         }
         vi++;
@@ -342,14 +353,16 @@ struct EntCompactSink {
         boff[t] = vals_rel + 2u * vi;
         return false;
     }
-    // after the decode loop: the values of the last, incomplete quad; the block still in progress (it belongs to the next
-    // subsequence as well)
+    // after the decode loop: the values of the last, incomplete quad (the newest m of the window); the block still in
+    // progress (it belongs to the next subsequence as well)
     ENT_HD void finish() {
-        if (vi > quad0) {
-            const unsigned n = (vi - quad0) & 3u;
-            for (unsigned j = 0; j < n; j++)
-                if (vi - n + j < vcap) vals[vi - n + j] = (int16_t)(acc >> (16u * j));
-        }
+        unsigned m = (vi + phase) & 3u;  // values behind the last aligned quad boundary
+        if (m > vi - vfirst) m = vi - vfirst;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (unsigned j = 0; j < m; j++)
+            if (vi - m + j < vcap) vals[vi - m + j] = window(4u - m + j);
         if (B < total && (own || bits)) ent_or64(&bm[t], bits | (own ? 1ull : 0ull));
     }
 };

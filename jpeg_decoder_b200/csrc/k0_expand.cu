@@ -112,7 +112,8 @@ __global__ void __launch_bounds__(K0_WARPS * 32) k0_expand(const K0Image* __rest
 // each value at its natural position (~15 values per block instead of 64 slots x rank computations in the warp-per-group
 // kernel above: 5x fewer instructions); the warp then stores its 32 rows cooperatively, four whole 128-byte blocks per
 // instruction.  Rows are swizzled in 16-byte chunks by (thread & 7), so both phases are free of bank conflicts beyond the
-// unavoidable ones of scattered 2-byte stores.
+// unavoidable ones of scattered 2-byte stores.  (Staging the CTA's values in shared memory with coalesced 16-byte loads first was
+// measured and loses: 101 -> 109 us per 27 images -- half the resident CTAs, and the scattered 2-byte stores remain.)
 constexpr int K0B_THREADS = 128;
 __global__ void __launch_bounds__(K0B_THREADS) k0_expand_blocks(const K0Image* __restrict__ images, const uint8_t* __restrict__ streams,
                                                                 short* __restrict__ slab) {

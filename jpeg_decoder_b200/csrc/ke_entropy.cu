@@ -18,9 +18,11 @@ namespace {
 
 constexpr int ENT_COLD = 0, ENT_WRITE = 2;
 #ifndef B200JPG_ENT_THREADS
-#define B200JPG_ENT_THREADS 128
+#define B200JPG_ENT_THREADS 256
 #endif
-constexpr unsigned ENT_THREADS = B200JPG_ENT_THREADS;  // subsequences per CTA (build-time knob, with ENT_SUB_BITS)
+// subsequences per CTA (build-time knob, with ENT_SUB_BITS).  Shared memory decides how many warps an SM holds: 16.6 KB of tables per CTA
+// + 136 B of scan per thread -- 64 / 128 / 256 threads: 16 / 24 / 32 warps per SM, 63.9 / 68.3 / 72.8 GP/s (profiles/r02_entropy_sync_variants.md)
+constexpr unsigned ENT_THREADS = B200JPG_ENT_THREADS;
 
 struct EntShared {
     EntImage im;
@@ -39,6 +41,7 @@ struct EntShared {
 constexpr unsigned SUB_WORDS = ENT_SUB_BITS / 32;
 constexpr unsigned COL_WORDS = SUB_WORDS + 2;
 constexpr unsigned TILE_WORDS = ENT_THREADS * SUB_WORDS;  // words of the scan a CTA owns
+constexpr size_t TILE_BYTES = (size_t)COL_WORDS * ENT_THREADS * 4;
 struct EntWordsColumn {
     const uint32_t* col;  // shared: word 0 of the subsequence
     uint32_t first;       // its index in the scan
@@ -110,7 +113,7 @@ __global__ void __launch_bounds__(ENT_THREADS) ent_pass(const EntImage* __restri
         if (!__syncthreads_or(active)) return;
     }
     __shared__ EntShared sh;
-    __shared__ uint32_t tile[COL_WORDS * ENT_THREADS];
+    extern __shared__ uint32_t tile[];  // COL_WORDS * ENT_THREADS words (dynamic: with the tables it passes 48 KB for 256-thread CTAs)
     const uint8_t* payload = streams + im.payload_off;
     const uint32_t* gwords = reinterpret_cast<const uint32_t*>(payload + im.data_off);
     stage_tile(tile, gwords, im.nwords, blockIdx.x * TILE_WORDS);
@@ -161,7 +164,8 @@ __global__ void __launch_bounds__(ENT_THREADS) ent_pass(const EntImage* __restri
 // (tests/cpp/entropy_emul.cpp with ENT_EMUL_ROUNDS=1).
 // Measured and not kept (profiles/r02_entropy_sync_variants.md): the rounds in a kernel of their own that stages nothing
 // (2 KB of shared memory per waiting CTA instead of 35, scan and tables through L1) -- 8 % slower under load, the L1 is
-// not the rounds' alone; a warp per pending subsequence probing 32 bit positions at once -- no faster per code word than
+// not the rounds' alone; the same with the tables staged and only the scan words through L1 -- no difference; a warp per
+// pending subsequence probing 32 bit positions at once -- no faster per code word than
 // the lone lane, and three times the instructions.
 template <class Words>
 __device__ __forceinline__ void sync_redecode(const EntImage& im, const EntWork& w, const Words& words, const uint16_t* tabs, const uint8_t* dcslot,
@@ -195,12 +199,13 @@ __global__ void __launch_bounds__(ENT_THREADS) ent_sync(const EntImage* __restri
     }
     // per subsequence of this CTA (index = threadIdx of its owner): last published state, flags; and the compacted work list
     __shared__ unsigned long long s_mine[ENT_THREADS];
-    __shared__ unsigned char s_pend[ENT_THREADS], s_chg[ENT_THREADS], s_ever[ENT_THREADS], s_list[ENT_THREADS];
+    __shared__ unsigned char s_pend[ENT_THREADS], s_chg[ENT_THREADS], s_ever[ENT_THREADS];
+    __shared__ unsigned short s_list[ENT_THREADS];
     __shared__ unsigned s_n;
     const uint8_t* payload = streams + im.payload_off;
     const uint32_t* gwords = reinterpret_cast<const uint32_t*>(payload + im.data_off);
     __shared__ EntShared sh;
-    __shared__ uint32_t tile[COL_WORDS * ENT_THREADS];
+    extern __shared__ uint32_t tile[];  // COL_WORDS * ENT_THREADS words (dynamic: with the tables it passes 48 KB for 256-thread CTAs)
     const unsigned t = threadIdx.x;
     s_mine[t] = valid ? ld_state(&w.state[g]) : 0ull;
     s_pend[t] = pending ? 1 : 0;
@@ -215,7 +220,7 @@ __global__ void __launch_bounds__(ENT_THREADS) ent_sync(const EntImage* __restri
     for (unsigned iter = 0; iter < ENT_LOCAL_ITERS; iter++) {
         if (t == 0) s_n = 0;
         __syncthreads();
-        if (s_pend[t]) s_list[atomicAdd(&s_n, 1u)] = (unsigned char)t;
+        if (s_pend[t]) s_list[atomicAdd(&s_n, 1u)] = (unsigned short)t;
         s_chg[t] = 0;
         __syncthreads();
         if (t < s_n) {
@@ -357,6 +362,14 @@ size_t ent_work_bytes(unsigned total_sub, unsigned nimages, unsigned max_comp_bl
 cudaError_t launch_entropy(const EntImage* d_images, unsigned nimages, unsigned max_nsub, unsigned total_sub, unsigned max_comp_blocks,
                            uint8_t* d_streams, void* d_work, int max_passes, unsigned** d_status, cudaStream_t stream, uint64_t* launches) {
     if (nimages == 0 || max_nsub == 0) return cudaSuccess;
+    static const cudaError_t attr = [] {  // the kernels' dynamic shared memory (per device attribute of the function: set once per process and device
+                                          // would be stricter; the library drives one device per process, like the reference's one decoder per thread)
+        cudaError_t e = cudaFuncSetAttribute(ent_pass<ENT_COLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ent_pass<ENT_WRITE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ent_sync, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_BYTES);
+        return e;
+    }();
+    if (attr != cudaSuccess) return attr;
     auto up = [](size_t x) { return (x + 255) / 256 * 256; };
     char* p = (char*)d_work;
     EntWork w;
@@ -393,10 +406,10 @@ cudaError_t launch_entropy(const EntImage* d_images, unsigned nimages, unsigned 
             if (e != cudaSuccess) return e;
         }
         const dim3 grid(sub_grid.x, cnt);
-        ent_pass<ENT_COLD><<<grid, ENT_THREADS, 0, stream>>>(imgs, d_streams, wc);
-for (int r = 1; r <= max_passes; r++) ent_sync<<<grid, ENT_THREADS, 0, stream>>>(imgs, d_streams, wc, (unsigned)r);
+        ent_pass<ENT_COLD><<<grid, ENT_THREADS, TILE_BYTES, stream>>>(imgs, d_streams, wc);
+        for (int r = 1; r <= max_passes; r++) ent_sync<<<grid, ENT_THREADS, TILE_BYTES, stream>>>(imgs, d_streams, wc, (unsigned)r);
         ent_prefix<<<cnt, SCAN_THREADS, 0, stream>>>(imgs, wc);
-        ent_pass<ENT_WRITE><<<grid, ENT_THREADS, 0, stream>>>(imgs, d_streams, wc);
+        ent_pass<ENT_WRITE><<<grid, ENT_THREADS, TILE_BYTES, stream>>>(imgs, d_streams, wc);
         ent_dc_sums<<<dim3(nchunks, 4, cnt), SCAN_THREADS, 0, stream>>>(imgs, d_streams, sums, nchunks);
         ent_dc_chunks<<<dim3(4, cnt), SCAN_THREADS, 0, stream>>>(imgs, sums, nchunks);
         ent_dc_apply<<<dim3(nchunks, 4, cnt), SCAN_THREADS, 0, stream>>>(imgs, d_streams, sums, nchunks);

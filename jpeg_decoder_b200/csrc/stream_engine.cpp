@@ -264,6 +264,10 @@ int stream_engine_run(b200jpg_ctx* ctx, JobSource& src, int nthreads) {
                 }
             }
             idle_ms += now_ms() - w0;
+            // lowest job numbers first: a group is then (nearly) a run of consecutive jobs, whose pixel buffers callers usually
+            // lay out back to back -- they leave the device as a few large copies instead of one per image.  (Every thread
+            // takes its jobs in ascending order, so this never overtakes an earlier region of a thread's ring.)
+            std::sort(queue.begin(), queue.end(), [](const SbsItem& a, const SbsItem& b) { return a.job < b.job; });
             size_t bytes = 0;
             while (!queue.empty() && group.size() < max_items && bytes < max_bytes) {
                 const SbsItem& it = queue.front();
@@ -280,9 +284,6 @@ int stream_engine_run(b200jpg_ctx* ctx, JobSource& src, int nthreads) {
             if (!group.empty()) {
                 ngroups++;
                 nitems += group.size();
-                // neighbouring jobs next to each other: callers usually lay their pixel buffers out that way, and pixels that are
-                // contiguous on both sides leave the device as one copy
-                std::sort(group.begin(), group.end(), [](const SbsItem& a, const SbsItem& b) { return a.job < b.job; });
                 std::vector<SbsItem> copy = group;
                 const int rc = pipe.submit(std::move(group));
                 if (rc != B200JPG_OK) {  // device-level failure: these images fail, their ring space is released

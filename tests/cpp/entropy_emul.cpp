@@ -103,7 +103,7 @@ static void emulate_interval(const std::vector<uint8_t>& payload, const EntImage
     // it is quiet (flags through "shared memory"), states are read and written in place, only the hand-over between
     // CTAs waits for the next launch.  g_cta_order: 0 = CTAs ascending, 1 = descending (the GPU runs them in any order).
     uint8_t *cin = chA.data(), *cout = chB.data();
-    const unsigned T = 128, LOCAL = 32;
+    const unsigned T = 256, LOCAL = 32;  // ENT_THREADS, ENT_LOCAL_ITERS of ke_entropy.cu
     for (int pass = 0; pass < max_passes; pass++) {
         unsigned any = 0;
         const unsigned nctas = (n + T - 1) / T;
