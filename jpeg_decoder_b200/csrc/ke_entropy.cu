@@ -4,7 +4,7 @@
 //                                  decoding tables and its 16 KB of the scan live in shared memory; the write pass
 //                                  appends to the image's compact stream, which K0 (k0_expand.cu) expands
 //   ent_prefix                     per image: exclusive sums of the blocks each subsequence completed and the values it met
-//   ent_dc_scan                    DC differences -> DC values (wrapping int16 prefix sum per component)
+//   ent_dc_sums/_chunks/_apply     DC differences -> DC values (wrapping int16 prefix sum per component), one thread per block
 //
 // grid.y = image, grid.x covers the longest scan of the launch; CTAs past the end of their image exit at once.
 #include <cuda_runtime.h>
@@ -292,55 +292,74 @@ __global__ void __launch_bounds__(SCAN_THREADS) ent_prefix(const EntImage* __res
     }
 }
 
+// the DC slot (compact stream, scan order) of the q-th block of component c of the interval (MCU by MCU, v then h inside an MCU)
+__device__ __forceinline__ short* dc_ptr(uint8_t* streams, const EntImage& im, unsigned c, unsigned q) {
+    const unsigned hv = (unsigned)im.h[c] * im.v[c];
+    const unsigned ml = q / hv, r = q - ml * hv;
+    short* dc = reinterpret_cast<short*>(streams + im.cs_off + 8ull * im.nb_pad);
+    return dc + (size_t)(im.mcu0 + ml) * im.bpm + im.comp_j0[c] + r;
+}
+
 // src/decoder.rs:1096-1110: dc_predictor = dc_predictor.wrapping_add(diff), per component, along the scan -- a prefix
-// sum over the DC differences the write pass stored (compact stream, scan order: the q-th block of component c of the
-// interval sits in MCU q / (h v) at slot comp_j0[c] + q % (h v)).  One CTA per (component, interval): every thread sums a
-// run of consecutive blocks, one block-wide scan of the run sums, then the run again with its offset.  A thread's run covers
-// a few hundred contiguous bytes, so the second walk is served by L1.  (Round 1 used three launches -- chunk sums, scan of
-// the chunk sums, apply: 16 + 5 + 18 us per 27 images, each bounded by launch and memory latency, not by work.)
-__global__ void __launch_bounds__(SCAN_THREADS) ent_dc_scan(const EntImage* __restrict__ imgs, uint8_t* streams) {
+// sum over the DC differences the write pass stored.  One thread per block, three short launches:
+//   ent_dc_sums  : sum of every chunk of SCAN_THREADS consecutive blocks (in scan order) of a component
+//   ent_dc_chunks: exclusive prefix of the chunk sums, one CTA per (component, image)
+//   ent_dc_apply : block-wide inclusive prefix inside the chunk + the chunk's offset, written back
+// grid = (chunks of the largest component of the launch, 4 components, images)
+// (One CTA per (component, interval) that walks runs of consecutive blocks twice around a single block-wide scan was measured:
+// 57 us whatever the number of images, against 16 + 5 + 18 us for these three -- a latency chain of 64 dependent-address loads
+// per thread where these kernels have one.)
+__global__ void __launch_bounds__(SCAN_THREADS) ent_dc_sums(const EntImage* __restrict__ imgs, uint8_t* streams,
+                                                            unsigned* __restrict__ chunk_sums, unsigned max_chunks) {
+    const EntImage& im = imgs[blockIdx.z];
+    const unsigned c = blockIdx.y;
+    if (c >= im.ncomp || blockIdx.x * SCAN_THREADS >= im.comp_blocks[c]) return;
+    const unsigned q = blockIdx.x * SCAN_THREADS + threadIdx.x;
+    const unsigned v = q < im.comp_blocks[c] ? (unsigned)(unsigned short)*dc_ptr(streams, im, c, q) : 0u;
+    unsigned total;
+    block_exclusive(v, &total);
+    if (threadIdx.x == 0) chunk_sums[((size_t)blockIdx.z * 4 + c) * max_chunks + blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) ent_dc_chunks(const EntImage* __restrict__ imgs, unsigned* __restrict__ chunk_sums, unsigned max_chunks) {
     const EntImage& im = imgs[blockIdx.y];
     const unsigned c = blockIdx.x;
     if (c >= im.ncomp) return;
-    const unsigned n = im.comp_blocks[c];
-    if (n == 0) return;
-    const unsigned hv = (unsigned)im.h[c] * im.v[c], bpm = im.bpm;
-    short* base = reinterpret_cast<short*>(streams + im.cs_off + 8ull * im.nb_pad) + (size_t)im.mcu0 * bpm + im.comp_j0[c];
-    const unsigned per = (n + SCAN_THREADS - 1) / SCAN_THREADS;
-    const unsigned lo = min(n, threadIdx.x * per), hi = min(n, lo + per);
-    const unsigned ml0 = lo / hv, r0 = lo - ml0 * hv;
-    unsigned sum = 0;
-    {
-        unsigned ml = ml0, r = r0;
-#pragma unroll 8
-        for (unsigned q = lo; q < hi; q++) {
-            sum += (unsigned)(unsigned short)base[(size_t)ml * bpm + r];
-            if (++r == hv) {
-                r = 0;
-                ml++;
-            }
-        }
+    unsigned* sums = chunk_sums + ((size_t)blockIdx.y * 4 + c) * max_chunks;
+    const unsigned n = (im.comp_blocks[c] + SCAN_THREADS - 1) / SCAN_THREADS;
+    unsigned carry = 0;
+    for (unsigned base = 0; base < n; base += SCAN_THREADS) {  // uniform trip count: block_exclusive has barriers
+        const unsigned k = base + threadIdx.x;
+        const unsigned v = k < n ? sums[k] : 0u;
+        unsigned total;
+        const unsigned ex = block_exclusive(v, &total);
+        if (k < n) sums[k] = carry + ex;
+        carry += total;
     }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) ent_dc_apply(const EntImage* __restrict__ imgs, uint8_t* streams,
+                                                             const unsigned* __restrict__ chunk_sums, unsigned max_chunks) {
+    const EntImage& im = imgs[blockIdx.z];
+    const unsigned c = blockIdx.y;
+    if (c >= im.ncomp || blockIdx.x * SCAN_THREADS >= im.comp_blocks[c]) return;
+    const unsigned q = blockIdx.x * SCAN_THREADS + threadIdx.x;
+    const bool valid = q < im.comp_blocks[c];
+    short* p = dc_ptr(streams, im, c, valid ? q : 0u);
+    const unsigned v = valid ? (unsigned)(unsigned short)*p : 0u;
     unsigned total;
-    unsigned acc = block_exclusive(sum, &total);
-    unsigned ml = ml0, r = r0;
-    for (unsigned q = lo; q < hi; q++) {
-        short* p = base + (size_t)ml * bpm + r;
-        acc += (unsigned)(unsigned short)*p;
-        *p = (short)(unsigned short)acc;
-        if (++r == hv) {
-            r = 0;
-            ml++;
-        }
-    }
+    const unsigned ex = block_exclusive(v, &total);
+    if (valid) *p = (short)(unsigned short)(chunk_sums[((size_t)blockIdx.z * 4 + c) * max_chunks + blockIdx.x] + ex + v);
 }
 
 }  // namespace
 
+static unsigned dc_chunks(unsigned max_comp_blocks) { return (max_comp_blocks + SCAN_THREADS - 1) / SCAN_THREADS; }
+
 size_t ent_work_bytes(unsigned total_sub, unsigned nimages, unsigned max_comp_blocks, int max_passes) {
     auto up = [](size_t x) { return (x + 255) / 256 * 256; };
-    (void)max_comp_blocks;
-    return up((size_t)total_sub * 8) + 3 * up((size_t)total_sub * 4) + 2 * up(total_sub) + up((size_t)(max_passes + 2) * 4) + up((size_t)nimages * 8);
+    return up((size_t)total_sub * 8) + 3 * up((size_t)total_sub * 4) + 2 * up(total_sub) + up((size_t)(max_passes + 2) * 4) + up((size_t)nimages * 8) +
+           up((size_t)nimages * 4 * dc_chunks(max_comp_blocks) * 4);
 }
 
 cudaError_t launch_entropy(const EntImage* d_images, unsigned nimages, unsigned max_nsub, unsigned total_sub, unsigned max_comp_blocks,
@@ -373,7 +392,8 @@ cudaError_t launch_entropy(const EntImage* d_images, unsigned nimages, unsigned 
     const size_t tail = up((size_t)(max_passes + 2) * 4) + up((size_t)nimages * 8);
     w.status = (unsigned*)(p + up((size_t)(max_passes + 2) * 4));
     *d_status = w.status;
-    (void)max_comp_blocks;
+    unsigned* chunk_sums = (unsigned*)(p + tail);
+    const unsigned nchunks = dc_chunks(max_comp_blocks);
     cudaError_t e = cudaMemsetAsync(w.counters, 0, tail, stream);
     if (e != cudaSuccess) return e;
     const dim3 sub_grid((max_nsub + ENT_THREADS - 1) / ENT_THREADS, 1);
@@ -383,6 +403,7 @@ cudaError_t launch_entropy(const EntImage* d_images, unsigned nimages, unsigned 
         const EntImage* imgs = d_images + base;
         EntWork wc = w;
         wc.status = w.status + 2 * (size_t)base;
+        unsigned* sums = chunk_sums + (size_t)base * 4 * nchunks;
         if (base) {
             e = cudaMemsetAsync(w.counters, 0, up((size_t)(max_passes + 2) * 4), stream);
             if (e != cudaSuccess) return e;
@@ -392,8 +413,10 @@ cudaError_t launch_entropy(const EntImage* d_images, unsigned nimages, unsigned 
         for (int r = 1; r <= max_passes; r++) ent_sync<<<grid, ENT_THREADS, TILE_BYTES, stream>>>(imgs, d_streams, wc, (unsigned)r);
         ent_prefix<<<cnt, SCAN_THREADS, 0, stream>>>(imgs, wc);
         ent_pass<ENT_WRITE><<<grid, ENT_THREADS, TILE_BYTES, stream>>>(imgs, d_streams, wc);
-        ent_dc_scan<<<dim3(4, cnt), SCAN_THREADS, 0, stream>>>(imgs, d_streams);
-        if (launches) *launches += (uint64_t)max_passes + 4;
+        ent_dc_sums<<<dim3(nchunks, 4, cnt), SCAN_THREADS, 0, stream>>>(imgs, d_streams, sums, nchunks);
+        ent_dc_chunks<<<dim3(4, cnt), SCAN_THREADS, 0, stream>>>(imgs, sums, nchunks);
+        ent_dc_apply<<<dim3(nchunks, 4, cnt), SCAN_THREADS, 0, stream>>>(imgs, d_streams, sums, nchunks);
+        if (launches) *launches += (uint64_t)max_passes + 6;
     }
     return cudaGetLastError();
 }
