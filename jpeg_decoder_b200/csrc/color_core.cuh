@@ -99,6 +99,22 @@ __device__ __forceinline__ void h2v1_16(unsigned lo, unsigned hi, unsigned L, un
     }
 }
 
+// H1V2 (4:4:0, src/upsampler.rs:165-189) for 16 output pixels of one row: out[x] = (3 near[x] + far[x] + 2) >> 2, the vertical
+// half of the triangle filter -- byte pairs (near, far) side by side, one IDP.4A per sample; results CENTRED (minus 128).
+// nv / fv = 16 samples of the near and the far chroma row.
+__device__ __forceinline__ void h1v2_16(const uint4 nv, const uint4 fv, int (&o)[16]) {
+    const unsigned n[4] = {nv.x, nv.y, nv.z, nv.w}, f[4] = {fv.x, fv.y, fv.z, fv.w};
+    constexpr unsigned BIAS = 2u - 128u * 4u;
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        const unsigned p01 = prmt(n[w], f[w], 0x5140), p23 = prmt(n[w], f[w], 0x7362);  // (n0 f0 n1 f1), (n2 f2 n3 f3)
+        o[4 * w + 0] = (int)__dp4a(p01, 0x00000103u, BIAS) >> 2;
+        o[4 * w + 1] = (int)__dp4a(p01, 0x01030000u, BIAS) >> 2;
+        o[4 * w + 2] = (int)__dp4a(p23, 0x00000103u, BIAS) >> 2;
+        o[4 * w + 3] = (int)__dp4a(p23, 0x01030000u, BIAS) >> 2;
+    }
+}
+
 __device__ __forceinline__ YccRegs make_ycc_regs(int3 sixteen, bool opaque) {
     YccRegs k;
     k.mul = sixteen.x;

@@ -38,7 +38,7 @@ struct __align__(16) DevTile {
 enum : unsigned { UP_H1V1 = 0, UP_H2V1 = 1, UP_H1V2 = 2, UP_H2V2 = 3, UP_GENERIC = 4 };
 enum : unsigned { CC_NOCONVERT = 0, CC_RGB = 1, CC_YCBCR = 2, CC_CMYK = 3, CC_YCCK = 4, CC_GRAY = 5 };
 enum : unsigned { K2_PATH_GENERIC = 0, K2_PATH_420 = 1, K2_PATH_444 = 2, K2_PATH_GRAY = 3, K2_PATH_420R = 4, K2_PATH_420T = 5, K2_PATH_422 = 6,
-                  K2_PATH_BYTES = 7, K2_NPATHS = 8 };
+                  K2_PATH_BYTES = 7, K2_PATH_440 = 8, K2_NPATHS = 9 };
 
 struct DevUpComp {
     unsigned long long plane_off;

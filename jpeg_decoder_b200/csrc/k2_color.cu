@@ -454,6 +454,34 @@ __global__ void __launch_bounds__(128) k2_ycbcr422(K2Params p, unsigned first, u
 }
 
 // ---------------------------------------------------------------------------------------------
+// 4:4:0 YCbCr (H1V2 chroma, src/upsampler.rs:165-189: what a losslessly rotated 4:2:2 file becomes): thread = 16 pixels of one
+// row, 16 samples of the near and of the far chroma row per component (far = the row above for even output rows, below for
+// odd ones, clamped: the f32 expression of upsampler.rs:174-180 as integer min / max).  grid.x = ceil(G/128) * height, grid.y = image
+// ---------------------------------------------------------------------------------------------
+template <bool SSSE3>
+__global__ void __launch_bounds__(128) k2_ycbcr440(K2Params p, unsigned first, unsigned gchunks) {
+    const DevImage& img = p.images[first + blockIdx.y];
+    if (img.path != K2_PATH_440) return;
+    const unsigned y = blockIdx.x / gchunks;
+    const unsigned g = (blockIdx.x % gchunks) * 128u + threadIdx.x;
+    const unsigned W = img.width;
+    if (y >= img.height || g * 16u >= W) return;
+    const uint4 yv = load_row16(p.planes + img.c[0].plane_off + (size_t)y * img.c[0].stride, g, img.c[0].stride);
+    const unsigned k = y >> 1;
+    int cb[16], cr[16];
+#pragma unroll
+    for (int c = 1; c <= 2; c++) {
+        const unsigned f = (y & 1u) ? min(k + 1u, img.c[c].in_h - 1u) : (k > 0u ? k - 1u : 0u);
+        const uint8_t* plane = p.planes + img.c[c].plane_off;
+        const uint4 nv = load_row16(plane + (size_t)k * img.c[c].stride, g, img.c[c].stride);
+        const uint4 fv = load_row16(plane + (size_t)f * img.c[c].stride, g, img.c[c].stride);
+        h1v2_16(nv, fv, c == 1 ? cb : cr);
+    }
+    ycbcr_store16<SSSE3>(yv, cb, cr, p.out + img.out_off + ((size_t)y * W + g * 16u) * 3u, make_ycc_regs(p.sixteen, true), min(16u, W - g * 16u),
+                         SSSE3 ? min(16u, max(img.ssse3_pixels, g * 16u) - g * 16u) : 0u);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Every component at full resolution and nothing to compute but bytes: RGB (src/decoder.rs:1391-1404), CMYK (1458-1474),
 // YCCK (1439-1456), ColorTransform::None (1476-1484).  Thread = 16 pixels of one row: 16-byte loads per component,
 // interleave with PRMT, 16-byte stores.  grid.x = ceil(G/128) * height, grid.y = image
@@ -649,13 +677,14 @@ cudaError_t launch_k3_format(const DevImage* images, unsigned first, unsigned co
     return cudaGetLastError();
 }
 
-// kernels whose grid is (ceil(G/128) * max_h, images): path selects k2_ycbcr444 / k2_ycbcr422 / k2_bytes
+// kernels whose grid is (ceil(G/128) * max_h, images): path selects k2_ycbcr444 / k2_ycbcr422 / k2_ycbcr440 / k2_bytes
 cudaError_t launch_k2_rows16(unsigned path, const K2Params& p, unsigned first, unsigned count, unsigned max_w, unsigned max_h, cudaStream_t stream) {
     if (count == 0 || max_w == 0 || max_h == 0) return cudaSuccess;
     const unsigned gchunks = ((max_w + 15u) / 16u + 127u) / 128u;
     dim3 grid(gchunks * max_h, count);
     const bool s3 = (p.flags & K2_FLAG_SSSE3) != 0;
     if (path == K2_PATH_422) s3 ? k2_ycbcr422<true><<<grid, 128, 0, stream>>>(p, first, gchunks) : k2_ycbcr422<false><<<grid, 128, 0, stream>>>(p, first, gchunks);
+    else if (path == K2_PATH_440) s3 ? k2_ycbcr440<true><<<grid, 128, 0, stream>>>(p, first, gchunks) : k2_ycbcr440<false><<<grid, 128, 0, stream>>>(p, first, gchunks);
     else if (path == K2_PATH_BYTES) k2_bytes<<<grid, 128, 0, stream>>>(p, first, gchunks);
     else s3 ? k2_ycbcr444<true><<<grid, 128, 0, stream>>>(p, first, gchunks) : k2_ycbcr444<false><<<grid, 128, 0, stream>>>(p, first, gchunks);
     return cudaGetLastError();

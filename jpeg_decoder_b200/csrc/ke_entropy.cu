@@ -365,13 +365,11 @@ size_t ent_work_bytes(unsigned total_sub, unsigned nimages, unsigned max_comp_bl
 cudaError_t launch_entropy(const EntImage* d_images, unsigned nimages, unsigned max_nsub, unsigned total_sub, unsigned max_comp_blocks,
                            uint8_t* d_streams, void* d_work, int max_passes, unsigned** d_status, cudaStream_t stream, uint64_t* launches) {
     if (nimages == 0 || max_nsub == 0) return cudaSuccess;
-    static const cudaError_t attr = [] {  // the kernels' dynamic shared memory (per device attribute of the function: set once per process and device
-                                          // would be stricter; the library drives one device per process, like the reference's one decoder per thread)
-        cudaError_t e = cudaFuncSetAttribute(ent_pass<ENT_COLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_BYTES);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(ent_pass<ENT_WRITE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_BYTES);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(ent_sync, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_BYTES);
-        return e;
-    }();
+    // tables + scan tile pass 48 KB: the opt-in is an attribute of the function ON THE CURRENT DEVICE, so it is set per call
+    // (microseconds per group) rather than once per process -- a process may drive several devices through several contexts
+    cudaError_t attr = cudaFuncSetAttribute(ent_pass<ENT_COLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_BYTES);
+    if (attr == cudaSuccess) attr = cudaFuncSetAttribute(ent_pass<ENT_WRITE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_BYTES);
+    if (attr == cudaSuccess) attr = cudaFuncSetAttribute(ent_sync, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_BYTES);
     if (attr != cudaSuccess) return attr;
     auto up = [](size_t x) { return (x + 255) / 256 * 256; };
     char* p = (char*)d_work;

@@ -328,6 +328,10 @@ static int plan_image(const b200jpg_ctx* ctx, const b200jpg_image_desc& d, DevIm
                  u[1].stride % 8 == 0 && u[2].stride % 8 == 0 && u[1].in_w == u[2].in_w && u[1].in_w == (d.width + 1u) / 2u &&
                  groups * 16u <= ((u[0].stride + 15u) & ~15u) && groups * 8u <= u[1].stride && groups * 8u <= u[2].stride)
             img->path = K2_PATH_422;
+        else if (u[0].kind == UP_H1V1 && u[1].kind == UP_H1V2 && u[2].kind == UP_H1V2 && u[0].stride % 8 == 0 && u[1].stride % 8 == 0 &&
+                 u[2].stride % 8 == 0 && u[1].stride >= d.width && u[2].stride >= d.width &&
+                 (d.height + 1u) / 2u <= u[1].in_h && (d.height + 1u) / 2u <= u[2].in_h)
+            img->path = K2_PATH_440;
     }
     // every component at full resolution, bytes only: RGB / CMYK / YCCK / None
     if (ctx->k2_kernel != B200JPG_KERNEL_GENERIC && (img->cc == CC_RGB || img->cc == CC_CMYK || img->cc == CC_YCCK || img->cc == CC_NOCONVERT)) {
