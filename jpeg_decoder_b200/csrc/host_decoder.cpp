@@ -566,7 +566,13 @@ int HostDecoder::parse_app(uint8_t marker) {
 }
 
 // ---- block decoding, src/decoder.rs:1086-1298 --------------------------------------------------
-int HostDecoder::decode_block(int16_t* c, const HuffTable& dc, const HuffTable& ac, const ScanInfo& s, uint16_t* eob_run,
+// nz (may be null): the block's non-zero map, kept in step with every AC coefficient written (a first pass that runs twice
+// over a band -- malformed files -- may overwrite a coefficient, and a value can shift out to zero: the bit follows the value)
+static inline void note_coef(uint64_t* nz, unsigned index, int16_t stored) {
+    if (nz) *nz = (*nz & ~((uint64_t)1 << index)) | ((uint64_t)(stored != 0) << index);
+}
+
+int HostDecoder::decode_block(int16_t* c, uint64_t* nz, const HuffTable& dc, const HuffTable& ac, const ScanInfo& s, uint16_t* eob_run,
                               int16_t* pred) {
     const uint8_t al = s.al, ss_end = s.ss_end;
     if (s.ss_start == 0) {
@@ -596,6 +602,7 @@ int HostDecoder::decode_block(int16_t* c, const HuffTable& dc, const HuffTable& 
             index = (uint8_t)(index + (rs >> 4));
             if (index >= ss_end) break;
             c[UNZIGZAG[index]] = (int16_t)((uint16_t)ac.ac_value[idx] << al);
+            note_coef(nz, index, c[UNZIGZAG[index]]);
             index++;
             continue;
         }
@@ -620,6 +627,7 @@ int HostDecoder::decode_block(int16_t* c, const HuffTable& dc, const HuffTable& 
             int16_t v;
             TRY(receive_extend(sz, &v));
             c[UNZIGZAG[index]] = (int16_t)((uint16_t)v << al);
+            note_coef(nz, index, c[UNZIGZAG[index]]);
             index++;
         }
     }
@@ -789,7 +797,44 @@ int HostDecoder::refine_non_zeroes(int16_t* c, uint8_t start, uint8_t end, uint8
     return 0;
 }
 
-int HostDecoder::decode_block_sa(int16_t* c, const HuffTable& ac, const ScanInfo& s, uint16_t* eob_run) {
+// refine_non_zeroes over the block's non-zero map: the same bits read in the same order, the same coefficients touched, the
+// same index returned.  The loop above stops at the (zrl + 1)-th ZERO coefficient of [start, end) and reads one correction bit
+// for every NON-ZERO one it passes; here the stop position is the (zrl + 1)-th set bit of the band's zero mask, and the
+// coefficients to correct are the set bits of the map below it.  (A correction never makes a coefficient zero, so the map
+// itself does not change.)
+int HostDecoder::refine_non_zeroes_map(int16_t* c, uint64_t nz, uint8_t start, uint8_t end, uint8_t zrl, int16_t bit, uint8_t* ret) {
+    const uint64_t below_end = end >= 64 ? ~(uint64_t)0 : (((uint64_t)1 << end) - 1);
+    const uint64_t band = start >= 64 ? 0 : below_end & ~(((uint64_t)1 << start) - 1);
+    unsigned stop = end;
+    bool found = false;
+    if (zrl < 64) {
+        uint64_t z = ~nz & band;
+        if ((unsigned)__builtin_popcountll(z) > zrl) {
+            for (unsigned r = zrl; r > 0; r--) z &= z - 1;
+            stop = (unsigned)__builtin_ctzll(z);
+            found = true;
+        }
+    }
+    uint64_t m = nz & band & (stop >= 64 ? ~(uint64_t)0 : (((uint64_t)1 << stop) - 1));
+    while (m) {
+        const unsigned i = (unsigned)__builtin_ctzll(m);
+        m &= m - 1;
+        if (num_bits_ < 1) TRY(read_bits());  // get_bits(1)
+        const bool b = (bits_ >> 63) != 0;
+        bits_ <<= 1;
+        num_bits_ = (uint8_t)(num_bits_ - 1);
+        int16_t* co = &c[UNZIGZAG[i]];
+        if (b && (*co & bit) == 0) {
+            const int32_t v = *co > 0 ? (int32_t)*co + bit : (int32_t)*co - bit;
+            if (v > 32767 || v < -32768) return fail(B200JPG_ERR_FORMAT, "Coefficient overflow");
+            *co = (int16_t)v;
+        }
+    }
+    *ret = found ? (uint8_t)stop : (uint8_t)(end - 1);
+    return 0;
+}
+
+int HostDecoder::decode_block_sa(int16_t* c, uint64_t* nz, const HuffTable& ac, const ScanInfo& s, uint16_t* eob_run) {
     const int16_t bit = (int16_t)(1 << s.al);
     if (s.ss_start == 0) {
         uint16_t b;
@@ -800,7 +845,7 @@ int HostDecoder::decode_block_sa(int16_t* c, const HuffTable& ac, const ScanInfo
     if (*eob_run > 0) {
         *eob_run -= 1;
         uint8_t r;
-        return refine_non_zeroes(c, s.ss_start, s.ss_end, 64, bit, &r);
+        return nz ? refine_non_zeroes_map(c, *nz, s.ss_start, s.ss_end, 64, bit, &r) : refine_non_zeroes(c, s.ss_start, s.ss_end, 64, bit, &r);
     }
     uint8_t index = s.ss_start;
     while (index < s.ss_end) {
@@ -826,8 +871,12 @@ int HostDecoder::decode_block_sa(int16_t* c, const HuffTable& ac, const ScanInfo
         } else {
             return fail(B200JPG_ERR_FORMAT, "unexpected huffman code");
         }
-        TRY(refine_non_zeroes(c, index, s.ss_end, zero_run_length, bit, &index));
-        if (value != 0) c[UNZIGZAG[index]] = value;
+        if (nz) TRY(refine_non_zeroes_map(c, *nz, index, s.ss_end, zero_run_length, bit, &index));
+        else TRY(refine_non_zeroes(c, index, s.ss_end, zero_run_length, bit, &index));
+        if (value != 0) {
+            c[UNZIGZAG[index]] = value;
+            note_coef(nz, index, value);
+        }
         index++;
     }
     return 0;
@@ -941,9 +990,11 @@ int HostDecoder::decode_scan(const ScanInfo& scan, const bool finished[4], bool*
                             continue;
                         }
                         int16_t* c;
+                        uint64_t* nz = nullptr;
                         if (target[i]) {
                             const size_t block_y = (size_t)mcu_y * mv[i] + v_pos, block_x = (size_t)mcu_x * mh[i] + h_pos;
                             c = target[i] + (block_y * comp.block_w + block_x) * 64;
+                            if (is_progressive) nz = nz_[scan.comp_index[i]].data() + (block_y * comp.block_w + block_x);
                             if (zero_per_block[i]) memset(c, 0, 128);
                         } else {
                             c = dummy;
@@ -952,10 +1003,15 @@ int HostDecoder::decode_scan(const ScanInfo& scan, const bool finished[4], bool*
                         if (sequential) {
                             DenseSink sink{c};
                             TRY(decode_block_seq(sink, dc_[scan.dc_table[i]], ac_[scan.ac_table[i]], &eob_run, &dc_predictors[i]));
+                            if (nz) {  // a full-band first pass inside a progressive frame: rebuild the block's map
+                                uint64_t m = 0;
+                                for (unsigned k = 1; k < 64; k++) m |= (uint64_t)(c[UNZIGZAG[k]] != 0) << k;
+                                *nz = m;
+                            }
                         } else if (scan.ah == 0)
-                            TRY(decode_block(c, dc_[scan.dc_table[i]], ac_[scan.ac_table[i]], scan, &eob_run, &dc_predictors[i]));
+                            TRY(decode_block(c, nz, dc_[scan.dc_table[i]], ac_[scan.ac_table[i]], scan, &eob_run, &dc_predictors[i]));
                         else
-                            TRY(decode_block_sa(c, ac_[scan.ac_table[i]], scan, &eob_run));
+                            TRY(decode_block_sa(c, nz, ac_[scan.ac_table[i]], scan, &eob_run));
                     }
             }
         }
@@ -1060,6 +1116,7 @@ int HostDecoder::decode_internal(bool stop_after_metadata) {
             if (frame.coding_process == B200JPG_CP_DCT_PROGRESSIVE && !has_work_) {
                 for (size_t i = 0; i < frame.comps.size(); i++)
                     work_[i].assign((size_t)frame.comps[i].block_w * frame.comps[i].block_h * 64, 0);
+                for (size_t i = 0; i < frame.comps.size(); i++) nz_[i].assign((size_t)frame.comps[i].block_w * frame.comps[i].block_h, 0);
                 has_work_ = true;
             }
             if (frame.coding_process == B200JPG_CP_LOSSLESS)

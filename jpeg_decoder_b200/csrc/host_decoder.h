@@ -147,12 +147,13 @@ private:
     int receive_extend(uint8_t count, int16_t* v);
     int huff_decode(const HuffTable& t, uint8_t* out);
     int take_marker(bool* has, uint8_t* m);
-    int decode_block(int16_t* c, const HuffTable& dc, const HuffTable& ac, const ScanInfo& s, uint16_t* eob_run, int16_t* pred);
+    int decode_block(int16_t* c, uint64_t* nz, const HuffTable& dc, const HuffTable& ac, const ScanInfo& s, uint16_t* eob_run, int16_t* pred);
     template <class Sink>
     int decode_block_seq(Sink& sink, const HuffTable& dc, const HuffTable& ac, uint16_t* eob_run, int16_t* pred);
     int finish_sbs();
-    int decode_block_sa(int16_t* c, const HuffTable& ac, const ScanInfo& s, uint16_t* eob_run);
+    int decode_block_sa(int16_t* c, uint64_t* nz, const HuffTable& ac, const ScanInfo& s, uint16_t* eob_run);
     int refine_non_zeroes(int16_t* c, uint8_t start, uint8_t end, uint8_t zrl, int16_t bit, uint8_t* ret);
+    int refine_non_zeroes_map(int16_t* c, uint64_t nz, uint8_t start, uint8_t end, uint8_t zrl, int16_t bit, uint8_t* ret);
 
     const uint8_t* data_;
     size_t len_, pos_ = 0;
@@ -173,6 +174,10 @@ private:
     size_t buffer_limit_ = (size_t)-1;
     // progressive working store (src/decoder.rs:124-126) and what the worker gets
     std::vector<int16_t> work_[4];
+    // progressive frames: per block of work_, bit k = the coefficient with zig-zag index k is non-zero.  The refinement scans
+    // (src/decoder.rs:1174-1298) walk "the non-zero coefficients of the band" and "the n-th zero coefficient" for every block
+    // of every scan; with the map both are bit scans over one word instead of 63 scattered loads per block and scan
+    std::vector<uint64_t> nz_[4];
     bool has_work_ = false;
     uint64_t finished_mask_[4] = {0, 0, 0, 0};
     std::vector<int16_t> final_[4];

@@ -97,6 +97,55 @@ def test_host_decoder_matches_oracle_feeder(oracle_mod, J):
     assert checked >= 38
 
 
+def test_corrupted_progressive_scans_agree_with_the_oracle(oracle_mod, J):
+    """The refinement scans of the product's host decoder walk a per-block non-zero map (host_decoder.cpp:
+    refine_non_zeroes_map) where the reference -- and the oracle -- walk the coefficients (src/decoder.rs:1250-1298).
+    On damaged progressive files (bit flips, scrambled and dropped runs inside the scans: repeated bands, runs that overshoot,
+    corrections of coefficients that shifted to zero) both must still end the same way: the same error class, or the same
+    coefficients bit for bit."""
+    rng = np.random.default_rng(20261017)
+    srcs = [os.path.join(GOLDEN, "benches", "tower_progressive.jpg")]
+    srcs += [p for p in reftest_files() if "progressive" in os.path.basename(p) and os.path.getsize(p) > 4096][:3]
+    agree_ok = agree_err = 0
+    for p in srcs:
+        data = bytearray(open(p, "rb").read())
+        first_sos = data.find(b"\xff\xda")
+        assert first_sos > 0
+        for t in range(60):
+            c = bytearray(data)
+            for _ in range(int(rng.integers(1, 4))):
+                at = int(rng.integers(first_sos + 14, len(c) - 4))
+                kind = int(rng.integers(0, 3))
+                if kind == 0:
+                    c[at] ^= 1 << int(rng.integers(0, 8))
+                elif kind == 1:
+                    n = int(rng.integers(1, 24))
+                    c[at:at + n] = bytes(int(x) for x in rng.integers(0, 255, size=n))   # no 0xFF: stays inside the scan
+                else:
+                    del c[at:at + int(rng.integers(1, 40))]
+            c = bytes(c)
+            o = oracle_mod.Decoder(c)
+            try:
+                o.decode()
+                oerr = 0
+            except oracle_mod.OracleError as e:
+                oerr = e.code
+            pd = J.Decoder(c)
+            try:
+                desc = pd.entropy_decode()
+                perr = 0
+            except J.B200JpgError as e:
+                perr = -e.code
+            assert oerr == perr, (p, t, oerr, perr)
+            if oerr:
+                agree_err += 1
+                continue
+            for i in range(desc.ncomp):
+                assert np.array_equal(pd.coefficients(desc, i), o.coefficients(i)), (p, t, i)
+            agree_ok += 1
+    assert agree_ok >= 20 and agree_ok + agree_err == 60 * len(srcs), (agree_ok, agree_err)
+
+
 def test_crashtest_corpus(oracle_mod, J):
     """tests/crashtest/mod.rs:8-17: malformed files must produce errors, never crash; both decoders agree on the class."""
     files = sorted(f for f in glob.glob(os.path.join(GOLDEN, "crashtest", "**", "*"), recursive=True) if os.path.isfile(f))
