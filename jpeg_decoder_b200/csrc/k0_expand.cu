@@ -174,6 +174,29 @@ __global__ void __launch_bounds__(256) k0_zero_headers(const K0Image* __restrict
     for (size_t q = (size_t)blockIdx.x * 256u + threadIdx.x; q < n16; q += (size_t)gridDim.x * 256u) p[q] = make_uint4(0u, 0u, 0u, 0u);
 }
 
+// Upload by kernel: the streams of a group lie scattered over the host threads' page-locked rings; one launch reads them all
+// through their device mappings (zero copy) and lays them out back to back in the device stream buffer.  One copy-engine
+// transfer per image made ~27 operations per group compete with the pixel download for the link (the download lost 9 %,
+// the uploads ran at 13-18 GB/s); a host-side gather into one staging buffer fixed that but cost the submitter thread a 0.3 B
+// per pixel memcpy at 4-7 GB/s, which became the bottleneck with two GPUs per box.  This kernel costs the host nothing and
+// the download 4 % (scripts/pcie_probe4.py: 29 GB/s next to a saturated download, 50 GB/s alone).
+// grid = (GATHER_CTAS, items); 16-byte words, both sides 16-byte aligned.
+constexpr unsigned GATHER_CTAS = 5, GATHER_THREADS = 256;
+__global__ void __launch_bounds__(GATHER_THREADS) k_gather_streams(const GatherItem* __restrict__ items, uint8_t* __restrict__ dst) {
+    const GatherItem it = items[blockIdx.y];
+    const uint4* src = reinterpret_cast<const uint4*>(it.src);
+    uint4* out = reinterpret_cast<uint4*>(dst + it.dst_off);
+    for (unsigned i = blockIdx.x * GATHER_THREADS + threadIdx.x; i < it.n16; i += GATHER_CTAS * GATHER_THREADS) out[i] = src[i];
+}
+
+cudaError_t launch_gather_streams(const GatherItem* d_items, unsigned nitems, uint8_t* d_streams, cudaStream_t stream) {
+    for (unsigned base = 0; base < nitems; base += 65535u) {
+        const unsigned cnt = min(65535u, nitems - base);
+        k_gather_streams<<<dim3(GATHER_CTAS, cnt), GATHER_THREADS, 0, stream>>>(d_items + base, d_streams);
+    }
+    return cudaGetLastError();
+}
+
 cudaError_t launch_k0_zero_headers(const K0Image* d_images, unsigned nimages, unsigned max_blocks, uint8_t* d_streams, cudaStream_t stream) {
     if (nimages == 0 || max_blocks == 0) return cudaSuccess;
     const unsigned n16 = (14u * ((max_blocks + 31u) & ~31u) + 15u) / 16u;

@@ -48,6 +48,13 @@ cudaError_t launch_entropy(const EntImage* d_images, unsigned nimages, unsigned 
 cudaError_t launch_k0_expand_blocks(const K0Image* d_images, unsigned nimages, unsigned max_blocks, const uint8_t* d_streams, short* d_slab,
                                     cudaStream_t stream);
 cudaError_t launch_k0_zero_headers(const K0Image* d_images, unsigned nimages, unsigned max_blocks, uint8_t* d_streams, cudaStream_t stream);
+// one entry per stream a group uploads by kernel (k0_expand.cu: k_gather_streams)
+struct GatherItem {
+    const void* src;             // page-locked host memory, read through its device mapping (unified addressing)
+    unsigned long long dst_off;  // byte offset inside the device stream buffer
+    unsigned n16, pad_;          // length in 16-byte words
+};
+cudaError_t launch_gather_streams(const GatherItem* d_items, unsigned nitems, uint8_t* d_streams, cudaStream_t stream);
 cudaError_t launch_k1_generic(const K1Params& p, int arith, cudaStream_t stream);
 size_t k1_tma_smem_bytes();
 cudaError_t launch_k1_tma(const CUtensorMap& tmap, const K1QCache& qc, const K1Params& p, int arith, bool scaled, int num_sms, cudaStream_t stream);

@@ -74,7 +74,6 @@ SbsPipeline::~SbsPipeline() {
         cudaFree(s.d_ent.p);
         if (s.h_tables.p) cudaFreeHost(s.h_tables.p);
         if (s.h_status.p) cudaFreeHost(s.h_status.p);
-        if (s.h_stage.p) cudaFreeHost(s.h_stage.p);
         if (s.e_h2d) cudaEventDestroy(s.e_h2d);
         if (s.e_comp) cudaEventDestroy(s.e_comp);
         if (s.e_done) cudaEventDestroy(s.e_done);
@@ -89,7 +88,10 @@ SbsPipeline::~SbsPipeline() {
 }
 
 int SbsPipeline::grow_device(Buf& b, size_t need, size_t hint) {
-    if (need <= b.cap) return B200JPG_OK;
+    // With a reservation the buffer goes to its full size the FIRST time the slot is used, whatever that group needs: a call
+    // that switches from host to device outputs raises the group cap fourfold, and a buffer that only grew when a group
+    // finally exceeded the old size stalled a call in mid-run (2 GPUs x 256 images per call: 15 instead of 60-97 GP/s).
+    if (std::max(need, hint) <= b.cap) return B200JPG_OK;
     const double t0 = now_ms();
     struct Tally { SbsPipeline* p; double t0; ~Tally() { p->grow_ms += now_ms() - t0; p->grows++; } } tally{this, t0};
     // doubling, so that a buffer regrows a handful of times in its life.  The slot is idle (its previous group has
@@ -112,7 +114,7 @@ int SbsPipeline::grow_device(Buf& b, size_t need, size_t hint) {
     return B200JPG_OK;
 }
 int SbsPipeline::grow_pinned(Buf& b, size_t need, size_t hint) {
-    if (need <= b.cap) return B200JPG_OK;
+    if (std::max(need, hint) <= b.cap) return B200JPG_OK;
     const double t0 = now_ms();
     struct Tally { SbsPipeline* p; double t0; ~Tally() { p->grow_ms += now_ms() - t0; p->grows++; } } tally{this, t0};
     if (b.p) cudaFreeHost(b.p);
@@ -280,7 +282,7 @@ int SbsPipeline::enqueue(Slot& s) {
         tbound += ((size_t)descs[i].width / 2048 + 1) * sizeof(K2Strip);
         tbound += ((size_t)descs[i].width / 960 + 2) * sizeof(FColumn);
     }
-    tbound += max_ent * sizeof(EntImage) + 1024;
+    tbound += max_ent * sizeof(EntImage) + n * sizeof(GatherItem) + 1024 + 256;
     // Pixel buffers in device memory (every image of the group): the kernels write them directly -- no pixel slab, no
     // device-to-device copy afterwards (unified addressing tells host from device pointers).
     bool device_outs = n > 0;
@@ -298,7 +300,7 @@ int SbsPipeline::enqueue(Slot& s) {
     TableArena arena;
     arena.d = (char*)s.d_tables.p;
     arena.h = (char*)s.h_tables.p;
-    arena.bytes = tbound - n * sizeof(K0Image) - max_ent * sizeof(EntImage) - 3 * 256;
+    arena.bytes = tbound - n * sizeof(K0Image) - max_ent * sizeof(EntImage) - n * sizeof(GatherItem) - 4 * 256;
     PlanOverrides ov;
     ov.arena = &arena;
     ov.upload_stream = s_in_;
@@ -314,7 +316,10 @@ int SbsPipeline::enqueue(Slot& s) {
     const size_t ent_at = up(k0_at + n * sizeof(K0Image), 256);
     EntImage* h_ent = (EntImage*)(arena.h + ent_at);
     const EntImage* d_ent = (const EntImage*)(arena.d + ent_at);
-    size_t nk0 = 0, nent = 0, stream_bytes = 0;
+    const size_t gat_at = up(ent_at + max_ent * sizeof(EntImage), 256);
+    GatherItem* h_gat = (GatherItem*)(arena.h + gat_at);
+    const GatherItem* d_gat = (const GatherItem*)(arena.d + gat_at);
+    size_t nk0 = 0, nent = 0, ngat = 0, stream_bytes = 0;
     unsigned max_nb = 0, max_nsub = 0, total_sub = 0, max_comp_blocks = 0;
     std::vector<size_t> soff(n, 0);
     s.ent_items.clear();
@@ -382,29 +387,23 @@ int SbsPipeline::enqueue(Slot& s) {
     // copy-in
     s.t_enq = now_ms();
     if (timeline_) CU_TRY(ctx_, cudaEventRecord(s.e_t0[0], s_in_));
-    // Pixels that leave over PCIe: the group's streams go up as ONE copy from a page-locked staging buffer the submitter
-    // fills.  While the download stream saturates the link every upload operation crawls (17 MB in 2.4 ms) and slows the
-    // download; ~27 of them per group cost the download 8 % more than one (scripts/pcie_probe3.py; 15.2 -> 16.0 GP/s,
-    // profiles/r02_files_gather_ab.jsonl).  The gather is a host memcpy of 0.3 B per pixel on the submitter thread, which
-    // otherwise waits for the download anyway; with pixels staying on the device it would be the bottleneck (measured:
-    // 65 -> 23 GP/s), so there the streams are uploaded from where the host threads wrote them.  B200JPG_GATHER=0/1 forces.
-    static const int gather_env = getenv("B200JPG_GATHER") ? atoi(getenv("B200JPG_GATHER")) : -1;
-    const bool gather = gather_env >= 0 ? gather_env != 0 : !device_outs;
-    if (gather && stream_bytes) {
-        rc = grow_pinned(s.h_stage, stream_bytes, reserve_ ? (size_t)48 << 20 : 0);
-        if (rc) return rc;
-        for (size_t i = 0; i < n; i++)
-            if (!s.group.statuses[i]) memcpy((char*)s.h_stage.p + soff[i], it[i].stream, it[i].len);
-        CU_TRY(ctx_, cudaMemcpyAsync(s.d_streams.p, s.h_stage.p, stream_bytes, cudaMemcpyHostToDevice, s_in_));
-        h2d_copies++;
-    }
-    if (!gather) {
+    // Streams in page-locked rings are uploaded by ONE kernel per group (k_gather_streams, k0_expand.cu: why); anything else
+    // (b200jpg_decode_batch_sbs takes whatever memory the caller has) goes through the copy engine, runs merged.
+    {
         const char* run_src = nullptr;
         size_t run_dst = 0, run_bytes = 0;
         for (size_t i = 0; i < n; i++) {
             if (s.group.statuses[i]) continue;
             const size_t dst = soff[i];
             const char* src = (const char*)it[i].stream;
+            if (it[i].mapped && it[i].len % 16 == 0 && ((uintptr_t)src & 15u) == 0 && dst % 16 == 0) {
+                h_gat[ngat].src = src;
+                h_gat[ngat].dst_off = dst;
+                h_gat[ngat].n16 = (unsigned)(it[i].len / 16);
+                h_gat[ngat].pad_ = 0;
+                ngat++;
+                continue;
+            }
             if (run_bytes && run_src + run_bytes == src && run_dst + run_bytes == dst) {
                 run_bytes += it[i].len;
             } else {
@@ -417,10 +416,16 @@ int SbsPipeline::enqueue(Slot& s) {
         }
         if (run_bytes) CU_TRY(ctx_, cudaMemcpyAsync((char*)s.d_streams.p + run_dst, run_src, run_bytes, cudaMemcpyHostToDevice, s_in_));
     }
-    // the K0 and entropy descriptors lie behind each other in the table arena: one copy
-    if (nk0 || nent)
-        CU_TRY(ctx_, cudaMemcpyAsync((void*)d_k0, h_k0, (nent ? ent_at + nent * sizeof(EntImage) : k0_at + nk0 * sizeof(K0Image)) - k0_at,
-                                     cudaMemcpyHostToDevice, s_in_));
+    // the K0, entropy and gather descriptors lie behind each other in the table arena: one copy
+    if (nk0 || nent || ngat) {
+        const size_t end = ngat ? gat_at + ngat * sizeof(GatherItem) : (nent ? ent_at + nent * sizeof(EntImage) : k0_at + nk0 * sizeof(K0Image));
+        CU_TRY(ctx_, cudaMemcpyAsync((void*)d_k0, h_k0, end - k0_at, cudaMemcpyHostToDevice, s_in_));
+    }
+    if (ngat) {
+        CU_TRY(ctx_, launch_gather_streams(d_gat, (unsigned)ngat, (uint8_t*)s.d_streams.p, s_in_));
+        h2d_copies++;
+        ctx_->launches++;
+    }
     CU_TRY(ctx_, cudaEventRecord(s.e_h2d, s_in_));
     // compute
     // Pixels that leave over PCIe: one compute stream, first in first out, so that the oldest group finishes (and starts

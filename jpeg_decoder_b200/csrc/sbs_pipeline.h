@@ -33,6 +33,7 @@ struct SbsItem {
     size_t job = 0;        // caller's cookie
     int thread = 0;        // caller's cookie
     uint64_t ring_end = 0; // caller's cookie
+    bool mapped = false;   // `stream` is page-locked memory the device can read in place (cudaHostAlloc): it may be uploaded by kernel
 };
 
 class SbsPipeline {
@@ -73,7 +74,7 @@ private:
         size_t cap = 0;
     };
     struct Slot {
-        Buf d_streams, d_coefs, d_planes, d_out, d_tables, h_tables, d_ent, h_status, h_stage;
+        Buf d_streams, d_coefs, d_planes, d_out, d_tables, h_tables, d_ent, h_status;
         std::vector<size_t> ent_items;  // group index of the image of every device-decoded restart interval
         size_t ent_images = 0;          // images of the group whose scan is decoded on the device
         cudaEvent_t e_h2d = nullptr, e_comp = nullptr, e_done = nullptr;

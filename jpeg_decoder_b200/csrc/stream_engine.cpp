@@ -200,6 +200,7 @@ int stream_engine_run(b200jpg_ctx* ctx, JobSource& src, int nthreads) {
             item.stream = ring.base + pos;
             item.job = i;
             item.thread = tid;
+            item.mapped = true;  // the rings are cudaHostAlloc'ed
             item.ring_end = ring.book.commit((item.len + 512 + 255) / 256 * 256);
             produce_us += (uint64_t)((now_ms() - t0) * 1e3);
             {
