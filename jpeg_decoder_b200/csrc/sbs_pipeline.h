@@ -54,6 +54,8 @@ public:
     int drain();                               // wait for everything in flight
     // optional: keep dense slab copies for debugging (tests): after drain(), the last group's coefficient slab
     const void* last_coef_slab() const { return last_coefs_; }
+    // groups submitted and not yet retired (as of the last poll)
+    size_t in_flight() const { return next_ - oldest_; }
 
     // The caller's bound on the dense coefficient bytes of one group (the stream engine's group cap): slot buffers are sized
     // for it the first time they are needed, so that nothing regrows in steady state.  A regrowth of a few hundred MB costs

@@ -257,10 +257,16 @@ int stream_engine_run(b200jpg_ctx* ctx, JobSource& src, int nthreads) {
             std::unique_lock<std::mutex> lk(mu);
             const double w0 = now_ms();
             if (queue.empty() && workers_active > 0) items_cv.wait_for(lk, std::chrono::microseconds(200));
-            // a bounded second wait lets more images join a small group (fewer, larger launches)
-            if (!queue.empty() && queue.size() < min_items && workers_active > 0) {
-                const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(fill_us);
-                while (queue.size() < min_items && workers_active > 0 && (ngroups > 0 || !dev_out) &&
+            // a bounded second wait lets more images join a small group (fewer, larger launches).  With pixels leaving over PCIe
+            // and two groups already queued behind the download there is no hurry at all: small groups download at 25-46 GB/s
+            // where groups of 16+ images reach 50 (per-group timeline), so wait up to a millisecond for 16: 16.4-16.7 GP/s in every
+            // run, where eager grouping gave 16.5 or -- one run in three, and with 4 CPUs -- 14.5 (profiles/r02_files_group_relax_ab.jsonl).
+            static const bool relax_off = getenv("B200JPG_GROUP_RELAX") && atoi(getenv("B200JPG_GROUP_RELAX")) == 0;
+            const bool relaxed = !relax_off && !dev_out && pipe.in_flight() >= 2;
+            const size_t want_items = relaxed ? std::max<size_t>(min_items, 16) : min_items;
+            if (!queue.empty() && queue.size() < want_items && workers_active > 0) {
+                const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(relaxed ? std::max(fill_us, 1000) : fill_us);
+                while (queue.size() < want_items && workers_active > 0 && (ngroups > 0 || !dev_out) &&
                        items_cv.wait_until(lk, deadline) != std::cv_status::timeout) {
                 }
             }
