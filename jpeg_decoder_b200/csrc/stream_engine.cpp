@@ -217,7 +217,8 @@ int stream_engine_run(b200jpg_ctx* ctx, JobSource& src, int nthreads) {
     };
 
     SbsPipeline& pipe = *eng->pipe;
-    pipe.reserve_for_group_bytes((size_t)(src.outputs_on_device() ? 640 : 160) << 20);
+    // (a call with a handful of images -- a lone Decoder::decode -- takes what it needs instead of 0.7-2 GB per slot)
+    pipe.reserve_for_group_bytes(n >= 32 ? (size_t)(src.outputs_on_device() ? 640 : 160) << 20 : 0);
     pipe.grow_ms = pipe.enqueue_ms = pipe.retire_wait_ms = 0;
     pipe.grows = pipe.h2d_copies = pipe.d2h_copies = 0;
     pipe.timeline_begin();
